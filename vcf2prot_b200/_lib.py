@@ -1,0 +1,75 @@
+"""ctypes binding of libv2p_engine.so (include/v2p_engine.h).  Fails loudly when the library is absent:
+there is no CPU implementation behind this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libv2p_engine.so")
+
+V2P_OK = 0
+ERR_INVALID_ARG, ERR_CUDA, ERR_BAD_ENGINE, ERR_BAD_STREAM, ERR_RES_OOB, ERR_SRC_OOB = 1, 2, 3, 4, 5, 6
+ERR_NOT_CONTIGUOUS, ERR_NOT_GPU_ENGINE = 7, 9
+ENGINE_ST, ENGINE_MT, ENGINE_GPU = 0, 1, 2
+FLAG_FILL_DOT, FLAG_VALIDATE, FLAG_DEVICE_PTRS, FLAG_ASYNC = 1, 2, 4, 8
+
+STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "BAD_ENGINE", 4: "BAD_STREAM", 5: "RES_OOB", 6: "SRC_OOB",
+                7: "NOT_CONTIGUOUS", 9: "NOT_GPU_ENGINE"}
+
+
+class Task16(C.Structure):
+    _fields_ = [("src_off", C.c_uint32), ("len", C.c_uint32), ("dst_off", C.c_uint32), ("stream", C.c_uint32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("task_begin", C.c_void_p), ("tasks", C.c_void_p), ("ref", C.c_void_p), ("ref_base", C.c_void_p),
+                ("n_ref", C.c_uint64), ("alt", C.c_void_p), ("alt_base", C.c_void_p), ("out", C.c_void_p),
+                ("out_base", C.c_void_p), ("n_hap", C.c_uint64), ("n_tasks", C.c_uint64), ("n_alt", C.c_uint64),
+                ("n_out", C.c_uint64)]
+
+
+class Result(C.Structure):
+    _fields_ = [("status", C.c_int), ("bad_hap", C.c_uint64), ("bad_task", C.c_uint64), ("kernel_ms", C.c_float)]
+
+
+# every symbol include/v2p_engine.h declares: (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "v2p_abi_version": (C.c_int, []),
+    "v2p_engine_from_str": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
+    "v2p_engine_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "v2p_engine_destroy": (None, [_P]),
+    "v2p_last_error": (C.c_char_p, [_P]),
+    "v2p_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "v2p_host_free": (C.c_int, [_P]),
+    "v2p_execute_soa": (C.c_int, [_P, C.c_size_t, _P, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t,
+                                  C.c_uint32, C.POINTER(C.c_uint64)]),
+    "v2p_gir_execute": (C.c_int, [_P, C.c_int, C.c_size_t, _P, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t, _P,
+                                  C.c_size_t, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "v2p_execute_batch": (C.c_int, [_P, C.POINTER(Batch), C.c_uint32, C.POINTER(Result), C.POINTER(_P)]),
+    "v2p_event_wait": (C.c_int, [_P, _P, C.POINTER(Result)]),
+    "v2p_kernel_launch_count": (C.c_uint64, [_P]),
+    "v2p_engine_set_tuning": (C.c_int, [_P, C.c_int, C.c_int]),
+    "v2p_engine_set_stream": (C.c_int, [_P, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the engine library and type every exported symbol.  Raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "vcf2prot_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C vcf2prot_b200/csrc`).  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

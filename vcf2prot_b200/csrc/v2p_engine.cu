@@ -1,0 +1,542 @@
+// v2p_engine.cu -- C ABI (include/v2p_engine.h) over the sm_100a kernels in v2p_kernels.cuh.
+//
+// Replaces the `Engine::GPU` arm of GIR::execute (/root/reference/src/data_structures/InternalRep/gir.rs:236-239)
+// and adds the batched native entry the host pipeline uses.  No CPU fallback exists in this file: every
+// result byte is produced by a CUDA kernel or the call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "v2p_engine.h"
+#include "v2p_kernels.cuh"
+
+using namespace v2p;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct v2p_event {
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    DevStatus* h_status = nullptr;  // pinned
+    KParams kp;                     // for the deferred serial fallback
+    uint32_t flags = 0;
+    // host-pointer mode bookkeeping
+    bool host_mode = false;
+    uint8_t* h_out = nullptr;
+    size_t out_bytes = 0;
+    const uint64_t* h_task_begin = nullptr;  // borrowed until the wait (host-pointer mode)
+};
+
+struct v2p_engine {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    int variant = 0;      // 0: TILE=4096, 1: TILE=2048
+    int ctas_per_sm = 0;  // 0 = default
+    DevBuf lb, tile_hap, status;
+    // staging for host-pointer calls
+    DevBuf d_tasks, d_task_begin, d_ref, d_ref_base, d_alt, d_alt_base, d_out, d_out_base;
+    // staging for the SoA call
+    DevBuf d_soa[4];
+    DevStatus* h_status = nullptr;  // pinned scratch for synchronous calls
+};
+
+namespace {
+
+int fail(v2p_engine* e, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    return code;
+}
+
+#define CUDA_TRY(e, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _st = (call);                                                                           \
+        if (_st != cudaSuccess)                                                                             \
+            return fail((e), V2P_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, \
+                        __LINE__);                                                                          \
+    } while (0)
+
+int reserve(v2p_engine* e, DevBuf& b, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    if (b.cap >= bytes) return V2P_OK;
+    if (b.p) CUDA_TRY(e, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(e, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return V2P_OK;
+}
+
+int tile_bytes_of(const v2p_engine* e) { return e->variant == 1 ? 2048 : 4096; }
+
+// plan + copy on e->stream.  kp.{lb,tile_hap,status,n_tiles,tile_bytes} are filled here.
+int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop, bool init_status = true) {
+    const int T = tile_bytes_of(e);
+    kp.tile_bytes = (uint32_t)T;
+    kp.n_tiles = (kp.n_out + T - 1) / T;
+    if (kp.n_tasks >= 0xFFFFFFFEull) return fail(e, V2P_ERR_INVALID_ARG, "more than 2^32-2 tasks in one launch");
+    int rc;
+    if ((rc = reserve(e, e->lb, (kp.n_tiles + 1) * sizeof(uint32_t)))) return rc;
+    if ((rc = reserve(e, e->tile_hap, std::max<uint64_t>(kp.n_tiles, 1) * sizeof(uint32_t)))) return rc;
+    if ((rc = reserve(e, e->status, sizeof(DevStatus)))) return rc;
+    kp.lb = (uint32_t*)e->lb.p;
+    kp.tile_hap = (uint32_t*)e->tile_hap.p;
+    kp.status = (DevStatus*)e->status.p;
+    cudaStream_t s = e->stream;
+    if (ev_start) CUDA_TRY(e, cudaEventRecord(ev_start, s));
+    CUDA_TRY(e, cudaMemsetAsync(kp.lb, 0xFF, (kp.n_tiles + 1) * sizeof(uint32_t), s));
+    CUDA_TRY(e, cudaMemsetAsync(kp.tile_hap, 0, std::max<uint64_t>(kp.n_tiles, 1) * sizeof(uint32_t), s));
+    if (init_status) {
+        k_init_status<<<1, 1, 0, s>>>(kp.status);
+        e->launches++;
+    }
+    if (kp.n_hap) {
+        k_plan_haps<<<(unsigned)((kp.n_hap + 255) / 256), 256, 0, s>>>(kp);
+        e->launches++;
+    }
+    if (kp.n_tasks) {
+        k_plan_tasks<<<(unsigned)((kp.n_tasks + 255) / 256), 256, 0, s>>>(kp);
+        e->launches++;
+    }
+    if (kp.n_tiles) {
+        const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : (T == 4096 ? 4 : 8);
+        uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+        unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
+        if (T == 4096) {
+            size_t smem = (size_t)kWarpsPerCta * (4096 + 256);
+            k_copy_tiles<4096><<<grid, kThreads, smem, s>>>(kp);
+        } else {
+            size_t smem = (size_t)kWarpsPerCta * (2048 + 128);
+            k_copy_tiles<2048><<<grid, kThreads, smem, s>>>(kp);
+        }
+        e->launches++;
+    }
+    if (ev_stop) CUDA_TRY(e, cudaEventRecord(ev_stop, s));
+    CUDA_TRY(e, cudaGetLastError());
+    return V2P_OK;
+}
+
+void decode_status(const DevStatus& st, const uint64_t* task_begin_host, uint64_t n_hap, uint64_t task_origin,
+                   v2p_result* res) {
+    res->status = V2P_OK;
+    res->bad_hap = 0;
+    res->bad_task = 0;
+    uint64_t bad = 0;
+    if (st.bad_args) {
+        res->status = V2P_ERR_INVALID_ARG;
+        return;
+    }
+    // Precedence follows the reference's own order of events: a bad stream code panics while the Task
+    // array is built (haplotype_instruction.rs:154), the contiguity validator runs before execution
+    // (gir.rs:203-229), slice panics happen during execution (task.rs:44/48).
+    const bool has_err = st.err_key != ~0ull, has_gap = st.gap_key != ~0ull;
+    if (has_err && (int)(st.err_key & 0xFF) == V2P_ERR_BAD_STREAM) {
+        res->status = V2P_ERR_BAD_STREAM;
+        bad = st.err_key >> 8;
+    } else if (has_gap) {
+        res->status = V2P_ERR_NOT_CONTIGUOUS;
+        bad = st.gap_key;
+    } else if (has_err) {
+        res->status = (int)(st.err_key & 0xFF);
+        bad = st.err_key >> 8;
+    } else {
+        return;
+    }
+    res->bad_task = bad;  // launch-relative global index unless task_begin is known on the host
+    if (task_begin_host && n_hap) {
+        const uint64_t abs_t = bad + task_origin;
+        size_t h = std::upper_bound(task_begin_host, task_begin_host + n_hap + 1, abs_t) - task_begin_host;
+        h = h ? h - 1 : 0;
+        if (h >= n_hap) h = n_hap - 1;
+        res->bad_hap = h;
+        res->bad_task = abs_t - task_begin_host[h];
+    }
+}
+
+// serial-order fallback, launched only after the plan reported unsorted/overlapping tasks
+int launch_serial(v2p_engine* e, const KParams& kp) {
+    unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(kp.n_hap, 1), (uint64_t)e->sm_count * 8);
+    k_serial<<<grid, kThreads, 0, e->stream>>>(kp);
+    e->launches++;
+    CUDA_TRY(e, cudaGetLastError());
+    return V2P_OK;
+}
+
+// Finish a launch group: fetch status, run the serial fallback when needed.
+int finish_group(v2p_engine* e, KParams& kp, DevStatus* h_status, bool* ran_serial) {
+    CUDA_TRY(e, cudaMemcpyAsync(h_status, kp.status, sizeof(DevStatus), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (ran_serial) *ran_serial = false;
+    if (!h_status->bad_args && h_status->err_key == ~0ull && h_status->gap_key == ~0ull && h_status->unsorted) {
+        int rc = launch_serial(e, kp);
+        if (rc) return rc;
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+        if (ran_serial) *ran_serial = true;
+    }
+    return V2P_OK;
+}
+
+int check_batch_args(v2p_engine* e, const v2p_batch* b) {
+    if (!b) return fail(e, V2P_ERR_INVALID_ARG, "batch is NULL");
+    if (b->n_hap == 0) return V2P_OK;
+    if (!b->task_begin || !b->alt_base || !b->out_base)
+        return fail(e, V2P_ERR_INVALID_ARG, "task_begin/alt_base/out_base must not be NULL");
+    return V2P_OK;
+}
+
+// Completes a launch group: status, serial fallback, D2H (host mode); destroys the event.
+int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
+    v2p_result local;
+    memset(&local, 0, sizeof local);
+    auto cleanup = [&](int code) {
+        if (ev->ev_start) cudaEventDestroy(ev->ev_start);
+        if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
+        if (ev->h_status) cudaFreeHost(ev->h_status);
+        delete ev;
+        if (res) *res = local;
+        return code;
+    };
+    cudaSetDevice(e->device);
+    int rc = finish_group(e, ev->kp, ev->h_status, nullptr);
+    if (rc) return cleanup(rc);
+    std::vector<uint64_t> tb_copy;
+    const uint64_t* tb = ev->h_task_begin;
+    const DevStatus& st = *ev->h_status;
+    if (!tb && ev->kp.n_hap && (st.err_key != ~0ull || st.gap_key != ~0ull)) {  // error path only: fetch task_begin
+        tb_copy.resize(ev->kp.n_hap + 1);
+        if (cudaMemcpy(tb_copy.data(), ev->kp.task_begin, tb_copy.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost) ==
+            cudaSuccess)
+            tb = tb_copy.data();
+    }
+    decode_status(st, tb, ev->kp.n_hap, ev->kp.task_origin, &local);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev->ev_start, ev->ev_stop) == cudaSuccess) local.kernel_ms = ms;
+    if (local.status == V2P_OK && ev->host_mode && ev->out_bytes) {
+        if (cudaMemcpyAsync(ev->h_out, ev->kp.out, ev->out_bytes, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess ||
+            cudaStreamSynchronize(e->stream) != cudaSuccess)
+            return cleanup(fail(e, V2P_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    if (local.status != V2P_OK)
+        fail(e, local.status, "haplotype %llu task %llu rejected with status %d", (unsigned long long)local.bad_hap,
+             (unsigned long long)local.bad_task, local.status);
+    return cleanup(local.status);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ ABI
+extern "C" {
+
+int v2p_abi_version(void) { return V2P_ABI_VERSION; }
+
+int v2p_engine_from_str(const char* s, int* engine_kind) {
+    if (!s || !engine_kind) return V2P_ERR_INVALID_ARG;
+    if (!strcmp(s, "st") || !strcmp(s, "ST")) return *engine_kind = V2P_ENGINE_ST, V2P_OK;
+    if (!strcmp(s, "mt") || !strcmp(s, "MT")) return *engine_kind = V2P_ENGINE_MT, V2P_OK;
+    if (!strcmp(s, "gpu") || !strcmp(s, "GPU")) return *engine_kind = V2P_ENGINE_GPU, V2P_OK;
+    return V2P_ERR_BAD_ENGINE;
+}
+
+int v2p_engine_create(int cuda_device, v2p_engine** out) {
+    if (!out) return V2P_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || cuda_device < 0 || cuda_device >= n) return V2P_ERR_CUDA;
+    v2p_engine* e = new (std::nothrow) v2p_engine();
+    if (!e) return V2P_ERR_INVALID_ARG;
+    e->device = cuda_device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(cuda_device) != cudaSuccess || cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&e->h_status, sizeof(DevStatus)) != cudaSuccess) {
+        delete e;
+        return V2P_ERR_CUDA;
+    }
+    e->sm_count = prop.multiProcessorCount;
+    *out = e;
+    return V2P_OK;
+}
+
+void v2p_engine_destroy(v2p_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->lb,      &e->tile_hap, &e->status, &e->d_tasks,    &e->d_task_begin, &e->d_ref,   &e->d_ref_base,
+                      &e->d_alt,   &e->d_alt_base, &e->d_out,  &e->d_out_base, &e->d_soa[0],     &e->d_soa[1], &e->d_soa[2],
+                      &e->d_soa[3]};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (e->h_status) cudaFreeHost(e->h_status);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char* v2p_last_error(v2p_engine* e) { return e ? e->err.c_str() : "engine is NULL"; }
+
+int v2p_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return V2P_ERR_INVALID_ARG;
+    return cudaMallocHost(ptr, std::max<size_t>(bytes, 16)) == cudaSuccess ? V2P_OK : V2P_ERR_CUDA;
+}
+int v2p_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? V2P_OK : V2P_ERR_CUDA; }
+
+uint64_t v2p_kernel_launch_count(v2p_engine* e) { return e ? e->launches : 0; }
+
+int v2p_engine_set_tuning(v2p_engine* e, int variant, int ctas_per_sm) {
+    if (!e || variant < 0 || variant > 1 || ctas_per_sm < 0 || ctas_per_sm > 32) return V2P_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->variant = variant;
+    e->ctas_per_sm = ctas_per_sm;
+    return V2P_OK;
+}
+
+int v2p_engine_set_stream(v2p_engine* e, void* cuda_stream) {
+    if (!e) return V2P_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    if (cuda_stream) {
+        e->stream = (cudaStream_t)cuda_stream;
+        e->own_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return V2P_ERR_CUDA;
+        e->own_stream = true;
+    }
+    return V2P_OK;
+}
+
+// ---- batched native call -------------------------------------------------------------------------
+int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_result* res, v2p_event** done) {
+    if (!e) return V2P_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->err.clear();
+    int rc = check_batch_args(e, b);
+    if (rc) return rc;
+    const bool async = (flags & V2P_FLAG_ASYNC) != 0;
+    if (async && !done) return fail(e, V2P_ERR_INVALID_ARG, "ASYNC needs an event out-pointer");
+    if (!async && !res) return fail(e, V2P_ERR_INVALID_ARG, "synchronous call needs a result out-pointer");
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    if (res) memset(res, 0, sizeof *res);
+
+    v2p_event* ev = new (std::nothrow) v2p_event();
+    if (!ev) return fail(e, V2P_ERR_INVALID_ARG, "out of memory");
+    auto cleanup = [&](int code) {
+        if (ev->ev_start) cudaEventDestroy(ev->ev_start);
+        if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
+        if (ev->h_status) cudaFreeHost(ev->h_status);
+        delete ev;
+        return code;
+    };
+    if (cudaEventCreate(&ev->ev_start) != cudaSuccess || cudaEventCreate(&ev->ev_stop) != cudaSuccess ||
+        cudaMallocHost((void**)&ev->h_status, sizeof(DevStatus)) != cudaSuccess)
+        return cleanup(fail(e, V2P_ERR_CUDA, "event/pinned allocation failed"));
+    ev->flags = flags;
+
+    KParams kp;
+    memset(&kp, 0, sizeof kp);
+    kp.n_hap = b->n_hap;
+    kp.fill_word = 0x2E2E2E2Eu;
+    kp.keep_out = 0;
+    kp.validate = (flags & V2P_FLAG_VALIDATE) ? 1 : 0;
+
+    if (flags & V2P_FLAG_DEVICE_PTRS) {
+        if (((uintptr_t)b->out & 15u) != 0) return cleanup(fail(e, V2P_ERR_INVALID_ARG, "out must be 16-byte aligned"));
+        kp.tasks = b->tasks;
+        kp.task_begin = b->task_begin;
+        kp.ref = b->ref;
+        kp.ref_base = b->ref_base;
+        kp.alt = b->alt;
+        kp.alt_base = b->alt_base;
+        kp.out = b->out;
+        kp.out_base = b->out_base;
+        kp.n_tasks = b->n_tasks;
+        kp.n_ref = b->n_ref;
+        kp.n_alt = b->n_alt;
+        kp.n_out = b->n_out;
+        // origins are 0: device-pointer batches are self-contained
+    } else {
+        // host pointers: stage everything through device buffers on the engine stream
+        const uint64_t H = b->n_hap;
+        const uint64_t t0 = H ? b->task_begin[0] : 0, t1 = H ? b->task_begin[H] : 0;
+        const uint64_t a0 = H ? b->alt_base[0] : 0, a1 = H ? b->alt_base[H] : 0;
+        const uint64_t o0 = H ? b->out_base[0] : 0, o1 = H ? b->out_base[H] : 0;
+        uint64_t r0 = 0, r1 = b->n_ref;
+        if (b->ref_base && H) r0 = b->ref_base[0], r1 = b->ref_base[H];
+        if (t1 < t0 || a1 < a0 || o1 < o0 || r1 < r0) return cleanup(fail(e, V2P_ERR_INVALID_ARG, "base arrays not monotone"));
+        kp.n_tasks = t1 - t0;
+        kp.n_alt = a1 - a0;
+        kp.n_out = o1 - o0;
+        kp.n_ref = r1 - r0;
+        kp.task_origin = t0;
+        kp.alt_origin = a0;
+        kp.out_origin = o0;
+        kp.ref_origin = r0;
+        if ((kp.n_tasks && !b->tasks) || (kp.n_out && !b->out) || (kp.n_ref && !b->ref) || (kp.n_alt && !b->alt))
+            return cleanup(fail(e, V2P_ERR_INVALID_ARG, "NULL data pointer"));
+        const size_t nb = (H + 1) * sizeof(uint64_t);
+        if ((rc = reserve(e, e->d_tasks, kp.n_tasks * sizeof(v2p_task16))) || (rc = reserve(e, e->d_task_begin, nb)) ||
+            (rc = reserve(e, e->d_ref, kp.n_ref + 32)) || (rc = reserve(e, e->d_ref_base, nb)) ||
+            (rc = reserve(e, e->d_alt, kp.n_alt + 32)) || (rc = reserve(e, e->d_alt_base, nb)) ||
+            (rc = reserve(e, e->d_out, kp.n_out + 32)) || (rc = reserve(e, e->d_out_base, nb)))
+            return cleanup(rc);
+        cudaStream_t s = e->stream;
+        auto h2d = [&](void* d, const void* h, size_t n) {
+            return n ? cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) : cudaSuccess;
+        };
+        if (h2d(e->d_tasks.p, b->tasks + t0, kp.n_tasks * sizeof(v2p_task16)) != cudaSuccess ||
+            h2d(e->d_task_begin.p, b->task_begin, nb) != cudaSuccess || h2d(e->d_ref.p, b->ref + r0, kp.n_ref) != cudaSuccess ||
+            (b->ref_base && h2d(e->d_ref_base.p, b->ref_base, nb) != cudaSuccess) ||
+            h2d(e->d_alt.p, b->alt + a0, kp.n_alt) != cudaSuccess || h2d(e->d_alt_base.p, b->alt_base, nb) != cudaSuccess ||
+            h2d(e->d_out_base.p, b->out_base, nb) != cudaSuccess)
+            return cleanup(fail(e, V2P_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(cudaGetLastError())));
+        kp.tasks = (const v2p_task16*)e->d_tasks.p;
+        kp.task_begin = (const uint64_t*)e->d_task_begin.p;
+        kp.ref = (const uint8_t*)e->d_ref.p;
+        kp.ref_base = b->ref_base ? (const uint64_t*)e->d_ref_base.p : nullptr;
+        kp.alt = (const uint8_t*)e->d_alt.p;
+        kp.alt_base = (const uint64_t*)e->d_alt_base.p;
+        kp.out = (uint8_t*)e->d_out.p;
+        kp.out_base = (const uint64_t*)e->d_out_base.p;
+        ev->host_mode = true;
+        ev->h_out = b->out + o0;
+        ev->out_bytes = kp.n_out;
+        ev->h_task_begin = b->task_begin;
+    }
+
+    rc = launch_group(e, kp, ev->ev_start, ev->ev_stop);
+    if (rc) return cleanup(rc);
+    ev->kp = kp;
+    if (async) {
+        *done = ev;
+        return V2P_OK;
+    }
+    return wait_locked(e, ev, res);
+}
+
+int v2p_event_wait(v2p_engine* e, v2p_event* ev, v2p_result* res) {
+    if (!e || !ev) return V2P_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    return wait_locked(e, ev, res);
+}
+
+// ---- reference-faithful single-haplotype call ------------------------------------------------------
+int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, const uint64_t* start_pos,
+                    const uint64_t* length, const uint64_t* start_pos_res, const uint32_t* ref_utf32, size_t n_ref,
+                    const uint32_t* alt_utf32, size_t n_alt, uint32_t* res_utf32, size_t n_res, uint32_t flags,
+                    uint64_t* bad_index) {
+    if (!e) return V2P_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->err.clear();
+    if (bad_index) *bad_index = 0;
+    if (n_tasks && (!exec_code || !start_pos || !length || !start_pos_res))
+        return fail(e, V2P_ERR_INVALID_ARG, "NULL task array");
+    if ((n_ref && !ref_utf32) || (n_alt && !alt_utf32) || (n_res && !res_utf32))
+        return fail(e, V2P_ERR_INVALID_ARG, "NULL tape");
+    const uint64_t lim = 0xFFFFFFFFull / 4;
+    if (n_ref > lim || n_alt > lim || n_res > lim)
+        return fail(e, V2P_ERR_INVALID_ARG, "tape longer than 2^30 residues: use v2p_execute_batch");
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    int rc;
+    const size_t tb = n_tasks * sizeof(uint64_t);
+    for (int i = 0; i < 4; ++i)
+        if ((rc = reserve(e, e->d_soa[i], tb))) return rc;
+    if ((rc = reserve(e, e->d_tasks, n_tasks * sizeof(v2p_task16))) || (rc = reserve(e, e->d_ref, n_ref * 4 + 32)) ||
+        (rc = reserve(e, e->d_alt, n_alt * 4 + 32)) || (rc = reserve(e, e->d_out, n_res * 4 + 32)) ||
+        (rc = reserve(e, e->d_task_begin, 16)) || (rc = reserve(e, e->d_alt_base, 16)) ||
+        (rc = reserve(e, e->d_out_base, 16)) || (rc = reserve(e, e->status, sizeof(DevStatus))))
+        return rc;
+    const uint64_t* soa[4] = {exec_code, start_pos, length, start_pos_res};
+    for (int i = 0; i < 4; ++i)
+        if (tb) CUDA_TRY(e, cudaMemcpyAsync(e->d_soa[i].p, soa[i], tb, cudaMemcpyHostToDevice, s));
+    if (n_ref) CUDA_TRY(e, cudaMemcpyAsync(e->d_ref.p, ref_utf32, n_ref * 4, cudaMemcpyHostToDevice, s));
+    if (n_alt) CUDA_TRY(e, cudaMemcpyAsync(e->d_alt.p, alt_utf32, n_alt * 4, cudaMemcpyHostToDevice, s));
+    const bool keep = !(flags & V2P_FLAG_FILL_DOT);
+    if (keep && n_res) CUDA_TRY(e, cudaMemcpyAsync(e->d_out.p, res_utf32, n_res * 4, cudaMemcpyHostToDevice, s));
+    const uint64_t tbeg[2] = {0, n_tasks}, abase[2] = {0, n_alt * 4}, obase[2] = {0, n_res * 4};
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_task_begin.p, tbeg, 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_alt_base.p, abase, 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_out_base.p, obase, 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(e, cudaStreamSynchronize(s));  // tbeg/abase/obase live on this stack frame
+
+    KParams kp;
+    memset(&kp, 0, sizeof kp);
+    kp.tasks = (const v2p_task16*)e->d_tasks.p;
+    kp.task_begin = (const uint64_t*)e->d_task_begin.p;
+    kp.ref = (const uint8_t*)e->d_ref.p;
+    kp.ref_base = nullptr;
+    kp.alt = (const uint8_t*)e->d_alt.p;
+    kp.alt_base = (const uint64_t*)e->d_alt_base.p;
+    kp.out = (uint8_t*)e->d_out.p;
+    kp.out_base = (const uint64_t*)e->d_out_base.p;
+    kp.n_hap = 1;
+    kp.n_tasks = n_tasks;
+    kp.n_ref = n_ref * 4;
+    kp.n_alt = n_alt * 4;
+    kp.n_out = n_res * 4;
+    kp.fill_word = 0x0000002Eu;  // '.' as one UTF-32 unit
+    kp.keep_out = keep ? 1 : 0;
+    kp.validate = (flags & V2P_FLAG_VALIDATE) ? 1 : 0;
+
+    // pack (and judge every reference panic on the original 64-bit values), then plan + copy
+    kp.status = (DevStatus*)e->status.p;
+    k_init_status<<<1, 1, 0, s>>>(kp.status);
+    e->launches++;
+    if (n_tasks) {
+        k_soa_pack<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(
+            n_tasks, (const uint64_t*)e->d_soa[0].p, (const uint64_t*)e->d_soa[1].p, (const uint64_t*)e->d_soa[2].p,
+            (const uint64_t*)e->d_soa[3].p, n_ref, n_alt, n_res, 4u, kp.validate, (v2p_task16*)e->d_tasks.p, kp.status);
+        e->launches++;
+    }
+    rc = launch_group(e, kp, nullptr, nullptr, /*init_status=*/false);
+    if (rc) return rc;
+    rc = finish_group(e, kp, e->h_status, nullptr);
+    if (rc) return rc;
+    v2p_result r;
+    memset(&r, 0, sizeof r);
+    decode_status(*e->h_status, nullptr, 0, 0, &r);
+    if (r.status != V2P_OK) {
+        if (bad_index) *bad_index = r.bad_task;
+        return fail(e, r.status, "task %llu rejected with status %d", (unsigned long long)r.bad_task, r.status);
+    }
+    if (n_res) {
+        CUDA_TRY(e, cudaMemcpyAsync(res_utf32, e->d_out.p, n_res * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(e, cudaStreamSynchronize(s));
+    }
+    return V2P_OK;
+}
+
+int v2p_gir_execute(v2p_engine* e, int engine_kind, size_t n_tasks, const uint64_t* exec_code, const uint64_t* start_pos,
+                    const uint64_t* length, const uint64_t* start_pos_res, const uint32_t* ref_utf32, size_t n_ref,
+                    const uint32_t* alt_utf32, size_t n_alt, uint32_t* res_utf32, size_t n_res, uint32_t flags,
+                    uint64_t* bad_index) {
+    if (engine_kind != V2P_ENGINE_GPU)
+        return fail(e, V2P_ERR_NOT_GPU_ENGINE, "engine kind %d is executed by the caller (gir.rs:201-235)", engine_kind);
+    return v2p_execute_soa(e, n_tasks, exec_code, start_pos, length, start_pos_res, ref_utf32, n_ref, alt_utf32, n_alt,
+                           res_utf32, n_res, flags, bad_index);
+}
+
+}  // extern "C"

@@ -1,0 +1,426 @@
+// v2p_kernels.cuh -- sm_100a kernels of the sequence-generation engine.
+//
+// The work is the reference's Task::execute (task.rs:38-50) looped as GIR::execute (gir.rs:230-234):
+//   res[dst .. dst+len] <- (stream==0 ? ref : alt)[src .. src+len]   for every task, '.' elsewhere.
+// It is byte-granular gather into a contiguous output stream: HBM/L2 bound, no flops, no tensor cores.
+//
+// Design (output-stationary, one warp per output tile):
+//   plan   k_plan_haps / k_plan_tasks   validate every task where the reference would panic, and build
+//                                       lb[k] = first task whose global dst >= k*TILE (one u32 per tile)
+//   copy   k_copy_tiles<TILE>           each warp owns TILE output bytes staged in shared memory:
+//            A. one lane per overlapping task: head/tail bytes (partial 16-B vectors) -> st.shared.u8,
+//               and lead[v0] = lane for the first fully covered vector of the task
+//            B. warp max-scan over lead[] -> owner task of every fully covered 16-B vector
+//            C. one lane per vector: 2 aligned 16-B loads + funnel-shift realign -> st.shared.v4
+//            D. one elected lane: TMA bulk store (cp.async.bulk.global.shared::cta) of the whole tile
+//          => every output byte is written exactly once with full-width stores, '.' gaps come for free
+//             from the tile prefill, and cost per byte is independent of task-length skew.
+//   serial k_serial                     tasks that are NOT sorted/non-overlapping by dst keep the
+//                                       reference's in-order semantics (later task wins) on the GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "v2p_engine.h"
+
+namespace v2p {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+
+// Device-side status block, written by the plan kernels with atomics.
+struct DevStatus {
+    unsigned long long err_key;  // min over ((global task idx << 8) | V2P_ERR_*) of hard errors; ~0 = none
+    unsigned long long gap_key;  // min global task idx violating gir.rs:208 contiguity (VALIDATE); ~0 = none
+    unsigned int unsorted;       // some haplotype's tasks are not sorted / overlap -> serial semantics needed
+    unsigned int bad_args;       // base arrays not monotone / totals inconsistent
+};
+
+struct KParams {
+    const v2p_task16* tasks;     // tasks[t - task_origin]
+    const uint64_t* task_begin;  // n_hap+1 (absolute task numbers)
+    const uint8_t* ref;
+    const uint64_t* ref_base;  // n_hap+1 or nullptr
+    const uint8_t* alt;        // alt[a - alt_origin]
+    const uint64_t* alt_base;  // n_hap+1 (absolute)
+    uint8_t* out;              // out[o - out_origin], 16-byte aligned
+    const uint64_t* out_base;  // n_hap+1 (absolute)
+    uint64_t n_hap, n_tasks, n_ref, n_alt, n_out;  // totals of THIS launch (relative sizes)
+    uint64_t task_origin, ref_origin, alt_origin, out_origin;
+    uint32_t* lb;        // n_tiles+1
+    uint32_t* tile_hap;  // n_tiles
+    uint64_t n_tiles;
+    uint32_t tile_bytes;
+    uint32_t fill_word;  // 0x2E2E2E2E for 1-byte residues, 0x0000002E for UTF-32 units
+    int keep_out;        // 1: uncovered bytes keep the caller's content (soa call without FILL_DOT)
+    int validate;        // V2P_FLAG_VALIDATE
+    DevStatus* status;
+};
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t upper_bound_u64(const uint64_t* __restrict__ a, uint64_t lo, uint64_t hi,
+                                                    uint64_t key) {
+    // first index in [lo,hi) with a[idx] > key
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) <= key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// haplotype owning absolute task number t: largest h with task_begin[h] <= t (skips empty haplotypes)
+__device__ __forceinline__ uint64_t hap_of_task(const KParams& p, uint64_t t, uint64_t hint) {
+    if (hint < p.n_hap && __ldg(p.task_begin + hint) <= t && t < __ldg(p.task_begin + hint + 1)) return hint;
+    return upper_bound_u64(p.task_begin, 0, p.n_hap + 1, t) - 1;
+}
+
+__global__ void k_init_status(DevStatus* s) {
+    s->err_key = ~0ull;
+    s->gap_key = ~0ull;
+    s->unsorted = 0;
+    s->bad_args = 0;
+}
+
+// One thread per haplotype: base-array sanity + tile -> haplotype map.
+__global__ void k_plan_haps(KParams p) {
+    uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (h >= p.n_hap) return;
+    uint64_t o0 = p.out_base[h], o1 = p.out_base[h + 1];
+    uint64_t t0 = p.task_begin[h], t1 = p.task_begin[h + 1];
+    uint64_t a0 = p.alt_base[h], a1 = p.alt_base[h + 1];
+    bool bad = o1 < o0 || t1 < t0 || a1 < a0;
+    if (p.ref_base) bad |= p.ref_base[h + 1] < p.ref_base[h];
+    if (h == 0) {
+        bad |= o0 != p.out_origin || t0 != p.task_origin || a0 != p.alt_origin;
+        if (p.ref_base) bad |= p.ref_base[0] != p.ref_origin;
+    }
+    if (h == p.n_hap - 1) {
+        bad |= o1 - p.out_origin != p.n_out || t1 - p.task_origin != p.n_tasks || a1 - p.alt_origin != p.n_alt;
+        if (p.ref_base) bad |= p.ref_base[h + 1] - p.ref_origin != p.n_ref;
+    }
+    if (bad) {
+        atomicExch(&p.status->bad_args, 1u);
+        return;
+    }
+    // tiles whose first byte lies in [o0,o1)
+    uint64_t r0 = o0 - p.out_origin, r1 = o1 - p.out_origin;
+    uint64_t T = p.tile_bytes;
+    for (uint64_t k = (r0 + T - 1) / T; k * T < r1 && k < p.n_tiles; ++k) p.tile_hap[k] = (uint32_t)h;
+}
+
+// One thread per task: everything the reference would panic on, plus lb[] (tile -> first task).
+__global__ void k_plan_tasks(KParams p) {
+    __shared__ uint64_t s_h0;
+    uint64_t tfirst = blockIdx.x * (uint64_t)blockDim.x;
+    if (threadIdx.x == 0) s_h0 = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, tfirst + p.task_origin) - 1;
+    __syncthreads();
+    if (p.status->bad_args) return;
+    uint64_t tr = tfirst + threadIdx.x;  // relative task index
+    if (tr >= p.n_tasks) return;
+    uint64_t t = tr + p.task_origin;
+    uint64_t h = s_h0;
+    while (h + 1 < p.n_hap && __ldg(p.task_begin + h + 1) <= t) ++h;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
+    const uint64_t src = raw.x, len = raw.y, dst = raw.z;
+    const uint32_t stream = raw.w;
+    const uint64_t o0 = __ldg(p.out_base + h), n_res = __ldg(p.out_base + h + 1) - o0;
+    unsigned long long key = (unsigned long long)tr << 8;
+    if (stream > 1u) {  // haplotype_instruction.rs:154
+        atomicMin(&p.status->err_key, key | V2P_ERR_BAD_STREAM);
+        return;
+    }
+    uint64_t n_src;
+    if (stream == 0)
+        n_src = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
+    else
+        n_src = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
+    if (dst + len > n_res) {  // task.rs:44/48 (result slice)
+        atomicMin(&p.status->err_key, key | V2P_ERR_RES_OOB);
+        return;
+    }
+    if (src + len > n_src) {  // task.rs:44/48 (source slice)
+        atomicMin(&p.status->err_key, key | V2P_ERR_SRC_OOB);
+        return;
+    }
+    const uint64_t g = o0 - p.out_origin + dst;  // global (launch-relative) output byte of this task
+    uint64_t k_lo = 0;
+    if (tr > 0) {
+        const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr - 1);
+        uint64_t gp;
+        if (t > __ldg(p.task_begin + h)) {  // same haplotype: gir.rs:208 contiguity + sortedness
+            uint64_t pend = (uint64_t)pr.z + pr.y;
+            if (dst < pend) atomicExch(&p.status->unsorted, 1u);
+            if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
+            gp = o0 - p.out_origin + pr.z;
+        } else {
+            uint64_t hp = h;
+            while (hp > 0 && __ldg(p.task_begin + hp) > t - 1) --hp;
+            gp = __ldg(p.out_base + hp) - p.out_origin + pr.z;
+        }
+        if (gp > g) return;  // cannot happen across haplotypes with monotone out_base; unsorted inside one
+        k_lo = gp / p.tile_bytes + 1;
+    }
+    uint64_t k_hi = g / p.tile_bytes;
+    if (k_hi > p.n_tiles) k_hi = p.n_tiles;
+    for (uint64_t k = k_lo; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
+}
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_addr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// bytes [sh, sh+16) of the 32-byte little-endian concatenation A||B  (sh in [0,16))
+__device__ __forceinline__ uint4 realign16(const uint4 A, const uint4 B, const uint32_t sh) {
+    const bool k2 = (sh & 8u) != 0, k1 = (sh & 4u) != 0;
+    const uint32_t x0 = k2 ? A.z : A.x, x1 = k2 ? A.w : A.y, x2 = k2 ? B.x : A.z, x3 = k2 ? B.y : A.w,
+                   x4 = k2 ? B.z : B.x, x5 = k2 ? B.w : B.y;
+    const uint32_t y0 = k1 ? x1 : x0, y1 = k1 ? x2 : x1, y2 = k1 ? x3 : x2, y3 = k1 ? x4 : x3, y4 = k1 ? x5 : x4;
+    const uint32_t s = (sh & 3u) * 8u;
+    uint4 r;
+    r.x = __funnelshift_r(y0, y1, s);
+    r.y = __funnelshift_r(y1, y2, s);
+    r.z = __funnelshift_r(y2, y3, s);
+    r.w = __funnelshift_r(y3, y4, s);
+    return r;
+}
+
+// inclusive max-scan of the 4 bytes of a word (byte 0 = lowest address)
+__device__ __forceinline__ uint32_t bytescan_max(uint32_t x) {
+    x = __vmaxu4(x, x << 8);
+    x = __vmaxu4(x, x << 16);
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------ copy kernel
+template <int TILE>
+__global__ void __launch_bounds__(kThreads) k_copy_tiles(const KParams p) {
+    constexpr int NV = TILE / 16;   // 16-byte vectors per tile
+    constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4 or 8)
+    constexpr int STRIDE = TILE + NV;
+    static_assert(LW == 4 || LW == 8, "TILE must be 2048 or 4096");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* const tile = smem + warp * STRIDE;
+    uint8_t* const lead = tile + TILE;
+
+    if (p.status->bad_args || p.status->unsorted || p.status->err_key != ~0ull || p.status->gap_key != ~0ull) return;
+
+    const uint64_t n_warps = (uint64_t)gridDim.x * kWarpsPerCta;
+    const uint4 fillv = make_uint4(p.fill_word, p.fill_word, p.fill_word, p.fill_word);
+
+    for (uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp; k < p.n_tiles; k += n_warps) {
+        const uint64_t tile_start = k * (uint64_t)TILE;
+        const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
+        uint8_t* const gout = p.out + tile_start;
+
+        // the previous tile's bulk store must have finished READING shared memory before we overwrite it
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+
+        // prefill: '.' (haplotype_instruction.rs:78) or the caller's current content
+        if (!p.keep_out) {
+#pragma unroll
+            for (int i = 0; i < NV / 32; ++i) reinterpret_cast<uint4*>(tile)[lane + 32 * i] = fillv;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV / 32; ++i) {
+                int v = lane + 32 * i;
+                if ((uint32_t)(v * 16 + 16) <= tile_len) {
+                    reinterpret_cast<uint4*>(tile)[v] = *reinterpret_cast<const uint4*>(gout + v * 16);
+                } else {
+                    for (int b = 0; b < 16; ++b)
+                        if ((uint32_t)(v * 16 + b) < tile_len) tile[v * 16 + b] = gout[v * 16 + b];
+                }
+            }
+        }
+        if (LW == 4)
+            reinterpret_cast<uint32_t*>(lead)[lane] = 0u;
+        else
+            reinterpret_cast<uint2*>(lead)[lane] = make_uint2(0u, 0u);
+        __syncwarp();
+
+        // tasks that can touch this tile: [t_lo, t_hi)
+        uint64_t t_lo = min((uint64_t)__ldg(p.lb + k), p.n_tasks);
+        const uint64_t t_hi = min((uint64_t)__ldg(p.lb + k + 1), p.n_tasks);
+        if (t_lo > 0) --t_lo;  // the task before may extend into the tile
+        const uint64_t h_hint = __ldg(p.tile_hap + k);
+
+        for (uint64_t tb = t_lo; tb < t_hi; tb += 32) {
+            // ---- A: one lane per task
+            const uint64_t tr = tb + lane;
+            long long p0 = 0;   // source address of tile byte 0 for this task (may point before the segment)
+            uint32_t v1 = 0;    // end (exclusive) of the fully covered vector range, in vectors
+            if (tr < t_hi) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
+                const uint64_t h = hap_of_task(p, tr + p.task_origin, h_hint);
+                const long long g = (long long)(__ldg(p.out_base + h) - p.out_origin + raw.z) - (long long)tile_start;
+                const long long ge = g + raw.y;
+                const int s = (int)max(g, 0ll), e = (int)min(ge, (long long)tile_len);
+                if (e > s) {
+                    const uint8_t* sb = raw.w ? p.alt + (__ldg(p.alt_base + h) - p.alt_origin)
+                                              : p.ref + (p.ref_base ? __ldg(p.ref_base + h) - p.ref_origin : 0ull);
+                    p0 = (long long)(sb + raw.x) - g;
+                    const uint8_t* __restrict__ sp = reinterpret_cast<const uint8_t*>(p0);
+                    const int v0b = (s + 15) & ~15, v1b = e & ~15;
+                    int hend = e, tbeg = e;
+                    if (v1b > v0b) {
+                        hend = v0b;
+                        tbeg = v1b;
+                        lead[v0b >> 4] = (uint8_t)(lane + 1);
+                        v1 = (uint32_t)(v1b >> 4);
+                    }
+                    const int n1 = hend - s, n = n1 + (e - tbeg);
+#pragma unroll 4
+                    for (int j = 0; j < n; ++j) {
+                        const int x = j < n1 ? s + j : tbeg + (j - n1);
+                        tile[x] = __ldg(sp + x);
+                    }
+                }
+            }
+            __syncwarp();
+
+            // ---- B: owner of every vector = last task (in this batch) whose covered range started at or before it
+            {
+                uint32_t w0, w1 = 0;
+                if (LW == 4) {
+                    w0 = reinterpret_cast<uint32_t*>(lead)[lane];
+                } else {
+                    uint2 t2 = reinterpret_cast<uint2*>(lead)[lane];
+                    w0 = t2.x;
+                    w1 = t2.y;
+                }
+                w0 = bytescan_max(w0);
+                uint32_t top = w0 >> 24;
+                if (LW == 8) {
+                    w1 = bytescan_max(w1);
+                    w1 = __vmaxu4(w1, top * 0x01010101u);
+                    top = w1 >> 24;
+                }
+                uint32_t incl = top;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl = max(incl, o);
+                }
+                uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 0;
+                const uint32_t bc = excl * 0x01010101u;
+                w0 = __vmaxu4(w0, bc);
+                if (LW == 4) {
+                    reinterpret_cast<uint32_t*>(lead)[lane] = w0;
+                } else {
+                    w1 = __vmaxu4(w1, bc);
+                    reinterpret_cast<uint2*>(lead)[lane] = make_uint2(w0, w1);
+                }
+            }
+            __syncwarp();
+
+            // ---- C: one lane per fully covered 16-byte vector
+            const uint32_t p0lo = (uint32_t)(unsigned long long)p0, p0hi = (uint32_t)((unsigned long long)p0 >> 32);
+#pragma unroll
+            for (int r = 0; r < NV / 32; ++r) {
+                const int v = lane + 32 * r;
+                const uint32_t owner = lead[v];
+                const int srcl = (int)((owner - 1u) & 31u);
+                const uint32_t qlo = __shfl_sync(0xffffffffu, p0lo, srcl);
+                const uint32_t qhi = __shfl_sync(0xffffffffu, p0hi, srcl);
+                const uint32_t qv1 = __shfl_sync(0xffffffffu, v1, srcl);
+                if (owner != 0u && (uint32_t)v < qv1) {
+                    const unsigned long long sa = (((unsigned long long)qhi << 32) | qlo) + (unsigned long long)(v * 16);
+                    const uint32_t sh = (uint32_t)sa & 15u;
+                    const uint4* ap = reinterpret_cast<const uint4*>(sa - sh);
+                    const uint4 A = __ldg(ap);
+                    uint4 B = A;
+                    if (sh) B = __ldg(ap + 1);
+                    reinterpret_cast<uint4*>(tile)[v] = realign16(A, B, sh);
+                }
+            }
+            __syncwarp();
+            if (tb + 32 < t_hi) {  // another batch follows: reset lead[]
+                if (LW == 4)
+                    reinterpret_cast<uint32_t*>(lead)[lane] = 0u;
+                else
+                    reinterpret_cast<uint2*>(lead)[lane] = make_uint2(0u, 0u);
+                __syncwarp();
+            }
+        }
+
+        // ---- D: publish the tile
+        fence_async_smem();
+        __syncwarp();
+        const uint32_t bulk = tile_len & ~15u;
+        if (lane == 0 && bulk) {
+            bulk_store_s2g(gout, tile, bulk);
+            bulk_commit();
+        }
+        if (bulk + lane < tile_len) gout[bulk + lane] = tile[bulk + lane];  // < 16 trailing bytes of the whole output
+    }
+    if (lane == 0) bulk_wait0();
+}
+
+// ------------------------------------------------------------------------------------------------ serial fallback
+// Reference order semantics for task arrays that are not sorted / non-overlapping by destination:
+// one CTA per haplotype, tasks applied strictly in array order (gir.rs:233), each copy spread over the CTA.
+__global__ void __launch_bounds__(kThreads) k_serial(const KParams p) {
+    if (p.status->bad_args || p.status->err_key != ~0ull || p.status->gap_key != ~0ull) return;
+    for (uint64_t h = blockIdx.x; h < p.n_hap; h += gridDim.x) {
+        const uint64_t o0 = p.out_base[h] - p.out_origin, n_res = p.out_base[h + 1] - p.out_base[h];
+        uint8_t* res = p.out + o0;
+        if (!p.keep_out)
+            for (uint64_t i = threadIdx.x; i < n_res; i += blockDim.x)
+                res[i] = (uint8_t)(p.fill_word >> (8u * (uint32_t)((o0 + i) & 3u)));
+        __syncthreads();
+        const uint8_t* ref = p.ref + (p.ref_base ? p.ref_base[h] - p.ref_origin : 0ull);
+        const uint8_t* alt = p.alt + (p.alt_base[h] - p.alt_origin);
+        const uint64_t t0 = p.task_begin[h] - p.task_origin, t1 = p.task_begin[h + 1] - p.task_origin;
+        for (uint64_t t = t0; t < t1; ++t) {
+            const v2p_task16 tk = p.tasks[t];
+            const uint8_t* src = (tk.stream ? alt : ref) + tk.src_off;
+            uint8_t* dst = res + tk.dst_off;
+            for (uint32_t i = threadIdx.x; i < tk.len; i += blockDim.x) dst[i] = src[i];
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ SoA hand-off
+// gir.rs:283-299 shape (four usize arrays) -> packed tasks in BYTES of `unit`-byte residues.
+// All reference panics are decided here on the ORIGINAL 64-bit values (before the u32 packing):
+// stream code (haplotype_instruction.rs:154), contiguity (gir.rs:208, when `validate`), slices (task.rs:44/48).
+__global__ void k_soa_pack(uint64_t n, const uint64_t* __restrict__ code, const uint64_t* __restrict__ sp,
+                           const uint64_t* __restrict__ len, const uint64_t* __restrict__ spr, uint64_t n_ref,
+                           uint64_t n_alt, uint64_t n_res, uint32_t unit, int validate, v2p_task16* __restrict__ out,
+                           DevStatus* status) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint64_t c = code[t], s = sp[t], l = len[t], d = spr[t];
+    unsigned long long key = (unsigned long long)t << 8;
+    v2p_task16 o = {0u, 0u, 0u, 0u};
+    if (validate && t > 0 && d != spr[t - 1] + len[t - 1]) atomicMin(&status->gap_key, (unsigned long long)t);
+    if (c > 1) {
+        atomicMin(&status->err_key, key | V2P_ERR_BAD_STREAM);
+    } else if (d + l < d || d + l > n_res) {
+        atomicMin(&status->err_key, key | V2P_ERR_RES_OOB);
+    } else if (s + l < s || s + l > (c == 0 ? n_ref : n_alt)) {
+        atomicMin(&status->err_key, key | V2P_ERR_SRC_OOB);
+    } else {
+        o.src_off = (uint32_t)(s * unit);
+        o.len = (uint32_t)(l * unit);
+        o.dst_off = (uint32_t)(d * unit);
+        o.stream = (uint32_t)c;
+    }
+    out[t] = o;
+}
+
+}  // namespace v2p
