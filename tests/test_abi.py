@@ -1,0 +1,90 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/v2p_engine.h declares (no compute)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "v2p_engine.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vcf2prot_b200 import _lib
+
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    return _lib.load()
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(v2p_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from vcf2prot_b200 import _lib
+
+    names = header_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "libv2p_engine.so does not export %s" % n
+        assert n in _lib.SYMBOLS, "ctypes binding lacks %s" % n
+    assert lib.v2p_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from vcf2prot_b200 import _lib
+
+    assert C.sizeof(_lib.Task16) == 16
+    assert C.sizeof(_lib.Batch) == 13 * 8
+    assert C.sizeof(_lib.Result) == 32
+
+
+def test_engine_from_str_contract(lib):
+    """engines.rs:20-29: exactly st|ST|mt|MT|gpu|GPU."""
+    from vcf2prot_b200 import Engine, EngineError
+
+    assert Engine.from_str("st") is Engine.ST and Engine.from_str("ST") is Engine.ST
+    assert Engine.from_str("mt") is Engine.MT and Engine.from_str("MT") is Engine.MT
+    assert Engine.from_str("gpu") is Engine.GPU and Engine.from_str("GPU") is Engine.GPU
+    for bad in ("Gpu", "cuda", "", "st ", "mT"):
+        with pytest.raises(EngineError):
+            Engine.from_str(bad)
+
+
+def test_library_is_sm100a_and_uses_tma_bulk_store():
+    from vcf2prot_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    txt = out.stdout.decode()
+    assert "sm_100a" in txt
+    assert "UBLKCP" in txt  # cp.async.bulk shared->global (TMA bulk copy)
+
+
+def test_no_cpu_fallback_without_device(lib):
+    """Without a CUDA device the product path must fail loudly, never compute on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from vcf2prot_b200 import EngineError, GpuEngine
+
+    with pytest.raises(EngineError):
+        GpuEngine(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vcf2prot_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), "%s references the oracle" % fn

@@ -1,0 +1,274 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle -- bit-exact.
+
+Oracle = oracle/ref_engine.c (restates task.rs:38-50 / gir.rs:197-241) and the golden vectors harvested from the
+reference binary.  Edge cases follow the reference's own tests and panics: empty/ragged inputs, '.' gaps,
+zero-length tasks, unsorted task arrays (task.rs:118-144), out-of-range slices, bad stream codes, the
+DEBUG_CPU_EXEC contiguity validator.
+"""
+import numpy as np
+import pytest
+
+from oracle import cengine, taskgen
+from tests.helpers import batch_from_girs, cohort_haplotype_csqs, hap_gir, load_golden, tape_to_str, u32, u8
+from tests.randtasks import random_batch
+from vcf2prot_b200 import GIR, Engine, EngineError
+from vcf2prot_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+UNIT = load_golden("unit_tests.json")
+COMBOS = load_golden("combos.json")
+
+
+def oracle_batch(b, validate=False, dtype=np.uint8):
+    out = np.zeros(int(b["out_base"][-1]) if len(b["out_base"]) else 0, dtype)
+    st, bh, bi = cengine.batch_execute(b["task_begin"], b["tasks"], b["ref"].astype(dtype), b["alt"].astype(dtype),
+                                       b["alt_base"], out, b["out_base"], ref_base=b.get("ref_base"),
+                                       validate=validate, threads=4)
+    return st, bh, bi, out
+
+
+def gpu_batch(eng, b, validate=False):
+    return eng.execute_batch(b["task_begin"], b["tasks"], b["ref"], b["alt"], b["alt_base"], b["out_base"],
+                             ref_base=b.get("ref_base"), validate=validate)
+
+
+# ---------------------------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("case", [c for c in UNIT if c["tasks"]], ids=[c["name"] for c in UNIT if c["tasks"]])
+def test_reference_unit_tests_through_gir_execute(gpu_engine, case):
+    """transcript_instructions.rs:884-1594 inputs: golden Task vectors -> GIR::execute(Engine::GPU) -> golden FASTA."""
+    refs = {case["transcript"]: case["ref"]}
+    muts = taskgen.alt_transcript(case["transcript"], case["csqs"])
+    g = taskgen.TranscriptInstruction.from_alt_transcript(case["transcript"], muts, refs).get_g_rep(refs)
+    gir = GIR(case["tasks"], {case["transcript"]: g.annotation}, g.alt, g.ref, "." * g.res_len)
+    res, ann = gir.execute(Engine.from_str("gpu"), gpu_engine)
+    s, e = ann[case["transcript"]]
+    assert tape_to_str(res)[s:e] == case["records"][0][1]
+    if case["asserted_len"] is not None:
+        assert len(res) == case["asserted_len"]
+
+
+@pytest.mark.parametrize("case", COMBOS, ids=[c["name"] for c in COMBOS])
+def test_combos_through_both_entries(gpu_engine, case):
+    g = hap_gir(case["csqs"], case["refs"])
+    res = gpu_engine.execute_soa(g.tasks, g.ref, g.alt, g.res_len, fill_dot=True)
+    recs = sorted(taskgen.sequence_tape_records(tape_to_str(res), g.annotation, 1))
+    assert [list(r) for r in recs] == [list(r) for r in case["records"]]
+    out, _ = gpu_batch(gpu_engine, batch_from_girs([g]))
+    assert tape_to_str(out) == tape_to_str(res)
+    if case["cpu_exec_table"]:  # the reference panics in the DEBUG_CPU_EXEC validator (gir.rs:223)
+        with pytest.raises(EngineError) as ei:
+            gpu_engine.execute_soa(g.tasks, g.ref, g.alt, g.res_len, fill_dot=True, validate=True)
+        st, bad = cengine.gir_execute(g.tasks, u8(g.ref), u8(g.alt), np.zeros(g.res_len, np.uint8), True, validate=True)
+        assert ei.value.status == L.ERR_NOT_CONTIGUOUS and st == cengine.REF_ERR_NOT_CONTIGUOUS
+        assert ei.value.bad_task == bad
+
+
+@pytest.mark.parametrize("name", ["cohort_a.json", "cohort_b.json"])
+def test_cohort_fasta_byte_identical_to_reference_binary(gpu_engine, name):
+    cohort = load_golden(name)
+    per_hap = cohort_haplotype_csqs(cohort)
+    keys = sorted(per_hap)
+    girs = [hap_gir(per_hap[k], cohort["refs"]) for k in keys]
+    b = batch_from_girs(girs)
+    out, _ = gpu_batch(gpu_engine, b)
+    st, _, _, want = oracle_batch(b)
+    assert st == 0 and np.array_equal(out, want)
+    fasta = {}
+    for (smp, hap), g, o0 in zip(keys, girs, b["out_base"][:-1]):
+        tape = tape_to_str(out[int(o0):int(o0) + g.res_len])
+        fasta.setdefault(smp, []).extend(taskgen.sequence_tape_records(tape, g.annotation, hap))
+    for smp in cohort["samples"]:
+        assert sorted([list(r) for r in fasta.get(smp, [])]) == [list(r) for r in cohort["fasta"].get(smp, [])]
+
+
+def test_task_rs_unit_vector_keeps_uncovered_units(gpu_engine):
+    """task.rs:118-144: unsorted tasks, 'x'-filled tape, no '.' fill -> serial-order kernel + keep_out."""
+    res = gpu_engine.execute_soa([(0, 1, 1, 8), (0, 4, 1, 4), (0, 6, 2, 6)], "ABCFEFGH", "HGFEFCBA", "x" * 10,
+                                 fill_dot=False)
+    assert tape_to_str(res) == "xxxxExGHBx"
+    # sorted variant takes the tile kernel with keep_out
+    res = gpu_engine.execute_soa([(0, 4, 1, 4), (0, 6, 2, 6), (0, 1, 1, 8)], "ABCFEFGH", "HGFEFCBA", "x" * 10,
+                                 fill_dot=False)
+    assert tape_to_str(res) == "xxxxExGHBx"
+
+
+def test_non_ascii_residues_ride_the_utf32_path(gpu_engine):
+    ref = "MEDLé中\U0001F9EC" * 5
+    res = gpu_engine.execute_soa([(0, 0, 20, 0), (1, 0, 2, 20), (0, 22, 13, 23)], ref, "αβ", 36, fill_dot=True)
+    want = np.zeros(36, np.uint32)
+    assert cengine.gir_execute([(0, 0, 20, 0), (1, 0, 2, 20), (0, 22, 13, 23)], u32(ref), u32("αβ"), want, True)[0] == 0
+    assert np.array_equal(res, want) and tape_to_str(res)[22] == "."
+
+
+# ---------------------------------------------------------------------------------------------- randomized parity
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("seed,n_hap,mean_res", [(1, 1, 100), (2, 7, 3000), (3, 40, 20000), (4, 300, 2000),
+                                                 (5, 3, 3_000_000), (6, 64, 150_000)])
+def test_random_batches_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
+    gpu_engine.set_tuning(variant, 0)
+    try:
+        b = random_batch(seed, n_hap, mean_res)
+        out, ms = gpu_batch(gpu_engine, b)
+        st, _, _, want = oracle_batch(b)
+        assert st == 0
+        assert out.shape == want.shape and np.array_equal(out, want)
+    finally:
+        gpu_engine.set_tuning(0, 0)
+
+
+@pytest.mark.parametrize("mix", [(1.0, 0, 0, 0), (0, 1.0, 0, 0), (0, 0, 0, 1.0), (0.5, 0.5, 0, 0)])
+def test_extreme_length_mixes(gpu_engine, mix):
+    """all 1-byte tasks (>32 tasks per tile -> multi-batch tiles), all short, all long (skew)."""
+    b = random_batch(11, 6, 30000, len_mix=mix, gap_prob=0.1)
+    out, _ = gpu_batch(gpu_engine, b)
+    st, _, _, want = oracle_batch(b)
+    assert st == 0 and np.array_equal(out, want)
+
+
+def test_edge_shapes(gpu_engine):
+    z64 = lambda *a: np.asarray(a, dtype=np.uint64)
+    ref = u8("ABCDEFGHIJKLMNOPQRSTUVWXYZ")
+    # no haplotypes at all
+    out, _ = gpu_engine.execute_batch(z64(0), np.zeros((0, 4), np.uint32), ref, u8(""), z64(0), z64(0))
+    assert out.size == 0
+    # one haplotype, zero tasks, 5-residue tape -> all dots; one with zero-length tape
+    out, _ = gpu_engine.execute_batch(z64(0, 0, 0), np.zeros((0, 4), np.uint32), ref, u8(""), z64(0, 0, 0), z64(0, 5, 5))
+    assert tape_to_str(out) == "....."
+    # zero-length tasks, a task ending exactly at the tape end, tapes whose sizes are not multiples of 16
+    tasks = np.asarray([(0, 0, 0, 0), (3, 4, 0, 0), (0, 0, 7, 0), (25, 1, 6, 0), (0, 3, 7, 1), (5, 0, 10, 1)], np.uint32)
+    out, _ = gpu_engine.execute_batch(z64(0, 2, 6), tasks, ref, u8("xyz"), z64(0, 0, 3), z64(0, 9, 9 + 23))
+    b = dict(task_begin=z64(0, 2, 6), tasks=tasks, ref=ref, alt=u8("xyz"), alt_base=z64(0, 0, 3), out_base=z64(0, 9, 32))
+    st, _, _, want = oracle_batch(b)
+    assert st == 0 and np.array_equal(out, want)
+
+
+def test_unsorted_and_overlapping_tasks_keep_serial_semantics(gpu_engine):
+    rng = np.random.default_rng(5)
+    b = random_batch(21, 12, 5000)
+    # shuffle tasks inside each haplotype and add overlapping rewrites: later task must win (gir.rs:233)
+    t = b["tasks"].copy()
+    tb = b["task_begin"]
+    for h in range(len(tb) - 1):
+        s, e = int(tb[h]), int(tb[h + 1])
+        if e - s > 2:
+            t[s:e] = t[s:e][rng.permutation(e - s)]
+            t[e - 1] = t[s]  # duplicate destination -> overlap
+            t[e - 1, 0] = 0
+            t[e - 1, 3] = 0
+            t[e - 1, 1] = min(t[e - 1, 1], 1000)
+    b["tasks"] = t
+    out, _ = gpu_batch(gpu_engine, b)
+    st, _, _, want = oracle_batch(b)
+    assert st == 0 and np.array_equal(out, want)
+
+
+def test_error_classes_match_the_reference_panics(gpu_engine):
+    base = random_batch(31, 9, 4000, gap_prob=0.0, empty_hap_prob=0.0)
+    tb = base["task_begin"]
+
+    def corrupt(h, k, col, val):
+        b = dict(base)
+        b["tasks"] = base["tasks"].copy()
+        b["tasks"][int(tb[h]) + k, col] = val
+        return b
+
+    # (haplotype, task, column, value, expected ABI status, expected oracle status)
+    cases = [(4, 2, 3, 2, L.ERR_BAD_STREAM, cengine.REF_ERR_BAD_STREAM),
+             (2, 1, 1, 0x7FFFFFFF, L.ERR_RES_OOB, cengine.REF_ERR_RES_OOB),
+             (6, 0, 0, 0x7FFFFF00, L.ERR_SRC_OOB, cengine.REF_ERR_SRC_OOB)]
+    for h, k, col, val, want_abi, want_ref in cases:
+        b = corrupt(h, k, col, val)
+        with pytest.raises(EngineError) as ei:
+            gpu_batch(gpu_engine, b)
+        st, bh, bi, _ = oracle_batch(b)
+        assert st == want_ref and ei.value.status == want_abi
+        assert (ei.value.bad_hap, ei.value.bad_task) == (bh, bi) == (h, k)
+    # DEBUG_CPU_EXEC contiguity validator: introduce a 1-residue gap in haplotype 3
+    b = dict(base)
+    b["tasks"] = base["tasks"].copy()
+    s = int(tb[3])
+    k = next(i for i in range(1, int(tb[4]) - s - 1) if b["tasks"][s + i, 1] >= 2)
+    b["tasks"][s + k, 1] -= 1  # shorten task k -> task k+1 no longer starts where it ends
+    with pytest.raises(EngineError) as ei:
+        gpu_batch(gpu_engine, b, validate=True)
+    st, bh, bi, _ = oracle_batch(b, validate=True)
+    assert st == cengine.REF_ERR_NOT_CONTIGUOUS and ei.value.status == L.ERR_NOT_CONTIGUOUS
+    assert (ei.value.bad_hap, ei.value.bad_task) == (bh, bi) == (3, k + 1)
+    # without VALIDATE the same input is legal: the gap reads '.'
+    out, _ = gpu_batch(gpu_engine, b)
+    st, _, _, want = oracle_batch(b)
+    assert st == 0 and np.array_equal(out, want) and (want == ord(".")).any()
+    # SoA entry: same classes, index reported
+    for tasks, want_abi in (([(0, 0, 9, 0)], L.ERR_RES_OOB), ([(1, 2, 2, 0)], L.ERR_SRC_OOB), ([(2, 0, 0, 0)], L.ERR_BAD_STREAM),
+                            ([(0, 0, 1, 0), (0, 2**40, 2**63, 1)], L.ERR_RES_OOB)):
+        with pytest.raises(EngineError) as ei:
+            gpu_engine.execute_soa(tasks, "ABCDEFGH", "xyz", 8, fill_dot=True)
+        assert ei.value.status == want_abi and ei.value.bad_task == len(tasks) - 1
+    with pytest.raises(EngineError) as ei:
+        GIR([(0, 0, 1, 0)], {}, "", "A", ".").execute(Engine.ST, gpu_engine)
+    assert ei.value.status == L.ERR_NOT_GPU_ENGINE
+
+
+def test_device_pointer_entry_and_async(gpu_engine):
+    import torch
+
+    b = random_batch(41, 50, 60000)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    d = {k: t(v) for k, v in b.items() if v is not None}
+    n_out = int(b["out_base"][-1])
+    out = torch.empty(n_out + 16, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    args = (len(b["task_begin"]) - 1, d["task_begin"], d["tasks"], d["ref"], d["alt"], d["alt_base"], out, d["out_base"],
+            len(b["tasks"]), len(b["alt"]), n_out)
+    ms = gpu_engine.execute_batch_device(*args)
+    st, _, _, want = oracle_batch(b)
+    assert st == 0 and np.array_equal(out[:n_out].cpu().numpy(), want) and ms > 0
+    out.zero_()
+    ev = gpu_engine.execute_batch_device(*args, wait=False)
+    ms2 = gpu_engine.wait_event(ev)
+    assert np.array_equal(out[:n_out].cpu().numpy(), want) and ms2 > 0
+    # inconsistent totals are rejected by the plan kernel, not trusted
+    bad = list(args)
+    bad[10] = n_out - 1
+    with pytest.raises(EngineError) as ei:
+        gpu_engine.execute_batch_device(*bad)
+    assert ei.value.status == L.ERR_INVALID_ARG
+    # caller-owned stream (torch's current stream)
+    side = torch.cuda.Stream()
+    gpu_engine.set_stream(side.cuda_stream)
+    try:
+        out.zero_()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(side):
+            t0.record()
+            gpu_engine.execute_batch_device(*args)
+            t1.record()
+        torch.cuda.synchronize()
+        assert np.array_equal(out[:n_out].cpu().numpy(), want) and t0.elapsed_time(t1) > 0
+    finally:
+        gpu_engine.set_stream(None)
+
+
+def test_full_size_properties(gpu_engine):
+    """At a size the scalar oracle would take too long for, use properties: every output byte is either '.' or
+    equals the source byte its task names; identity Task arrays reproduce the reference tape (round trip)."""
+    n_ref = 64 << 20
+    rng = np.random.default_rng(7)
+    ref = rng.integers(65, 91, size=n_ref, dtype=np.uint8)
+    # identity: one haplotype = the whole tape cut into irregular chunks
+    cuts = np.unique(np.concatenate([[0, n_ref], rng.integers(0, n_ref, size=200000)]))
+    tasks = np.zeros((len(cuts) - 1, 4), np.uint32)
+    tasks[:, 0] = cuts[:-1]
+    tasks[:, 1] = np.diff(cuts)
+    tasks[:, 2] = cuts[:-1]
+    z = lambda *a: np.asarray(a, dtype=np.uint64)
+    out, ms = gpu_engine.execute_batch(z(0, len(tasks)), tasks, ref, np.zeros(0, np.uint8), z(0, 0), z(0, n_ref))
+    assert np.array_equal(out, ref)
+    # shifted copy: dst = src + 3 everywhere except the first 3 bytes ('.')
+    tasks[:, 2] = cuts[:-1] + 3
+    tasks[-1, 1] -= 3
+    out, ms = gpu_engine.execute_batch(z(0, len(tasks)), tasks, ref, np.zeros(0, np.uint8), z(0, 0), z(0, n_ref))
+    assert (out[:3] == ord(".")).all() and np.array_equal(out[3:], ref[:-3])

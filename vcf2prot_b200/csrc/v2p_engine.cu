@@ -29,8 +29,8 @@ struct DevBuf {
 }  // namespace
 
 struct v2p_event {
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-    DevStatus* h_status = nullptr;  // pinned
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    DevStatus* h_status = nullptr;  // pinned; filled by a stream-ordered D2H right behind the launch group
     KParams kp;                     // for the deferred serial fallback
     uint32_t flags = 0;
     // host-pointer mode bookkeeping
@@ -93,7 +93,8 @@ int reserve(v2p_engine* e, DevBuf& b, size_t bytes) {
 int tile_bytes_of(const v2p_engine* e) { return e->variant == 1 ? 2048 : 4096; }
 
 // plan + copy on e->stream.  kp.{lb,tile_hap,status,n_tiles,tile_bytes} are filled here.
-int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop, bool init_status = true) {
+int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop, DevStatus* h_status,
+                 cudaEvent_t ev_done, bool init_status = true) {
     const int T = tile_bytes_of(e);
     kp.tile_bytes = (uint32_t)T;
     kp.n_tiles = (kp.n_out + T - 1) / T;
@@ -136,6 +137,9 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
     }
     if (ev_stop) CUDA_TRY(e, cudaEventRecord(ev_stop, s));
     CUDA_TRY(e, cudaGetLastError());
+    // status rides the stream right behind the kernels, so a later launch cannot overwrite it first
+    CUDA_TRY(e, cudaMemcpyAsync(h_status, kp.status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    if (ev_done) CUDA_TRY(e, cudaEventRecord(ev_done, s));
     return V2P_OK;
 }
 
@@ -185,16 +189,16 @@ int launch_serial(v2p_engine* e, const KParams& kp) {
     return V2P_OK;
 }
 
-// Finish a launch group: fetch status, run the serial fallback when needed.
-int finish_group(v2p_engine* e, KParams& kp, DevStatus* h_status, bool* ran_serial) {
-    CUDA_TRY(e, cudaMemcpyAsync(h_status, kp.status, sizeof(DevStatus), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    if (ran_serial) *ran_serial = false;
+// Finish a launch group: wait for its status, run the serial fallback when needed.
+int finish_group(v2p_engine* e, KParams& kp, DevStatus* h_status, cudaEvent_t ev_done) {
+    if (ev_done)
+        CUDA_TRY(e, cudaEventSynchronize(ev_done));
+    else
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (!h_status->bad_args && h_status->err_key == ~0ull && h_status->gap_key == ~0ull && h_status->unsorted) {
         int rc = launch_serial(e, kp);
         if (rc) return rc;
         CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-        if (ran_serial) *ran_serial = true;
     }
     return V2P_OK;
 }
@@ -214,13 +218,14 @@ int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
     auto cleanup = [&](int code) {
         if (ev->ev_start) cudaEventDestroy(ev->ev_start);
         if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
+        if (ev->ev_done) cudaEventDestroy(ev->ev_done);
         if (ev->h_status) cudaFreeHost(ev->h_status);
         delete ev;
         if (res) *res = local;
         return code;
     };
     cudaSetDevice(e->device);
-    int rc = finish_group(e, ev->kp, ev->h_status, nullptr);
+    int rc = finish_group(e, ev->kp, ev->h_status, ev->ev_done);
     if (rc) return cleanup(rc);
     std::vector<uint64_t> tb_copy;
     const uint64_t* tb = ev->h_task_begin;
@@ -346,11 +351,13 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
     auto cleanup = [&](int code) {
         if (ev->ev_start) cudaEventDestroy(ev->ev_start);
         if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
+        if (ev->ev_done) cudaEventDestroy(ev->ev_done);
         if (ev->h_status) cudaFreeHost(ev->h_status);
         delete ev;
         return code;
     };
     if (cudaEventCreate(&ev->ev_start) != cudaSuccess || cudaEventCreate(&ev->ev_stop) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev->ev_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void**)&ev->h_status, sizeof(DevStatus)) != cudaSuccess)
         return cleanup(fail(e, V2P_ERR_CUDA, "event/pinned allocation failed"));
     ev->flags = flags;
@@ -426,7 +433,7 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         ev->h_task_begin = b->task_begin;
     }
 
-    rc = launch_group(e, kp, ev->ev_start, ev->ev_stop);
+    rc = launch_group(e, kp, ev->ev_start, ev->ev_stop, ev->h_status, ev->ev_done);
     if (rc) return cleanup(rc);
     ev->kp = kp;
     if (async) {
@@ -511,7 +518,7 @@ int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, co
             (const uint64_t*)e->d_soa[3].p, n_ref, n_alt, n_res, 4u, kp.validate, (v2p_task16*)e->d_tasks.p, kp.status);
         e->launches++;
     }
-    rc = launch_group(e, kp, nullptr, nullptr, /*init_status=*/false);
+    rc = launch_group(e, kp, nullptr, nullptr, e->h_status, nullptr, /*init_status=*/false);
     if (rc) return rc;
     rc = finish_group(e, kp, e->h_status, nullptr);
     if (rc) return rc;

@@ -372,8 +372,9 @@ __global__ void __launch_bounds__(kThreads) k_copy_tiles(const KParams p) {
 // ------------------------------------------------------------------------------------------------ serial fallback
 // Reference order semantics for task arrays that are not sorted / non-overlapping by destination:
 // one CTA per haplotype, tasks applied strictly in array order (gir.rs:233), each copy spread over the CTA.
+// Launched by the host only after the plan reported `unsorted` and no error (status is not re-read here:
+// a later asynchronous launch may already have re-initialised the shared status block).
 __global__ void __launch_bounds__(kThreads) k_serial(const KParams p) {
-    if (p.status->bad_args || p.status->err_key != ~0ull || p.status->gap_key != ~0ull) return;
     for (uint64_t h = blockIdx.x; h < p.n_hap; h += gridDim.x) {
         const uint64_t o0 = p.out_base[h] - p.out_origin, n_res = p.out_base[h + 1] - p.out_base[h];
         uint8_t* res = p.out + o0;
