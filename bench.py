@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the sequence-generation engine (Task-array execution) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4] [--samples S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (validate + plan + copy launch group) over one cohort of synthetic,
+device-resident Task arrays: every haplotype's result tape is materialised once.
+Workload (config.workload):
+  c2  BASELINE.json configs[1]: 2,504 phased samples (5,008 haplotypes) x 20k-transcript proteome,
+      missense-dominated csq mix.  Default.  ~17 GB of residues per step per GPU.
+  c4  skewed-segment stress (configs[3] mix), same sample count unless --samples is given.
+N > 1: every rank owns its own contiguous sample range of the same size (weak scaling, no data-path collective);
+value = residues produced by all ranks / max-over-ranks device time.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference-equivalent CPU engine (the oracle's C
+restatement of gir.rs:230-234 on UTF-32 tapes, haplotypes spread over all host threads like rayon par_iter,
+exec.rs:34-40) on a bounded sample of the same workload; the reference itself is Rust and cannot be rebuilt here
+(its prebuilt whole-tool binary is timed beside it when oracle/_ref/vcf2prot is present).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--samples", type=int, default=2504, help="phased samples per GPU (2 haplotypes each)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-chunk-haps", type=int, default=256)
+    ap.add_argument("--cpu-sample-haps", type=int, default=64)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="kernel tile variant (0: 4 KiB/warp, 1: 2 KiB/warp)")
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--ref-binary-samples", type=int, default=0,
+                    help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_workload(kind: str, n_samples: int, rank: int):
+    from vcf2prot_b200 import cohort as C
+
+    prot = C.make_proteome(seed=0x5EED0001, giant=(20 if kind == "c4" else 0))
+    if kind == "c2":
+        cat = C.make_catalogue(prot, 280000, seed=0x5EED0002)
+    else:
+        cat = C.make_catalogue(prot, 120000, seed=0x5EED0004, mix=C.MIX_C4, fs_mean=60, fs_max=4000, sl_max=500,
+                               long_ins_mean=50, long_ins_max=5000, lognormal_tails=True)
+    n_hap = 2 * n_samples
+    parts = []
+    step = 256
+    for i, h0 in enumerate(range(0, n_hap, step)):
+        parts.append(C.synth_batch(prot, cat, min(step, n_hap - h0), seed=(0x5EED0002 + 7919 * rank) * 1000 + i))
+    return prot, cat, C.concat_batches(parts)
+
+
+def alg_bytes(batch) -> int:
+    """sum(len) read + sum(len) written + '.' gap bytes + 16 B per packed task."""
+    covered = int(batch.tasks[:, 1].astype(np.int64).sum())
+    n_out = batch.n_residues
+    return covered + n_out + 16 * len(batch.tasks)  # n_out = covered + gap bytes
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                clk, mxc, p = float(f[1]), float(f[2]), float(f[3])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.1:
+                sm.append(clk)
+                pw.append(p)
+                for n, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------------ CPU side
+def cpu_engine_rate(batch, prot, n_haps: int, seconds: float, threads: int, width: int, check_against=None):
+    """Reference-equivalent CPU engine (oracle port) on the first n_haps haplotypes; returns residues/s."""
+    from oracle import cengine
+
+    n_haps = min(n_haps, batch.n_hap)
+    t1 = int(batch.task_begin[n_haps])
+    a1, o1 = int(batch.alt_base[n_haps]), int(batch.out_base[n_haps])
+    dt = np.uint32 if width == 4 else np.uint8
+    ref = prot.residues.astype(dt)
+    alt = batch.alt[:a1].astype(dt)
+    out = np.zeros(o1, dt)
+    args = (batch.task_begin[:n_haps + 1], batch.tasks[:t1], ref, alt, batch.alt_base[:n_haps + 1], out,
+            batch.out_base[:n_haps + 1])
+    st, _, _ = cengine.batch_execute(*args, threads=threads)  # warm-up + page-in
+    assert st == 0
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        st, _, _ = cengine.batch_execute(*args, threads=threads)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or reps >= 1000:
+            break
+    ok = None
+    if check_against is not None:
+        ok = bool(np.array_equal(out.astype(np.uint8), check_against[:o1]))
+    return o1 * reps / el, el, reps, n_haps, o1, ok
+
+
+def reference_binary_rate(prot, cat, batch, n_samples: int):
+    """Whole-tool timing of the reference's own prebuilt binary on the first n_samples of the cohort."""
+    from oracle import refbin
+    from vcf2prot_b200 import cohort as C
+
+    if not refbin.available() or n_samples <= 0:
+        return None
+    n_samples = min(n_samples, batch.n_hap // 2)
+    sel = batch.kept_hap < 2 * n_samples if batch.kept_hap is not None else None
+    return None if sel is None else _ref_binary_run(prot, cat, batch, n_samples, sel, refbin, C)
+
+
+def _ref_binary_run(prot, cat, batch, n_samples, sel, refbin, C):
+    hap, site = batch.kept_hap[sel], batch.kept_site[sel]
+    used, inv = np.unique(site, return_inverse=True)
+    mask = np.zeros((len(used), n_samples), np.uint8)
+    np.bitwise_or.at(mask, (inv, hap // 2), (1 << (hap % 2)).astype(np.uint8))  # both haplotypes may carry a site
+    refs = {prot.name(t): prot.seq(t) for t in range(prot.n_tx)}
+    samples = ["S%05d" % i for i in range(n_samples)]
+    lines = [refbin.VCF_HEADER, "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples) + "\n"]
+    cell = ["0|0:0", "1|0:1", "0|1:2", "1|1:3"]
+    for r, i in enumerate(used):
+        lines.append("1\t%d\t.\tC\tT\t.\t.\tAC=1;BCSQ=%s\tGT:BCSQ\t%s\n" %
+                     (100 + r, C.site_csq(prot, cat, int(i)), "\t".join(cell[m] for m in mask[r])))
+    t0 = time.perf_counter()
+    recs, stdout, rc = refbin.run_reference("".join(lines), refs, "mt", verbose=True, timeout=1200)
+    wall = time.perf_counter() - t0
+    st = refbin.stage_seconds(stdout)
+    n_res = sum(len(s) for v in recs.values() for _, s in v)
+    if rc != 0 or not st:
+        return {"error": "reference binary rc=%d" % rc}
+    return {"samples": n_samples, "residues": n_res, "wall_s": round(wall, 2), "parse_s": round(st["parse"], 2),
+            "exec_stage_s": round(st["exec"], 3), "write_s": round(st["write"], 2),
+            "exec_stage_residues_per_s": n_res / max(st["exec"], 1e-9), "whole_tool_residues_per_s": n_res / st["total"],
+            "engine": "mt", "version": "0.1.2 (bins/Linux/vcf2prot)"}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from vcf2prot_b200 import GpuEngine
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    t_gen = time.perf_counter()
+    prot, cat, batch = make_workload(args.workload, args.samples, rank)
+    t_gen = time.perf_counter() - t_gen
+    n_hap, n_res, n_tasks = batch.n_hap, batch.n_residues, len(batch.tasks)
+    b_alg = alg_bytes(batch)
+
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    d_task_begin, d_tasks, d_ref = to_dev(batch.task_begin), to_dev(batch.tasks), to_dev(batch.ref)
+    d_alt, d_alt_base, d_out_base = to_dev(batch.alt), to_dev(batch.alt_base), to_dev(batch.out_base)
+    d_out = torch.empty(n_res + 64, dtype=torch.uint8, device=dev)
+
+    eng = GpuEngine(local_rank)
+    eng.set_tuning(args.variant, args.ctas_per_sm)
+    side = torch.cuda.Stream(device=dev)
+    eng.set_stream(side.cuda_stream)
+    dargs = (n_hap, d_task_begin, d_tasks, d_ref, d_alt, d_alt_base, d_out, d_out_base, n_tasks, len(batch.alt), n_res)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        eng.execute_batch_device(*dargs)
+    barrier()
+
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    group_ms, copy_ms = [], []
+    barrier()
+    w0 = time.time()
+    with torch.cuda.stream(side):
+        ev0.record()
+        for _ in range(args.steps):
+            group_ms.append(eng.execute_batch_device(*dargs))
+            copy_ms.append(eng.last_copy_ms)
+        ev1.record()
+    barrier()
+    w1 = time.time()
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    dev_ms = ev0.elapsed_time(ev1)  # CUDA events on the launching stream, all K steps
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    ms_per_step = max_ms / args.steps
+
+    # ---- end to end through the C ABI with HOST buffers: per step, every chunk's tasks/alt go H2D from pinned
+    #      memory and every result tape comes back D2H into a pinned staging buffer (the FASTA writer's input)
+    eng.set_stream(None)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h_tasks, h_alt, h_ref = pin(batch.tasks), pin(batch.alt), pin(batch.ref)
+    h_task_begin, h_alt_base, h_out_base = (np.ascontiguousarray(batch.task_begin), np.ascontiguousarray(batch.alt_base),
+                                            np.ascontiguousarray(batch.out_base))
+    chunks = [(h0, min(n_hap, h0 + args.e2e_chunk_haps)) for h0 in range(0, n_hap, args.e2e_chunk_haps)]
+    max_chunk = max(int(batch.out_base[b] - batch.out_base[a]) for a, b in chunks)
+    h_out = torch.empty(max_chunk + 64, dtype=torch.uint8).pin_memory().numpy()
+    h2d = sum(int(batch.task_begin[b] - batch.task_begin[a]) * 16 + int(batch.alt_base[b] - batch.alt_base[a]) +
+              3 * 8 * (b - a + 1) + len(batch.ref) for a, b in chunks)
+
+    def e2e_step():
+        for a, b in chunks:
+            eng.execute_hap_range(a, b, h_task_begin, h_tasks, h_ref, h_alt, h_alt_base, h_out_base, h_out)
+
+    e2e_step()  # warm-up (allocates the engine's device staging)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    # the last chunk sits in h_out: keep it for the parity spot-check against the device-resident result
+    a, b = chunks[-1]
+    o0, o1 = int(batch.out_base[a]), int(batch.out_base[b])
+    e2e_matches_device = bool(np.array_equal(h_out[:o1 - o0], d_out[o0:o1].cpu().numpy()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline (rank 0, N == 1 only): oracle port on a bounded sample, also the parity checker
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        nh = min(args.cpu_sample_haps, n_hap)
+        o1 = int(batch.out_base[nh])
+        gpu_sample = d_out[:o1].cpu().numpy()
+        rate32, el, reps, nh, nres, ok = cpu_engine_rate(batch, prot, nh, args.cpu_seconds, threads, 4, gpu_sample)
+        rate8, _, _, _, _, ok8 = cpu_engine_rate(batch, prot, nh, min(3.0, args.cpu_seconds), threads, 1, gpu_sample)
+        parity = {"checked_haplotypes": nh, "residues": nres, "gpu_equals_oracle": bool(ok and ok8),
+                  "e2e_equals_device_path": e2e_matches_device}
+        cpu = {"value": rate32, "unit": "residues/s", "cores": threads, "kind": "port",
+               "sample": "first %d haplotypes (%d residues) of the same cohort, UTF-32 tapes like the reference "
+                         "(gir.rs:18-22), %d passes in %.1f s, haplotypes over %d threads (exec.rs:34-40)" %
+                         (nh, nres, reps, el, threads),
+               "value_u8_tapes": rate8}
+        rb = reference_binary_rate(prot, cat, batch, args.ref_binary_samples)
+        if rb:
+            cpu["reference_binary"] = rb
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    copy_avg_ms = float(np.mean(copy_ms))
+    achieved = b_alg / (copy_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        key = "%s_%d_v%d" % (args.workload, args.samples, args.variant)
+        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+
+    total_res = n_res * world  # every rank holds a same-sized cohort (weak scaling)
+    value = total_res / (ms_per_step * 1e-3)
+    line = {
+        "metric": "generated residues/sec", "value": value, "unit": "residues/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%s: %d phased samples/GPU (%d haplotypes) x 20k-transcript proteome (%d residues), "
+                               "%s csq mix" % (args.workload, args.samples, n_hap, len(batch.ref),
+                                               "missense-dominated" if args.workload == "c2" else "skewed frameshift/insertion"),
+                   "haplotypes_per_gpu": n_hap, "tasks_per_gpu": n_tasks, "residues_per_gpu": n_res,
+                   "mean_task_bytes": n_res / max(n_tasks, 1), "l2_policy": "inputs_larger_than_l2 (output %.1f GB, tasks %.2f GB "
+                   "per step; the %.1f MB proteome is L2-resident by design)" % (n_res / 1e9, n_tasks * 16 / 1e9, len(batch.ref) / 1e6),
+                   "tile_variant": args.variant, "parallelism": "sample-sharded x%d, no collective" % world},
+        "haplotypes_per_s": n_hap * world / (ms_per_step * 1e-3),
+        "alg_gbs": b_alg * world / (ms_per_step * 1e-3) / 1e9,
+        "clocks": clocks,
+        "e2e": {"value": total_res * args.e2e_steps / e2e_s, "unit": "residues/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": n_res, "steps": args.e2e_steps, "chunk_haplotypes": args.e2e_chunk_haps,
+                "api": "v2p_execute_batch (host pointers, pinned), one call per chunk"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "k_copy_tiles", "peak_source": peak_src,
+                     "alg_bytes_per_launch": b_alg, "kernel_ms": copy_avg_ms, "launch_group_ms": float(np.mean(group_ms)),
+                     "kernel_share_of_step": copy_avg_ms / ms_per_step},
+        "cpu_baseline": cpu, "parity": parity, "gen_seconds": round(t_gen, 1),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_reference_arm(args):
+    """Reference arm: the reference's CPU implementation of the path on this box's host cores."""
+    threads = os.cpu_count() or 1
+    nh = args.cpu_sample_haps
+    prot, cat, batch = make_workload(args.workload, max(1, (nh + 1) // 2), 0)
+    steps = max(1, args.steps)
+    rates = []
+    # each step = one bounded pass budget; keep the whole run within a few minutes
+    per_step = min(args.cpu_seconds, max(1.0, 120.0 / (steps + max(args.warmup, 0))))
+    for i in range(max(args.warmup, 0) + steps):
+        rate, el, reps, nhh, nres, _ = cpu_engine_rate(batch, prot, nh, per_step, threads, 4)
+        if i >= args.warmup:
+            rates.append(rate)
+    value = float(np.mean(rates))
+    cpu = {"value": value, "unit": "residues/s", "cores": threads, "kind": "port",
+           "sample": "%d haplotypes (%d residues) of the %s cohort, UTF-32 tapes (gir.rs:18-22), haplotypes over %d "
+                     "threads (exec.rs:34-40); the Rust reference cannot be compiled in this image" %
+                     (nhh, nres, args.workload, threads)}
+    rb = reference_binary_rate(prot, cat, batch, args.ref_binary_samples or min(32, batch.n_hap // 2))
+    if rb:
+        cpu["reference_binary"] = rb
+    line = {"impl": "reference", "metric": "generated residues/sec", "value": value, "unit": "residues/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": nres / value * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (Rust char)",
+            "data": "synthetic",
+            "config": {"workload": "%s: bounded sample of %d haplotypes of the same synthetic cohort" % (args.workload, nhh)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": "residues/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -127,6 +127,7 @@ typedef struct {
     uint64_t bad_hap;  /* haplotype of the lowest offending task (when status != V2P_OK) */
     uint64_t bad_task; /* its index within that haplotype                                */
     float kernel_ms;   /* device time of the launch group (plan + copy), CUDA events     */
+    float copy_ms;     /* device time of the dominant kernel alone (k_copy_tiles)        */
 } v2p_result;
 
 /* Executes every haplotype of the batch == n_hap calls of GIR::execute (gir.rs:197-241), one launch group.

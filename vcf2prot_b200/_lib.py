@@ -30,7 +30,7 @@ class Batch(C.Structure):
 
 
 class Result(C.Structure):
-    _fields_ = [("status", C.c_int), ("bad_hap", C.c_uint64), ("bad_task", C.c_uint64), ("kernel_ms", C.c_float)]
+    _fields_ = [("status", C.c_int), ("bad_hap", C.c_uint64), ("bad_task", C.c_uint64), ("kernel_ms", C.c_float), ("copy_ms", C.c_float)]
 
 
 # every symbol include/v2p_engine.h declares: (restype, argtypes)

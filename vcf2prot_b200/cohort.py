@@ -377,7 +377,9 @@ def concat_batches(parts: List[Batch]) -> Batch:
                  cat_base("alt_base"), cat_base("out_base"), None, parts[0].ref,
                  np.concatenate([b.ann_hap + o for b, o in zip(parts, hap_off)]),
                  np.concatenate([b.ann_tx for b in parts]), np.concatenate([b.ann_start for b in parts]),
-                 np.concatenate([b.ann_end for b in parts]))
+                 np.concatenate([b.ann_end for b in parts]),
+                 np.concatenate([b.kept_hap + o for b, o in zip(parts, hap_off)]),
+                 np.concatenate([b.kept_site for b in parts]))
 
 
 def fasta_records(prot: Proteome, batch: Batch, out: np.ndarray, h: int, hap_label: int) -> List[Tuple[str, str]]:

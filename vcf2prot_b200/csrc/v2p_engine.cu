@@ -29,7 +29,7 @@ struct DevBuf {
 }  // namespace
 
 struct v2p_event {
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr, ev_copy = nullptr;
     DevStatus* h_status = nullptr;  // pinned; filled by a stream-ordered D2H right behind the launch group
     KParams kp;                     // for the deferred serial fallback
     uint32_t flags = 0;
@@ -94,7 +94,7 @@ int tile_bytes_of(const v2p_engine* e) { return e->variant == 1 ? 2048 : 4096; }
 
 // plan + copy on e->stream.  kp.{lb,tile_hap,status,n_tiles,tile_bytes} are filled here.
 int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop, DevStatus* h_status,
-                 cudaEvent_t ev_done, bool init_status = true) {
+                 cudaEvent_t ev_done, bool init_status = true, cudaEvent_t ev_copy = nullptr) {
     const int T = tile_bytes_of(e);
     kp.tile_bytes = (uint32_t)T;
     kp.n_tiles = (kp.n_out + T - 1) / T;
@@ -122,6 +122,7 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
         k_plan_tasks<<<(unsigned)((kp.n_tasks + 255) / 256), 256, 0, s>>>(kp);
         e->launches++;
     }
+    if (ev_copy) CUDA_TRY(e, cudaEventRecord(ev_copy, s));
     if (kp.n_tiles) {
         const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : (T == 4096 ? 4 : 8);
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -219,6 +220,7 @@ int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
         if (ev->ev_start) cudaEventDestroy(ev->ev_start);
         if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
         if (ev->ev_done) cudaEventDestroy(ev->ev_done);
+        if (ev->ev_copy) cudaEventDestroy(ev->ev_copy);
         if (ev->h_status) cudaFreeHost(ev->h_status);
         delete ev;
         if (res) *res = local;
@@ -239,6 +241,7 @@ int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
     decode_status(st, tb, ev->kp.n_hap, ev->kp.task_origin, &local);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev->ev_start, ev->ev_stop) == cudaSuccess) local.kernel_ms = ms;
+    if (cudaEventElapsedTime(&ms, ev->ev_copy, ev->ev_stop) == cudaSuccess) local.copy_ms = ms;
     if (local.status == V2P_OK && ev->host_mode && ev->out_bytes) {
         if (cudaMemcpyAsync(ev->h_out, ev->kp.out, ev->out_bytes, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess ||
             cudaStreamSynchronize(e->stream) != cudaSuccess)
@@ -352,11 +355,13 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         if (ev->ev_start) cudaEventDestroy(ev->ev_start);
         if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
         if (ev->ev_done) cudaEventDestroy(ev->ev_done);
+        if (ev->ev_copy) cudaEventDestroy(ev->ev_copy);
         if (ev->h_status) cudaFreeHost(ev->h_status);
         delete ev;
         return code;
     };
     if (cudaEventCreate(&ev->ev_start) != cudaSuccess || cudaEventCreate(&ev->ev_stop) != cudaSuccess ||
+        cudaEventCreate(&ev->ev_copy) != cudaSuccess ||
         cudaEventCreateWithFlags(&ev->ev_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void**)&ev->h_status, sizeof(DevStatus)) != cudaSuccess)
         return cleanup(fail(e, V2P_ERR_CUDA, "event/pinned allocation failed"));
@@ -433,7 +438,7 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         ev->h_task_begin = b->task_begin;
     }
 
-    rc = launch_group(e, kp, ev->ev_start, ev->ev_stop, ev->h_status, ev->ev_done);
+    rc = launch_group(e, kp, ev->ev_start, ev->ev_stop, ev->h_status, ev->ev_done, true, ev->ev_copy);
     if (rc) return cleanup(rc);
     ev->kp = kp;
     if (async) {

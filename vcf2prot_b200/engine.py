@@ -175,7 +175,33 @@ class GpuEngine:
         st = self._lib.v2p_execute_batch(self._h, C.byref(b), L.FLAG_VALIDATE if validate else 0, C.byref(res), None)
         if st != L.V2P_OK:
             raise EngineError(st, self.last_error(), res.bad_hap, res.bad_task)
+        self.last_copy_ms = float(res.copy_ms)
         return out, float(res.kernel_ms)
+
+    def execute_hap_range(self, h0: int, h1: int, task_begin: np.ndarray, tasks: np.ndarray, ref: np.ndarray,
+                          alt: np.ndarray, alt_base: np.ndarray, out_base: np.ndarray, out_chunk: np.ndarray,
+                          validate: bool = False) -> float:
+        """Host-pointer call on haplotypes [h0,h1) of a larger host-resident cohort (the streaming shape: the
+        caller's pinned staging buffer `out_chunk` receives just this range's result tapes).  The base arrays keep
+        their cohort-absolute values; the library rebases on entry [0] of each slice."""
+        b = L.Batch()
+        addr = lambda x: x.ctypes.data
+        b.task_begin = addr(task_begin) + 8 * h0
+        b.tasks = addr(tasks)
+        b.ref, b.ref_base, b.n_ref = addr(ref), None, len(ref)
+        b.alt = addr(alt)
+        b.alt_base = addr(alt_base) + 8 * h0
+        b.out_base = addr(out_base) + 8 * h0
+        o0, o1 = int(out_base[h0]), int(out_base[h1])
+        assert out_chunk.size >= o1 - o0 and out_chunk.dtype == np.uint8
+        b.out = addr(out_chunk) - o0  # virtual base: out[o0] is out_chunk[0]
+        b.n_hap = h1 - h0
+        res = L.Result()
+        st = self._lib.v2p_execute_batch(self._h, C.byref(b), L.FLAG_VALIDATE if validate else 0, C.byref(res), None)
+        if st != L.V2P_OK:
+            raise EngineError(st, self.last_error(), res.bad_hap, res.bad_task)
+        self.last_copy_ms = float(res.copy_ms)
+        return float(res.kernel_ms)
 
     def execute_batch_device(self, n_hap: int, task_begin, tasks, ref, alt, alt_base, out, out_base, n_tasks: int,
                              n_alt: int, n_out: int, ref_base=None, validate: bool = False, wait: bool = True):
@@ -193,6 +219,7 @@ class GpuEngine:
             st = self._lib.v2p_execute_batch(self._h, C.byref(b), flags, C.byref(res), None)
             if st != L.V2P_OK:
                 raise EngineError(st, self.last_error(), res.bad_hap, res.bad_task)
+            self.last_copy_ms = float(res.copy_ms)
             return float(res.kernel_ms)
         ev = C.c_void_p()
         st = self._lib.v2p_execute_batch(self._h, C.byref(b), flags | L.FLAG_ASYNC, None, C.byref(ev))
@@ -205,6 +232,7 @@ class GpuEngine:
         st = self._lib.v2p_event_wait(self._h, ev, C.byref(res))
         if st != L.V2P_OK:
             raise EngineError(st, self.last_error(), res.bad_hap, res.bad_task)
+        self.last_copy_ms = float(res.copy_ms)
         return float(res.kernel_ms)
 
 
