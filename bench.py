@@ -294,13 +294,14 @@ def main():
         for a, b in chunks:
             eng.execute_hap_range(a, b, h_task_begin, h_tasks, h_ref, h_alt, h_alt_base, h_out_base, h_out)
 
-    e2e_step()  # warm-up (allocates the engine's device staging)
+    if args.e2e_steps > 0:
+        e2e_step()  # warm-up (allocates the engine's device staging)
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - e0
+    e2e_s = max(time.perf_counter() - e0, 1e-9)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -308,7 +309,7 @@ def main():
     # the last chunk sits in h_out: keep it for the parity spot-check against the device-resident result
     a, b = chunks[-1]
     o0, o1 = int(batch.out_base[a]), int(batch.out_base[b])
-    e2e_matches_device = bool(np.array_equal(h_out[:o1 - o0], d_out[o0:o1].cpu().numpy()))
+    e2e_matches_device = bool(np.array_equal(h_out[:o1 - o0], d_out[o0:o1].cpu().numpy())) if args.e2e_steps > 0 else None
 
     if rank != 0:
         if world > 1:

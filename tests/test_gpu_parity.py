@@ -102,7 +102,7 @@ def test_non_ascii_residues_ride_the_utf32_path(gpu_engine):
 
 
 # ---------------------------------------------------------------------------------------------- randomized parity
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("seed,n_hap,mean_res", [(1, 1, 100), (2, 7, 3000), (3, 40, 20000), (4, 300, 2000),
                                                  (5, 3, 3_000_000), (6, 64, 150_000)])
 def test_random_batches_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):

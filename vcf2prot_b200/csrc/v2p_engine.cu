@@ -90,7 +90,23 @@ int reserve(v2p_engine* e, DevBuf& b, size_t bytes) {
     return V2P_OK;
 }
 
-int tile_bytes_of(const v2p_engine* e) { return e->variant == 1 ? 2048 : 4096; }
+// Copy-kernel variants selectable through v2p_engine_set_tuning (profiling sweeps); 0 is the shipped default.
+struct CopyVariant {
+    int tile;
+    int ctas_per_sm;
+    void (*fn)(const KParams);
+};
+const CopyVariant kVariants[] = {
+    {4096, 4, k_copy_tiles<4096, 4, 4>},  // 0: 4 KiB tiles, 4 vectors in flight per lane, 64 regs
+    {2048, 5, k_copy_tiles<2048, 4, 5>},  // 1: 2 KiB tiles, 51 regs
+    {4096, 3, k_copy_tiles<4096, 4, 3>},  // 2: 4 KiB tiles, 85 regs
+    {4096, 4, k_copy_tiles<4096, 2, 4>},  // 3: 4 KiB tiles, 2 vectors in flight per lane
+    {2048, 4, k_copy_tiles<2048, 4, 4>},  // 4: 2 KiB tiles, 64 regs
+    {4096, 2, k_copy_tiles<4096, 8, 2>},  // 5: 4 KiB tiles, all 8 vectors in flight, 128 regs
+};
+constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+
+int tile_bytes_of(const v2p_engine* e) { return kVariants[e->variant].tile; }
 
 // plan + copy on e->stream.  kp.{lb,tile_hap,status,n_tiles,tile_bytes} are filled here.
 int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop, DevStatus* h_status,
@@ -109,7 +125,6 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
     cudaStream_t s = e->stream;
     if (ev_start) CUDA_TRY(e, cudaEventRecord(ev_start, s));
     CUDA_TRY(e, cudaMemsetAsync(kp.lb, 0xFF, (kp.n_tiles + 1) * sizeof(uint32_t), s));
-    CUDA_TRY(e, cudaMemsetAsync(kp.tile_hap, 0, std::max<uint64_t>(kp.n_tiles, 1) * sizeof(uint32_t), s));
     if (init_status) {
         k_init_status<<<1, 1, 0, s>>>(kp.status);
         e->launches++;
@@ -117,6 +132,10 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
     if (kp.n_hap) {
         k_plan_haps<<<(unsigned)((kp.n_hap + 255) / 256), 256, 0, s>>>(kp);
         e->launches++;
+        if (kp.n_tiles) {
+            k_plan_tiles<<<(unsigned)((kp.n_tiles + 255) / 256), 256, 0, s>>>(kp);
+            e->launches++;
+        }
     }
     if (kp.n_tasks) {
         k_plan_tasks<<<(unsigned)((kp.n_tasks + 255) / 256), 256, 0, s>>>(kp);
@@ -124,16 +143,14 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
     }
     if (ev_copy) CUDA_TRY(e, cudaEventRecord(ev_copy, s));
     if (kp.n_tiles) {
-        const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : (T == 4096 ? 4 : 8);
+        const CopyVariant& cv = kVariants[e->variant];
+        const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : cv.ctas_per_sm;
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
-        if (T == 4096) {
-            size_t smem = (size_t)kWarpsPerCta * (4096 + 256);
-            k_copy_tiles<4096><<<grid, kThreads, smem, s>>>(kp);
-        } else {
-            size_t smem = (size_t)kWarpsPerCta * (2048 + 128);
-            k_copy_tiles<2048><<<grid, kThreads, smem, s>>>(kp);
-        }
+        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16);
+        if (smem > 48 * 1024)
+            CUDA_TRY(e, cudaFuncSetAttribute(cv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cv.fn<<<grid, kThreads, smem, s>>>(kp);
         e->launches++;
     }
     if (ev_stop) CUDA_TRY(e, cudaEventRecord(ev_stop, s));
@@ -313,7 +330,7 @@ int v2p_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? V2P_OK 
 uint64_t v2p_kernel_launch_count(v2p_engine* e) { return e ? e->launches : 0; }
 
 int v2p_engine_set_tuning(v2p_engine* e, int variant, int ctas_per_sm) {
-    if (!e || variant < 0 || variant > 1 || ctas_per_sm < 0 || ctas_per_sm > 32) return V2P_ERR_INVALID_ARG;
+    if (!e || variant < 0 || variant >= kNumVariants || ctas_per_sm < 0 || ctas_per_sm > 32) return V2P_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);
     e->variant = variant;
     e->ctas_per_sm = ctas_per_sm;

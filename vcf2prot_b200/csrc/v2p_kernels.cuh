@@ -84,7 +84,7 @@ __global__ void k_init_status(DevStatus* s) {
     s->bad_args = 0;
 }
 
-// One thread per haplotype: base-array sanity + tile -> haplotype map.
+// One thread per haplotype: base-array sanity (monotone, consistent with the totals the caller passed).
 __global__ void k_plan_haps(KParams p) {
     uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (h >= p.n_hap) return;
@@ -101,57 +101,74 @@ __global__ void k_plan_haps(KParams p) {
         bad |= o1 - p.out_origin != p.n_out || t1 - p.task_origin != p.n_tasks || a1 - p.alt_origin != p.n_alt;
         if (p.ref_base) bad |= p.ref_base[h + 1] - p.ref_origin != p.n_ref;
     }
-    if (bad) {
-        atomicExch(&p.status->bad_args, 1u);
-        return;
-    }
-    // tiles whose first byte lies in [o0,o1)
-    uint64_t r0 = o0 - p.out_origin, r1 = o1 - p.out_origin;
-    uint64_t T = p.tile_bytes;
-    for (uint64_t k = (r0 + T - 1) / T; k * T < r1 && k < p.n_tiles; ++k) p.tile_hap[k] = (uint32_t)h;
+    if (bad) atomicExch(&p.status->bad_args, 1u);
+}
+
+// One thread per output tile: the haplotype that owns the tile's first byte (binary search over out_base).
+__global__ void k_plan_tiles(KParams p) {
+    uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (k >= p.n_tiles) return;
+    const uint64_t x = k * (uint64_t)p.tile_bytes + p.out_origin;
+    uint64_t h = upper_bound_u64(p.out_base, 0, p.n_hap + 1, x);  // first h with out_base[h] > x
+    h = h ? h - 1 : 0;
+    if (h >= p.n_hap) h = p.n_hap - 1;
+    p.tile_hap[k] = (uint32_t)h;
 }
 
 // One thread per task: everything the reference would panic on, plus lb[] (tile -> first task).
-__global__ void k_plan_tasks(KParams p) {
-    __shared__ uint64_t s_h0;
-    uint64_t tfirst = blockIdx.x * (uint64_t)blockDim.x;
-    if (threadIdx.x == 0) s_h0 = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, tfirst + p.task_origin) - 1;
+// A CTA's 256 tasks almost always sit inside one haplotype: its bases are staged once in shared memory.
+__global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
+    __shared__ uint64_t sh[8];  // h0, task_begin[h0], task_begin[h0+1], out_base[h0], out_base[h0+1], n_alt(h0), n_ref(h0)
+    const uint64_t tfirst = blockIdx.x * (uint64_t)blockDim.x;
+    if (threadIdx.x == 0) {
+        const uint64_t h0 = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, tfirst + p.task_origin) - 1;
+        sh[0] = h0;
+        sh[1] = p.task_begin[h0];
+        sh[2] = p.task_begin[h0 + 1];
+        sh[3] = p.out_base[h0];
+        sh[4] = p.out_base[h0 + 1];
+        sh[5] = p.alt_base[h0 + 1] - p.alt_base[h0];
+        sh[6] = p.ref_base ? p.ref_base[h0 + 1] - p.ref_base[h0] : p.n_ref;
+    }
+    const uint64_t tr = tfirst + threadIdx.x;  // launch-relative task index
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u), pr = raw;
+    if (tr < p.n_tasks) {
+        raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
+        if (tr > 0) pr = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr - 1);
+    }
     __syncthreads();
-    if (p.status->bad_args) return;
-    uint64_t tr = tfirst + threadIdx.x;  // relative task index
-    if (tr >= p.n_tasks) return;
-    uint64_t t = tr + p.task_origin;
-    uint64_t h = s_h0;
-    while (h + 1 < p.n_hap && __ldg(p.task_begin + h + 1) <= t) ++h;
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
+    if (p.status->bad_args || tr >= p.n_tasks) return;
+    const uint64_t t = tr + p.task_origin;
+    uint64_t h = sh[0], tb0 = sh[1], o0 = sh[3], n_res = sh[4] - sh[3], n_alt = sh[5], n_ref = sh[6];
+    if (t >= sh[2]) {  // not the CTA's first haplotype
+        while (h + 1 < p.n_hap && __ldg(p.task_begin + h + 1) <= t) ++h;
+        tb0 = __ldg(p.task_begin + h);
+        o0 = __ldg(p.out_base + h);
+        n_res = __ldg(p.out_base + h + 1) - o0;
+        n_alt = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
+        n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
+    }
     const uint64_t src = raw.x, len = raw.y, dst = raw.z;
     const uint32_t stream = raw.w;
-    const uint64_t o0 = __ldg(p.out_base + h), n_res = __ldg(p.out_base + h + 1) - o0;
     unsigned long long key = (unsigned long long)tr << 8;
     if (stream > 1u) {  // haplotype_instruction.rs:154
         atomicMin(&p.status->err_key, key | V2P_ERR_BAD_STREAM);
         return;
     }
-    uint64_t n_src;
-    if (stream == 0)
-        n_src = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
-    else
-        n_src = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
     if (dst + len > n_res) {  // task.rs:44/48 (result slice)
         atomicMin(&p.status->err_key, key | V2P_ERR_RES_OOB);
         return;
     }
-    if (src + len > n_src) {  // task.rs:44/48 (source slice)
+    if (src + len > (stream == 0 ? n_ref : n_alt)) {  // task.rs:44/48 (source slice)
         atomicMin(&p.status->err_key, key | V2P_ERR_SRC_OOB);
         return;
     }
     const uint64_t g = o0 - p.out_origin + dst;  // global (launch-relative) output byte of this task
     uint64_t k_lo = 0;
     if (tr > 0) {
-        const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr - 1);
         uint64_t gp;
-        if (t > __ldg(p.task_begin + h)) {  // same haplotype: gir.rs:208 contiguity + sortedness
-            uint64_t pend = (uint64_t)pr.z + pr.y;
+        if (t > tb0) {  // same haplotype: gir.rs:208 contiguity + sortedness
+            const uint64_t pend = (uint64_t)pr.z + pr.y;
             if (dst < pend) atomicExch(&p.status->unsorted, 1u);
             if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
             gp = o0 - p.out_origin + pr.z;
@@ -203,8 +220,36 @@ __device__ __forceinline__ uint32_t bytescan_max(uint32_t x) {
 }
 
 // ------------------------------------------------------------------------------------------------ copy kernel
-template <int TILE>
-__global__ void __launch_bounds__(kThreads) k_copy_tiles(const KParams p) {
+// One partial 16-byte vector ("piece") of a task: vector `vx` of the tile, bytes [a,b) of it, 0 <= a < b <= 16.
+// The source bytes are fetched as (at most) two aligned 16-byte loads, realigned in registers, and the valid
+// bytes are stored with statically indexed word / byte stores (no per-byte loop over global memory).
+__device__ __forceinline__ void store_piece(uint8_t* __restrict__ tile, const long long p0, const int vx, const int a,
+                                            const int b) {
+    const unsigned long long sa = (unsigned long long)(p0 + (long long)vx * 16);
+    const uint32_t sh = (uint32_t)sa & 15u;
+    const uint4* ap = reinterpret_cast<const uint4*>(sa - sh);
+    uint4 A = make_uint4(0u, 0u, 0u, 0u), B = A;
+    if (a < 16 - (int)sh) A = __ldg(ap);      // some valid byte lives in the first aligned chunk
+    if (b > 16 - (int)sh) B = __ldg(ap + 1);  // ... in the second one (implies sh != 0)
+    const uint4 r = realign16(A, B, sh);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint8_t* dst = tile + vx * 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (a <= 4 * j && 4 * j + 4 <= b) {
+            reinterpret_cast<uint32_t*>(dst)[j] = w[j];
+        } else if (a < 4 * j + 4 && 4 * j < b) {
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+                if (a <= 4 * j + bb && 4 * j + bb < b) dst[4 * j + bb] = (uint8_t)(w[j] >> (8 * bb));
+        }
+    }
+}
+
+// TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
+// parallelism); MINB: CTAs per SM the register allocation is held to.
+template <int TILE, int G, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) {
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
     constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4 or 8)
     constexpr int STRIDE = TILE + NV;
@@ -219,10 +264,34 @@ __global__ void __launch_bounds__(kThreads) k_copy_tiles(const KParams p) {
     const uint64_t n_warps = (uint64_t)gridDim.x * kWarpsPerCta;
     const uint4 fillv = make_uint4(p.fill_word, p.fill_word, p.fill_word, p.fill_word);
 
-    for (uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp; k < p.n_tiles; k += n_warps) {
+    uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
+    // tile metadata is fetched one tile ahead (software prefetch: lb[k], lb[k+1], tile_hap[k])
+    uint32_t m_lo = 0, m_hi = 0, m_hap = 0;
+    if (k < p.n_tiles) {
+        m_lo = __ldg(p.lb + k);
+        m_hi = __ldg(p.lb + k + 1);
+        m_hap = __ldg(p.tile_hap + k);
+    }
+    for (; k < p.n_tiles; k += n_warps) {
         const uint64_t tile_start = k * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
+        uint64_t t_lo = min((uint64_t)m_lo, p.n_tasks);
+        const uint64_t t_hi = min((uint64_t)m_hi, p.n_tasks);
+        if (t_lo > 0) --t_lo;  // the task before may extend into the tile
+        const uint64_t h_hint = m_hap;
+        {
+            const uint64_t kn = k + n_warps;
+            if (kn < p.n_tiles) {
+                m_lo = __ldg(p.lb + kn);
+                m_hi = __ldg(p.lb + kn + 1);
+                m_hap = __ldg(p.tile_hap + kn);
+            }
+        }
+        // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
+        const uint64_t hb_t0 = __ldg(p.task_begin + h_hint), hb_t1 = __ldg(p.task_begin + h_hint + 1);
+        const uint64_t hb_out = __ldg(p.out_base + h_hint), hb_alt = __ldg(p.alt_base + h_hint);
+        const uint64_t hb_ref = p.ref_base ? __ldg(p.ref_base + h_hint) : p.ref_origin;
 
         // the previous tile's bulk store must have finished READING shared memory before we overwrite it
         if (lane == 0) bulk_wait_read0();
@@ -250,42 +319,39 @@ __global__ void __launch_bounds__(kThreads) k_copy_tiles(const KParams p) {
             reinterpret_cast<uint2*>(lead)[lane] = make_uint2(0u, 0u);
         __syncwarp();
 
-        // tasks that can touch this tile: [t_lo, t_hi)
-        uint64_t t_lo = min((uint64_t)__ldg(p.lb + k), p.n_tasks);
-        const uint64_t t_hi = min((uint64_t)__ldg(p.lb + k + 1), p.n_tasks);
-        if (t_lo > 0) --t_lo;  // the task before may extend into the tile
-        const uint64_t h_hint = __ldg(p.tile_hap + k);
-
         for (uint64_t tb = t_lo; tb < t_hi; tb += 32) {
-            // ---- A: one lane per task
+            // ---- A: one lane per task: partial head/tail vectors, and the start of its fully covered vector range
             const uint64_t tr = tb + lane;
             long long p0 = 0;   // source address of tile byte 0 for this task (may point before the segment)
             uint32_t v1 = 0;    // end (exclusive) of the fully covered vector range, in vectors
             if (tr < t_hi) {
                 const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
-                const uint64_t h = hap_of_task(p, tr + p.task_origin, h_hint);
-                const long long g = (long long)(__ldg(p.out_base + h) - p.out_origin + raw.z) - (long long)tile_start;
+                const uint64_t t_abs = tr + p.task_origin;
+                uint64_t o_b = hb_out, a_b = hb_alt, r_b = hb_ref;
+                if (t_abs < hb_t0 || t_abs >= hb_t1) {  // another haplotype (tile spans a haplotype boundary)
+                    const uint64_t h = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, t_abs) - 1;
+                    o_b = __ldg(p.out_base + h);
+                    a_b = __ldg(p.alt_base + h);
+                    r_b = p.ref_base ? __ldg(p.ref_base + h) : p.ref_origin;
+                }
+                const long long g = (long long)(o_b - p.out_origin + raw.z) - (long long)tile_start;
                 const long long ge = g + raw.y;
                 const int s = (int)max(g, 0ll), e = (int)min(ge, (long long)tile_len);
                 if (e > s) {
-                    const uint8_t* sb = raw.w ? p.alt + (__ldg(p.alt_base + h) - p.alt_origin)
-                                              : p.ref + (p.ref_base ? __ldg(p.ref_base + h) - p.ref_origin : 0ull);
+                    const uint8_t* sb = raw.w ? p.alt + (a_b - p.alt_origin) : p.ref + (r_b - p.ref_origin);
                     p0 = (long long)(sb + raw.x) - g;
-                    const uint8_t* __restrict__ sp = reinterpret_cast<const uint8_t*>(p0);
+                    const int vh = s >> 4, vt = (e - 1) >> 4;
                     const int v0b = (s + 15) & ~15, v1b = e & ~15;
-                    int hend = e, tbeg = e;
                     if (v1b > v0b) {
-                        hend = v0b;
-                        tbeg = v1b;
                         lead[v0b >> 4] = (uint8_t)(lane + 1);
                         v1 = (uint32_t)(v1b >> 4);
                     }
-                    const int n1 = hend - s, n = n1 + (e - tbeg);
-#pragma unroll 4
-                    for (int j = 0; j < n; ++j) {
-                        const int x = j < n1 ? s + j : tbeg + (j - n1);
-                        tile[x] = __ldg(sp + x);
-                    }
+                    // head piece: bytes [s&15, min(e-16vh,16)) of vector vh unless that is the whole vector
+                    const int a1 = s & 15, b1 = min(e - (vh << 4), 16);
+                    if (a1 != 0 || b1 != 16) store_piece(tile, p0, vh, a1, b1);
+                    // tail piece: bytes [0, e-16vt) of vector vt (when the task reaches into a later vector)
+                    const int b2 = e - (vt << 4);
+                    if (vt > vh && b2 != 16) store_piece(tile, p0, vt, 0, b2);
                 }
             }
             __syncwarp();
@@ -326,24 +392,34 @@ __global__ void __launch_bounds__(kThreads) k_copy_tiles(const KParams p) {
             }
             __syncwarp();
 
-            // ---- C: one lane per fully covered 16-byte vector
+            // ---- C: one lane per fully covered 16-byte vector; loads of G vectors are issued before any is used
             const uint32_t p0lo = (uint32_t)(unsigned long long)p0, p0hi = (uint32_t)((unsigned long long)p0 >> 32);
 #pragma unroll
-            for (int r = 0; r < NV / 32; ++r) {
-                const int v = lane + 32 * r;
-                const uint32_t owner = lead[v];
-                const int srcl = (int)((owner - 1u) & 31u);
-                const uint32_t qlo = __shfl_sync(0xffffffffu, p0lo, srcl);
-                const uint32_t qhi = __shfl_sync(0xffffffffu, p0hi, srcl);
-                const uint32_t qv1 = __shfl_sync(0xffffffffu, v1, srcl);
-                if (owner != 0u && (uint32_t)v < qv1) {
+            for (int r0 = 0; r0 < NV / 32; r0 += G) {
+                uint4 A[G], B[G];
+                uint32_t shv[G];
+                bool on[G];
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const int v = lane + 32 * (r0 + i);
+                    const uint32_t owner = lead[v];
+                    const int srcl = (int)((owner - 1u) & 31u);
+                    const uint32_t qlo = __shfl_sync(0xffffffffu, p0lo, srcl);
+                    const uint32_t qhi = __shfl_sync(0xffffffffu, p0hi, srcl);
+                    const uint32_t qv1 = __shfl_sync(0xffffffffu, v1, srcl);
+                    on[i] = owner != 0u && (uint32_t)v < qv1;
                     const unsigned long long sa = (((unsigned long long)qhi << 32) | qlo) + (unsigned long long)(v * 16);
-                    const uint32_t sh = (uint32_t)sa & 15u;
-                    const uint4* ap = reinterpret_cast<const uint4*>(sa - sh);
-                    const uint4 A = __ldg(ap);
-                    uint4 B = A;
-                    if (sh) B = __ldg(ap + 1);
-                    reinterpret_cast<uint4*>(tile)[v] = realign16(A, B, sh);
+                    shv[i] = (uint32_t)sa & 15u;
+                    const uint4* ap = reinterpret_cast<const uint4*>(sa - shv[i]);
+                    A[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (on[i]) A[i] = __ldg(ap);
+                    B[i] = A[i];
+                    if (on[i] && shv[i]) B[i] = __ldg(ap + 1);
+                }
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const int v = lane + 32 * (r0 + i);
+                    if (on[i]) reinterpret_cast<uint4*>(tile)[v] = realign16(A[i], B[i], shv[i]);
                 }
             }
             __syncwarp();
