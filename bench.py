@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="kernel tile variant (0: 4 KiB/warp, 1: 2 KiB/warp)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--no-registered-ref", action="store_true",
+                    help="pass the proteome with every call (generic register path) instead of registering it once")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
                     help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
     return ap.parse_args()
@@ -236,9 +238,14 @@ def main():
 
     eng = GpuEngine(local_rank)
     eng.set_tuning(args.variant, args.ctas_per_sm)
+    if not args.no_registered_ref:
+        eng.set_reference(d_ref)  # proteome registered once (as the FASTA is loaded once): TMA replica path
+        d_ref_arg = None
+    else:
+        d_ref_arg = d_ref
     side = torch.cuda.Stream(device=dev)
     eng.set_stream(side.cuda_stream)
-    dargs = (n_hap, d_task_begin, d_tasks, d_ref, d_alt, d_alt_base, d_out, d_out_base, n_tasks, len(batch.alt), n_res)
+    dargs = (n_hap, d_task_begin, d_tasks, d_ref_arg, d_alt, d_alt_base, d_out, d_out_base, n_tasks, len(batch.alt), n_res)
 
     def barrier():
         torch.cuda.synchronize()
@@ -288,11 +295,12 @@ def main():
     max_chunk = max(int(batch.out_base[b] - batch.out_base[a]) for a, b in chunks)
     h_out = torch.empty(max_chunk + 64, dtype=torch.uint8).pin_memory().numpy()
     h2d = sum(int(batch.task_begin[b] - batch.task_begin[a]) * 16 + int(batch.alt_base[b] - batch.alt_base[a]) +
-              3 * 8 * (b - a + 1) + len(batch.ref) for a, b in chunks)
+              3 * 8 * (b - a + 1) + (len(batch.ref) if args.no_registered_ref else 0) for a, b in chunks)
 
     def e2e_step():
         for a, b in chunks:
-            eng.execute_hap_range(a, b, h_task_begin, h_tasks, h_ref, h_alt, h_alt_base, h_out_base, h_out)
+            eng.execute_hap_range(a, b, h_task_begin, h_tasks, None if not args.no_registered_ref else h_ref, h_alt,
+                                  h_alt_base, h_out_base, h_out)
 
     if args.e2e_steps > 0:
         e2e_step()  # warm-up (allocates the engine's device staging)
@@ -363,7 +371,8 @@ def main():
                    "haplotypes_per_gpu": n_hap, "tasks_per_gpu": n_tasks, "residues_per_gpu": n_res,
                    "mean_task_bytes": n_res / max(n_tasks, 1), "l2_policy": "inputs_larger_than_l2 (output %.1f GB, tasks %.2f GB "
                    "per step; the %.1f MB proteome is L2-resident by design)" % (n_res / 1e9, n_tasks * 16 / 1e9, len(batch.ref) / 1e6),
-                   "tile_variant": args.variant, "parallelism": "sample-sharded x%d, no collective" % world},
+                   "tile_variant": args.variant, "reference_tape": "caller-supplied per call" if args.no_registered_ref else
+                   "registered once (v2p_engine_set_reference): 16 shifted replicas, TMA bulk loads", "parallelism": "sample-sharded x%d, no collective" % world},
         "haplotypes_per_s": n_hap * world / (ms_per_step * 1e-3),
         "alg_gbs": b_alg * world / (ms_per_step * 1e-3) / 1e9,
         "clocks": clocks,

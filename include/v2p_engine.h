@@ -73,6 +73,13 @@ int v2p_abi_version(void);
 int v2p_host_alloc(void** ptr, size_t bytes);
 int v2p_host_free(void* ptr);
 
+/* Register the reference proteome (the reference keeps it in a HashMap<String,String>, readers.rs:58-98; here it is
+ * one concatenated residue tape).  The tape is copied into HBM once, together with 16 byte-shifted replicas, so
+ * that whatever (destination - source) phase a reference run has, its fully covered 16-byte vectors are served by
+ * plain aligned TMA bulk copies out of L2.  Batches that pass ref == NULL and ref_base == NULL index this tape
+ * (Task.start_pos = transcript offset in the tape + position).  flags: 0 (host pointer) or V2P_FLAG_DEVICE_PTRS. */
+int v2p_engine_set_reference(v2p_engine* e, const uint8_t* ref, uint64_t n_ref, uint32_t flags);
+
 /* ---- (i) reference-faithful single-haplotype call == GIR::execute(Engine::GPU) ------------------- */
 /* Replaces gir.rs:236-239.  The SoA shape is the reference's own hand-off,
  * GIR::consume_and_produce_produce_content (gir.rs:283-299): four `usize` arrays (exe_code widened,
@@ -107,7 +114,7 @@ typedef struct {
 typedef struct {
     const uint64_t* task_begin; /* n_hap+1: tasks of haplotype h are tasks[task_begin[h] .. task_begin[h+1])    */
     const v2p_task16* tasks;    /* task_begin[n_hap] entries                                                  */
-    const uint8_t* ref;         /* reference residues                                                         */
+    const uint8_t* ref;         /* reference residues; NULL (with ref_base NULL) = the registered reference   */
     const uint64_t* ref_base;   /* n_hap+1 per-haplotype ref-tape bounds, or NULL: all haplotypes share the   */
     uint64_t n_ref;             /*   whole tape ref[0..n_ref) (the proteome; tasks then carry global offsets) */
     const uint8_t* alt;         /* concatenated alteration tapes                                              */

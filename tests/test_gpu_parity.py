@@ -117,6 +117,52 @@ def test_random_batches_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
         gpu_engine.set_tuning(0, 0)
 
 
+@pytest.mark.parametrize("variant", [0, 2, 3])
+@pytest.mark.parametrize("seed,n_hap,mean_res", [(51, 5, 400), (52, 30, 30000), (53, 4, 2_000_000)])
+def test_registered_reference_tma_path_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
+    """ref == NULL: tasks index the registered proteome; long reference runs are TMA bulk copies from the
+    16 byte-shifted replicas, everything else takes the register path.  Same bytes as the oracle."""
+    gpu_engine.set_tuning(variant, 0)
+    try:
+        b = random_batch(seed, n_hap, mean_res, n_ref=200_003)
+        gpu_engine.set_reference(b["ref"])
+        out, _ = gpu_engine.execute_batch(b["task_begin"], b["tasks"], None, b["alt"], b["alt_base"], b["out_base"])
+        st, _, _, want = oracle_batch(b)
+        assert st == 0 and np.array_equal(out, want)
+        # the generic (caller-supplied tape) path still works on the same engine afterwards
+        out2, _ = gpu_batch(gpu_engine, b)
+        assert np.array_equal(out2, want)
+    finally:
+        gpu_engine.set_tuning(0, 0)
+
+
+def test_registered_reference_cohort_and_errors(gpu_engine):
+    from vcf2prot_b200 import GpuEngine
+    from vcf2prot_b200 import cohort as C
+
+    prot = C.make_proteome(seed=5, n_tx=400, mu=5.5, sigma=0.7, hi=6000)
+    cat = C.make_catalogue(prot, 9000, seed=6, mix=(0.7, 0.06, 0.06, 0.08, 0.04, 0.03, 0.03), fs_mean=40, fs_max=900)
+    b = C.synth_batch(prot, cat, 40, 7, ref_mode="global")
+    gpu_engine.set_reference(prot.residues)
+    out, _ = gpu_engine.execute_batch(b.task_begin, b.tasks, None, b.alt, b.alt_base, b.out_base, validate=True)
+    want = np.zeros(b.n_residues, np.uint8)
+    assert cengine.batch_execute(b.task_begin, b.tasks, prot.residues, b.alt, b.alt_base, want, b.out_base)[0] == 0
+    assert np.array_equal(out, want)
+    # a source slice beyond the registered tape is still the reference's slice panic
+    bad = b.tasks.copy()
+    k = int(np.flatnonzero(bad[:, 3] == 0)[5])
+    bad[k, 0] = len(prot.residues) - 1
+    bad[k, 1] = max(bad[k, 1], 2)
+    with pytest.raises(EngineError) as ei:
+        gpu_engine.execute_batch(b.task_begin, bad, None, b.alt, b.alt_base, b.out_base)
+    assert ei.value.status in (L.ERR_SRC_OOB, L.ERR_RES_OOB)
+    # no registered reference on a fresh engine -> loud failure, not a guess
+    with GpuEngine(0) as fresh:
+        with pytest.raises(EngineError) as ei:
+            fresh.execute_batch(b.task_begin, b.tasks, None, b.alt, b.alt_base, b.out_base)
+        assert ei.value.status == L.ERR_INVALID_ARG
+
+
 @pytest.mark.parametrize("mix", [(1.0, 0, 0, 0), (0, 1.0, 0, 0), (0, 0, 0, 1.0), (0.5, 0.5, 0, 0)])
 def test_extreme_length_mixes(gpu_engine, mix):
     """all 1-byte tasks (>32 tasks per tile -> multi-batch tiles), all short, all long (skew)."""

@@ -52,6 +52,7 @@ SYMBOLS = {
     "v2p_kernel_launch_count": (C.c_uint64, [_P]),
     "v2p_engine_set_tuning": (C.c_int, [_P, C.c_int, C.c_int]),
     "v2p_engine_set_stream": (C.c_int, [_P, _P]),
+    "v2p_engine_set_reference": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32]),
 }
 
 _lib = None

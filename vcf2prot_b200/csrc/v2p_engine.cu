@@ -56,6 +56,10 @@ struct v2p_engine {
     // staging for the SoA call
     DevBuf d_soa[4];
     DevStatus* h_status = nullptr;  // pinned scratch for synchronous calls
+    // registered reference: replica r (0..15) at ref_rep + r*rep_stride, holding ref[x] at offset x + r
+    DevBuf ref_rep;
+    uint64_t rep_stride = 0, reg_n_ref = 0;
+    bool has_ref = false;
 };
 
 namespace {
@@ -113,6 +117,7 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
                  cudaEvent_t ev_done, bool init_status = true, cudaEvent_t ev_copy = nullptr) {
     const int T = tile_bytes_of(e);
     kp.tile_bytes = (uint32_t)T;
+    kp.tile_shift = T == 4096 ? 12u : 11u;
     kp.n_tiles = (kp.n_out + T - 1) / T;
     if (kp.n_tasks >= 0xFFFFFFFEull) return fail(e, V2P_ERR_INVALID_ARG, "more than 2^32-2 tasks in one launch");
     int rc;
@@ -147,7 +152,7 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
         const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : cv.ctas_per_sm;
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
-        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16);
+        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + 16);
         if (smem > 48 * 1024)
             CUDA_TRY(e, cudaFuncSetAttribute(cv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cv.fn<<<grid, kThreads, smem, s>>>(kp);
@@ -311,7 +316,7 @@ void v2p_engine_destroy(v2p_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->lb,      &e->tile_hap, &e->status, &e->d_tasks,    &e->d_task_begin, &e->d_ref,   &e->d_ref_base,
                       &e->d_alt,   &e->d_alt_base, &e->d_out,  &e->d_out_base, &e->d_soa[0],     &e->d_soa[1], &e->d_soa[2],
-                      &e->d_soa[3]};
+                      &e->d_soa[3], &e->ref_rep};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->h_status) cudaFreeHost(e->h_status);
@@ -353,6 +358,33 @@ int v2p_engine_set_stream(v2p_engine* e, void* cuda_stream) {
     return V2P_OK;
 }
 
+int v2p_engine_set_reference(v2p_engine* e, const uint8_t* ref, uint64_t n_ref, uint32_t flags) {
+    if (!e || (n_ref && !ref)) return V2P_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->err.clear();
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->has_ref = false;
+    const uint64_t stride = (n_ref + 64 + 255) & ~255ull;
+    int rc = reserve(e, e->ref_rep, 16 * stride + 256);
+    if (rc) return rc;
+    uint8_t* rep = (uint8_t*)e->ref_rep.p;
+    CUDA_TRY(e, cudaMemsetAsync(rep, 0, 16 * stride + 256, e->stream));
+    if (n_ref) {
+        CUDA_TRY(e, cudaMemcpyAsync(rep, ref, n_ref,
+                                    (flags & V2P_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                    e->stream));
+        k_build_replicas<<<(unsigned)((n_ref + 255) / 256), 256, 0, e->stream>>>(rep, n_ref, rep, stride);
+        e->launches++;
+        CUDA_TRY(e, cudaGetLastError());
+    }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->rep_stride = stride;
+    e->reg_n_ref = n_ref;
+    e->has_ref = true;
+    return V2P_OK;
+}
+
 // ---- batched native call -------------------------------------------------------------------------
 int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_result* res, v2p_event** done) {
     if (!e) return V2P_ERR_INVALID_ARG;
@@ -391,6 +423,9 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
     kp.keep_out = 0;
     kp.validate = (flags & V2P_FLAG_VALIDATE) ? 1 : 0;
 
+    const bool use_reg_ref = b->ref == nullptr && b->ref_base == nullptr;
+    if (use_reg_ref && !e->has_ref)
+        return cleanup(fail(e, V2P_ERR_INVALID_ARG, "ref == NULL but no reference was registered (v2p_engine_set_reference)"));
     if (flags & V2P_FLAG_DEVICE_PTRS) {
         if (((uintptr_t)b->out & 15u) != 0) return cleanup(fail(e, V2P_ERR_INVALID_ARG, "out must be 16-byte aligned"));
         kp.tasks = b->tasks;
@@ -412,7 +447,7 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         const uint64_t t0 = H ? b->task_begin[0] : 0, t1 = H ? b->task_begin[H] : 0;
         const uint64_t a0 = H ? b->alt_base[0] : 0, a1 = H ? b->alt_base[H] : 0;
         const uint64_t o0 = H ? b->out_base[0] : 0, o1 = H ? b->out_base[H] : 0;
-        uint64_t r0 = 0, r1 = b->n_ref;
+        uint64_t r0 = 0, r1 = use_reg_ref ? 0 : b->n_ref;
         if (b->ref_base && H) r0 = b->ref_base[0], r1 = b->ref_base[H];
         if (t1 < t0 || a1 < a0 || o1 < o0 || r1 < r0) return cleanup(fail(e, V2P_ERR_INVALID_ARG, "base arrays not monotone"));
         kp.n_tasks = t1 - t0;
@@ -455,6 +490,14 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         ev->h_task_begin = b->task_begin;
     }
 
+    if (use_reg_ref) {
+        kp.ref = (const uint8_t*)e->ref_rep.p;  // replica 0 is the plain tape
+        kp.ref_base = nullptr;
+        kp.ref_origin = 0;
+        kp.n_ref = e->reg_n_ref;
+        kp.ref_rep = (const uint8_t*)e->ref_rep.p;
+        kp.rep_stride = e->rep_stride;
+    }
     rc = launch_group(e, kp, ev->ev_start, ev->ev_stop, ev->h_status, ev->ev_done, true, ev->ev_copy);
     if (rc) return cleanup(rc);
     ev->kp = kp;

@@ -41,6 +41,8 @@ struct KParams {
     const uint64_t* task_begin;  // n_hap+1 (absolute task numbers)
     const uint8_t* ref;
     const uint64_t* ref_base;  // n_hap+1 or nullptr
+    const uint8_t* ref_rep;    // 16 byte-shifted replicas of the registered reference (TMA path) or nullptr
+    uint64_t rep_stride;       // bytes between replicas; replica r stores ref[x] at ref_rep + r*rep_stride + x + r
     const uint8_t* alt;        // alt[a - alt_origin]
     const uint64_t* alt_base;  // n_hap+1 (absolute)
     uint8_t* out;              // out[o - out_origin], 16-byte aligned
@@ -51,6 +53,7 @@ struct KParams {
     uint32_t* tile_hap;  // n_tiles
     uint64_t n_tiles;
     uint32_t tile_bytes;
+    uint32_t tile_shift;  // log2(tile_bytes)
     uint32_t fill_word;  // 0x2E2E2E2E for 1-byte residues, 0x0000002E for UTF-32 units
     int keep_out;        // 1: uncovered bytes keep the caller's content (soa call without FILL_DOT)
     int validate;        // V2P_FLAG_VALIDATE
@@ -108,7 +111,7 @@ __global__ void k_plan_haps(KParams p) {
 __global__ void k_plan_tiles(KParams p) {
     uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (k >= p.n_tiles) return;
-    const uint64_t x = k * (uint64_t)p.tile_bytes + p.out_origin;
+    const uint64_t x = (k << p.tile_shift) + p.out_origin;
     uint64_t h = upper_bound_u64(p.out_base, 0, p.n_hap + 1, x);  // first h with out_base[h] > x
     h = h ? h - 1 : 0;
     if (h >= p.n_hap) h = p.n_hap - 1;
@@ -178,9 +181,9 @@ __global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
             gp = __ldg(p.out_base + hp) - p.out_origin + pr.z;
         }
         if (gp > g) return;  // cannot happen across haplotypes with monotone out_base; unsorted inside one
-        k_lo = gp / p.tile_bytes + 1;
+        k_lo = (gp >> p.tile_shift) + 1;
     }
-    uint64_t k_hi = g / p.tile_bytes;
+    uint64_t k_hi = g >> p.tile_shift;
     if (k_hi > p.n_tiles) k_hi = p.n_tiles;
     for (uint64_t k = k_lo; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
 }
@@ -195,6 +198,33 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned both sides)
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // bytes [sh, sh+16) of the 32-byte little-endian concatenation A||B  (sh in [0,16))
@@ -252,14 +282,18 @@ template <int TILE, int G, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) {
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
     constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4 or 8)
-    constexpr int STRIDE = TILE + NV;
+    constexpr int STRIDE = TILE + NV + 16;  // tile | lead[] | mbarrier
     static_assert(LW == 4 || LW == 8, "TILE must be 2048 or 4096");
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* const tile = smem + warp * STRIDE;
     uint8_t* const lead = tile + TILE;
+    const uint32_t mbar = smem_addr(tile + TILE + NV);
+    uint32_t mbar_phase = 0;
 
     if (p.status->bad_args || p.status->unsorted || p.status->err_key != ~0ull || p.status->gap_key != ~0ull) return;
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncwarp();
 
     const uint64_t n_warps = (uint64_t)gridDim.x * kWarpsPerCta;
     const uint4 fillv = make_uint4(p.fill_word, p.fill_word, p.fill_word, p.fill_word);
@@ -317,13 +351,18 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             reinterpret_cast<uint32_t*>(lead)[lane] = 0u;
         else
             reinterpret_cast<uint2*>(lead)[lane] = make_uint2(0u, 0u);
+        if (p.ref_rep) fence_async_smem();  // the prefill must be ordered before TMA loads land in the same bytes
         __syncwarp();
+        bool tma_used = false;
 
         for (uint64_t tb = t_lo; tb < t_hi; tb += 32) {
             // ---- A: one lane per task: partial head/tail vectors, and the start of its fully covered vector range
             const uint64_t tr = tb + lane;
             long long p0 = 0;   // source address of tile byte 0 for this task (may point before the segment)
             uint32_t v1 = 0;    // end (exclusive) of the fully covered vector range, in vectors
+            uint32_t tma_bytes = 0, tma_dst = 0;  // fully covered range served by a TMA bulk copy from a replica
+            const uint8_t* tma_src = nullptr;
+            bool has_lead = false;
             if (tr < t_hi) {
                 const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
                 const uint64_t t_abs = tr + p.task_origin;
@@ -343,8 +382,18 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     const int vh = s >> 4, vt = (e - 1) >> 4;
                     const int v0b = (s + 15) & ~15, v1b = e & ~15;
                     if (v1b > v0b) {
-                        lead[v0b >> 4] = (uint8_t)(lane + 1);
-                        v1 = (uint32_t)(v1b >> 4);
+                        if (p.ref_rep && raw.w == 0u) {
+                            // replica r = (-q) mod 16 holds this run at the same 16-byte phase as the output
+                            const long long q = p0 - (long long)p.ref;  // ref offset of tile byte 0
+                            const uint32_t r = (uint32_t)(-q) & 15u;
+                            tma_src = p.ref_rep + (uint64_t)r * p.rep_stride + (uint64_t)(q + v0b) + r;
+                            tma_dst = (uint32_t)v0b;
+                            tma_bytes = (uint32_t)(v1b - v0b);
+                        } else {
+                            lead[v0b >> 4] = (uint8_t)(lane + 1);
+                            v1 = (uint32_t)(v1b >> 4);
+                            has_lead = true;
+                        }
                     }
                     // head piece: bytes [s&15, min(e-16vh,16)) of vector vh unless that is the whole vector
                     const int a1 = s & 15, b1 = min(e - (vh << 4), 16);
@@ -354,6 +403,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     if (vt > vh && b2 != 16) store_piece(tile, p0, vt, 0, b2);
                 }
             }
+            if (p.ref_rep) {  // warp-uniform
+                const uint32_t total = __reduce_add_sync(0xffffffffu, tma_bytes);
+                if (total) {
+                    if (lane == 0) mbar_expect_tx(mbar, total);
+                    __syncwarp();
+                    if (tma_bytes) bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar);
+                    tma_used = true;
+                }
+            }
+            if (!__any_sync(0xffffffffu, has_lead)) continue;  // nothing for the register path in this batch
             __syncwarp();
 
             // ---- B: owner of every vector = last task (in this batch) whose covered range started at or before it
@@ -432,7 +491,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             }
         }
 
-        // ---- D: publish the tile
+        // ---- D: publish the tile (after every TMA load of this tile has landed)
+        if (tma_used) {
+            if (lane == 0) mbar_arrive(mbar);
+            mbar_wait(mbar, mbar_phase);
+            mbar_phase ^= 1u;
+        }
         fence_async_smem();
         __syncwarp();
         const uint32_t bulk = tile_len & ~15u;
@@ -469,6 +533,17 @@ __global__ void __launch_bounds__(kThreads) k_serial(const KParams p) {
             __syncthreads();
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ replicas
+// rep[r*stride + x + r] = ref[x] for r in 0..15: whatever (dst - src) mod 16 a run has, one replica holds it at
+// the output's 16-byte phase, so its fully covered vectors are plain aligned TMA bulk copies.
+// `ref` may be replica 0 itself (already in place): then only replicas 1..15 are written.
+__global__ void k_build_replicas(const uint8_t* ref, uint64_t n_ref, uint8_t* rep, uint64_t stride) {
+    const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (x >= n_ref) return;
+    const uint8_t v = ref[x];
+    for (int r = (ref == rep) ? 1 : 0; r < 16; ++r) rep[(uint64_t)r * stride + x + r] = v;
 }
 
 // ------------------------------------------------------------------------------------------------ SoA hand-off

@@ -123,6 +123,17 @@ class GpuEngine:
         if st:
             raise EngineError(st, "set_stream")
 
+    def set_reference(self, ref) -> None:
+        """Register the proteome tape (numpy uint8 host array or a torch CUDA uint8 tensor); batches that pass
+        ref=None then index it and long reference runs ride the TMA replica path."""
+        if hasattr(ref, "data_ptr"):
+            st = self._lib.v2p_engine_set_reference(self._h, C.c_void_p(ref.data_ptr()), int(ref.numel()), L.FLAG_DEVICE_PTRS)
+        else:
+            ref = np.ascontiguousarray(ref, dtype=np.uint8)
+            st = self._lib.v2p_engine_set_reference(self._h, ref.ctypes.data_as(C.c_void_p), len(ref), 0)
+        if st:
+            raise EngineError(st, self.last_error())
+
     # ------------------------------------------------------------------ (i) GIR::execute(Engine::GPU)
     def execute_soa(self, tasks: Sequence[Tuple[int, int, int, int]], ref, alt, res, fill_dot: bool = True,
                     validate: bool = False, engine: Engine = Engine.GPU) -> np.ndarray:
@@ -155,7 +166,7 @@ class GpuEngine:
         """Host (numpy) buffers in, host result tape out.  Returns (out u8[out_base[-1]-out_base[0]...], kernel_ms)."""
         task_begin = np.ascontiguousarray(task_begin, dtype=np.uint64)
         tasks = np.ascontiguousarray(tasks, dtype=np.uint32)
-        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        ref = None if ref is None else np.ascontiguousarray(ref, dtype=np.uint8)
         alt = np.ascontiguousarray(alt, dtype=np.uint8)
         alt_base = np.ascontiguousarray(alt_base, dtype=np.uint64)
         out_base = np.ascontiguousarray(out_base, dtype=np.uint64)
@@ -168,7 +179,7 @@ class GpuEngine:
         if ref_base is not None:
             ref_base = np.ascontiguousarray(ref_base, dtype=np.uint64)
             b.ref_base = p(ref_base)
-        b.n_ref = len(ref)
+        b.n_ref = 0 if ref is None else len(ref)
         b.alt, b.alt_base, b.out, b.out_base = p(alt), p(alt_base), p(out), p(out_base)
         b.n_hap = max(n_hap, 0)
         res = L.Result()
@@ -188,7 +199,7 @@ class GpuEngine:
         addr = lambda x: x.ctypes.data
         b.task_begin = addr(task_begin) + 8 * h0
         b.tasks = addr(tasks)
-        b.ref, b.ref_base, b.n_ref = addr(ref), None, len(ref)
+        b.ref, b.ref_base, b.n_ref = (None, None, 0) if ref is None else (addr(ref), None, len(ref))
         b.alt = addr(alt)
         b.alt_base = addr(alt_base) + 8 * h0
         b.out_base = addr(out_base) + 8 * h0
@@ -210,7 +221,7 @@ class GpuEngine:
         ptr = lambda x: None if x is None else (x if isinstance(x, int) else x.data_ptr())
         b = L.Batch()
         b.task_begin, b.tasks, b.ref, b.ref_base = ptr(task_begin), ptr(tasks), ptr(ref), ptr(ref_base)
-        b.n_ref = int(ref.numel()) if hasattr(ref, "numel") else 0
+        b.n_ref = int(ref.numel()) if hasattr(ref, "numel") else 0  # ref=None -> the registered reference
         b.alt, b.alt_base, b.out, b.out_base = ptr(alt), ptr(alt_base), ptr(out), ptr(out_base)
         b.n_hap, b.n_tasks, b.n_alt, b.n_out = n_hap, n_tasks, n_alt, n_out
         flags = L.FLAG_DEVICE_PTRS | (L.FLAG_VALIDATE if validate else 0)
