@@ -107,6 +107,9 @@ const CopyVariant kVariants[] = {
     {4096, 4, k_copy_tiles<4096, 2, 4>},  // 3: 4 KiB tiles, 2 vectors in flight per lane
     {2048, 4, k_copy_tiles<2048, 4, 4>},  // 4: 2 KiB tiles, 64 regs
     {4096, 2, k_copy_tiles<4096, 8, 2>},  // 5: 4 KiB tiles, all 8 vectors in flight, 128 regs
+    {4096, 6, k_copy_tiles<4096, 1, 6>},  // 6: 4 KiB tiles, 1 vector in flight, 40 regs, 48 warps/SM
+    {4096, 5, k_copy_tiles<4096, 2, 5>},  // 7: 4 KiB tiles, 2 vectors in flight, 48 regs, 40 warps/SM
+    {2048, 8, k_copy_tiles<2048, 1, 8>},  // 8: 2 KiB tiles, 32 regs, 64 warps/SM
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
@@ -143,7 +146,7 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
         }
     }
     if (kp.n_tasks) {
-        k_plan_tasks<<<(unsigned)((kp.n_tasks + 255) / 256), 256, 0, s>>>(kp);
+        k_plan_tasks<<<(unsigned)((kp.n_tasks + kPlanChunk - 1) / kPlanChunk), 256, 0, s>>>(kp);
         e->launches++;
     }
     if (ev_copy) CUDA_TRY(e, cudaEventRecord(ev_copy, s));

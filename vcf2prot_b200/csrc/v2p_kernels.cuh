@@ -118,11 +118,15 @@ __global__ void k_plan_tiles(KParams p) {
     p.tile_hap[k] = (uint32_t)h;
 }
 
-// One thread per task: everything the reference would panic on, plus lb[] (tile -> first task).
-// A CTA's 256 tasks almost always sit inside one haplotype: its bases are staged once in shared memory.
+// One thread per task (kPlanChunk tasks per CTA): everything the reference would panic on, plus lb[]
+// (tile -> first task).  A CTA's tasks almost always sit inside one haplotype: that haplotype is found once per
+// CTA (binary search by thread 0) and its bases are staged in shared memory.
+constexpr int kPlanIters = 16;
+constexpr int kPlanChunk = 256 * kPlanIters;
+
 __global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
     __shared__ uint64_t sh[8];  // h0, task_begin[h0], task_begin[h0+1], out_base[h0], out_base[h0+1], n_alt(h0), n_ref(h0)
-    const uint64_t tfirst = blockIdx.x * (uint64_t)blockDim.x;
+    const uint64_t tfirst = blockIdx.x * (uint64_t)kPlanChunk;
     if (threadIdx.x == 0) {
         const uint64_t h0 = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, tfirst + p.task_origin) - 1;
         sh[0] = h0;
@@ -133,66 +137,79 @@ __global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
         sh[5] = p.alt_base[h0 + 1] - p.alt_base[h0];
         sh[6] = p.ref_base ? p.ref_base[h0 + 1] - p.ref_base[h0] : p.n_ref;
     }
-    const uint64_t tr = tfirst + threadIdx.x;  // launch-relative task index
-    uint4 raw = make_uint4(0u, 0u, 0u, 0u), pr = raw;
-    if (tr < p.n_tasks) {
-        raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
-        if (tr > 0) pr = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr - 1);
-    }
     __syncthreads();
-    if (p.status->bad_args || tr >= p.n_tasks) return;
-    const uint64_t t = tr + p.task_origin;
-    uint64_t h = sh[0], tb0 = sh[1], o0 = sh[3], n_res = sh[4] - sh[3], n_alt = sh[5], n_ref = sh[6];
-    if (t >= sh[2]) {  // not the CTA's first haplotype
-        while (h + 1 < p.n_hap && __ldg(p.task_begin + h + 1) <= t) ++h;
-        tb0 = __ldg(p.task_begin + h);
-        o0 = __ldg(p.out_base + h);
-        n_res = __ldg(p.out_base + h + 1) - o0;
-        n_alt = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
-        n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
-    }
-    const uint64_t src = raw.x, len = raw.y, dst = raw.z;
-    const uint32_t stream = raw.w;
-    unsigned long long key = (unsigned long long)tr << 8;
-    if (stream > 1u) {  // haplotype_instruction.rs:154
-        atomicMin(&p.status->err_key, key | V2P_ERR_BAD_STREAM);
-        return;
-    }
-    if (dst + len > n_res) {  // task.rs:44/48 (result slice)
-        atomicMin(&p.status->err_key, key | V2P_ERR_RES_OOB);
-        return;
-    }
-    if (src + len > (stream == 0 ? n_ref : n_alt)) {  // task.rs:44/48 (source slice)
-        atomicMin(&p.status->err_key, key | V2P_ERR_SRC_OOB);
-        return;
-    }
-    const uint64_t g = o0 - p.out_origin + dst;  // global (launch-relative) output byte of this task
-    uint64_t k_lo = 0;
-    if (tr > 0) {
-        uint64_t gp;
-        if (t > tb0) {  // same haplotype: gir.rs:208 contiguity + sortedness
-            const uint64_t pend = (uint64_t)pr.z + pr.y;
-            if (dst < pend) atomicExch(&p.status->unsorted, 1u);
-            if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
-            gp = o0 - p.out_origin + pr.z;
-        } else {
-            uint64_t hp = h;
-            while (hp > 0 && __ldg(p.task_begin + hp) > t - 1) --hp;
-            gp = __ldg(p.out_base + hp) - p.out_origin + pr.z;
+    if (p.status->bad_args) return;
+    const uint4* __restrict__ tk = reinterpret_cast<const uint4*>(p.tasks);
+#pragma unroll 4
+    for (int it = 0; it < kPlanIters; ++it) {
+        const uint64_t tr = tfirst + (uint64_t)it * 256 + threadIdx.x;  // launch-relative task index
+        if (tr >= p.n_tasks) break;
+        const uint4 raw = __ldg(tk + tr);
+        const uint4 pr = tr > 0 ? __ldg(tk + tr - 1) : make_uint4(0u, 0u, 0u, 0u);
+        const uint64_t t = tr + p.task_origin;
+        uint64_t h = sh[0], tb0 = sh[1], o0 = sh[3], n_res = sh[4] - sh[3], n_alt = sh[5], n_ref = sh[6];
+        if (t >= sh[2]) {  // not the CTA's first haplotype
+            h = upper_bound_u64(p.task_begin, h + 1, p.n_hap + 1, t) - 1;
+            tb0 = __ldg(p.task_begin + h);
+            o0 = __ldg(p.out_base + h);
+            n_res = __ldg(p.out_base + h + 1) - o0;
+            n_alt = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
+            n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
         }
-        if (gp > g) return;  // cannot happen across haplotypes with monotone out_base; unsorted inside one
-        k_lo = (gp >> p.tile_shift) + 1;
+        const uint32_t src = raw.x, len = raw.y, dst = raw.z, stream = raw.w;
+        const unsigned long long key = (unsigned long long)tr << 8;
+        if (stream > 1u) {  // haplotype_instruction.rs:154
+            atomicMin(&p.status->err_key, key | V2P_ERR_BAD_STREAM);
+            continue;
+        }
+        if ((uint64_t)dst + len > n_res) {  // task.rs:44/48 (result slice)
+            atomicMin(&p.status->err_key, key | V2P_ERR_RES_OOB);
+            continue;
+        }
+        if ((uint64_t)src + len > (stream == 0 ? n_ref : n_alt)) {  // task.rs:44/48 (source slice)
+            atomicMin(&p.status->err_key, key | V2P_ERR_SRC_OOB);
+            continue;
+        }
+        const uint64_t g = o0 - p.out_origin + dst;  // global (launch-relative) output byte of this task
+        uint64_t k_lo = 0;
+        if (tr > 0) {
+            uint64_t gp;
+            if (t > tb0) {  // same haplotype: gir.rs:208 contiguity + sortedness
+                const uint64_t pend = (uint64_t)pr.z + pr.y;
+                if (dst < pend) atomicExch(&p.status->unsorted, 1u);
+                if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
+                gp = o0 - p.out_origin + pr.z;
+            } else {
+                uint64_t hp = h;
+                while (hp > 0 && __ldg(p.task_begin + hp) > t - 1) --hp;
+                gp = __ldg(p.out_base + hp) - p.out_origin + pr.z;
+            }
+            if (gp > g) continue;  // cannot happen across haplotypes with monotone out_base; unsorted inside one
+            k_lo = (gp >> p.tile_shift) + 1;
+        }
+        uint64_t k_hi = g >> p.tile_shift;
+        if (k_hi > p.n_tiles) k_hi = p.n_tiles;
+        for (uint64_t k = k_lo; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
     }
-    uint64_t k_hi = g >> p.tile_shift;
-    if (k_hi > p.n_tiles) k_hi = p.n_tiles;
-    for (uint64_t k = k_lo; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
 }
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_addr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)),
-                 "r"(bytes)
+// L2 policies: the result stream is written once and never re-read (evict_first), the reference tape / replicas are
+// re-read by every haplotype (evict_last) -- keeps the proteome resident in the 126 MB L2 under a multi-GB write stream.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(smem_addr(ssrc)), "r"(bytes), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -219,11 +236,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     } while (!ok);
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned both sides)
-__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"(mbar)
-                 : "memory");
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint32_t mbar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_addr(sdst)),
+        "l"(gsrc), "r"(bytes), "r"(mbar), "l"(pol)
+        : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -253,15 +271,25 @@ __device__ __forceinline__ uint32_t bytescan_max(uint32_t x) {
 // One partial 16-byte vector ("piece") of a task: vector `vx` of the tile, bytes [a,b) of it, 0 <= a < b <= 16.
 // The source bytes are fetched as (at most) two aligned 16-byte loads, realigned in registers, and the valid
 // bytes are stored with statically indexed word / byte stores (no per-byte loop over global memory).
-__device__ __forceinline__ void store_piece(uint8_t* __restrict__ tile, const long long p0, const int vx, const int a,
-                                            const int b) {
+// Split in two so that the loads of a task's head AND tail piece are in flight together.
+struct Piece {
+    uint4 A, B;
+    uint32_t sh;
+};
+__device__ __forceinline__ Piece piece_load(const long long p0, const int vx, const int a, const int b, const bool on) {
+    Piece pc;
     const unsigned long long sa = (unsigned long long)(p0 + (long long)vx * 16);
-    const uint32_t sh = (uint32_t)sa & 15u;
-    const uint4* ap = reinterpret_cast<const uint4*>(sa - sh);
-    uint4 A = make_uint4(0u, 0u, 0u, 0u), B = A;
-    if (a < 16 - (int)sh) A = __ldg(ap);      // some valid byte lives in the first aligned chunk
-    if (b > 16 - (int)sh) B = __ldg(ap + 1);  // ... in the second one (implies sh != 0)
-    const uint4 r = realign16(A, B, sh);
+    pc.sh = (uint32_t)sa & 15u;
+    const uint4* ap = reinterpret_cast<const uint4*>(sa - pc.sh);
+    pc.A = make_uint4(0u, 0u, 0u, 0u);
+    pc.B = pc.A;
+    if (on && a < 16 - (int)pc.sh) pc.A = __ldg(ap);      // some valid byte lives in the first aligned chunk
+    if (on && b > 16 - (int)pc.sh) pc.B = __ldg(ap + 1);  // ... in the second one (implies sh != 0)
+    return pc;
+}
+__device__ __forceinline__ void piece_store(uint8_t* __restrict__ tile, const Piece& pc, const int vx, const int a,
+                                            const int b) {
+    const uint4 r = realign16(pc.A, pc.B, pc.sh);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
     uint8_t* dst = tile + vx * 16;
 #pragma unroll
@@ -296,36 +324,57 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     __syncwarp();
 
     const uint64_t n_warps = (uint64_t)gridDim.x * kWarpsPerCta;
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     const uint4 fillv = make_uint4(p.fill_word, p.fill_word, p.fill_word, p.fill_word);
 
+    // Software pipeline over this warp's tiles: metadata (lb[k], lb[k+1], tile_hap[k]) is fetched two tiles ahead,
+    // the first batch of tasks and the owning haplotype's bases one tile ahead, so that a tile starts with its
+    // dependent loads already landed.
+    auto load_meta = [&](uint64_t kk, uint32_t& lo, uint32_t& hi, uint32_t& hp) {
+        lo = hi = hp = 0;
+        if (kk < p.n_tiles) {
+            lo = __ldg(p.lb + kk);
+            hi = __ldg(p.lb + kk + 1);
+            hp = __ldg(p.tile_hap + kk);
+        }
+    };
+    auto first_task = [&](uint32_t lo) -> uint64_t {
+        uint64_t t = min((uint64_t)lo, p.n_tasks);
+        return t > 0 ? t - 1 : 0;  // the task before may extend into the tile
+    };
+    auto load_tasks = [&](uint32_t lo, uint32_t hi, uint32_t hp, uint4& raw, uint64_t& base) {
+        const uint64_t tr = first_task(lo) + lane;
+        raw = make_uint4(0u, 0u, 0u, 0u);
+        if (tr < min((uint64_t)hi, p.n_tasks)) raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
+        base = 0;  // lane j < 5 holds field j of the haplotype's bases
+        if (lane == 0) base = __ldg(p.task_begin + hp);
+        if (lane == 1) base = __ldg(p.task_begin + hp + 1);
+        if (lane == 2) base = __ldg(p.out_base + hp);
+        if (lane == 3) base = __ldg(p.alt_base + hp);
+        if (lane == 4) base = p.ref_base ? __ldg(p.ref_base + hp) : p.ref_origin;
+    };
     uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
-    // tile metadata is fetched one tile ahead (software prefetch: lb[k], lb[k+1], tile_hap[k])
-    uint32_t m_lo = 0, m_hi = 0, m_hap = 0;
-    if (k < p.n_tiles) {
-        m_lo = __ldg(p.lb + k);
-        m_hi = __ldg(p.lb + k + 1);
-        m_hap = __ldg(p.tile_hap + k);
-    }
+    uint32_t c_lo, c_hi, c_hap, n_lo, n_hi, n_hap;
+    uint4 pf_raw;
+    uint64_t pf_base;
+    load_meta(k, c_lo, c_hi, c_hap);
+    load_meta(k + n_warps, n_lo, n_hi, n_hap);
+    if (k < p.n_tiles) load_tasks(c_lo, c_hi, c_hap, pf_raw, pf_base);
     for (; k < p.n_tiles; k += n_warps) {
         const uint64_t tile_start = k * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
-        uint64_t t_lo = min((uint64_t)m_lo, p.n_tasks);
-        const uint64_t t_hi = min((uint64_t)m_hi, p.n_tasks);
-        if (t_lo > 0) --t_lo;  // the task before may extend into the tile
-        const uint64_t h_hint = m_hap;
-        {
-            const uint64_t kn = k + n_warps;
-            if (kn < p.n_tiles) {
-                m_lo = __ldg(p.lb + kn);
-                m_hi = __ldg(p.lb + kn + 1);
-                m_hap = __ldg(p.tile_hap + kn);
-            }
-        }
+        const uint64_t t_lo = first_task(c_lo);
+        const uint64_t t_hi = min((uint64_t)c_hi, p.n_tasks);
+        const uint4 raw0 = pf_raw;
         // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
-        const uint64_t hb_t0 = __ldg(p.task_begin + h_hint), hb_t1 = __ldg(p.task_begin + h_hint + 1);
-        const uint64_t hb_out = __ldg(p.out_base + h_hint), hb_alt = __ldg(p.alt_base + h_hint);
-        const uint64_t hb_ref = p.ref_base ? __ldg(p.ref_base + h_hint) : p.ref_origin;
+        const uint64_t hb_t0 = __shfl_sync(0xffffffffu, pf_base, 0), hb_t1 = __shfl_sync(0xffffffffu, pf_base, 1);
+        const uint64_t hb_out = __shfl_sync(0xffffffffu, pf_base, 2), hb_alt = __shfl_sync(0xffffffffu, pf_base, 3);
+        const uint64_t hb_ref = __shfl_sync(0xffffffffu, pf_base, 4);
+        // advance the pipeline: next tile's metadata is resident by now -> fetch its tasks; fetch metadata two ahead
+        c_lo = n_lo, c_hi = n_hi, c_hap = n_hap;
+        if (k + n_warps < p.n_tiles) load_tasks(c_lo, c_hi, c_hap, pf_raw, pf_base);
+        load_meta(k + 2 * n_warps, n_lo, n_hi, n_hap);
 
         // the previous tile's bulk store must have finished READING shared memory before we overwrite it
         if (lane == 0) bulk_wait_read0();
@@ -364,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             const uint8_t* tma_src = nullptr;
             bool has_lead = false;
             if (tr < t_hi) {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
+                const uint4 raw = tb == t_lo ? raw0 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
                 const uint64_t t_abs = tr + p.task_origin;
                 uint64_t o_b = hb_out, a_b = hb_alt, r_b = hb_ref;
                 if (t_abs < hb_t0 || t_abs >= hb_t1) {  // another haplotype (tile spans a haplotype boundary)
@@ -396,11 +445,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                         }
                     }
                     // head piece: bytes [s&15, min(e-16vh,16)) of vector vh unless that is the whole vector
-                    const int a1 = s & 15, b1 = min(e - (vh << 4), 16);
-                    if (a1 != 0 || b1 != 16) store_piece(tile, p0, vh, a1, b1);
                     // tail piece: bytes [0, e-16vt) of vector vt (when the task reaches into a later vector)
-                    const int b2 = e - (vt << 4);
-                    if (vt > vh && b2 != 16) store_piece(tile, p0, vt, 0, b2);
+                    const int a1 = s & 15, b1 = min(e - (vh << 4), 16), b2 = e - (vt << 4);
+                    const bool on1 = a1 != 0 || b1 != 16, on2 = vt > vh && b2 != 16;
+                    const Piece pc1 = piece_load(p0, vh, a1, b1, on1), pc2 = piece_load(p0, vt, 0, b2, on2);
+                    if (on1) piece_store(tile, pc1, vh, a1, b1);
+                    if (on2) piece_store(tile, pc2, vt, 0, b2);
                 }
             }
             if (p.ref_rep) {  // warp-uniform
@@ -408,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 if (total) {
                     if (lane == 0) mbar_expect_tx(mbar, total);
                     __syncwarp();
-                    if (tma_bytes) bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar);
+                    if (tma_bytes) bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar, pol_keep);
                     tma_used = true;
                 }
             }
@@ -501,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         __syncwarp();
         const uint32_t bulk = tile_len & ~15u;
         if (lane == 0 && bulk) {
-            bulk_store_s2g(gout, tile, bulk);
+            bulk_store_s2g(gout, tile, bulk, pol_stream);
             bulk_commit();
         }
         if (bulk + lane < tile_len) gout[bulk + lane] = tile[bulk + lane];  // < 16 trailing bytes of the whole output
