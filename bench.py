@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="kernel tile variant (0: 4 KiB/warp, 1: 2 KiB/warp)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--ref-mode", default="tensormap", choices=["tensormap", "replicas", "plain"])
     ap.add_argument("--no-registered-ref", action="store_true",
                     help="pass the proteome with every call (generic register path) instead of registering it once")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
@@ -239,7 +240,7 @@ def main():
     eng = GpuEngine(local_rank)
     eng.set_tuning(args.variant, args.ctas_per_sm)
     if not args.no_registered_ref:
-        eng.set_reference(d_ref)  # proteome registered once (as the FASTA is loaded once): TMA replica path
+        eng.set_reference(d_ref, args.ref_mode)  # proteome registered once, as the FASTA is loaded once
         d_ref_arg = None
     else:
         d_ref_arg = d_ref
@@ -372,7 +373,7 @@ def main():
                    "mean_task_bytes": n_res / max(n_tasks, 1), "l2_policy": "inputs_larger_than_l2 (output %.1f GB, tasks %.2f GB "
                    "per step; the %.1f MB proteome is L2-resident by design)" % (n_res / 1e9, n_tasks * 16 / 1e9, len(batch.ref) / 1e6),
                    "tile_variant": args.variant, "reference_tape": "caller-supplied per call" if args.no_registered_ref else
-                   "registered once (v2p_engine_set_reference): 16 shifted replicas, TMA bulk loads", "parallelism": "sample-sharded x%d, no collective" % world},
+                   "registered once (v2p_engine_set_reference, mode %s)" % args.ref_mode, "parallelism": "sample-sharded x%d, no collective" % world},
         "haplotypes_per_s": n_hap * world / (ms_per_step * 1e-3),
         "alg_gbs": b_alg * world / (ms_per_step * 1e-3) / 1e9,
         "clocks": clocks,

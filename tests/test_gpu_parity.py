@@ -117,15 +117,16 @@ def test_random_batches_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
         gpu_engine.set_tuning(0, 0)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3, 6, 7, 8])
+@pytest.mark.parametrize("mode", ["tensormap", "replicas", "plain"])
+@pytest.mark.parametrize("variant", [0, 4, 6, 8])
 @pytest.mark.parametrize("seed,n_hap,mean_res", [(51, 5, 400), (52, 30, 30000), (53, 4, 2_000_000)])
-def test_registered_reference_tma_path_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
+def test_registered_reference_tma_path_bit_exact(gpu_engine, mode, variant, seed, n_hap, mean_res):
     """ref == NULL: tasks index the registered proteome; long reference runs are TMA bulk copies from the
     16 byte-shifted replicas, everything else takes the register path.  Same bytes as the oracle."""
     gpu_engine.set_tuning(variant, 0)
     try:
         b = random_batch(seed, n_hap, mean_res, n_ref=200_003)
-        gpu_engine.set_reference(b["ref"])
+        gpu_engine.set_reference(b["ref"], mode)
         out, _ = gpu_engine.execute_batch(b["task_begin"], b["tasks"], None, b["alt"], b["alt_base"], b["out_base"])
         st, _, _, want = oracle_batch(b)
         assert st == 0 and np.array_equal(out, want)

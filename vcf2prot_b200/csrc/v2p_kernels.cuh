@@ -18,6 +18,7 @@
 //   serial k_serial                     tasks that are NOT sorted/non-overlapping by dst keep the
 //                                       reference's in-order semantics (later task wins) on the GPU.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,6 +28,13 @@ namespace v2p {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
+
+// 1-D uint8 tensor maps over the registered reference tape, one per box size 16 << i bytes (i = 0..4).  TMA tensor
+// loads take an arbitrary byte coordinate, so a run whose source is misaligned by any amount relative to the output
+// still lands 16-byte aligned in the shared-memory tile -- the realignment is done by the TMA unit, not by the SM.
+struct alignas(64) TmaMaps {
+    CUtensorMap m[5];
+};
 
 // Device-side status block, written by the plan kernels with atomics.
 struct DevStatus {
@@ -41,8 +49,9 @@ struct KParams {
     const uint64_t* task_begin;  // n_hap+1 (absolute task numbers)
     const uint8_t* ref;
     const uint64_t* ref_base;  // n_hap+1 or nullptr
-    const uint8_t* ref_rep;    // 16 byte-shifted replicas of the registered reference (TMA path) or nullptr
+    const uint8_t* ref_rep;    // 16 byte-shifted replicas of the registered reference (tma_mode 1) or nullptr
     uint64_t rep_stride;       // bytes between replicas; replica r stores ref[x] at ref_rep + r*rep_stride + x + r
+    int tma_mode;              // 0: register path only; 1: bulk copies from replicas; 2: 1-D tensor-map loads
     const uint8_t* alt;        // alt[a - alt_origin]
     const uint64_t* alt_base;  // n_hap+1 (absolute)
     uint8_t* out;              // out[o - out_origin], 16-byte aligned
@@ -212,6 +221,12 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
                  "r"(smem_addr(ssrc)), "r"(bytes), "l"(pol)
                  : "memory");
 }
+__device__ __forceinline__ void bulk_store_s2g_nohint(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -242,6 +257,18 @@ __device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint
             smem_addr(sdst)),
         "l"(gsrc), "r"(bytes), "r"(mbar), "l"(pol)
         : "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s_nohint(void* sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void tensor_load_1d(void* sdst, const CUtensorMap* map, int32_t c0, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];" ::"r"(
+                     smem_addr(sdst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(mbar)
+                 : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -306,8 +333,10 @@ __device__ __forceinline__ void piece_store(uint8_t* __restrict__ tile, const Pi
 
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
 // parallelism); MINB: CTAs per SM the register allocation is held to.
-template <int TILE, int G, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) {
+// FLAGS: 1 = L2 cache-policy hints, 2 = prefetch the next tile's tasks/bases, 4 = load both pieces before storing.
+template <int TILE, int G, int MINB, int FLAGS>
+__global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p, const __grid_constant__ TmaMaps maps) {
+    constexpr bool kHints = (FLAGS & 1) != 0, kPrefetch = (FLAGS & 2) != 0, kBatchPieces = (FLAGS & 4) != 0;
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
     constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4 or 8)
     constexpr int STRIDE = TILE + NV + 16;  // tile | lead[] | mbarrier
@@ -359,13 +388,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     uint64_t pf_base;
     load_meta(k, c_lo, c_hi, c_hap);
     load_meta(k + n_warps, n_lo, n_hi, n_hap);
-    if (k < p.n_tiles) load_tasks(c_lo, c_hi, c_hap, pf_raw, pf_base);
+    pf_raw = make_uint4(0u, 0u, 0u, 0u);
+    pf_base = 0;
     for (; k < p.n_tiles; k += n_warps) {
         const uint64_t tile_start = k * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
         const uint64_t t_lo = first_task(c_lo);
         const uint64_t t_hi = min((uint64_t)c_hi, p.n_tasks);
+        load_tasks(c_lo, c_hi, c_hap, pf_raw, pf_base);
         const uint4 raw0 = pf_raw;
         // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
         const uint64_t hb_t0 = __shfl_sync(0xffffffffu, pf_base, 0), hb_t1 = __shfl_sync(0xffffffffu, pf_base, 1);
@@ -373,7 +404,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         const uint64_t hb_ref = __shfl_sync(0xffffffffu, pf_base, 4);
         // advance the pipeline: next tile's metadata is resident by now -> fetch its tasks; fetch metadata two ahead
         c_lo = n_lo, c_hi = n_hi, c_hap = n_hap;
-        if (k + n_warps < p.n_tiles) load_tasks(c_lo, c_hi, c_hap, pf_raw, pf_base);
+        if (kPrefetch && k + n_warps < p.n_tiles) {
+            // fire-and-forget L2 prefetch of the next tile's tasks (no register, no scoreboard slot held)
+            const uint64_t tn = first_task(c_lo) + lane;
+            if (tn < min((uint64_t)c_hi, p.n_tasks)) prefetch_l2(reinterpret_cast<const uint4*>(p.tasks) + tn);
+        }
         load_meta(k + 2 * n_warps, n_lo, n_hi, n_hap);
 
         // the previous tile's bulk store must have finished READING shared memory before we overwrite it
@@ -400,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             reinterpret_cast<uint32_t*>(lead)[lane] = 0u;
         else
             reinterpret_cast<uint2*>(lead)[lane] = make_uint2(0u, 0u);
-        if (p.ref_rep) fence_async_smem();  // the prefill must be ordered before TMA loads land in the same bytes
+        if (p.tma_mode) fence_async_smem();  // the prefill must be ordered before TMA loads land in the same bytes
         __syncwarp();
         bool tma_used = false;
 
@@ -411,7 +446,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             uint32_t v1 = 0;    // end (exclusive) of the fully covered vector range, in vectors
             uint32_t tma_bytes = 0, tma_dst = 0;  // fully covered range served by a TMA bulk copy from a replica
             const uint8_t* tma_src = nullptr;
-            bool has_lead = false;
+            int32_t tma_coord = 0;
+            bool has_lead = false, on1 = false, on2 = false;
+            int pvh = 0, pvt = 0, pa1 = 0, pb1 = 16, pb2 = 16;
             if (tr < t_hi) {
                 const uint4 raw = tb == t_lo ? raw0 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
                 const uint64_t t_abs = tr + p.task_origin;
@@ -431,11 +468,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     const int vh = s >> 4, vt = (e - 1) >> 4;
                     const int v0b = (s + 15) & ~15, v1b = e & ~15;
                     if (v1b > v0b) {
-                        if (p.ref_rep && raw.w == 0u) {
-                            // replica r = (-q) mod 16 holds this run at the same 16-byte phase as the output
+                        if (p.tma_mode && raw.w == 0u) {
                             const long long q = p0 - (long long)p.ref;  // ref offset of tile byte 0
-                            const uint32_t r = (uint32_t)(-q) & 15u;
-                            tma_src = p.ref_rep + (uint64_t)r * p.rep_stride + (uint64_t)(q + v0b) + r;
+                            if (p.tma_mode == 1) {
+                                // replica r = (-q) mod 16 holds this run at the same 16-byte phase as the output
+                                const uint32_t r = (uint32_t)(-q) & 15u;
+                                tma_src = p.ref_rep + (uint64_t)r * p.rep_stride + (uint64_t)(q + v0b) + r;
+                            } else {
+                                tma_coord = (int32_t)(q + v0b);  // byte coordinate in the registered tape
+                            }
                             tma_dst = (uint32_t)v0b;
                             tma_bytes = (uint32_t)(v1b - v0b);
                         } else {
@@ -446,21 +487,52 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     }
                     // head piece: bytes [s&15, min(e-16vh,16)) of vector vh unless that is the whole vector
                     // tail piece: bytes [0, e-16vt) of vector vt (when the task reaches into a later vector)
-                    const int a1 = s & 15, b1 = min(e - (vh << 4), 16), b2 = e - (vt << 4);
-                    const bool on1 = a1 != 0 || b1 != 16, on2 = vt > vh && b2 != 16;
-                    const Piece pc1 = piece_load(p0, vh, a1, b1, on1), pc2 = piece_load(p0, vt, 0, b2, on2);
-                    if (on1) piece_store(tile, pc1, vh, a1, b1);
-                    if (on2) piece_store(tile, pc2, vt, 0, b2);
+                    pvh = vh, pvt = vt;
+                    pa1 = s & 15, pb1 = min(e - (vh << 4), 16), pb2 = e - (vt << 4);
+                    on1 = pa1 != 0 || pb1 != 16;
+                    on2 = vt > vh && pb2 != 16;
                 }
             }
-            if (p.ref_rep) {  // warp-uniform
+            // TMA bulk loads first (they take the longest), the register-path pieces overlap with them
+            if (p.tma_mode) {  // warp-uniform
                 const uint32_t total = __reduce_add_sync(0xffffffffu, tma_bytes);
                 if (total) {
                     if (lane == 0) mbar_expect_tx(mbar, total);
                     __syncwarp();
-                    if (tma_bytes) bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar, pol_keep);
+                    if (p.tma_mode == 1) {
+                        if (tma_bytes) {
+                            if (kHints)
+                                bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar, pol_keep);
+                            else
+                                bulk_load_g2s_nohint(tile + tma_dst, tma_src, tma_bytes, mbar);
+                        }
+                    } else {
+                        // power-of-two boxes: 256-byte boxes while they fit, then one box per set bit of the rest
+                        uint32_t nb = tma_bytes, d = tma_dst;
+                        int32_t c = tma_coord;
+                        while (nb >= 256u) {
+                            tensor_load_1d(tile + d, &maps.m[4], c, mbar);
+                            d += 256u, c += 256, nb -= 256u;
+                        }
+#pragma unroll
+                        for (int i = 3; i >= 0; --i) {
+                            const uint32_t w = 16u << i;
+                            if (nb & w) {
+                                tensor_load_1d(tile + d, &maps.m[i], c, mbar);
+                                d += w, c += (int32_t)w;
+                            }
+                        }
+                    }
                     tma_used = true;
                 }
+            }
+            if (kBatchPieces) {
+                const Piece pc1 = piece_load(p0, pvh, pa1, pb1, on1), pc2 = piece_load(p0, pvt, 0, pb2, on2);
+                if (on1) piece_store(tile, pc1, pvh, pa1, pb1);
+                if (on2) piece_store(tile, pc2, pvt, 0, pb2);
+            } else {
+                if (on1) piece_store(tile, piece_load(p0, pvh, pa1, pb1, true), pvh, pa1, pb1);
+                if (on2) piece_store(tile, piece_load(p0, pvt, 0, pb2, true), pvt, 0, pb2);
             }
             if (!__any_sync(0xffffffffu, has_lead)) continue;  // nothing for the register path in this batch
             __syncwarp();
@@ -551,7 +623,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         __syncwarp();
         const uint32_t bulk = tile_len & ~15u;
         if (lane == 0 && bulk) {
-            bulk_store_s2g(gout, tile, bulk, pol_stream);
+            if (kHints)
+                bulk_store_s2g(gout, tile, bulk, pol_stream);
+            else
+                bulk_store_s2g_nohint(gout, tile, bulk);
             bulk_commit();
         }
         if (bulk + lane < tile_len) gout[bulk + lane] = tile[bulk + lane];  // < 16 trailing bytes of the whole output

@@ -123,14 +123,17 @@ class GpuEngine:
         if st:
             raise EngineError(st, "set_stream")
 
-    def set_reference(self, ref) -> None:
+    def set_reference(self, ref, mode: str = "tensormap") -> None:
         """Register the proteome tape (numpy uint8 host array or a torch CUDA uint8 tensor); batches that pass
-        ref=None then index it and long reference runs ride the TMA replica path."""
+        ref=None then index it.  mode: "tensormap" (TMA tensor loads, default), "replicas" (16 shifted copies +
+        TMA bulk copies) or "plain" (register path only)."""
+        mflag = {"tensormap": 0, "replicas": L.REF_REPLICAS, "plain": L.REF_NO_TMA}[mode]
         if hasattr(ref, "data_ptr"):
-            st = self._lib.v2p_engine_set_reference(self._h, C.c_void_p(ref.data_ptr()), int(ref.numel()), L.FLAG_DEVICE_PTRS)
+            st = self._lib.v2p_engine_set_reference(self._h, C.c_void_p(ref.data_ptr()), int(ref.numel()),
+                                                    L.FLAG_DEVICE_PTRS | mflag)
         else:
             ref = np.ascontiguousarray(ref, dtype=np.uint8)
-            st = self._lib.v2p_engine_set_reference(self._h, ref.ctypes.data_as(C.c_void_p), len(ref), 0)
+            st = self._lib.v2p_engine_set_reference(self._h, ref.ctypes.data_as(C.c_void_p), len(ref), mflag)
         if st:
             raise EngineError(st, self.last_error())
 
