@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="kernel tile variant (0: 4 KiB/warp, 1: 2 KiB/warp)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--ref-mode", default="tensormap", choices=["tensormap", "replicas", "plain"])
+    ap.add_argument("--ref-mode", default="replicas", choices=["replicas", "plain"])
     ap.add_argument("--no-registered-ref", action="store_true",
                     help="pass the proteome with every call (generic register path) instead of registering it once")
     ap.add_argument("--ref-binary-samples", type=int, default=0,

@@ -74,13 +74,13 @@ int v2p_host_alloc(void** ptr, size_t bytes);
 int v2p_host_free(void* ptr);
 
 /* Register the reference proteome (the reference keeps it in a HashMap<String,String>, readers.rs:58-98; here it is
- * one concatenated residue tape).  The tape is copied into HBM once and described by 1-D TMA tensor maps, so that
- * the fully covered 16-byte vectors of every reference run -- whatever (destination - source) phase it has -- are
- * moved by the TMA unit straight into the shared-memory output tile (the unit realigns; no SM instructions).
- * Batches that pass ref == NULL and ref_base == NULL index this tape (Task.start_pos = transcript offset in the
- * tape + position).  flags: V2P_FLAG_DEVICE_PTRS if `ref` is device memory, plus optionally one of:            */
-#define V2P_REF_REPLICAS 0x100u /* instead of tensor maps: 16 byte-shifted replicas + plain bulk copies (16x memory) */
-#define V2P_REF_NO_TMA 0x200u   /* register path only (2 aligned loads + funnel shift per vector)                    */
+ * one concatenated residue tape).  The tape is copied into HBM once together with 16 byte-shifted replicas, so that
+ * whatever (destination - source) phase a reference run has, one replica holds it at the output's 16-byte phase and
+ * its fully covered vectors are plain aligned TMA bulk copies into the shared-memory output tile (TMA cannot start at
+ * an arbitrary byte: a tensor load with a coordinate that is not 16-byte aligned faults, profiles/dev/tma_probe.cu).
+ * Batches that pass ref == NULL and ref_base == NULL index this tape (Task.start_pos = transcript offset in the tape
+ * + position).  flags: V2P_FLAG_DEVICE_PTRS if `ref` is device memory, optionally V2P_REF_NO_TMA.               */
+#define V2P_REF_NO_TMA 0x200u /* keep one copy only; every run takes the register path (2 aligned loads + funnel shift) */
 int v2p_engine_set_reference(v2p_engine* e, const uint8_t* ref, uint64_t n_ref, uint32_t flags);
 
 /* ---- (i) reference-faithful single-haplotype call == GIR::execute(Engine::GPU) ------------------- */

@@ -13,7 +13,7 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_BAD_ENGINE, ERR_BAD_STREAM, ERR_RES_OOB, ERR_SRC_
 ERR_NOT_CONTIGUOUS, ERR_NOT_GPU_ENGINE = 7, 9
 ENGINE_ST, ENGINE_MT, ENGINE_GPU = 0, 1, 2
 FLAG_FILL_DOT, FLAG_VALIDATE, FLAG_DEVICE_PTRS, FLAG_ASYNC = 1, 2, 4, 8
-REF_REPLICAS, REF_NO_TMA = 0x100, 0x200
+REF_NO_TMA = 0x200
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "BAD_ENGINE", 4: "BAD_STREAM", 5: "RES_OOB", 6: "SRC_OOB",
                 7: "NOT_CONTIGUOUS", 9: "NOT_GPU_ENGINE"}

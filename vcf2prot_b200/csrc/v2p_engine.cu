@@ -60,8 +60,7 @@ struct v2p_engine {
     DevBuf ref_rep;
     uint64_t rep_stride = 0, reg_n_ref = 0;
     bool has_ref = false;
-    int ref_tma_mode = 0;  // 1: replicas + bulk copies, 2: tensor maps (default), 0: register path only
-    TmaMaps maps;
+    int ref_tma_mode = 0;  // 1: 16 replicas + TMA bulk copies (default), 0: register path only
 };
 
 namespace {
@@ -96,24 +95,21 @@ int reserve(v2p_engine* e, DevBuf& b, size_t bytes) {
     return V2P_OK;
 }
 
-const TmaMaps kNoMaps = {};
-
 // Copy-kernel variants selectable through v2p_engine_set_tuning (profiling sweeps); 0 is the shipped default.
 struct CopyVariant {
     int tile;
     int ctas_per_sm;
-    void (*fn)(const KParams, const TmaMaps);
+    void (*fn)(const KParams);
 };
 const CopyVariant kVariants[] = {
-    {4096, 4, k_copy_tiles<4096, 2, 4, 0>},  // 0: baseline v3 (no hints, no prefetch, pieces one by one)
-    {4096, 4, k_copy_tiles<4096, 2, 4, 1>},  // 1: + L2 hints
-    {4096, 4, k_copy_tiles<4096, 2, 4, 2>},  // 2: + task prefetch
-    {4096, 4, k_copy_tiles<4096, 2, 4, 4>},  // 3: + batched pieces
-    {4096, 4, k_copy_tiles<4096, 2, 4, 7>},  // 4: all three
-    {4096, 3, k_copy_tiles<4096, 4, 3, 0>},  // 5: G=4, 3 CTAs/SM, baseline flags
-    {4096, 3, k_copy_tiles<4096, 4, 3, 7>},  // 6: G=4, 3 CTAs/SM, all three
-    {4096, 5, k_copy_tiles<4096, 2, 5, 0>},  // 7: 5 CTAs/SM
-    {2048, 6, k_copy_tiles<2048, 2, 6, 0>},  // 8: 2 KiB tiles
+    {4096, 4, k_copy_tiles<4096, 2, 4, 1>},  // 0: 4 KiB tiles, 4 CTAs/SM (64 regs), L2 hints  [default]
+    {4096, 4, k_copy_tiles<4096, 2, 4, 0>},  // 1: no L2 hints
+    {4096, 4, k_copy_tiles<4096, 2, 4, 3>},  // 2: hints + L2 prefetch of the next tile's tasks
+    {4096, 5, k_copy_tiles<4096, 2, 5, 1>},  // 3: 5 CTAs/SM (48 regs)
+    {4096, 6, k_copy_tiles<4096, 1, 6, 1>},  // 4: 6 CTAs/SM (40 regs)
+    {4096, 3, k_copy_tiles<4096, 4, 3, 1>},  // 5: 3 CTAs/SM (80 regs), 4 vectors in flight
+    {2048, 6, k_copy_tiles<2048, 2, 6, 1>},  // 6: 2 KiB tiles, 6 CTAs/SM
+    {2048, 8, k_copy_tiles<2048, 1, 8, 1>},  // 7: 2 KiB tiles, 8 CTAs/SM (32 regs)
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
@@ -159,10 +155,10 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
         const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : cv.ctas_per_sm;
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
-        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + 16);
+        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + 16) + 17 * 16;
         if (smem > 48 * 1024)
             CUDA_TRY(e, cudaFuncSetAttribute(cv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cv.fn<<<grid, kThreads, smem, s>>>(kp, kp.tma_mode == 2 ? e->maps : kNoMaps);
+        cv.fn<<<grid, kThreads, smem, s>>>(kp);
         e->launches++;
     }
     if (ev_stop) CUDA_TRY(e, cudaEventRecord(ev_stop, s));
@@ -372,7 +368,7 @@ int v2p_engine_set_reference(v2p_engine* e, const uint8_t* ref, uint64_t n_ref, 
     CUDA_TRY(e, cudaSetDevice(e->device));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     e->has_ref = false;
-    const bool replicas = (flags & V2P_REF_REPLICAS) != 0, plain = (flags & V2P_REF_NO_TMA) != 0;
+    const bool replicas = (flags & V2P_REF_NO_TMA) == 0;
     const uint64_t stride = (n_ref + 64 + 255) & ~255ull;
     const uint64_t bytes = (replicas ? 16 : 1) * stride + 256;
     int rc = reserve(e, e->ref_rep, bytes);
@@ -390,31 +386,7 @@ int v2p_engine_set_reference(v2p_engine* e, const uint8_t* ref, uint64_t n_ref, 
         }
     }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    e->ref_tma_mode = plain ? 0 : (replicas ? 1 : 2);
-    if (e->ref_tma_mode == 2) {
-        if (n_ref + 512 >= (1ull << 31)) {
-            e->ref_tma_mode = 0;  // byte coordinates are int32: longer tapes take the register path
-        } else {
-            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-                qres != cudaDriverEntryPointSuccess)
-                return fail(e, V2P_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-            const cuuint64_t gdim[1] = {(cuuint64_t)stride};  // whole padded buffer: reads past n_ref see zeros
-            const cuuint64_t gstr[1] = {0};
-            const cuuint32_t estr[1] = {1};
-            for (int i = 0; i < 5; ++i) {
-                const cuuint32_t box[1] = {16u << i};
-                CUresult cr = ((EncodeFn)fn)(&e->maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, rep, gdim, gstr, box, estr,
-                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (cr != CUDA_SUCCESS) return fail(e, V2P_ERR_CUDA, "cuTensorMapEncodeTiled(box %u) failed: %d", 16u << i, (int)cr);
-            }
-        }
-    }
+    e->ref_tma_mode = replicas ? 1 : 0;
     e->rep_stride = stride;
     e->reg_n_ref = n_ref;
     e->has_ref = true;

@@ -18,7 +18,6 @@
 //   serial k_serial                     tasks that are NOT sorted/non-overlapping by dst keep the
 //                                       reference's in-order semantics (later task wins) on the GPU.
 #pragma once
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,13 +27,6 @@ namespace v2p {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-
-// 1-D uint8 tensor maps over the registered reference tape, one per box size 16 << i bytes (i = 0..4).  TMA tensor
-// loads take an arbitrary byte coordinate, so a run whose source is misaligned by any amount relative to the output
-// still lands 16-byte aligned in the shared-memory tile -- the realignment is done by the TMA unit, not by the SM.
-struct alignas(64) TmaMaps {
-    CUtensorMap m[5];
-};
 
 // Device-side status block, written by the plan kernels with atomics.
 struct DevStatus {
@@ -51,7 +43,7 @@ struct KParams {
     const uint64_t* ref_base;  // n_hap+1 or nullptr
     const uint8_t* ref_rep;    // 16 byte-shifted replicas of the registered reference (tma_mode 1) or nullptr
     uint64_t rep_stride;       // bytes between replicas; replica r stores ref[x] at ref_rep + r*rep_stride + x + r
-    int tma_mode;              // 0: register path only; 1: bulk copies from replicas; 2: 1-D tensor-map loads
+    int tma_mode;              // 0: register path only; 1: TMA bulk copies from the replicas
     const uint8_t* alt;        // alt[a - alt_origin]
     const uint64_t* alt_base;  // n_hap+1 (absolute)
     uint8_t* out;              // out[o - out_origin], 16-byte aligned
@@ -264,12 +256,6 @@ __device__ __forceinline__ void bulk_load_g2s_nohint(void* sdst, const void* gsr
                  "l"(gsrc), "r"(bytes), "r"(mbar)
                  : "memory");
 }
-__device__ __forceinline__ void tensor_load_1d(void* sdst, const CUtensorMap* map, int32_t c0, uint32_t mbar) {
-    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];" ::"r"(
-                     smem_addr(sdst)),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(mbar)
-                 : "memory");
-}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // bytes [sh, sh+16) of the 32-byte little-endian concatenation A||B  (sh in [0,16))
@@ -295,14 +281,18 @@ __device__ __forceinline__ uint32_t bytescan_max(uint32_t x) {
 }
 
 // ------------------------------------------------------------------------------------------------ copy kernel
-// One partial 16-byte vector ("piece") of a task: vector `vx` of the tile, bytes [a,b) of it, 0 <= a < b <= 16.
-// The source bytes are fetched as (at most) two aligned 16-byte loads, realigned in registers, and the valid
-// bytes are stored with statically indexed word / byte stores (no per-byte loop over global memory).
-// Split in two so that the loads of a task's head AND tail piece are in flight together.
+// Partial 16-byte vectors ("pieces") of a task.  Tasks are disjoint and sorted, so in any output vector at most one
+// piece starts at byte 0 and ends inside (T: the tail of a task that came in from the left), at most one starts inside
+// and ends at byte 16 (H: the head of a task that continues to the right), and any number lie strictly inside (M).
+// T and H pieces are merged as whole vectors: source fetched with (at most) two aligned 16-byte loads, realigned in
+// registers, then  new = (old & ~mask) | (val & mask)  on the shared-memory tile; the two classes run in separate
+// warp-synchronous passes so no two lanes ever read-modify-write the same vector at once.  M pieces (a 1-residue
+// missense patch, typically) are byte copies after both passes.
 struct Piece {
     uint4 A, B;
     uint32_t sh;
 };
+// bytes [a,b) of tile vector vx come from p0 + 16*vx + [a,b)
 __device__ __forceinline__ Piece piece_load(const long long p0, const int vx, const int a, const int b, const bool on) {
     Piece pc;
     const unsigned long long sa = (unsigned long long)(p0 + (long long)vx * 16);
@@ -314,29 +304,31 @@ __device__ __forceinline__ Piece piece_load(const long long p0, const int vx, co
     if (on && b > 16 - (int)pc.sh) pc.B = __ldg(ap + 1);  // ... in the second one (implies sh != 0)
     return pc;
 }
-__device__ __forceinline__ void piece_store(uint8_t* __restrict__ tile, const Piece& pc, const int vx, const int a,
-                                            const int b) {
+// lo16[x] = 16-byte mask whose first x bytes are 0xFF (x = 0..16), staged in shared memory
+__device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const uint4* __restrict__ lo16, const Piece& pc,
+                                            const int vx, const int nlow, const bool keep_low) {
+    // keep_low: the piece is [nlow,16) (H) -> old bytes below nlow are kept; else the piece is [0,nlow) (T)
     const uint4 r = realign16(pc.A, pc.B, pc.sh);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    uint8_t* dst = tile + vx * 16;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (a <= 4 * j && 4 * j + 4 <= b) {
-            reinterpret_cast<uint32_t*>(dst)[j] = w[j];
-        } else if (a < 4 * j + 4 && 4 * j < b) {
-#pragma unroll
-            for (int bb = 0; bb < 4; ++bb)
-                if (a <= 4 * j + bb && 4 * j + bb < b) dst[4 * j + bb] = (uint8_t)(w[j] >> (8 * bb));
-        }
+    const uint4 m = lo16[nlow];
+    uint4* dst = reinterpret_cast<uint4*>(tile) + vx;
+    const uint4 o = *dst;
+    uint4 n;
+    if (keep_low) {
+        n.x = (o.x & m.x) | (r.x & ~m.x), n.y = (o.y & m.y) | (r.y & ~m.y);
+        n.z = (o.z & m.z) | (r.z & ~m.z), n.w = (o.w & m.w) | (r.w & ~m.w);
+    } else {
+        n.x = (r.x & m.x) | (o.x & ~m.x), n.y = (r.y & m.y) | (o.y & ~m.y);
+        n.z = (r.z & m.z) | (o.z & ~m.z), n.w = (r.w & m.w) | (o.w & ~m.w);
     }
+    *dst = n;
 }
 
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
 // parallelism); MINB: CTAs per SM the register allocation is held to.
-// FLAGS: 1 = L2 cache-policy hints, 2 = prefetch the next tile's tasks/bases, 4 = load both pieces before storing.
+// FLAGS: 1 = L2 cache-policy hints, 2 = L2 prefetch of the next tile's tasks.
 template <int TILE, int G, int MINB, int FLAGS>
-__global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p, const __grid_constant__ TmaMaps maps) {
-    constexpr bool kHints = (FLAGS & 1) != 0, kPrefetch = (FLAGS & 2) != 0, kBatchPieces = (FLAGS & 4) != 0;
+__global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) {
+    constexpr bool kHints = (FLAGS & 1) != 0, kPrefetch = (FLAGS & 2) != 0;
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
     constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4 or 8)
     constexpr int STRIDE = TILE + NV + 16;  // tile | lead[] | mbarrier
@@ -347,6 +339,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p, 
     uint8_t* const lead = tile + TILE;
     const uint32_t mbar = smem_addr(tile + TILE + NV);
     uint32_t mbar_phase = 0;
+    uint4* const lo16 = reinterpret_cast<uint4*>(smem + kWarpsPerCta * STRIDE);  // 17 masks, shared by the CTA
+    if (threadIdx.x < 17 * 4) {
+        const int x = threadIdx.x >> 2, w = threadIdx.x & 3, nb = min(max(x - 4 * w, 0), 4);
+        reinterpret_cast<uint32_t*>(lo16)[threadIdx.x] = nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+    }
+    __syncthreads();
 
     if (p.status->bad_args || p.status->unsorted || p.status->err_key != ~0ull || p.status->gap_key != ~0ull) return;
     if (lane == 0) mbar_init(mbar, 1);
@@ -446,9 +444,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p, 
             uint32_t v1 = 0;    // end (exclusive) of the fully covered vector range, in vectors
             uint32_t tma_bytes = 0, tma_dst = 0;  // fully covered range served by a TMA bulk copy from a replica
             const uint8_t* tma_src = nullptr;
-            int32_t tma_coord = 0;
-            bool has_lead = false, on1 = false, on2 = false;
-            int pvh = 0, pvt = 0, pa1 = 0, pb1 = 16, pb2 = 16;
+            bool has_lead = false, onT = false, onH = false, onM = false;
+            int pvh = 0, pvt = 0, pa1 = 0, pb2 = 16;
             if (tr < t_hi) {
                 const uint4 raw = tb == t_lo ? raw0 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
                 const uint64_t t_abs = tr + p.task_origin;
@@ -470,13 +467,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p, 
                     if (v1b > v0b) {
                         if (p.tma_mode && raw.w == 0u) {
                             const long long q = p0 - (long long)p.ref;  // ref offset of tile byte 0
-                            if (p.tma_mode == 1) {
-                                // replica r = (-q) mod 16 holds this run at the same 16-byte phase as the output
-                                const uint32_t r = (uint32_t)(-q) & 15u;
-                                tma_src = p.ref_rep + (uint64_t)r * p.rep_stride + (uint64_t)(q + v0b) + r;
-                            } else {
-                                tma_coord = (int32_t)(q + v0b);  // byte coordinate in the registered tape
-                            }
+                            // replica r = (-q) mod 16 holds this run at the same 16-byte phase as the output
+                            const uint32_t r = (uint32_t)(-q) & 15u;
+                            tma_src = p.ref_rep + (uint64_t)r * p.rep_stride + (uint64_t)(q + v0b) + r;
                             tma_dst = (uint32_t)v0b;
                             tma_bytes = (uint32_t)(v1b - v0b);
                         } else {
@@ -485,12 +478,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p, 
                             has_lead = true;
                         }
                     }
-                    // head piece: bytes [s&15, min(e-16vh,16)) of vector vh unless that is the whole vector
-                    // tail piece: bytes [0, e-16vt) of vector vt (when the task reaches into a later vector)
+                    // classify the partial vectors (see Piece): H = [a1,16) of vh, T = [0,b2) of vt, M = [a1,b1) of vh
                     pvh = vh, pvt = vt;
-                    pa1 = s & 15, pb1 = min(e - (vh << 4), 16), pb2 = e - (vt << 4);
-                    on1 = pa1 != 0 || pb1 != 16;
-                    on2 = vt > vh && pb2 != 16;
+                    pa1 = s & 15, pb2 = e - (vt << 4);
+                    if (vt > vh) {
+                        onH = pa1 != 0;
+                        onT = pb2 != 16;
+                    } else if (pa1 != 0 || pb2 != 16) {  // the whole (clipped) task sits inside one vector
+                        if (pa1 == 0) onT = true;
+                        else if (pb2 == 16) onH = true;
+                        else onM = true;
+                    }
                 }
             }
             // TMA bulk loads first (they take the longest), the register-path pieces overlap with them
@@ -499,40 +497,26 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p, 
                 if (total) {
                     if (lane == 0) mbar_expect_tx(mbar, total);
                     __syncwarp();
-                    if (p.tma_mode == 1) {
-                        if (tma_bytes) {
-                            if (kHints)
-                                bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar, pol_keep);
-                            else
-                                bulk_load_g2s_nohint(tile + tma_dst, tma_src, tma_bytes, mbar);
-                        }
-                    } else {
-                        // power-of-two boxes: 256-byte boxes while they fit, then one box per set bit of the rest
-                        uint32_t nb = tma_bytes, d = tma_dst;
-                        int32_t c = tma_coord;
-                        while (nb >= 256u) {
-                            tensor_load_1d(tile + d, &maps.m[4], c, mbar);
-                            d += 256u, c += 256, nb -= 256u;
-                        }
-#pragma unroll
-                        for (int i = 3; i >= 0; --i) {
-                            const uint32_t w = 16u << i;
-                            if (nb & w) {
-                                tensor_load_1d(tile + d, &maps.m[i], c, mbar);
-                                d += w, c += (int32_t)w;
-                            }
-                        }
+                    if (tma_bytes) {
+                        if (kHints)
+                            bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar, pol_keep);
+                        else
+                            bulk_load_g2s_nohint(tile + tma_dst, tma_src, tma_bytes, mbar);
                     }
                     tma_used = true;
                 }
             }
-            if (kBatchPieces) {
-                const Piece pc1 = piece_load(p0, pvh, pa1, pb1, on1), pc2 = piece_load(p0, pvt, 0, pb2, on2);
-                if (on1) piece_store(tile, pc1, pvh, pa1, pb1);
-                if (on2) piece_store(tile, pc2, pvt, 0, pb2);
-            } else {
-                if (on1) piece_store(tile, piece_load(p0, pvh, pa1, pb1, true), pvh, pa1, pb1);
-                if (on2) piece_store(tile, piece_load(p0, pvt, 0, pb2, true), pvt, 0, pb2);
+            {
+                const Piece pcT = piece_load(p0, pvt, 0, pb2, onT), pcH = piece_load(p0, pvh, pa1, 16, onH);
+                if (onT) piece_merge(tile, lo16, pcT, pvt, pb2, false);
+                __syncwarp();
+                if (onH) piece_merge(tile, lo16, pcH, pvh, pa1, true);
+                __syncwarp();
+                if (onM) {
+                    const uint8_t* __restrict__ sp = reinterpret_cast<const uint8_t*>(p0) + (pvh << 4);
+                    uint8_t* d = tile + (pvh << 4);
+                    for (int j = pa1; j < pb2; ++j) d[j] = __ldg(sp + j);
+                }
             }
             if (!__any_sync(0xffffffffu, has_lead)) continue;  // nothing for the register path in this batch
             __syncwarp();

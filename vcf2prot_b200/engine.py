@@ -123,11 +123,11 @@ class GpuEngine:
         if st:
             raise EngineError(st, "set_stream")
 
-    def set_reference(self, ref, mode: str = "tensormap") -> None:
+    def set_reference(self, ref, mode: str = "replicas") -> None:
         """Register the proteome tape (numpy uint8 host array or a torch CUDA uint8 tensor); batches that pass
-        ref=None then index it.  mode: "tensormap" (TMA tensor loads, default), "replicas" (16 shifted copies +
-        TMA bulk copies) or "plain" (register path only)."""
-        mflag = {"tensormap": 0, "replicas": L.REF_REPLICAS, "plain": L.REF_NO_TMA}[mode]
+        ref=None then index it.  mode: "replicas" (16 shifted copies + TMA bulk copies, default) or "plain"
+        (one copy, register path only)."""
+        mflag = {"replicas": 0, "plain": L.REF_NO_TMA}[mode]
         if hasattr(ref, "data_ptr"):
             st = self._lib.v2p_engine_set_reference(self._h, C.c_void_p(ref.data_ptr()), int(ref.numel()),
                                                     L.FLAG_DEVICE_PTRS | mflag)
