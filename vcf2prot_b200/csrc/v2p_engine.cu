@@ -104,7 +104,7 @@ struct CopyVariant {
 const CopyVariant kVariants[] = {
     {4096, 4, k_copy_tiles<4096, 2, 4, 1>},  // 0: 4 KiB tiles, 4 CTAs/SM (64 regs), L2 hints  [default]
     {4096, 4, k_copy_tiles<4096, 2, 4, 0>},  // 1: no L2 hints
-    {4096, 4, k_copy_tiles<4096, 2, 4, 3>},  // 2: hints + L2 prefetch of the next tile's tasks
+    {4096, 4, k_copy_tiles<4096, 1, 4, 1>},  // 2: one vector in flight per lane
     {4096, 5, k_copy_tiles<4096, 2, 5, 1>},  // 3: 5 CTAs/SM (48 regs)
     {4096, 6, k_copy_tiles<4096, 1, 6, 1>},  // 4: 6 CTAs/SM (40 regs)
     {4096, 3, k_copy_tiles<4096, 4, 3, 1>},  // 5: 3 CTAs/SM (80 regs), 4 vectors in flight
@@ -155,7 +155,7 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
         const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : cv.ctas_per_sm;
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
-        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + 16) + 17 * 16;
+        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + 16 + 576) + 17 * 16;
         if (smem > 48 * 1024)
             CUDA_TRY(e, cudaFuncSetAttribute(cv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cv.fn<<<grid, kThreads, smem, s>>>(kp);

@@ -218,6 +218,15 @@ __device__ __forceinline__ void bulk_store_s2g_nohint(void* gdst, const void* ss
                  "r"(bytes)
                  : "memory");
 }
+// classic cp.async (LDGSTS): global -> shared without a destination register, completion by commit/wait groups
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -325,13 +334,13 @@ __device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const ui
 
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
 // parallelism); MINB: CTAs per SM the register allocation is held to.
-// FLAGS: 1 = L2 cache-policy hints, 2 = L2 prefetch of the next tile's tasks.
+// FLAGS: 1 = L2 cache-policy hints.
 template <int TILE, int G, int MINB, int FLAGS>
 __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) {
-    constexpr bool kHints = (FLAGS & 1) != 0, kPrefetch = (FLAGS & 2) != 0;
+    constexpr bool kHints = (FLAGS & 1) != 0;
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
     constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4 or 8)
-    constexpr int STRIDE = TILE + NV + 16;  // tile | lead[] | mbarrier
+    constexpr int STRIDE = TILE + NV + 16 + 576;  // tile | lead[] | mbarrier | staged tasks (32 x 16 B) + bases (5 x 8 B)
     static_assert(LW == 4 || LW == 8, "TILE must be 2048 or 4096");
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -339,6 +348,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     uint8_t* const lead = tile + TILE;
     const uint32_t mbar = smem_addr(tile + TILE + NV);
     uint32_t mbar_phase = 0;
+    uint4* const st_tasks = reinterpret_cast<uint4*>(tile + TILE + NV + 16);
+    uint64_t* const st_bases = reinterpret_cast<uint64_t*>(tile + TILE + NV + 16 + 512);
     uint4* const lo16 = reinterpret_cast<uint4*>(smem + kWarpsPerCta * STRIDE);  // 17 masks, shared by the CTA
     if (threadIdx.x < 17 * 4) {
         const int x = threadIdx.x >> 2, w = threadIdx.x & 3, nb = min(max(x - 4 * w, 0), 4);
@@ -369,44 +380,39 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         uint64_t t = min((uint64_t)lo, p.n_tasks);
         return t > 0 ? t - 1 : 0;  // the task before may extend into the tile
     };
-    auto load_tasks = [&](uint32_t lo, uint32_t hi, uint32_t hp, uint4& raw, uint64_t& base) {
+    // stage(): cp.async the first 32 tasks of a tile and its haplotype's five bases into this warp's staging area
+    auto stage = [&](uint32_t lo, uint32_t hi, uint32_t hp) {
         const uint64_t tr = first_task(lo) + lane;
-        raw = make_uint4(0u, 0u, 0u, 0u);
-        if (tr < min((uint64_t)hi, p.n_tasks)) raw = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
-        base = 0;  // lane j < 5 holds field j of the haplotype's bases
-        if (lane == 0) base = __ldg(p.task_begin + hp);
-        if (lane == 1) base = __ldg(p.task_begin + hp + 1);
-        if (lane == 2) base = __ldg(p.out_base + hp);
-        if (lane == 3) base = __ldg(p.alt_base + hp);
-        if (lane == 4) base = p.ref_base ? __ldg(p.ref_base + hp) : p.ref_origin;
+        if (tr < min((uint64_t)hi, p.n_tasks)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
+        if (lane == 0) cp_async8(st_bases + 0, p.task_begin + hp);
+        if (lane == 1) cp_async8(st_bases + 1, p.task_begin + hp + 1);
+        if (lane == 2) cp_async8(st_bases + 2, p.out_base + hp);
+        if (lane == 3) cp_async8(st_bases + 3, p.alt_base + hp);
+        if (lane == 4 && p.ref_base) cp_async8(st_bases + 4, p.ref_base + hp);
+        cp_async_commit();
     };
     uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
     uint32_t c_lo, c_hi, c_hap, n_lo, n_hi, n_hap;
-    uint4 pf_raw;
-    uint64_t pf_base;
     load_meta(k, c_lo, c_hi, c_hap);
     load_meta(k + n_warps, n_lo, n_hi, n_hap);
-    pf_raw = make_uint4(0u, 0u, 0u, 0u);
-    pf_base = 0;
+    if (k < p.n_tiles) stage(c_lo, c_hi, c_hap);
     for (; k < p.n_tiles; k += n_warps) {
         const uint64_t tile_start = k * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
         const uint64_t t_lo = first_task(c_lo);
         const uint64_t t_hi = min((uint64_t)c_hi, p.n_tasks);
-        load_tasks(c_lo, c_hi, c_hap, pf_raw, pf_base);
-        const uint4 raw0 = pf_raw;
+        // this tile's tasks and bases were staged while the previous tile was being assembled
+        cp_async_wait0();
+        __syncwarp();
+        const uint4 raw0 = st_tasks[lane];
         // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
-        const uint64_t hb_t0 = __shfl_sync(0xffffffffu, pf_base, 0), hb_t1 = __shfl_sync(0xffffffffu, pf_base, 1);
-        const uint64_t hb_out = __shfl_sync(0xffffffffu, pf_base, 2), hb_alt = __shfl_sync(0xffffffffu, pf_base, 3);
-        const uint64_t hb_ref = __shfl_sync(0xffffffffu, pf_base, 4);
-        // advance the pipeline: next tile's metadata is resident by now -> fetch its tasks; fetch metadata two ahead
+        const uint64_t hb_t0 = st_bases[0], hb_t1 = st_bases[1], hb_out = st_bases[2], hb_alt = st_bases[3];
+        const uint64_t hb_ref = p.ref_base ? st_bases[4] : p.ref_origin;
+        __syncwarp();
+        // advance the pipeline: stage the next tile (its metadata was fetched one tile ago), fetch metadata two ahead
         c_lo = n_lo, c_hi = n_hi, c_hap = n_hap;
-        if (kPrefetch && k + n_warps < p.n_tiles) {
-            // fire-and-forget L2 prefetch of the next tile's tasks (no register, no scoreboard slot held)
-            const uint64_t tn = first_task(c_lo) + lane;
-            if (tn < min((uint64_t)c_hi, p.n_tasks)) prefetch_l2(reinterpret_cast<const uint4*>(p.tasks) + tn);
-        }
+        if (k + n_warps < p.n_tiles) stage(c_lo, c_hi, c_hap);
         load_meta(k + 2 * n_warps, n_lo, n_hi, n_hap);
 
         // the previous tile's bulk store must have finished READING shared memory before we overwrite it
