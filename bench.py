@@ -218,7 +218,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from vcf2prot_b200 import GpuEngine
+    from vcf2prot_b200 import GpuEngine, shard
 
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -279,10 +279,10 @@ def main():
     launches = eng.launch_count() - launches0
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     dev_ms = ev0.elapsed_time(ev1)  # CUDA events on the launching stream, all K steps
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
+    max_ms = shard.max_over_ranks(dev_ms, dev)  # the slowest rank's device time
+    total_res = shard.sum_over_ranks(n_res, dev)  # residues produced by all ranks in one step
+    total_haps = shard.sum_over_ranks(n_hap, dev)
+    total_alg = shard.sum_over_ranks(b_alg, dev)
     ms_per_step = max_ms / args.steps
 
     # ---- end to end through the C ABI with HOST buffers: per step, every chunk's tasks/alt go H2D from pinned
@@ -311,10 +311,7 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = max(time.perf_counter() - e0, 1e-9)
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = shard.max_over_ranks(e2e_s, dev)
     # the last chunk sits in h_out: keep it for the parity spot-check against the device-resident result
     a, b = chunks[-1]
     o0, o1 = int(batch.out_base[a]), int(batch.out_base[b])
@@ -353,15 +350,22 @@ def main():
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     copy_avg_ms = float(np.mean(copy_ms))
     achieved = b_alg / (copy_avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath):
         tj = json.load(open(tpath))
-        key = "%s_%d_v%d" % (args.workload, args.samples, args.variant)
-        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+        mode = "plain" if (args.no_registered_ref or args.ref_mode == "plain") else "replicas"
+        key = "%s_%d_v%d%s" % (args.workload, args.samples, args.variant, "_plain" if mode == "plain" else "")
+        if key in tj:
+            traffic, traffic_note = tj[key]["dram_bytes_per_launch"], "ncu --set full capture of this configuration"
+        else:  # same workload mix and reference mode at another cohort size: DRAM bytes scale with residues
+            for k2, v in tj.items():
+                if isinstance(v, dict) and k2.startswith(args.workload + "_") and v.get("mode") == mode:
+                    traffic = int(v["dram_bytes_per_launch"] * (n_res / v["residues"]))
+                    traffic_note = "scaled by residues from the ncu --set full capture %s" % k2
+                    break
 
-    total_res = n_res * world  # every rank holds a same-sized cohort (weak scaling)
-    value = total_res / (ms_per_step * 1e-3)
+    value = total_res / (ms_per_step * 1e-3)  # every rank holds its own same-sized sample range (weak scaling)
     line = {
         "metric": "generated residues/sec", "value": value, "unit": "residues/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -374,15 +378,15 @@ def main():
                    "per step; the %.1f MB proteome is L2-resident by design)" % (n_res / 1e9, n_tasks * 16 / 1e9, len(batch.ref) / 1e6),
                    "tile_variant": args.variant, "reference_tape": "caller-supplied per call" if args.no_registered_ref else
                    "registered once (v2p_engine_set_reference, mode %s)" % args.ref_mode, "parallelism": "sample-sharded x%d, no collective" % world},
-        "haplotypes_per_s": n_hap * world / (ms_per_step * 1e-3),
-        "alg_gbs": b_alg * world / (ms_per_step * 1e-3) / 1e9,
+        "haplotypes_per_s": total_haps / (ms_per_step * 1e-3),
+        "alg_gbs": total_alg / (ms_per_step * 1e-3) / 1e9,
         "clocks": clocks,
         "e2e": {"value": total_res * args.e2e_steps / e2e_s, "unit": "residues/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": n_res, "steps": args.e2e_steps, "chunk_haplotypes": args.e2e_chunk_haps,
                 "api": "v2p_execute_batch (host pointers, pinned), one call per chunk"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_copy_tiles", "peak_source": peak_src,
+                     "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_copy_tiles", "peak_source": peak_src,
                      "alg_bytes_per_launch": b_alg, "kernel_ms": copy_avg_ms, "launch_group_ms": float(np.mean(group_ms)),
                      "kernel_share_of_step": copy_avg_ms / ms_per_step},
         "cpu_baseline": cpu, "parity": parity, "gen_seconds": round(t_gen, 1),
