@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="kernel tile variant (0: 4 KiB/warp, 1: 2 KiB/warp)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--ref-mode", default="replicas", choices=["replicas", "plain"])
+    ap.add_argument("--layout", default="packed", choices=["packed", "aligned"],
+                    help="result-tape layout: packed = the reference's (res_counter); aligned = transcripts in phase "
+                         "with the proteome tape (<=30 '.' pad bytes per transcript, never seen by the consumer)")
     ap.add_argument("--no-registered-ref", action="store_true",
                     help="pass the proteome with every call (generic register path) instead of registering it once")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
@@ -62,7 +65,7 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_workload(kind: str, n_samples: int, rank: int):
+def make_workload(kind: str, n_samples: int, rank: int, layout: str = "packed"):
     from vcf2prot_b200 import cohort as C
 
     prot = C.make_proteome(seed=0x5EED0001, giant=(20 if kind == "c4" else 0))
@@ -75,7 +78,8 @@ def make_workload(kind: str, n_samples: int, rank: int):
     parts = []
     step = 256
     for i, h0 in enumerate(range(0, n_hap, step)):
-        parts.append(C.synth_batch(prot, cat, min(step, n_hap - h0), seed=(0x5EED0002 + 7919 * rank) * 1000 + i))
+        parts.append(C.synth_batch(prot, cat, min(step, n_hap - h0), seed=(0x5EED0002 + 7919 * rank) * 1000 + i,
+                                   layout=layout))
     return prot, cat, C.concat_batches(parts)
 
 
@@ -227,15 +231,16 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     t_gen = time.perf_counter()
-    prot, cat, batch = make_workload(args.workload, args.samples, rank)
+    prot, cat, batch = make_workload(args.workload, args.samples, rank, args.layout)
     t_gen = time.perf_counter() - t_gen
-    n_hap, n_res, n_tasks = batch.n_hap, batch.n_residues, len(batch.tasks)
+    n_hap, n_out, n_tasks = batch.n_hap, batch.n_residues, len(batch.tasks)
+    n_res = int(batch.tasks[:, 1].astype(np.int64).sum())  # residues produced (the aligned layout also writes '.' pads)
     b_alg = alg_bytes(batch)
 
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
     d_task_begin, d_tasks, d_ref = to_dev(batch.task_begin), to_dev(batch.tasks), to_dev(batch.ref)
     d_alt, d_alt_base, d_out_base = to_dev(batch.alt), to_dev(batch.alt_base), to_dev(batch.out_base)
-    d_out = torch.empty(n_res + 64, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n_out + 64, dtype=torch.uint8, device=dev)
 
     eng = GpuEngine(local_rank)
     eng.set_tuning(args.variant, args.ctas_per_sm)
@@ -246,7 +251,7 @@ def main():
         d_ref_arg = d_ref
     side = torch.cuda.Stream(device=dev)
     eng.set_stream(side.cuda_stream)
-    dargs = (n_hap, d_task_begin, d_tasks, d_ref_arg, d_alt, d_alt_base, d_out, d_out_base, n_tasks, len(batch.alt), n_res)
+    dargs = (n_hap, d_task_begin, d_tasks, d_ref_arg, d_alt, d_alt_base, d_out, d_out_base, n_tasks, len(batch.alt), n_out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -373,16 +378,16 @@ def main():
         "config": {"workload": "%s: %d phased samples/GPU (%d haplotypes) x 20k-transcript proteome (%d residues), "
                                "%s csq mix" % (args.workload, args.samples, n_hap, len(batch.ref),
                                                "missense-dominated" if args.workload == "c2" else "skewed frameshift/insertion"),
-                   "haplotypes_per_gpu": n_hap, "tasks_per_gpu": n_tasks, "residues_per_gpu": n_res,
+                   "haplotypes_per_gpu": n_hap, "tasks_per_gpu": n_tasks, "residues_per_gpu": n_res, "result_tape_bytes_per_gpu": n_out,
                    "mean_task_bytes": n_res / max(n_tasks, 1), "l2_policy": "inputs_larger_than_l2 (output %.1f GB, tasks %.2f GB "
-                   "per step; the %.1f MB proteome is L2-resident by design)" % (n_res / 1e9, n_tasks * 16 / 1e9, len(batch.ref) / 1e6),
-                   "tile_variant": args.variant, "reference_tape": "caller-supplied per call" if args.no_registered_ref else
+                   "per step; the %.1f MB proteome is L2-resident by design)" % (n_out / 1e9, n_tasks * 16 / 1e9, len(batch.ref) / 1e6),
+                   "tile_variant": args.variant, "layout": args.layout, "reference_tape": "caller-supplied per call" if args.no_registered_ref else
                    "registered once (v2p_engine_set_reference, mode %s)" % args.ref_mode, "parallelism": "sample-sharded x%d, no collective" % world},
         "haplotypes_per_s": total_haps / (ms_per_step * 1e-3),
         "alg_gbs": total_alg / (ms_per_step * 1e-3) / 1e9,
         "clocks": clocks,
         "e2e": {"value": total_res * args.e2e_steps / e2e_s, "unit": "residues/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": n_res, "steps": args.e2e_steps, "chunk_haplotypes": args.e2e_chunk_haps,
+                "d2h_bytes_per_step": n_out, "steps": args.e2e_steps, "chunk_haplotypes": args.e2e_chunk_haps,
                 "api": "v2p_execute_batch (host pointers, pinned), one call per chunk"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -61,6 +61,26 @@ def test_global_and_per_hap_layouts_produce_identical_bytes(small):
     assert np.array_equal(outs[0], outs[1]) and not (outs[0] == ord(".")).any()
 
 
+def test_aligned_layout_yields_identical_records(small):
+    """B200 layout: transcripts placed in phase with the proteome tape, pad bytes read '.', records unchanged."""
+    prot, cat = small
+    recs = []
+    for layout in ("packed", "aligned"):
+        b = C.synth_batch(prot, cat, 12, 21, ref_mode="global", layout=layout)
+        out = np.zeros(b.n_residues, np.uint8)
+        assert cengine.batch_execute(b.task_begin, b.tasks, b.ref, b.alt, b.alt_base, out, b.out_base)[0] == 0
+        recs.append([C.fasta_records(prot, b, out, h, 1) for h in range(12)])
+        if layout == "aligned":
+            starts = b.ann_start[b.ann_end > b.ann_start]
+            tx = b.ann_tx[b.ann_end > b.ann_start]
+            assert ((starts - prot.offsets[tx]) % 16 == 0).all() and (b.out_base % 16 == 0).all()
+            # sorted, non-overlapping, inside the tape (what the engine's fast path needs)
+            for h in range(12):
+                t = b.tasks[int(b.task_begin[h]):int(b.task_begin[h + 1])].astype(np.int64)
+                assert (t[1:, 2] >= t[:-1, 2] + t[:-1, 1]).all()
+    assert recs[0] == recs[1] and sum(len(r) for r in recs[0]) > 100
+
+
 def test_fasta_records_match_reference_binary(small, tmp_path):
     """End to end against the reference's own binary when it is present (authoring container)."""
     from oracle import refbin

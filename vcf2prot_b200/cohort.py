@@ -222,9 +222,19 @@ def select_sites(cat: Catalogue, n_hap: int, rng: np.random.Generator) -> Tuple[
 
 
 def build_batch(prot: Proteome, cat: Catalogue, hap: np.ndarray, site: np.ndarray, n_hap: int,
-                ref_mode: str = "global") -> Batch:
+                ref_mode: str = "global", layout: str = "packed") -> Batch:
     """(hap, site) pairs sorted by (hap, transcript, position) -> Task batch.  Vectorised restatement of the
-    reference's emission rules for the seven classes (file:line in the module docstring)."""
+    reference's emission rules for the seven classes (file:line in the module docstring).
+
+    layout="packed"   result tapes exactly as the reference lays them out (res_counter, haplotype_instruction.rs:132).
+    layout="aligned"  B200 layout (global ref mode only): every transcript's result starts at an offset congruent
+                      (mod 16) to its offset in the proteome tape, inside a 16-byte-multiple slot.  start_pos_res is
+                      authoritative and uncovered bytes read '.', so the engine contract is unchanged; the consumer
+                      slices by annotation and never sees the <= 30 pad bytes per transcript.  Runs of unshifted
+                      (missense-only) transcripts then have source and destination in phase: one aligned TMA bulk
+                      copy from replica 0, which stays L2-resident."""
+    if layout == "aligned" and ref_mode != "global":
+        raise ValueError("aligned layout needs the shared proteome tape")
     t, p, cls = cat.t[site], cat.p[site], cat.cls[site]
     # ---- truncation: nothing after F/G/L/0 on the same haplotype+transcript
     newg = np.ones(len(site), bool)
@@ -308,17 +318,35 @@ def build_batch(prot: Proteome, cat: Catalogue, hap: np.ndarray, site: np.ndarra
 
     # ---- per-haplotype bases; dst = running sum of lengths inside the haplotype (no gaps for these classes)
     task_hap = np.repeat(hap, cnt)
+    task_gid = np.repeat(gid, cnt)
     task_begin = np.zeros(n_hap + 1, np.uint64)
     np.cumsum(np.bincount(task_hap, minlength=n_hap), out=task_begin[1:])
     l_excl = np.cumsum(ln) - ln
-    res_per_hap = np.bincount(task_hap, weights=ln, minlength=n_hap).astype(np.int64)
+    g_len = np.bincount(task_gid, weights=ln, minlength=n_groups).astype(np.int64)
+    hfirst = np.ones(n_groups, bool)
+    hfirst[1:] = g_hap[1:] != g_hap[:-1]
+    if layout == "aligned":
+        # slot of a transcript: 16-byte aligned base, result at base + (proteome offset mod 16), slot = multiple of 16
+        c = prot.offsets[g_tx] & 15
+        slot = np.where(g_len > 0, (c + g_len + 15) & ~15, 0)
+        g_base = np.cumsum(slot) - slot
+        if n_groups:
+            g_base = g_base - g_base[np.flatnonzero(hfirst)][np.cumsum(hfirst) - 1]
+        g_start = g_base + np.where(g_len > 0, c, 0)
+        res_per_hap = np.bincount(g_hap, weights=slot, minlength=n_hap).astype(np.int64)
+        g_l0 = (np.cumsum(g_len) - g_len)  # l_excl of the group's first task
+        tasks[:, 2] = g_start[task_gid] + (l_excl - g_l0[task_gid])
+    else:
+        res_per_hap = np.bincount(task_hap, weights=ln, minlength=n_hap).astype(np.int64)
+        g_excl = np.cumsum(g_len) - g_len
+        g_start = g_excl - g_excl[np.flatnonzero(hfirst)][np.cumsum(hfirst) - 1] if n_groups else g_excl
+        tb = task_begin[:-1].astype(np.int64)
+        nonempty = np.flatnonzero(task_begin[1:] > task_begin[:-1])
+        hap_l0 = np.zeros(n_hap, np.int64)
+        hap_l0[nonempty] = l_excl[tb[nonempty]]
+        tasks[:, 2] = l_excl - hap_l0[task_hap]
     out_base = np.zeros(n_hap + 1, np.uint64)
     np.cumsum(res_per_hap, out=out_base[1:])
-    tb = task_begin[:-1].astype(np.int64)
-    nonempty = np.flatnonzero(task_begin[1:] > task_begin[:-1])
-    hap_l0 = np.zeros(n_hap, np.int64)
-    hap_l0[nonempty] = l_excl[tb[nonempty]]
-    tasks[:, 2] = l_excl - hap_l0[task_hap]
 
     alt_per_hap = np.bincount(hap, weights=acontrib, minlength=n_hap).astype(np.int64)
     alt_base = np.zeros(n_hap + 1, np.uint64)
@@ -330,14 +358,7 @@ def build_batch(prot: Proteome, cat: Catalogue, hap: np.ndarray, site: np.ndarra
     src = doff[rep] + np.where(cls[rep] == CLS_M, 0, within)
     alt = cat.pool[src] if tot else np.zeros(0, np.uint8)
 
-    # ---- annotations: (start,end) of every altered transcript on its haplotype's result tape
-    g_cnt = np.bincount(gid, weights=cnt, minlength=n_groups).astype(np.int64)
-    g_len = np.bincount(np.repeat(gid, cnt), weights=ln, minlength=n_groups).astype(np.int64)
-    g_excl = np.cumsum(g_len) - g_len
-    hfirst = np.ones(n_groups, bool)
-    hfirst[1:] = g_hap[1:] != g_hap[:-1]
-    g_start = g_excl - g_excl[np.flatnonzero(hfirst)][np.cumsum(hfirst) - 1] if n_groups else g_excl
-    del g_cnt
+    # ---- annotations: (start,end) of every altered transcript on its haplotype's result tape = (g_start, +g_len)
 
     if ref_mode == "global":
         ref_base, ref = None, prot.residues
@@ -356,10 +377,11 @@ def build_batch(prot: Proteome, cat: Catalogue, hap: np.ndarray, site: np.ndarra
                  hap, site)
 
 
-def synth_batch(prot: Proteome, cat: Catalogue, n_hap: int, seed: int, ref_mode: str = "global") -> Batch:
+def synth_batch(prot: Proteome, cat: Catalogue, n_hap: int, seed: int, ref_mode: str = "global",
+                layout: str = "packed") -> Batch:
     rng = np.random.default_rng(seed)
     hap, site = select_sites(cat, n_hap, rng)
-    return build_batch(prot, cat, hap, site, n_hap, ref_mode)
+    return build_batch(prot, cat, hap, site, n_hap, ref_mode, layout)
 
 
 def concat_batches(parts: List[Batch]) -> Batch:
