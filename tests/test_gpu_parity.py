@@ -319,3 +319,42 @@ def test_full_size_properties(gpu_engine):
     tasks[-1, 1] -= 3
     out, ms = gpu_engine.execute_batch(z(0, len(tasks)), tasks, ref, np.zeros(0, np.uint8), z(0, 0), z(0, n_ref))
     assert (out[:3] == ord(".")).all() and np.array_equal(out[3:], ref[:-3])
+
+
+def test_host_pointer_pipeline_three_chunks_in_flight(gpu_engine):
+    """The streaming shape: per-chunk host-pointer calls with V2P_FLAG_ASYNC rotate over the engine's 3 staging slots
+    (copy-back of chunk i overlaps upload + kernels of chunk i+1); a 4th un-waited batch is refused, not queued."""
+    from vcf2prot_b200 import cohort as C
+
+    prot = C.make_proteome(seed=15, n_tx=300, mu=5.5, sigma=0.7, hi=5000)
+    cat = C.make_catalogue(prot, 6000, seed=16, mix=(0.8, 0.05, 0.05, 0.05, 0.02, 0.02, 0.01))
+    cat.af[:] = 0.15
+    b = C.synth_batch(prot, cat, 48, 17, ref_mode="global", layout="aligned")
+    want = np.zeros(b.n_residues, np.uint8)
+    assert cengine.batch_execute(b.task_begin, b.tasks, prot.residues, b.alt, b.alt_base, want, b.out_base)[0] == 0
+    gpu_engine.set_reference(prot.residues)
+    chunks = [(h, min(48, h + 7)) for h in range(0, 48, 7)]
+    bufs = [np.zeros(int(max(b.out_base[c[1]] - b.out_base[c[0]] for c in chunks)) + 16, np.uint8) for _ in range(3)]
+    got = np.zeros_like(want)
+    pending = []
+
+    def drain_one():
+        ev, (a, z), buf = pending.pop(0)
+        gpu_engine.wait_event(ev)
+        o0, o1 = int(b.out_base[a]), int(b.out_base[z])
+        got[o0:o1] = buf[:o1 - o0]
+
+    for i, (a, z) in enumerate(chunks):
+        if len(pending) == 3:
+            drain_one()
+        ev = gpu_engine.execute_hap_range(a, z, b.task_begin, b.tasks, None, b.alt, b.alt_base, b.out_base, bufs[i % 3],
+                                          wait=False)
+        pending.append((ev, (a, z), bufs[i % 3]))
+    assert len(pending) == 3
+    with pytest.raises(EngineError) as ei:  # all three slots busy
+        gpu_engine.execute_hap_range(0, 1, b.task_begin, b.tasks, None, b.alt, b.alt_base, b.out_base,
+                                     np.zeros(int(b.out_base[1]) + 16, np.uint8), wait=False)
+    assert ei.value.status == L.ERR_INVALID_ARG
+    while pending:
+        drain_one()
+    assert np.array_equal(got, want)

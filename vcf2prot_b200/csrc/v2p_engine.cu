@@ -3,6 +3,11 @@
 // Replaces the `Engine::GPU` arm of GIR::execute (/root/reference/src/data_structures/InternalRep/gir.rs:236-239)
 // and adds the batched native entry the host pipeline uses.  No CPU fallback exists in this file: every
 // result byte is produced by a CUDA kernel or the call fails.
+//
+// Streams: device-pointer batches and the SoA call run on the engine stream (or the caller's, v2p_engine_set_stream).
+// Host-pointer batches rotate over kSlots staging slots, each with its own stream and device staging, so that with
+// V2P_FLAG_ASYNC chunk i's copy-back (D2H) overlaps chunk i+1's upload (H2D) and kernels -- the per-GPU pinned
+// staging / async copy-back pipeline of BASELINE.json:north_star.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -26,15 +31,27 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+struct Scratch {  // per-stream planning scratch
+    DevBuf lb, tile_hap, status;
+};
+
+constexpr int kSlots = 3;
+
+struct Slot {  // one in-flight host-pointer batch
+    cudaStream_t stream = nullptr;
+    Scratch sc;
+    DevBuf d_tasks, d_task_begin, d_ref, d_ref_base, d_alt, d_alt_base, d_out, d_out_base;
+    bool busy = false;
+};
+
 }  // namespace
 
 struct v2p_event {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr, ev_copy = nullptr;
     DevStatus* h_status = nullptr;  // pinned; filled by a stream-ordered D2H right behind the launch group
     KParams kp;                     // for the deferred serial fallback
-    uint32_t flags = 0;
-    // host-pointer mode bookkeeping
-    bool host_mode = false;
+    cudaStream_t stream = nullptr;
+    Slot* slot = nullptr;  // host-pointer mode
     uint8_t* h_out = nullptr;
     size_t out_bytes = 0;
     const uint64_t* h_task_begin = nullptr;  // borrowed until the wait (host-pointer mode)
@@ -48,14 +65,15 @@ struct v2p_engine {
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
-    int variant = 0;      // 0: TILE=4096, 1: TILE=2048
-    int ctas_per_sm = 0;  // 0 = default
-    DevBuf lb, tile_hap, status;
-    // staging for host-pointer calls
-    DevBuf d_tasks, d_task_begin, d_ref, d_ref_base, d_alt, d_alt_base, d_out, d_out_base;
+    int variant = 0;
+    int ctas_per_sm = 0;  // 0 = the variant's default
+    Scratch sc;           // for e->stream
+    Slot slots[kSlots];
+    int next_slot = 0;
+    std::vector<v2p_event*> event_pool;  // CUDA events + pinned status blocks are recycled (no per-call alloc/free)
     // staging for the SoA call
-    DevBuf d_soa[4];
-    DevStatus* h_status = nullptr;  // pinned scratch for synchronous calls
+    DevBuf d_soa[4], soa_tasks, soa_ref, soa_alt, soa_out, soa_bases;
+    DevStatus* h_status = nullptr;  // pinned scratch for the SoA call
     // registered reference: replica r (0..15) at ref_rep + r*rep_stride, holding ref[x] at offset x + r
     DevBuf ref_rep;
     uint64_t rep_stride = 0, reg_n_ref = 0;
@@ -95,6 +113,12 @@ int reserve(v2p_engine* e, DevBuf& b, size_t bytes) {
     return V2P_OK;
 }
 
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
 // Copy-kernel variants selectable through v2p_engine_set_tuning (profiling sweeps); 0 is the shipped default.
 struct CopyVariant {
     int tile;
@@ -113,24 +137,22 @@ const CopyVariant kVariants[] = {
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
-int tile_bytes_of(const v2p_engine* e) { return kVariants[e->variant].tile; }
-
-// plan + copy on e->stream.  kp.{lb,tile_hap,status,n_tiles,tile_bytes} are filled here.
-int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop, DevStatus* h_status,
-                 cudaEvent_t ev_done, bool init_status = true, cudaEvent_t ev_copy = nullptr) {
-    const int T = tile_bytes_of(e);
+// plan + copy on stream s.  kp.{lb,tile_hap,status,n_tiles,tile_bytes} are filled here.
+int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                 DevStatus* h_status, bool init_status, cudaEvent_t ev_copy) {
+    const CopyVariant& cv = kVariants[e->variant];
+    const int T = cv.tile;
     kp.tile_bytes = (uint32_t)T;
     kp.tile_shift = T == 4096 ? 12u : 11u;
     kp.n_tiles = (kp.n_out + T - 1) / T;
     if (kp.n_tasks >= 0xFFFFFFFEull) return fail(e, V2P_ERR_INVALID_ARG, "more than 2^32-2 tasks in one launch");
     int rc;
-    if ((rc = reserve(e, e->lb, (kp.n_tiles + 1) * sizeof(uint32_t)))) return rc;
-    if ((rc = reserve(e, e->tile_hap, std::max<uint64_t>(kp.n_tiles, 1) * sizeof(uint32_t)))) return rc;
-    if ((rc = reserve(e, e->status, sizeof(DevStatus)))) return rc;
-    kp.lb = (uint32_t*)e->lb.p;
-    kp.tile_hap = (uint32_t*)e->tile_hap.p;
-    kp.status = (DevStatus*)e->status.p;
-    cudaStream_t s = e->stream;
+    if ((rc = reserve(e, sc.lb, (kp.n_tiles + 1) * sizeof(uint32_t)))) return rc;
+    if ((rc = reserve(e, sc.tile_hap, std::max<uint64_t>(kp.n_tiles, 1) * sizeof(uint32_t)))) return rc;
+    if ((rc = reserve(e, sc.status, sizeof(DevStatus)))) return rc;
+    kp.lb = (uint32_t*)sc.lb.p;
+    kp.tile_hap = (uint32_t*)sc.tile_hap.p;
+    kp.status = (DevStatus*)sc.status.p;
     if (ev_start) CUDA_TRY(e, cudaEventRecord(ev_start, s));
     CUDA_TRY(e, cudaMemsetAsync(kp.lb, 0xFF, (kp.n_tiles + 1) * sizeof(uint32_t), s));
     if (init_status) {
@@ -151,7 +173,6 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
     }
     if (ev_copy) CUDA_TRY(e, cudaEventRecord(ev_copy, s));
     if (kp.n_tiles) {
-        const CopyVariant& cv = kVariants[e->variant];
         const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : cv.ctas_per_sm;
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
@@ -165,7 +186,6 @@ int launch_group(v2p_engine* e, KParams& kp, cudaEvent_t ev_start, cudaEvent_t e
     CUDA_TRY(e, cudaGetLastError());
     // status rides the stream right behind the kernels, so a later launch cannot overwrite it first
     CUDA_TRY(e, cudaMemcpyAsync(h_status, kp.status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
-    if (ev_done) CUDA_TRY(e, cudaEventRecord(ev_done, s));
     return V2P_OK;
 }
 
@@ -206,57 +226,80 @@ void decode_status(const DevStatus& st, const uint64_t* task_begin_host, uint64_
     }
 }
 
+bool needs_serial(const DevStatus& st) {
+    return !st.bad_args && st.err_key == ~0ull && st.gap_key == ~0ull && st.unsorted;
+}
+
 // serial-order fallback, launched only after the plan reported unsorted/overlapping tasks
-int launch_serial(v2p_engine* e, const KParams& kp) {
+int launch_serial(v2p_engine* e, cudaStream_t s, const KParams& kp) {
     unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(kp.n_hap, 1), (uint64_t)e->sm_count * 8);
-    k_serial<<<grid, kThreads, 0, e->stream>>>(kp);
+    k_serial<<<grid, kThreads, 0, s>>>(kp);
     e->launches++;
     CUDA_TRY(e, cudaGetLastError());
     return V2P_OK;
 }
 
-// Finish a launch group: wait for its status, run the serial fallback when needed.
-int finish_group(v2p_engine* e, KParams& kp, DevStatus* h_status, cudaEvent_t ev_done) {
-    if (ev_done)
-        CUDA_TRY(e, cudaEventSynchronize(ev_done));
-    else
-        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    if (!h_status->bad_args && h_status->err_key == ~0ull && h_status->gap_key == ~0ull && h_status->unsorted) {
-        int rc = launch_serial(e, kp);
-        if (rc) return rc;
-        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+void free_event(v2p_event* ev) {
+    if (ev->ev_start) cudaEventDestroy(ev->ev_start);
+    if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
+    if (ev->ev_done) cudaEventDestroy(ev->ev_done);
+    if (ev->ev_copy) cudaEventDestroy(ev->ev_copy);
+    if (ev->h_status) cudaFreeHost(ev->h_status);
+    delete ev;
+}
+
+// returns the event object to the engine's pool (its slot becomes free again)
+void destroy_event(v2p_engine* e, v2p_event* ev) {
+    if (ev->slot) ev->slot->busy = false;
+    ev->slot = nullptr;
+    ev->h_out = nullptr;
+    ev->out_bytes = 0;
+    ev->h_task_begin = nullptr;
+    e->event_pool.push_back(ev);
+}
+
+v2p_event* acquire_event(v2p_engine* e) {
+    if (!e->event_pool.empty()) {
+        v2p_event* ev = e->event_pool.back();
+        e->event_pool.pop_back();
+        return ev;
     }
-    return V2P_OK;
+    v2p_event* ev = new (std::nothrow) v2p_event();
+    if (!ev) return nullptr;
+    if (cudaEventCreate(&ev->ev_start) != cudaSuccess || cudaEventCreate(&ev->ev_stop) != cudaSuccess ||
+        cudaEventCreate(&ev->ev_copy) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost((void**)&ev->h_status, sizeof(DevStatus)) != cudaSuccess) {
+        free_event(ev);
+        return nullptr;
+    }
+    return ev;
 }
 
-int check_batch_args(v2p_engine* e, const v2p_batch* b) {
-    if (!b) return fail(e, V2P_ERR_INVALID_ARG, "batch is NULL");
-    if (b->n_hap == 0) return V2P_OK;
-    if (!b->task_begin || !b->alt_base || !b->out_base)
-        return fail(e, V2P_ERR_INVALID_ARG, "task_begin/alt_base/out_base must not be NULL");
-    return V2P_OK;
-}
-
-// Completes a launch group: status, serial fallback, D2H (host mode); destroys the event.
+// Completes a launch group: status, serial fallback (+ repeated copy-back in host mode); destroys the event.
 int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
     v2p_result local;
     memset(&local, 0, sizeof local);
-    auto cleanup = [&](int code) {
-        if (ev->ev_start) cudaEventDestroy(ev->ev_start);
-        if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
-        if (ev->ev_done) cudaEventDestroy(ev->ev_done);
-        if (ev->ev_copy) cudaEventDestroy(ev->ev_copy);
-        if (ev->h_status) cudaFreeHost(ev->h_status);
-        delete ev;
+    auto finish = [&](int code) {
+        destroy_event(e, ev);
         if (res) *res = local;
         return code;
     };
     cudaSetDevice(e->device);
-    int rc = finish_group(e, ev->kp, ev->h_status, ev->ev_done);
-    if (rc) return cleanup(rc);
+    if (cudaEventSynchronize(ev->ev_done) != cudaSuccess)
+        return finish(fail(e, V2P_ERR_CUDA, "launch group failed: %s", cudaGetErrorString(cudaGetLastError())));
+    const DevStatus& st = *ev->h_status;
+    if (needs_serial(st)) {
+        int rc = launch_serial(e, ev->stream, ev->kp);
+        if (rc) return finish(rc);
+        if (ev->slot && ev->out_bytes &&
+            cudaMemcpyAsync(ev->h_out, ev->kp.out, ev->out_bytes, cudaMemcpyDeviceToHost, ev->stream) != cudaSuccess)
+            return finish(fail(e, V2P_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(cudaGetLastError())));
+        if (cudaStreamSynchronize(ev->stream) != cudaSuccess)
+            return finish(fail(e, V2P_ERR_CUDA, "serial-order kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
     std::vector<uint64_t> tb_copy;
     const uint64_t* tb = ev->h_task_begin;
-    const DevStatus& st = *ev->h_status;
     if (!tb && ev->kp.n_hap && (st.err_key != ~0ull || st.gap_key != ~0ull)) {  // error path only: fetch task_begin
         tb_copy.resize(ev->kp.n_hap + 1);
         if (cudaMemcpy(tb_copy.data(), ev->kp.task_begin, tb_copy.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost) ==
@@ -267,15 +310,10 @@ int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev->ev_start, ev->ev_stop) == cudaSuccess) local.kernel_ms = ms;
     if (cudaEventElapsedTime(&ms, ev->ev_copy, ev->ev_stop) == cudaSuccess) local.copy_ms = ms;
-    if (local.status == V2P_OK && ev->host_mode && ev->out_bytes) {
-        if (cudaMemcpyAsync(ev->h_out, ev->kp.out, ev->out_bytes, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess ||
-            cudaStreamSynchronize(e->stream) != cudaSuccess)
-            return cleanup(fail(e, V2P_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(cudaGetLastError())));
-    }
     if (local.status != V2P_OK)
         fail(e, local.status, "haplotype %llu task %llu rejected with status %d", (unsigned long long)local.bad_hap,
              (unsigned long long)local.bad_task, local.status);
-    return cleanup(local.status);
+    return finish(local.status);
 }
 
 }  // namespace
@@ -302,10 +340,13 @@ int v2p_engine_create(int cuda_device, v2p_engine** out) {
     if (!e) return V2P_ERR_INVALID_ARG;
     e->device = cuda_device;
     cudaDeviceProp prop;
-    if (cudaSetDevice(cuda_device) != cudaSuccess || cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void**)&e->h_status, sizeof(DevStatus)) != cudaSuccess) {
-        delete e;
+    bool ok = cudaSetDevice(cuda_device) == cudaSuccess && cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMallocHost((void**)&e->h_status, sizeof(DevStatus)) == cudaSuccess;
+    for (int i = 0; ok && i < kSlots; ++i)
+        ok = cudaStreamCreateWithFlags(&e->slots[i].stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
+        v2p_engine_destroy(e);
         return V2P_ERR_CUDA;
     }
     e->sm_count = prop.multiProcessorCount;
@@ -316,12 +357,17 @@ int v2p_engine_create(int cuda_device, v2p_engine** out) {
 void v2p_engine_destroy(v2p_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
-    DevBuf* bufs[] = {&e->lb,      &e->tile_hap, &e->status, &e->d_tasks,    &e->d_task_begin, &e->d_ref,   &e->d_ref_base,
-                      &e->d_alt,   &e->d_alt_base, &e->d_out,  &e->d_out_base, &e->d_soa[0],     &e->d_soa[1], &e->d_soa[2],
-                      &e->d_soa[3], &e->ref_rep};
-    for (DevBuf* b : bufs)
-        if (b->p) cudaFree(b->p);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&e->sc.lb,     &e->sc.tile_hap, &e->sc.status, &e->d_soa[0], &e->d_soa[1],  &e->d_soa[2], &e->d_soa[3],
+                      &e->soa_tasks, &e->soa_ref,     &e->soa_alt,   &e->soa_out,  &e->soa_bases, &e->ref_rep};
+    for (DevBuf* b : bufs) release(*b);
+    for (Slot& sl : e->slots) {
+        DevBuf* sb[] = {&sl.sc.lb,      &sl.sc.tile_hap, &sl.sc.status,  &sl.d_tasks, &sl.d_task_begin, &sl.d_ref,
+                        &sl.d_ref_base, &sl.d_alt,       &sl.d_alt_base, &sl.d_out,   &sl.d_out_base};
+        for (DevBuf* b : sb) release(*b);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    for (v2p_event* ev : e->event_pool) free_event(ev);
     if (e->h_status) cudaFreeHost(e->h_status);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -366,7 +412,7 @@ int v2p_engine_set_reference(v2p_engine* e, const uint8_t* ref, uint64_t n_ref, 
     std::lock_guard<std::mutex> g(e->mu);
     e->err.clear();
     CUDA_TRY(e, cudaSetDevice(e->device));
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaDeviceSynchronize());  // nothing in flight may still read the previous tape
     e->has_ref = false;
     const bool replicas = (flags & V2P_REF_NO_TMA) == 0;
     const uint64_t stride = (n_ref + 64 + 255) & ~255ull;
@@ -398,44 +444,36 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
     if (!e) return V2P_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);
     e->err.clear();
-    int rc = check_batch_args(e, b);
-    if (rc) return rc;
+    if (!b) return fail(e, V2P_ERR_INVALID_ARG, "batch is NULL");
+    if (b->n_hap && (!b->task_begin || !b->alt_base || !b->out_base))
+        return fail(e, V2P_ERR_INVALID_ARG, "task_begin/alt_base/out_base must not be NULL");
     const bool async = (flags & V2P_FLAG_ASYNC) != 0;
     if (async && !done) return fail(e, V2P_ERR_INVALID_ARG, "ASYNC needs an event out-pointer");
     if (!async && !res) return fail(e, V2P_ERR_INVALID_ARG, "synchronous call needs a result out-pointer");
     CUDA_TRY(e, cudaSetDevice(e->device));
     if (res) memset(res, 0, sizeof *res);
+    const bool use_reg_ref = b->ref == nullptr && b->ref_base == nullptr;
+    if (use_reg_ref && !e->has_ref)
+        return fail(e, V2P_ERR_INVALID_ARG, "ref == NULL but no reference was registered (v2p_engine_set_reference)");
 
-    v2p_event* ev = new (std::nothrow) v2p_event();
-    if (!ev) return fail(e, V2P_ERR_INVALID_ARG, "out of memory");
-    auto cleanup = [&](int code) {
-        if (ev->ev_start) cudaEventDestroy(ev->ev_start);
-        if (ev->ev_stop) cudaEventDestroy(ev->ev_stop);
-        if (ev->ev_done) cudaEventDestroy(ev->ev_done);
-        if (ev->ev_copy) cudaEventDestroy(ev->ev_copy);
-        if (ev->h_status) cudaFreeHost(ev->h_status);
-        delete ev;
+    v2p_event* ev = acquire_event(e);
+    if (!ev) return fail(e, V2P_ERR_CUDA, "event/pinned allocation failed");
+    auto bail = [&](int code) {
+        destroy_event(e, ev);
         return code;
     };
-    if (cudaEventCreate(&ev->ev_start) != cudaSuccess || cudaEventCreate(&ev->ev_stop) != cudaSuccess ||
-        cudaEventCreate(&ev->ev_copy) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev->ev_done, cudaEventDisableTiming) != cudaSuccess ||
-        cudaMallocHost((void**)&ev->h_status, sizeof(DevStatus)) != cudaSuccess)
-        return cleanup(fail(e, V2P_ERR_CUDA, "event/pinned allocation failed"));
-    ev->flags = flags;
 
     KParams kp;
     memset(&kp, 0, sizeof kp);
     kp.n_hap = b->n_hap;
     kp.fill_word = 0x2E2E2E2Eu;
-    kp.keep_out = 0;
     kp.validate = (flags & V2P_FLAG_VALIDATE) ? 1 : 0;
+    cudaStream_t s = e->stream;
+    Scratch* sc = &e->sc;
+    int rc;
 
-    const bool use_reg_ref = b->ref == nullptr && b->ref_base == nullptr;
-    if (use_reg_ref && !e->has_ref)
-        return cleanup(fail(e, V2P_ERR_INVALID_ARG, "ref == NULL but no reference was registered (v2p_engine_set_reference)"));
     if (flags & V2P_FLAG_DEVICE_PTRS) {
-        if (((uintptr_t)b->out & 15u) != 0) return cleanup(fail(e, V2P_ERR_INVALID_ARG, "out must be 16-byte aligned"));
+        if (((uintptr_t)b->out & 15u) != 0) return bail(fail(e, V2P_ERR_INVALID_ARG, "out must be 16-byte aligned"));
         kp.tasks = b->tasks;
         kp.task_begin = b->task_begin;
         kp.ref = b->ref;
@@ -447,17 +485,20 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         kp.n_tasks = b->n_tasks;
         kp.n_ref = b->n_ref;
         kp.n_alt = b->n_alt;
-        kp.n_out = b->n_out;
-        // origins are 0: device-pointer batches are self-contained
+        kp.n_out = b->n_out;  // origins stay 0: device-pointer batches are self-contained
     } else {
-        // host pointers: stage everything through device buffers on the engine stream
+        // host pointers: stage through the next slot's device buffers on that slot's stream
+        Slot* sl = &e->slots[e->next_slot];
+        if (sl->busy)
+            return bail(fail(e, V2P_ERR_INVALID_ARG,
+                             "%d host-pointer batches already in flight: wait for the oldest event first", kSlots));
         const uint64_t H = b->n_hap;
         const uint64_t t0 = H ? b->task_begin[0] : 0, t1 = H ? b->task_begin[H] : 0;
         const uint64_t a0 = H ? b->alt_base[0] : 0, a1 = H ? b->alt_base[H] : 0;
         const uint64_t o0 = H ? b->out_base[0] : 0, o1 = H ? b->out_base[H] : 0;
         uint64_t r0 = 0, r1 = use_reg_ref ? 0 : b->n_ref;
         if (b->ref_base && H) r0 = b->ref_base[0], r1 = b->ref_base[H];
-        if (t1 < t0 || a1 < a0 || o1 < o0 || r1 < r0) return cleanup(fail(e, V2P_ERR_INVALID_ARG, "base arrays not monotone"));
+        if (t1 < t0 || a1 < a0 || o1 < o0 || r1 < r0) return bail(fail(e, V2P_ERR_INVALID_ARG, "base arrays not monotone"));
         kp.n_tasks = t1 - t0;
         kp.n_alt = a1 - a0;
         kp.n_out = o1 - o0;
@@ -467,37 +508,40 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         kp.out_origin = o0;
         kp.ref_origin = r0;
         if ((kp.n_tasks && !b->tasks) || (kp.n_out && !b->out) || (kp.n_ref && !b->ref) || (kp.n_alt && !b->alt))
-            return cleanup(fail(e, V2P_ERR_INVALID_ARG, "NULL data pointer"));
+            return bail(fail(e, V2P_ERR_INVALID_ARG, "NULL data pointer"));
         const size_t nb = (H + 1) * sizeof(uint64_t);
-        if ((rc = reserve(e, e->d_tasks, kp.n_tasks * sizeof(v2p_task16))) || (rc = reserve(e, e->d_task_begin, nb)) ||
-            (rc = reserve(e, e->d_ref, kp.n_ref + 32)) || (rc = reserve(e, e->d_ref_base, nb)) ||
-            (rc = reserve(e, e->d_alt, kp.n_alt + 32)) || (rc = reserve(e, e->d_alt_base, nb)) ||
-            (rc = reserve(e, e->d_out, kp.n_out + 32)) || (rc = reserve(e, e->d_out_base, nb)))
-            return cleanup(rc);
-        cudaStream_t s = e->stream;
+        if ((rc = reserve(e, sl->d_tasks, kp.n_tasks * sizeof(v2p_task16))) || (rc = reserve(e, sl->d_task_begin, nb)) ||
+            (rc = reserve(e, sl->d_ref, kp.n_ref + 32)) || (rc = reserve(e, sl->d_ref_base, nb)) ||
+            (rc = reserve(e, sl->d_alt, kp.n_alt + 32)) || (rc = reserve(e, sl->d_alt_base, nb)) ||
+            (rc = reserve(e, sl->d_out, kp.n_out + 32)) || (rc = reserve(e, sl->d_out_base, nb)))
+            return bail(rc);
+        s = sl->stream;
+        sc = &sl->sc;
         auto h2d = [&](void* d, const void* h, size_t n) {
-            return n ? cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) : cudaSuccess;
+            return (n && H) ? cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) : cudaSuccess;
         };
-        if (h2d(e->d_tasks.p, b->tasks + t0, kp.n_tasks * sizeof(v2p_task16)) != cudaSuccess ||
-            h2d(e->d_task_begin.p, b->task_begin, nb) != cudaSuccess || h2d(e->d_ref.p, b->ref + r0, kp.n_ref) != cudaSuccess ||
-            (b->ref_base && h2d(e->d_ref_base.p, b->ref_base, nb) != cudaSuccess) ||
-            h2d(e->d_alt.p, b->alt + a0, kp.n_alt) != cudaSuccess || h2d(e->d_alt_base.p, b->alt_base, nb) != cudaSuccess ||
-            h2d(e->d_out_base.p, b->out_base, nb) != cudaSuccess)
-            return cleanup(fail(e, V2P_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(cudaGetLastError())));
-        kp.tasks = (const v2p_task16*)e->d_tasks.p;
-        kp.task_begin = (const uint64_t*)e->d_task_begin.p;
-        kp.ref = (const uint8_t*)e->d_ref.p;
-        kp.ref_base = b->ref_base ? (const uint64_t*)e->d_ref_base.p : nullptr;
-        kp.alt = (const uint8_t*)e->d_alt.p;
-        kp.alt_base = (const uint64_t*)e->d_alt_base.p;
-        kp.out = (uint8_t*)e->d_out.p;
-        kp.out_base = (const uint64_t*)e->d_out_base.p;
-        ev->host_mode = true;
-        ev->h_out = b->out + o0;
+        if (h2d(sl->d_tasks.p, b->tasks + t0, kp.n_tasks * sizeof(v2p_task16)) != cudaSuccess ||
+            h2d(sl->d_task_begin.p, b->task_begin, nb) != cudaSuccess ||
+            h2d(sl->d_ref.p, b->ref + r0, kp.n_ref) != cudaSuccess ||
+            (b->ref_base && h2d(sl->d_ref_base.p, b->ref_base, nb) != cudaSuccess) ||
+            h2d(sl->d_alt.p, b->alt + a0, kp.n_alt) != cudaSuccess || h2d(sl->d_alt_base.p, b->alt_base, nb) != cudaSuccess ||
+            h2d(sl->d_out_base.p, b->out_base, nb) != cudaSuccess)
+            return bail(fail(e, V2P_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(cudaGetLastError())));
+        kp.tasks = (const v2p_task16*)sl->d_tasks.p;
+        kp.task_begin = (const uint64_t*)sl->d_task_begin.p;
+        kp.ref = (const uint8_t*)sl->d_ref.p;
+        kp.ref_base = b->ref_base ? (const uint64_t*)sl->d_ref_base.p : nullptr;
+        kp.alt = (const uint8_t*)sl->d_alt.p;
+        kp.alt_base = (const uint64_t*)sl->d_alt_base.p;
+        kp.out = (uint8_t*)sl->d_out.p;
+        kp.out_base = (const uint64_t*)sl->d_out_base.p;
+        ev->slot = sl;
+        sl->busy = true;
+        e->next_slot = (e->next_slot + 1) % kSlots;
+        ev->h_out = H ? b->out + o0 : nullptr;
         ev->out_bytes = kp.n_out;
         ev->h_task_begin = b->task_begin;
     }
-
     if (use_reg_ref) {
         kp.ref = (const uint8_t*)e->ref_rep.p;  // replica 0 is the plain tape
         kp.ref_base = nullptr;
@@ -507,8 +551,15 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         kp.rep_stride = e->rep_stride;
         kp.tma_mode = e->ref_tma_mode;
     }
-    rc = launch_group(e, kp, ev->ev_start, ev->ev_stop, ev->h_status, ev->ev_done, true, ev->ev_copy);
-    if (rc) return cleanup(rc);
+    ev->stream = s;
+    rc = launch_group(e, s, *sc, kp, ev->ev_start, ev->ev_stop, ev->h_status, true, ev->ev_copy);
+    if (rc) return bail(rc);
+    // host mode: the copy-back is enqueued right away (a batch that needs the serial-order kernel repeats it later)
+    if (ev->slot && ev->out_bytes &&
+        cudaMemcpyAsync(ev->h_out, kp.out, ev->out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        return bail(fail(e, V2P_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaEventRecord(ev->ev_done, s) != cudaSuccess)
+        return bail(fail(e, V2P_ERR_CUDA, "event record failed: %s", cudaGetErrorString(cudaGetLastError())));
     ev->kp = kp;
     if (async) {
         *done = ev;
@@ -545,34 +596,32 @@ int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, co
     const size_t tb = n_tasks * sizeof(uint64_t);
     for (int i = 0; i < 4; ++i)
         if ((rc = reserve(e, e->d_soa[i], tb))) return rc;
-    if ((rc = reserve(e, e->d_tasks, n_tasks * sizeof(v2p_task16))) || (rc = reserve(e, e->d_ref, n_ref * 4 + 32)) ||
-        (rc = reserve(e, e->d_alt, n_alt * 4 + 32)) || (rc = reserve(e, e->d_out, n_res * 4 + 32)) ||
-        (rc = reserve(e, e->d_task_begin, 16)) || (rc = reserve(e, e->d_alt_base, 16)) ||
-        (rc = reserve(e, e->d_out_base, 16)) || (rc = reserve(e, e->status, sizeof(DevStatus))))
+    if ((rc = reserve(e, e->soa_tasks, n_tasks * sizeof(v2p_task16))) || (rc = reserve(e, e->soa_ref, n_ref * 4 + 32)) ||
+        (rc = reserve(e, e->soa_alt, n_alt * 4 + 32)) || (rc = reserve(e, e->soa_out, n_res * 4 + 32)) ||
+        (rc = reserve(e, e->soa_bases, 64)) || (rc = reserve(e, e->sc.status, sizeof(DevStatus))))
         return rc;
     const uint64_t* soa[4] = {exec_code, start_pos, length, start_pos_res};
     for (int i = 0; i < 4; ++i)
         if (tb) CUDA_TRY(e, cudaMemcpyAsync(e->d_soa[i].p, soa[i], tb, cudaMemcpyHostToDevice, s));
-    if (n_ref) CUDA_TRY(e, cudaMemcpyAsync(e->d_ref.p, ref_utf32, n_ref * 4, cudaMemcpyHostToDevice, s));
-    if (n_alt) CUDA_TRY(e, cudaMemcpyAsync(e->d_alt.p, alt_utf32, n_alt * 4, cudaMemcpyHostToDevice, s));
+    if (n_ref) CUDA_TRY(e, cudaMemcpyAsync(e->soa_ref.p, ref_utf32, n_ref * 4, cudaMemcpyHostToDevice, s));
+    if (n_alt) CUDA_TRY(e, cudaMemcpyAsync(e->soa_alt.p, alt_utf32, n_alt * 4, cudaMemcpyHostToDevice, s));
     const bool keep = !(flags & V2P_FLAG_FILL_DOT);
-    if (keep && n_res) CUDA_TRY(e, cudaMemcpyAsync(e->d_out.p, res_utf32, n_res * 4, cudaMemcpyHostToDevice, s));
-    const uint64_t tbeg[2] = {0, n_tasks}, abase[2] = {0, n_alt * 4}, obase[2] = {0, n_res * 4};
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_task_begin.p, tbeg, 16, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_alt_base.p, abase, 16, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_out_base.p, obase, 16, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(e, cudaStreamSynchronize(s));  // tbeg/abase/obase live on this stack frame
+    if (keep && n_res) CUDA_TRY(e, cudaMemcpyAsync(e->soa_out.p, res_utf32, n_res * 4, cudaMemcpyHostToDevice, s));
+    // task_begin | alt_base | out_base, two entries each
+    const uint64_t bases[6] = {0, n_tasks, 0, n_alt * 4, 0, n_res * 4};
+    CUDA_TRY(e, cudaMemcpyAsync(e->soa_bases.p, bases, sizeof bases, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(e, cudaStreamSynchronize(s));  // `bases` lives on this stack frame
 
     KParams kp;
     memset(&kp, 0, sizeof kp);
-    kp.tasks = (const v2p_task16*)e->d_tasks.p;
-    kp.task_begin = (const uint64_t*)e->d_task_begin.p;
-    kp.ref = (const uint8_t*)e->d_ref.p;
-    kp.ref_base = nullptr;
-    kp.alt = (const uint8_t*)e->d_alt.p;
-    kp.alt_base = (const uint64_t*)e->d_alt_base.p;
-    kp.out = (uint8_t*)e->d_out.p;
-    kp.out_base = (const uint64_t*)e->d_out_base.p;
+    const uint64_t* db = (const uint64_t*)e->soa_bases.p;
+    kp.tasks = (const v2p_task16*)e->soa_tasks.p;
+    kp.task_begin = db;
+    kp.ref = (const uint8_t*)e->soa_ref.p;
+    kp.alt = (const uint8_t*)e->soa_alt.p;
+    kp.alt_base = db + 2;
+    kp.out = (uint8_t*)e->soa_out.p;
+    kp.out_base = db + 4;
     kp.n_hap = 1;
     kp.n_tasks = n_tasks;
     kp.n_ref = n_ref * 4;
@@ -583,19 +632,22 @@ int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, co
     kp.validate = (flags & V2P_FLAG_VALIDATE) ? 1 : 0;
 
     // pack (and judge every reference panic on the original 64-bit values), then plan + copy
-    kp.status = (DevStatus*)e->status.p;
+    kp.status = (DevStatus*)e->sc.status.p;
     k_init_status<<<1, 1, 0, s>>>(kp.status);
     e->launches++;
     if (n_tasks) {
         k_soa_pack<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(
             n_tasks, (const uint64_t*)e->d_soa[0].p, (const uint64_t*)e->d_soa[1].p, (const uint64_t*)e->d_soa[2].p,
-            (const uint64_t*)e->d_soa[3].p, n_ref, n_alt, n_res, 4u, kp.validate, (v2p_task16*)e->d_tasks.p, kp.status);
+            (const uint64_t*)e->d_soa[3].p, n_ref, n_alt, n_res, 4u, kp.validate, (v2p_task16*)e->soa_tasks.p, kp.status);
         e->launches++;
     }
-    rc = launch_group(e, kp, nullptr, nullptr, e->h_status, nullptr, /*init_status=*/false);
+    rc = launch_group(e, s, e->sc, kp, nullptr, nullptr, e->h_status, /*init_status=*/false, nullptr);
     if (rc) return rc;
-    rc = finish_group(e, kp, e->h_status, nullptr);
-    if (rc) return rc;
+    CUDA_TRY(e, cudaStreamSynchronize(s));
+    if (needs_serial(*e->h_status)) {
+        if ((rc = launch_serial(e, s, kp))) return rc;
+        CUDA_TRY(e, cudaStreamSynchronize(s));
+    }
     v2p_result r;
     memset(&r, 0, sizeof r);
     decode_status(*e->h_status, nullptr, 0, 0, &r);
@@ -604,7 +656,7 @@ int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, co
         return fail(e, r.status, "task %llu rejected with status %d", (unsigned long long)r.bad_task, r.status);
     }
     if (n_res) {
-        CUDA_TRY(e, cudaMemcpyAsync(res_utf32, e->d_out.p, n_res * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(e, cudaMemcpyAsync(res_utf32, e->soa_out.p, n_res * 4, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(e, cudaStreamSynchronize(s));
     }
     return V2P_OK;

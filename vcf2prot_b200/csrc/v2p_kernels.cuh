@@ -141,56 +141,75 @@ __global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
     __syncthreads();
     if (p.status->bad_args) return;
     const uint4* __restrict__ tk = reinterpret_cast<const uint4*>(p.tasks);
-#pragma unroll 4
-    for (int it = 0; it < kPlanIters; ++it) {
-        const uint64_t tr = tfirst + (uint64_t)it * 256 + threadIdx.x;  // launch-relative task index
-        if (tr >= p.n_tasks) break;
-        const uint4 raw = __ldg(tk + tr);
-        const uint4 pr = tr > 0 ? __ldg(tk + tr - 1) : make_uint4(0u, 0u, 0u, 0u);
-        const uint64_t t = tr + p.task_origin;
-        uint64_t h = sh[0], tb0 = sh[1], o0 = sh[3], n_res = sh[4] - sh[3], n_alt = sh[5], n_ref = sh[6];
-        if (t >= sh[2]) {  // not the CTA's first haplotype
-            h = upper_bound_u64(p.task_begin, h + 1, p.n_hap + 1, t) - 1;
-            tb0 = __ldg(p.task_begin + h);
-            o0 = __ldg(p.out_base + h);
-            n_res = __ldg(p.out_base + h + 1) - o0;
-            n_alt = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
-            n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
+    constexpr int U = 4;  // tasks per thread whose loads are issued together
+    for (int it0 = 0; it0 < kPlanIters; it0 += U) {
+        uint4 raw[U], prv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t tr = tfirst + (uint64_t)(it0 + u) * 256 + threadIdx.x;
+            raw[u] = tr < p.n_tasks ? __ldg(tk + tr) : make_uint4(0u, 0u, 0u, 0u);
         }
-        const uint32_t src = raw.x, len = raw.y, dst = raw.z, stream = raw.w;
-        const unsigned long long key = (unsigned long long)tr << 8;
-        if (stream > 1u) {  // haplotype_instruction.rs:154
-            atomicMin(&p.status->err_key, key | V2P_ERR_BAD_STREAM);
-            continue;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            // the previous task sits in the neighbouring lane, except for lane 0
+            const uint64_t tr = tfirst + (uint64_t)(it0 + u) * 256 + threadIdx.x;
+            prv[u].x = __shfl_up_sync(0xffffffffu, raw[u].x, 1);
+            prv[u].y = __shfl_up_sync(0xffffffffu, raw[u].y, 1);
+            prv[u].z = __shfl_up_sync(0xffffffffu, raw[u].z, 1);
+            prv[u].w = 0u;
+            if ((threadIdx.x & 31) == 0 && tr > 0 && tr < p.n_tasks) prv[u] = __ldg(tk + tr - 1);
         }
-        if ((uint64_t)dst + len > n_res) {  // task.rs:44/48 (result slice)
-            atomicMin(&p.status->err_key, key | V2P_ERR_RES_OOB);
-            continue;
-        }
-        if ((uint64_t)src + len > (stream == 0 ? n_ref : n_alt)) {  // task.rs:44/48 (source slice)
-            atomicMin(&p.status->err_key, key | V2P_ERR_SRC_OOB);
-            continue;
-        }
-        const uint64_t g = o0 - p.out_origin + dst;  // global (launch-relative) output byte of this task
-        uint64_t k_lo = 0;
-        if (tr > 0) {
-            uint64_t gp;
-            if (t > tb0) {  // same haplotype: gir.rs:208 contiguity + sortedness
-                const uint64_t pend = (uint64_t)pr.z + pr.y;
-                if (dst < pend) atomicExch(&p.status->unsorted, 1u);
-                if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
-                gp = o0 - p.out_origin + pr.z;
-            } else {
-                uint64_t hp = h;
-                while (hp > 0 && __ldg(p.task_begin + hp) > t - 1) --hp;
-                gp = __ldg(p.out_base + hp) - p.out_origin + pr.z;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t tr = tfirst + (uint64_t)(it0 + u) * 256 + threadIdx.x;  // launch-relative task index
+            if (tr >= p.n_tasks) continue;
+            const uint4 pr = prv[u];
+            const uint64_t t = tr + p.task_origin;
+            uint64_t h = sh[0], tb0 = sh[1], o0 = sh[3], n_res = sh[4] - sh[3], n_alt = sh[5], n_ref = sh[6];
+            if (t >= sh[2]) {  // not the CTA's first haplotype
+                h = upper_bound_u64(p.task_begin, h + 1, p.n_hap + 1, t) - 1;
+                tb0 = __ldg(p.task_begin + h);
+                o0 = __ldg(p.out_base + h);
+                n_res = __ldg(p.out_base + h + 1) - o0;
+                n_alt = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
+                n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
             }
-            if (gp > g) continue;  // cannot happen across haplotypes with monotone out_base; unsorted inside one
-            k_lo = (gp >> p.tile_shift) + 1;
+            const uint32_t src = raw[u].x, len = raw[u].y, dst = raw[u].z, stream = raw[u].w;
+            const unsigned long long key = (unsigned long long)tr << 8;
+            if (stream > 1u) {  // haplotype_instruction.rs:154
+                atomicMin(&p.status->err_key, key | V2P_ERR_BAD_STREAM);
+                continue;
+            }
+            if ((uint64_t)dst + len > n_res) {  // task.rs:44/48 (result slice)
+                atomicMin(&p.status->err_key, key | V2P_ERR_RES_OOB);
+                continue;
+            }
+            if ((uint64_t)src + len > (stream == 0 ? n_ref : n_alt)) {  // task.rs:44/48 (source slice)
+                atomicMin(&p.status->err_key, key | V2P_ERR_SRC_OOB);
+                continue;
+            }
+            const uint64_t g = o0 - p.out_origin + dst;  // global (launch-relative) output byte of this task
+            uint64_t k_lo = 0;
+            if (tr > 0) {
+                uint64_t gp;
+                if (t > tb0) {  // same haplotype: gir.rs:208 contiguity + sortedness
+                    const uint64_t pend = (uint64_t)pr.z + pr.y;
+                    if (dst < pend) atomicExch(&p.status->unsorted, 1u);
+                    if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
+                    gp = o0 - p.out_origin + pr.z;
+                } else {
+                    uint64_t hp = h;
+                    while (hp > 0 && __ldg(p.task_begin + hp) > t - 1) --hp;
+                    gp = __ldg(p.out_base + hp) - p.out_origin + pr.z;
+                }
+                if (gp > g) continue;  // cannot happen across haplotypes with monotone out_base; unsorted inside one
+                k_lo = (gp >> p.tile_shift) + 1;
+            }
+            uint64_t k_hi = g >> p.tile_shift;
+            if (k_hi > p.n_tiles) k_hi = p.n_tiles;
+            if (k_lo <= k_hi)  // only tasks that start a new tile (or follow a gap of whole tiles) write lb[]
+                for (uint64_t k = k_lo; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
         }
-        uint64_t k_hi = g >> p.tile_shift;
-        if (k_hi > p.n_tiles) k_hi = p.n_tiles;
-        for (uint64_t k = k_lo; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
     }
 }
 

@@ -194,7 +194,7 @@ class GpuEngine:
 
     def execute_hap_range(self, h0: int, h1: int, task_begin: np.ndarray, tasks: np.ndarray, ref: np.ndarray,
                           alt: np.ndarray, alt_base: np.ndarray, out_base: np.ndarray, out_chunk: np.ndarray,
-                          validate: bool = False) -> float:
+                          validate: bool = False, wait: bool = True):
         """Host-pointer call on haplotypes [h0,h1) of a larger host-resident cohort (the streaming shape: the
         caller's pinned staging buffer `out_chunk` receives just this range's result tapes).  The base arrays keep
         their cohort-absolute values; the library rebases on entry [0] of each slice."""
@@ -211,7 +211,14 @@ class GpuEngine:
         b.out = addr(out_chunk) - o0  # virtual base: out[o0] is out_chunk[0]
         b.n_hap = h1 - h0
         res = L.Result()
-        st = self._lib.v2p_execute_batch(self._h, C.byref(b), L.FLAG_VALIDATE if validate else 0, C.byref(res), None)
+        flags = L.FLAG_VALIDATE if validate else 0
+        if not wait:  # returns an event; up to 3 host-pointer batches may be in flight (copy-back overlaps upload)
+            ev = C.c_void_p()
+            st = self._lib.v2p_execute_batch(self._h, C.byref(b), flags | L.FLAG_ASYNC, None, C.byref(ev))
+            if st != L.V2P_OK:
+                raise EngineError(st, self.last_error())
+            return ev
+        st = self._lib.v2p_execute_batch(self._h, C.byref(b), flags, C.byref(res), None)
         if st != L.V2P_OK:
             raise EngineError(st, self.last_error(), res.bad_hap, res.bad_task)
         self.last_copy_ms = float(res.copy_ms)
