@@ -60,13 +60,16 @@ def parse_args():
                          "with the proteome tape (<=30 '.' pad bytes per transcript, never seen by the consumer)")
     ap.add_argument("--no-registered-ref", action="store_true",
                     help="pass the proteome with every call (generic register path) instead of registering it once")
+    ap.add_argument("--fasta-image", action="store_true",
+                    help="emit `>{transcript}_{hap}\\n{seq}\\n` framing as extra copy segments (packed layout only): "
+                         "the result tape is the FASTA file image")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
                     help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_workload(kind: str, n_samples: int, rank: int, layout: str = "packed"):
+def make_workload(kind: str, n_samples: int, rank: int, layout: str = "packed", fasta: bool = False):
     from vcf2prot_b200 import cohort as C
 
     prot = C.make_proteome(seed=0x5EED0001, giant=(20 if kind == "c4" else 0))
@@ -81,6 +84,8 @@ def make_workload(kind: str, n_samples: int, rank: int, layout: str = "packed"):
     for i, h0 in enumerate(range(0, n_hap, step)):
         parts.append(C.synth_batch(prot, cat, min(step, n_hap - h0), seed=(0x5EED0002 + 7919 * rank) * 1000 + i,
                                    layout=layout))
+    if fasta:  # record framing as copy segments: the result tape is the .fasta file image
+        parts = [C.fasta_image(prot, b) for b in parts]
     return prot, cat, C.concat_batches(parts)
 
 
@@ -232,7 +237,7 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     t_gen = time.perf_counter()
-    prot, cat, batch = make_workload(args.workload, args.samples, rank, args.layout)
+    prot, cat, batch = make_workload(args.workload, args.samples, rank, args.layout, args.fasta_image)
     t_gen = time.perf_counter() - t_gen
     n_hap, n_out, n_tasks = batch.n_hap, batch.n_residues, len(batch.tasks)
     n_res = int(batch.tasks[:, 1].astype(np.int64).sum())  # residues produced (the aligned layout also writes '.' pads)
@@ -392,7 +397,7 @@ def main():
                    "haplotypes_per_gpu": n_hap, "tasks_per_gpu": n_tasks, "residues_per_gpu": n_res, "result_tape_bytes_per_gpu": n_out,
                    "mean_task_bytes": n_res / max(n_tasks, 1), "l2_policy": "inputs_larger_than_l2 (output %.1f GB, tasks %.2f GB "
                    "per step; the %.1f MB proteome is L2-resident by design)" % (n_out / 1e9, n_tasks * 16 / 1e9, len(batch.ref) / 1e6),
-                   "tile_variant": args.variant, "layout": args.layout, "reference_tape": "caller-supplied per call" if args.no_registered_ref else
+                   "tile_variant": args.variant, "layout": args.layout, "fasta_image": bool(args.fasta_image), "reference_tape": "caller-supplied per call" if args.no_registered_ref else
                    "registered once (v2p_engine_set_reference, mode %s)" % args.ref_mode, "parallelism": "sample-sharded x%d, no collective" % world},
         "haplotypes_per_s": total_haps / (ms_per_step * 1e-3),
         "alg_gbs": total_alg / (ms_per_step * 1e-3) / 1e9,

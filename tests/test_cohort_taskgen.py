@@ -105,6 +105,12 @@ def test_fasta_records_match_reference_binary(small, tmp_path):
         records.append(([C.site_csq(prot, cat, int(i))], cells))
     recs, stdout, rc = refbin.run_reference(refbin.vcf_text(samples, records), refs, "st")
     assert rc == 0, stdout[-1500:]
+    # device-side FASTA framing (headers/newlines as copy segments): the result tape is the file image
+    fb = C.fasta_image(prot, b)
+    img = np.zeros(fb.n_residues, np.uint8)
+    assert cengine.batch_execute(fb.task_begin, fb.tasks, fb.ref, fb.alt, fb.alt_base, img, fb.out_base, validate=True)[0] == 0
     for s, name in enumerate(samples):
         mine = sorted(C.fasta_records(prot, b, out, 2 * s, 1) + C.fasta_records(prot, b, out, 2 * s + 1, 2))
         assert mine == [tuple(r) for r in recs.get(name, [])], name
+        file_image = img[int(fb.out_base[2 * s]):int(fb.out_base[2 * s + 2])]
+        assert C.parse_fasta_image(file_image) == [tuple(r) for r in recs.get(name, [])], name

@@ -358,3 +358,26 @@ def test_host_pointer_pipeline_three_chunks_in_flight(gpu_engine):
     while pending:
         drain_one()
     assert np.array_equal(got, want)
+
+
+def test_fasta_file_image_on_device(gpu_engine):
+    """record framing as copy segments -> the D2H buffer is the .fasta file image, byte for byte what
+    the oracle produces, and it parses into exactly the records of the plain batch."""
+    from vcf2prot_b200 import cohort as C
+
+    prot = C.make_proteome(seed=25, n_tx=200, mu=5.2, sigma=0.6, hi=3000)
+    cat = C.make_catalogue(prot, 5000, seed=26, mix=(0.7, 0.06, 0.06, 0.08, 0.04, 0.03, 0.03), fs_mean=30, fs_max=500)
+    cat.af[:] = 0.2
+    b = C.synth_batch(prot, cat, 20, 27, ref_mode="global")
+    fb = C.fasta_image(prot, b)
+    gpu_engine.set_reference(prot.residues)
+    img, _ = gpu_engine.execute_batch(fb.task_begin, fb.tasks, None, fb.alt, fb.alt_base, fb.out_base, validate=True)
+    want = np.zeros(fb.n_residues, np.uint8)
+    assert cengine.batch_execute(fb.task_begin, fb.tasks, prot.residues, fb.alt, fb.alt_base, want, fb.out_base)[0] == 0
+    assert np.array_equal(img, want)
+    plain = np.zeros(b.n_residues, np.uint8)
+    assert cengine.batch_execute(b.task_begin, b.tasks, prot.residues, b.alt, b.alt_base, plain, b.out_base)[0] == 0
+    for s in range(10):
+        image = img[int(fb.out_base[2 * s]):int(fb.out_base[2 * s + 2])]
+        recs = sorted(C.fasta_records(prot, b, plain, 2 * s, 1) + C.fasta_records(prot, b, plain, 2 * s + 1, 2))
+        assert C.parse_fasta_image(image) == recs and (len(image) == 0 or image[0] == ord(">"))

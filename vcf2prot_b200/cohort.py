@@ -198,6 +198,7 @@ class Batch:
     ann_end: np.ndarray  # int64
     kept_hap: Optional[np.ndarray] = None  # the (hap, site) pairs that survived the truncation rule
     kept_site: Optional[np.ndarray] = None
+    ann_ntasks: Optional[np.ndarray] = None  # tasks per annotation row (0 for a start_lost transcript)
 
     @property
     def n_hap(self) -> int:
@@ -373,8 +374,9 @@ def build_batch(prot: Proteome, cat: Catalogue, hap: np.ndarray, site: np.ndarra
         rep = np.repeat(prot.offsets[g_tx][live], lens)
         within = np.arange(tot) - np.repeat(np.cumsum(lens) - lens, lens)
         ref = prot.residues[rep + within] if tot else np.zeros(0, np.uint8)
+    g_ntasks = np.bincount(gid, weights=cnt, minlength=n_groups).astype(np.int64)
     return Batch(task_begin, tasks, alt, alt_base, out_base, ref_base, ref, g_hap, g_tx, g_start, g_start + g_len,
-                 hap, site)
+                 hap, site, g_ntasks)
 
 
 def synth_batch(prot: Proteome, cat: Catalogue, n_hap: int, seed: int, ref_mode: str = "global",
@@ -401,7 +403,8 @@ def concat_batches(parts: List[Batch]) -> Batch:
                  np.concatenate([b.ann_tx for b in parts]), np.concatenate([b.ann_start for b in parts]),
                  np.concatenate([b.ann_end for b in parts]),
                  np.concatenate([b.kept_hap + o for b, o in zip(parts, hap_off)]),
-                 np.concatenate([b.kept_site for b in parts]))
+                 np.concatenate([b.kept_site for b in parts]),
+                 np.concatenate([b.ann_ntasks for b in parts]) if parts[0].ann_ntasks is not None else None)
 
 
 def fasta_records(prot: Proteome, batch: Batch, out: np.ndarray, h: int, hap_label: int) -> List[Tuple[str, str]]:
@@ -414,3 +417,86 @@ def fasta_records(prot: Proteome, batch: Batch, out: np.ndarray, h: int, hap_lab
         s, e = int(batch.ann_start[r]), int(batch.ann_end[r])
         recs.append(("%s_%d" % (prot.name(int(batch.ann_tx[r])), hap_label), out[o0 + s:o0 + e].tobytes().decode("ascii")))
     return recs
+
+
+def fasta_image(prot: Proteome, b: Batch) -> Batch:
+    """SURVEY 8(f) rank 1 -- FASTA record formatting on the device, with NO new kernel: the record framing of
+    `write_altered_only` (personalized_genome.rs:97,107: `>{transcript}_{1|2}\n{seq}\n`) becomes two more copy
+    segments per transcript, fed from a name tape appended to the haplotype's alt tape:
+
+        header task  (1, n_alt + 20*j,      19, record start)      ">ENST00000000042_1\n"
+        ... the transcript's own tasks, shifted ...
+        newline task (1, n_alt + 20*j + 19,  1, after the sequence)
+
+    so haplotype h's result tape IS the text of its records and `out[out_base[2s] : out_base[2s+2]]` is sample s's
+    .fasta file image (hap-1 records, then hap-2 records; the reference's own record order is HashMap-random).
+    Needs the packed layout (a file image cannot contain pad bytes) and haplotype index = 2*sample + (hap-1)."""
+    if b.ref_base is not None or b.ann_ntasks is None:
+        raise ValueError("fasta_image needs a global-ref batch built by build_batch")
+    G, n_hap, n_old = len(b.ann_hap), b.n_hap, len(b.tasks)
+    c = b.ann_ntasks
+    gstart = np.cumsum(c) - c
+    gid_of_task = np.repeat(np.arange(G), c)
+    new_idx = np.arange(n_old) + 2 * gid_of_task + 1
+    hdr_idx = gstart + 2 * np.arange(G)
+    nl_idx = gstart + c + 2 * np.arange(G) + 1
+    # j = index of the group inside its haplotype
+    hfirst = np.ones(G, bool)
+    hfirst[1:] = b.ann_hap[1:] != b.ann_hap[:-1]
+    j = np.arange(G) - np.flatnonzero(hfirst)[np.cumsum(hfirst) - 1] if G else np.zeros(0, np.int64)
+    n_alt_h = (b.alt_base[1:] - b.alt_base[:-1]).astype(np.int64)
+    tasks = np.zeros((n_old + 2 * G, 4), np.uint32)
+    tasks[new_idx] = b.tasks
+    tasks[hdr_idx, 0] = n_alt_h[b.ann_hap] + 20 * j
+    tasks[hdr_idx, 1] = 19
+    tasks[hdr_idx, 3] = 1
+    tasks[nl_idx, 0] = n_alt_h[b.ann_hap] + 20 * j + 19
+    tasks[nl_idx, 1] = 1
+    tasks[nl_idx, 3] = 1
+    # destinations: running sum of lengths inside each haplotype, in the new order
+    task_hap = np.empty(len(tasks), np.int64)
+    task_hap[new_idx] = np.repeat(b.ann_hap, c)
+    task_hap[hdr_idx] = b.ann_hap
+    task_hap[nl_idx] = b.ann_hap
+    ln = tasks[:, 1].astype(np.int64)
+    l_excl = np.cumsum(ln) - ln
+    task_begin = np.zeros(n_hap + 1, np.uint64)
+    np.cumsum(np.bincount(task_hap, minlength=n_hap), out=task_begin[1:])
+    nonempty = np.flatnonzero(task_begin[1:] > task_begin[:-1])
+    hap_l0 = np.zeros(n_hap, np.int64)
+    hap_l0[nonempty] = l_excl[task_begin[:-1].astype(np.int64)[nonempty]]
+    tasks[:, 2] = l_excl - hap_l0[task_hap]
+    out_base = np.zeros(n_hap + 1, np.uint64)
+    np.cumsum(np.bincount(task_hap, weights=ln, minlength=n_hap).astype(np.int64), out=out_base[1:])
+    # name tape: 20 bytes per transcript appended behind the haplotype's alteration bytes
+    groups_per_hap = np.bincount(b.ann_hap, minlength=n_hap)
+    alt_base = np.zeros(n_hap + 1, np.uint64)
+    np.cumsum(n_alt_h + 20 * groups_per_hap, out=alt_base[1:])
+    alt = np.zeros(int(alt_base[-1]), np.uint8)
+    old_pos = np.arange(len(b.alt)) + (alt_base[:-1].astype(np.int64) - b.alt_base[:-1].astype(np.int64))[
+        np.repeat(np.arange(n_hap), n_alt_h)]
+    alt[old_pos] = b.alt
+    names = np.zeros((G, 20), np.uint8)
+    names[:, 0] = ord(">")
+    names[:, 1:5] = np.frombuffer(b"ENST", np.uint8)
+    names[:, 5:16] = (b.ann_tx[:, None] // 10 ** np.arange(10, -1, -1)[None, :]) % 10 + ord("0")
+    names[:, 16] = ord("_")
+    names[:, 17] = ord("1") + (b.ann_hap & 1)
+    names[:, 18] = ord("\n")
+    names[:, 19] = ord("\n")
+    base = alt_base[:-1].astype(np.int64)[b.ann_hap] + n_alt_h[b.ann_hap] + 20 * j
+    alt[(base[:, None] + np.arange(20)[None, :]).reshape(-1)] = names.reshape(-1)
+    seq_start = tasks[hdr_idx, 2].astype(np.int64) + 19
+    return Batch(task_begin, tasks, alt, alt_base, out_base, None, b.ref, b.ann_hap, b.ann_tx, seq_start,
+                 seq_start + (b.ann_end - b.ann_start), b.kept_hap, b.kept_site, c + 2)
+
+
+def parse_fasta_image(image: np.ndarray) -> List[Tuple[str, str]]:
+    """`>{name}\n{seq}\n` records of a file image (sequences may be empty), sorted like the test oracle does."""
+    lines = image.tobytes().decode("ascii").split("\n")
+    assert lines[-1] == ""
+    recs = []
+    for i in range(0, len(lines) - 1, 2):
+        assert lines[i].startswith(">")
+        recs.append((lines[i][1:], lines[i + 1]))
+    return sorted(recs)
