@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="kernel tile variant (0: 4 KiB/warp, 1: 2 KiB/warp)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--ref-mode", default="replicas", choices=["replicas", "plain"])
-    ap.add_argument("--layout", default="packed", choices=["packed", "aligned"],
+    ap.add_argument("--layout", default="aligned", choices=["packed", "aligned"],
                     help="result-tape layout: packed = the reference's (res_counter); aligned = transcripts in phase "
                          "with the proteome tape (<=30 '.' pad bytes per transcript, never seen by the consumer)")
     ap.add_argument("--no-registered-ref", action="store_true",
@@ -216,6 +216,8 @@ def _ref_binary_run(prot, cat, batch, n_samples, sel, refbin, C):
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse_args()
+    if args.fasta_image:
+        args.layout = "packed"  # a file image cannot contain pad bytes
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,7 +242,8 @@ def main():
     prot, cat, batch = make_workload(args.workload, args.samples, rank, args.layout, args.fasta_image)
     t_gen = time.perf_counter() - t_gen
     n_hap, n_out, n_tasks = batch.n_hap, batch.n_residues, len(batch.tasks)
-    n_res = int(batch.tasks[:, 1].astype(np.int64).sum())  # residues produced (the aligned layout also writes '.' pads)
+    # residues produced: the aligned layout also writes '.' pads and the FASTA image also writes headers -- not counted
+    n_res = int((batch.ann_end - batch.ann_start).sum())
     b_alg = alg_bytes(batch)
 
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
