@@ -376,18 +376,16 @@ def main():
     achieved = b_alg / (copy_avg_ms * 1e-3) / 1e9
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.isfile(tpath):
-        tj = json.load(open(tpath))
+    if os.path.isfile(tpath) and not args.fasta_image:
         mode = "plain" if (args.no_registered_ref or args.ref_mode == "plain") else "replicas"
-        key = "%s_%d_v%d%s" % (args.workload, args.samples, args.variant, "_plain" if mode == "plain" else "")
-        if key in tj:
-            traffic, traffic_note = tj[key]["dram_bytes_per_launch"], "ncu --set full capture of this configuration"
-        else:  # same workload mix and reference mode at another cohort size: DRAM bytes scale with residues
-            for k2, v in tj.items():
-                if isinstance(v, dict) and k2.startswith(args.workload + "_") and v.get("mode") == mode:
-                    traffic = int(v["dram_bytes_per_launch"] * (n_res / v["residues"]))
-                    traffic_note = "scaled by residues from the ncu --set full capture %s" % k2
-                    break
+        for ent in json.load(open(tpath)).get("entries", []):
+            if (ent["workload"], ent["mode"], ent["layout"]) == (args.workload, mode, args.layout) and ent["dram_bytes_per_launch"]:
+                if ent["samples"] == args.samples:
+                    traffic, traffic_note = ent["dram_bytes_per_launch"], "ncu --set full capture of this configuration (%s)" % ent["capture"]
+                else:  # same mix, reference mode and layout at another cohort size: DRAM bytes scale with residues
+                    traffic = int(ent["dram_bytes_per_launch"] * (n_res / ent["residues"]))
+                    traffic_note = "scaled by residues from the %d-sample ncu --set full capture (%s)" % (ent["samples"], ent["capture"])
+                break
 
     value = total_res / (ms_per_step * 1e-3)  # every rank holds its own same-sized sample range (weak scaling)
     line = {
