@@ -102,7 +102,7 @@ def test_non_ascii_residues_ride_the_utf32_path(gpu_engine):
 
 
 # ---------------------------------------------------------------------------------------------- randomized parity
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("seed,n_hap,mean_res", [(1, 1, 100), (2, 7, 3000), (3, 40, 20000), (4, 300, 2000),
                                                  (5, 3, 3_000_000), (6, 64, 150_000)])
 def test_random_batches_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
@@ -118,7 +118,7 @@ def test_random_batches_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
 
 
 @pytest.mark.parametrize("mode", ["replicas", "plain"])
-@pytest.mark.parametrize("variant", [0, 2, 4, 5, 7])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5, 7, 8])
 @pytest.mark.parametrize("seed,n_hap,mean_res", [(51, 5, 400), (52, 30, 30000), (53, 4, 2_000_000)])
 def test_registered_reference_tma_path_bit_exact(gpu_engine, mode, variant, seed, n_hap, mean_res):
     """ref == NULL: tasks index the registered proteome; long reference runs are TMA bulk copies from the

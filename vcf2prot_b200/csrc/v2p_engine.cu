@@ -134,6 +134,8 @@ const CopyVariant kVariants[] = {
     {4096, 3, k_copy_tiles<4096, 4, 3, 1>},  // 5: 3 CTAs/SM (80 regs), 4 vectors in flight
     {2048, 6, k_copy_tiles<2048, 2, 6, 1>},  // 6: 2 KiB tiles, 6 CTAs/SM
     {2048, 8, k_copy_tiles<2048, 1, 8, 1>},  // 7: 2 KiB tiles, 8 CTAs/SM (32 regs)
+    {8192, 3, k_copy_tiles<8192, 2, 3, 1>},  // 8: 8 KiB tiles, 3 CTAs/SM (80 regs)
+    {8192, 2, k_copy_tiles<8192, 4, 2, 1>},  // 9: 8 KiB tiles, 2 CTAs/SM
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
@@ -143,7 +145,7 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     const CopyVariant& cv = kVariants[e->variant];
     const int T = cv.tile;
     kp.tile_bytes = (uint32_t)T;
-    kp.tile_shift = T == 4096 ? 12u : 11u;
+    kp.tile_shift = T == 8192 ? 13u : T == 4096 ? 12u : 11u;
     kp.n_tiles = (kp.n_out + T - 1) / T;
     if (kp.n_tasks >= 0xFFFFFFFEull) return fail(e, V2P_ERR_INVALID_ARG, "more than 2^32-2 tasks in one launch");
     int rc;

@@ -358,9 +358,10 @@ template <int TILE, int G, int MINB, int FLAGS>
 __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) {
     constexpr bool kHints = (FLAGS & 1) != 0;
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
-    constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4 or 8)
+    constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4, 8 or 16)
+    constexpr int LWW = LW / 4;     // ... as 32-bit words
     constexpr int STRIDE = TILE + NV + 16 + 576;  // tile | lead[] | mbarrier | staged tasks (32 x 16 B) + bases (5 x 8 B)
-    static_assert(LW == 4 || LW == 8, "TILE must be 2048 or 4096");
+    static_assert(LW == 4 || LW == 8 || LW == 16, "TILE must be 2048, 4096 or 8192");
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* const tile = smem + warp * STRIDE;
@@ -395,19 +396,20 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             hp = __ldg(p.tile_hap + kk);
         }
     };
-    auto first_task = [&](uint32_t lo) -> uint64_t {
-        uint64_t t = min((uint64_t)lo, p.n_tasks);
-        return t > 0 ? t - 1 : 0;  // the task before may extend into the tile
+    const uint32_t n_tasks32 = (uint32_t)p.n_tasks;  // < 2^32 - 1 (checked by the host)
+    auto first_task = [&](uint32_t lo) -> uint32_t {
+        const uint32_t t = min(lo, n_tasks32);
+        return t > 0u ? t - 1u : 0u;  // the task before may extend into the tile
     };
     // stage(): cp.async the first 32 tasks of a tile and its haplotype's five bases into this warp's staging area
+    // lane j < 5 fetches base j of a haplotype: task_begin[h], task_begin[h+1], out_base[h], alt_base[h], ref_base[h]
+    const uint64_t* const base_arr = lane < 2 ? p.task_begin : lane == 2 ? p.out_base : lane == 3 ? p.alt_base : p.ref_base;
+    const bool base_on = lane < 5 && base_arr != nullptr;
+    const uint32_t base_add = lane == 1 ? 1u : 0u;
     auto stage = [&](uint32_t lo, uint32_t hi, uint32_t hp) {
-        const uint64_t tr = first_task(lo) + lane;
-        if (tr < min((uint64_t)hi, p.n_tasks)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
-        if (lane == 0) cp_async8(st_bases + 0, p.task_begin + hp);
-        if (lane == 1) cp_async8(st_bases + 1, p.task_begin + hp + 1);
-        if (lane == 2) cp_async8(st_bases + 2, p.out_base + hp);
-        if (lane == 3) cp_async8(st_bases + 3, p.alt_base + hp);
-        if (lane == 4 && p.ref_base) cp_async8(st_bases + 4, p.ref_base + hp);
+        const uint32_t tr = first_task(lo) + lane;
+        if (tr < min(hi, n_tasks32)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
+        if (base_on) cp_async8(st_bases + lane, base_arr + hp + base_add);
         cp_async_commit();
     };
     uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
@@ -419,8 +421,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         const uint64_t tile_start = k * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
-        const uint64_t t_lo = first_task(c_lo);
-        const uint64_t t_hi = min((uint64_t)c_hi, p.n_tasks);
+        const uint32_t t_lo = first_task(c_lo);
+        const uint32_t t_hi = min(c_hi, n_tasks32);
         // this tile's tasks and bases were staged while the previous tile was being assembled
         cp_async_wait0();
         __syncwarp();
@@ -454,17 +456,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 }
             }
         }
-        if (LW == 4)
-            reinterpret_cast<uint32_t*>(lead)[lane] = 0u;
-        else
-            reinterpret_cast<uint2*>(lead)[lane] = make_uint2(0u, 0u);
+#pragma unroll
+        for (int w = 0; w < LWW; ++w) reinterpret_cast<uint32_t*>(lead)[lane * LWW + w] = 0u;
         if (p.tma_mode) fence_async_smem();  // the prefill must be ordered before TMA loads land in the same bytes
         __syncwarp();
         bool tma_used = false;
 
-        for (uint64_t tb = t_lo; tb < t_hi; tb += 32) {
+        for (uint32_t tb = t_lo; tb < t_hi; tb += 32) {
             // ---- A: one lane per task: partial head/tail vectors, and the start of its fully covered vector range
-            const uint64_t tr = tb + lane;
+            const uint32_t tr = tb + lane;
             long long p0 = 0;   // source address of tile byte 0 for this task (may point before the segment)
             uint32_t v1 = 0;    // end (exclusive) of the fully covered vector range, in vectors
             uint32_t tma_bytes = 0, tma_dst = 0;  // fully covered range served by a TMA bulk copy from a replica
@@ -548,20 +548,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
 
             // ---- B: owner of every vector = last task (in this batch) whose covered range started at or before it
             {
-                uint32_t w0, w1 = 0;
-                if (LW == 4) {
-                    w0 = reinterpret_cast<uint32_t*>(lead)[lane];
-                } else {
-                    uint2 t2 = reinterpret_cast<uint2*>(lead)[lane];
-                    w0 = t2.x;
-                    w1 = t2.y;
-                }
-                w0 = bytescan_max(w0);
-                uint32_t top = w0 >> 24;
-                if (LW == 8) {
-                    w1 = bytescan_max(w1);
-                    w1 = __vmaxu4(w1, top * 0x01010101u);
-                    top = w1 >> 24;
+                uint32_t wv[LWW];
+                uint32_t top = 0;
+#pragma unroll
+                for (int w = 0; w < LWW; ++w) {  // inclusive max-scan over this lane's LW owner bytes
+                    wv[w] = bytescan_max(reinterpret_cast<uint32_t*>(lead)[lane * LWW + w]);
+                    wv[w] = __vmaxu4(wv[w], top * 0x01010101u);
+                    top = wv[w] >> 24;
                 }
                 uint32_t incl = top;
 #pragma unroll
@@ -572,13 +565,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
                 if (lane == 0) excl = 0;
                 const uint32_t bc = excl * 0x01010101u;
-                w0 = __vmaxu4(w0, bc);
-                if (LW == 4) {
-                    reinterpret_cast<uint32_t*>(lead)[lane] = w0;
-                } else {
-                    w1 = __vmaxu4(w1, bc);
-                    reinterpret_cast<uint2*>(lead)[lane] = make_uint2(w0, w1);
-                }
+#pragma unroll
+                for (int w = 0; w < LWW; ++w) reinterpret_cast<uint32_t*>(lead)[lane * LWW + w] = __vmaxu4(wv[w], bc);
             }
             __syncwarp();
 
@@ -613,11 +601,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 }
             }
             __syncwarp();
-            if (tb + 32 < t_hi) {  // another batch follows: reset lead[]
-                if (LW == 4)
-                    reinterpret_cast<uint32_t*>(lead)[lane] = 0u;
-                else
-                    reinterpret_cast<uint2*>(lead)[lane] = make_uint2(0u, 0u);
+            if (tb + 32u < t_hi) {  // another batch follows: reset lead[]
+#pragma unroll
+                for (int w = 0; w < LWW; ++w) reinterpret_cast<uint32_t*>(lead)[lane * LWW + w] = 0u;
                 __syncwarp();
             }
         }
