@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-haps", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", type=int, default=0, help="kernel tile variant (0: 4 KiB/warp, 1: 2 KiB/warp)")
+    ap.add_argument("--variant", type=int, default=-1, help="copy-kernel variant (-1: engine's automatic choice)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--ref-mode", default="replicas", choices=["replicas", "plain"])
     ap.add_argument("--layout", default="aligned", choices=["packed", "aligned"],

@@ -153,7 +153,8 @@ int v2p_event_wait(v2p_engine* e, v2p_event* ev, v2p_result* res); /* also relea
 
 /* Launch-level introspection for bench.py: kernels launched by this context since creation. */
 uint64_t v2p_kernel_launch_count(v2p_engine* e);
-/* Kernel tunables (tile bytes per warp, CTAs per SM); 0 keeps the default.  For profiling sweeps only. */
+/* Kernel tunables for profiling sweeps: copy-kernel variant (-1 = automatic choice, the default) and CTAs per SM
+ * (0 = the variant's own). */
 int v2p_engine_set_tuning(v2p_engine* e, int variant, int ctas_per_sm);
 /* Run on a caller-owned CUDA stream (a cudaStream_t / CUstream handle, e.g. torch's current stream) so the
  * caller's own events bracket the kernels; NULL restores the engine's private non-blocking stream. */

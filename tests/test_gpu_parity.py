@@ -114,7 +114,7 @@ def test_random_batches_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
         assert st == 0
         assert out.shape == want.shape and np.array_equal(out, want)
     finally:
-        gpu_engine.set_tuning(0, 0)
+        gpu_engine.set_tuning(-1, 0)
 
 
 @pytest.mark.parametrize("mode", ["replicas", "plain"])
@@ -134,7 +134,7 @@ def test_registered_reference_tma_path_bit_exact(gpu_engine, mode, variant, seed
         out2, _ = gpu_batch(gpu_engine, b)
         assert np.array_equal(out2, want)
     finally:
-        gpu_engine.set_tuning(0, 0)
+        gpu_engine.set_tuning(-1, 0)
 
 
 def test_registered_reference_cohort_and_errors(gpu_engine):

@@ -65,7 +65,7 @@ struct v2p_engine {
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
-    int variant = 0;
+    int variant = -1;     // -1 = auto: 8 KiB tiles on the TMA path, 4 KiB tiles on the register path
     int ctas_per_sm = 0;  // 0 = the variant's default
     Scratch sc;           // for e->stream
     Slot slots[kSlots];
@@ -138,11 +138,12 @@ const CopyVariant kVariants[] = {
     {8192, 2, k_copy_tiles<8192, 4, 2, 1>},  // 9: 8 KiB tiles, 2 CTAs/SM
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+constexpr int kAutoTma = 8, kAutoPlain = 0;  // measured best per path (profiles/r1)
 
 // plan + copy on stream s.  kp.{lb,tile_hap,status,n_tiles,tile_bytes} are filled here.
 int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop,
                  DevStatus* h_status, bool init_status, cudaEvent_t ev_copy) {
-    const CopyVariant& cv = kVariants[e->variant];
+    const CopyVariant& cv = kVariants[e->variant >= 0 ? e->variant : (kp.tma_mode ? kAutoTma : kAutoPlain)];
     const int T = cv.tile;
     kp.tile_bytes = (uint32_t)T;
     kp.tile_shift = T == 8192 ? 13u : T == 4096 ? 12u : 11u;
@@ -386,7 +387,7 @@ int v2p_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? V2P_OK 
 uint64_t v2p_kernel_launch_count(v2p_engine* e) { return e ? e->launches : 0; }
 
 int v2p_engine_set_tuning(v2p_engine* e, int variant, int ctas_per_sm) {
-    if (!e || variant < 0 || variant >= kNumVariants || ctas_per_sm < 0 || ctas_per_sm > 32) return V2P_ERR_INVALID_ARG;
+    if (!e || variant < -1 || variant >= kNumVariants || ctas_per_sm < 0 || ctas_per_sm > 32) return V2P_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);
     e->variant = variant;
     e->ctas_per_sm = ctas_per_sm;

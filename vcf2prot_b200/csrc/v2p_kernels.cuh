@@ -165,9 +165,12 @@ __global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
             if (tr >= p.n_tasks) continue;
             const uint4 pr = prv[u];
             const uint64_t t = tr + p.task_origin;
+            // bases of the owning haplotype: the CTA's first one (staged), else the next one, else a search
             uint64_t h = sh[0], tb0 = sh[1], o0 = sh[3], n_res = sh[4] - sh[3], n_alt = sh[5], n_ref = sh[6];
-            if (t >= sh[2]) {  // not the CTA's first haplotype
-                h = upper_bound_u64(p.task_begin, h + 1, p.n_hap + 1, t) - 1;
+            if (t >= sh[2]) {
+                h = h + 1;
+                if (h + 1 > p.n_hap || t >= __ldg(p.task_begin + h + 1) || t < __ldg(p.task_begin + h))
+                    h = upper_bound_u64(p.task_begin, sh[0] + 1, p.n_hap + 1, t) - 1;
                 tb0 = __ldg(p.task_begin + h);
                 o0 = __ldg(p.out_base + h);
                 n_res = __ldg(p.out_base + h + 1) - o0;
@@ -175,40 +178,38 @@ __global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
                 n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
             }
             const uint32_t src = raw[u].x, len = raw[u].y, dst = raw[u].z, stream = raw[u].w;
-            const unsigned long long key = (unsigned long long)tr << 8;
-            if (stream > 1u) {  // haplotype_instruction.rs:154
-                atomicMin(&p.status->err_key, key | V2P_ERR_BAD_STREAM);
+            // every reference panic, one predicate each (error paths are cold)
+            const bool bad_stream = stream > 1u;                                              // haplotype_instruction.rs:154
+            const bool bad_res = (uint64_t)dst + len > n_res;                                 // task.rs:44/48 (result slice)
+            const bool bad_src = (uint64_t)src + len > (stream == 0 ? n_ref : n_alt);         // task.rs:44/48 (source slice)
+            if (bad_stream | bad_res | bad_src) {
+                const unsigned long long key = (unsigned long long)tr << 8;
+                atomicMin(&p.status->err_key,
+                          key | (bad_stream ? V2P_ERR_BAD_STREAM : bad_res ? V2P_ERR_RES_OOB : V2P_ERR_SRC_OOB));
                 continue;
             }
-            if ((uint64_t)dst + len > n_res) {  // task.rs:44/48 (result slice)
-                atomicMin(&p.status->err_key, key | V2P_ERR_RES_OOB);
-                continue;
-            }
-            if ((uint64_t)src + len > (stream == 0 ? n_ref : n_alt)) {  // task.rs:44/48 (source slice)
-                atomicMin(&p.status->err_key, key | V2P_ERR_SRC_OOB);
-                continue;
-            }
-            const uint64_t g = o0 - p.out_origin + dst;  // global (launch-relative) output byte of this task
-            uint64_t k_lo = 0;
-            if (tr > 0) {
-                uint64_t gp;
-                if (t > tb0) {  // same haplotype: gir.rs:208 contiguity + sortedness
-                    const uint64_t pend = (uint64_t)pr.z + pr.y;
-                    if (dst < pend) atomicExch(&p.status->unsorted, 1u);
-                    if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
-                    gp = o0 - p.out_origin + pr.z;
-                } else {
-                    uint64_t hp = h;
-                    while (hp > 0 && __ldg(p.task_begin + hp) > t - 1) --hp;
-                    gp = __ldg(p.out_base + hp) - p.out_origin + pr.z;
+            const uint64_t orel = o0 - p.out_origin;               // launch-relative start of the haplotype's tape
+            const uint64_t kt = (orel + dst) >> p.tile_shift;      // tile in which this task starts
+            uint64_t kprev;                                        // tile in which the previous task starts (+1 = first lb to write)
+            if (t > tb0) {  // previous task is in the same haplotype: gir.rs:208 contiguity + sortedness
+                const uint64_t pend = (uint64_t)pr.z + pr.y;
+                if (dst < pend) {
+                    atomicExch(&p.status->unsorted, 1u);
+                    continue;
                 }
-                if (gp > g) continue;  // cannot happen across haplotypes with monotone out_base; unsorted inside one
-                k_lo = (gp >> p.tile_shift) + 1;
+                if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
+                kprev = (orel + pr.z) >> p.tile_shift;
+            } else if (tr == 0) {
+                kprev = ~0ull;  // so that lb[0..kt] = 0
+            } else {  // first task of a haplotype: the previous task belongs to the last non-empty haplotype before
+                uint64_t hp = h;
+                while (hp > 0 && __ldg(p.task_begin + hp) > t - 1) --hp;
+                kprev = (__ldg(p.out_base + hp) - p.out_origin + pr.z) >> p.tile_shift;
             }
-            uint64_t k_hi = g >> p.tile_shift;
-            if (k_hi > p.n_tiles) k_hi = p.n_tiles;
-            if (k_lo <= k_hi)  // only tasks that start a new tile (or follow a gap of whole tiles) write lb[]
-                for (uint64_t k = k_lo; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
+            if (kt != kprev) {  // only tasks that start a new tile (or follow whole tiles of '.') write lb[]
+                const uint64_t k_hi = min(kt, p.n_tiles);
+                for (uint64_t k = kprev + 1; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
+            }
         }
     }
 }

@@ -113,7 +113,7 @@ class GpuEngine:
     def launch_count(self) -> int:
         return int(self._lib.v2p_kernel_launch_count(self._h))
 
-    def set_tuning(self, variant: int = 0, ctas_per_sm: int = 0):
+    def set_tuning(self, variant: int = -1, ctas_per_sm: int = 0):
         st = self._lib.v2p_engine_set_tuning(self._h, variant, ctas_per_sm)
         if st:
             raise EngineError(st, "set_tuning")
