@@ -148,6 +148,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
+def oracle_check_range(batch, prot, h0: int, h1: int, gpu_bytes: np.ndarray) -> bool:
+    """Oracle (1-byte port) on haplotypes [h0,h1) of the cohort vs the GPU's bytes for the same range."""
+    from oracle import cengine
+
+    t0, t1 = int(batch.task_begin[h0]), int(batch.task_begin[h1])
+    a0, a1 = int(batch.alt_base[h0]), int(batch.alt_base[h1])
+    o0, o1 = int(batch.out_base[h0]), int(batch.out_base[h1])
+    out = np.zeros(o1 - o0, np.uint8)
+    rebase = lambda a, x: (a[h0:h1 + 1] - np.uint64(x)).astype(np.uint64)
+    st, _, _ = cengine.batch_execute(rebase(batch.task_begin, t0), batch.tasks[t0:t1], prot.residues, batch.alt[a0:a1],
+                                     rebase(batch.alt_base, a0), out, rebase(batch.out_base, o0), threads=os.cpu_count() or 1)
+    return st == 0 and bool(np.array_equal(out, gpu_bytes))
+
+
 def cpu_engine_rate(batch, prot, n_haps: int, seconds: float, threads: int, width: int, check_against=None):
     """Reference-equivalent CPU engine (oracle port) on the first n_haps haplotypes; returns residues/s."""
     from oracle import cengine
@@ -356,7 +370,12 @@ def main():
         gpu_sample = d_out[:o1].cpu().numpy()
         rate32, el, reps, nh, nres, ok = cpu_engine_rate(batch, prot, nh, args.cpu_seconds, threads, 4, gpu_sample)
         rate8, _, _, _, _, ok8 = cpu_engine_rate(batch, prot, nh, min(3.0, args.cpu_seconds), threads, 1, gpu_sample)
-        parity = {"checked_haplotypes": nh, "residues": nres, "gpu_equals_oracle": bool(ok and ok8),
+        # the tail of the cohort sits beyond 4 GiB of result tape: check those offsets against the oracle too
+        nt = min(16, n_hap)
+        t_o0, t_o1 = int(batch.out_base[n_hap - nt]), int(batch.out_base[n_hap])
+        tail_ok = oracle_check_range(batch, prot, n_hap - nt, n_hap, d_out[t_o0:t_o1].cpu().numpy())
+        parity = {"checked_haplotypes": nh + nt, "residues": nres + (t_o1 - t_o0), "gpu_equals_oracle": bool(ok and ok8 and tail_ok),
+                  "head_haplotypes": nh, "tail_haplotypes": nt, "tail_result_tape_offset": t_o0,
                   "e2e_equals_device_path": e2e_matches_device}
         cpu = {"value": rate32, "unit": "residues/s", "cores": threads, "kind": "port",
                "sample": "first %d haplotypes (%d residues) of the same cohort, UTF-32 tapes like the reference "

@@ -74,6 +74,10 @@ def test_aligned_layout_yields_identical_records(small):
             starts = b.ann_start[b.ann_end > b.ann_start]
             tx = b.ann_tx[b.ann_end > b.ann_start]
             assert ((starts - prot.offsets[tx]) % 16 == 0).all() and (b.out_base % 16 == 0).all()
+            # long alteration payloads sit in phase with their destination, every tape base is 16-byte aligned
+            longt = (b.tasks[:, 3] == 1) & (b.tasks[:, 1] >= 32)
+            assert longt.any() and ((b.tasks[longt, 0].astype(np.int64) - b.tasks[longt, 2]) % 16 == 0).all()
+            assert (b.alt_base % 16 == 0).all()
             # sorted, non-overlapping, inside the tape (what the engine's fast path needs)
             for h in range(12):
                 t = b.tasks[int(b.task_begin[h]):int(b.task_begin[h + 1])].astype(np.int64)

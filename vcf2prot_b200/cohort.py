@@ -349,15 +349,40 @@ def build_batch(prot: Proteome, cat: Catalogue, hap: np.ndarray, site: np.ndarra
     out_base = np.zeros(n_hap + 1, np.uint64)
     np.cumsum(res_per_hap, out=out_base[1:])
 
-    alt_per_hap = np.bincount(hap, weights=acontrib, minlength=n_hap).astype(np.int64)
-    alt_base = np.zeros(n_hap + 1, np.uint64)
-    np.cumsum(alt_per_hap, out=alt_base[1:])
-    # alt bytes: ragged gather from the payload pool (M twice)
+    # ---- alt tape.  packed: payloads in site order (the reference's alt_stream).  aligned: short payloads packed first,
+    #      then every payload of >= 32 bytes (frameshift / stop-lost tails, long insertions) in a 16-byte-multiple slot
+    #      at an offset congruent (mod 16) to its destination, so its full vectors are direct TMA bulk copies.
     tot = int(acontrib.sum())
     rep = np.repeat(np.arange(n), acontrib)
     within = np.arange(tot) - np.repeat(a_excl, acontrib)
     src = doff[rep] + np.where(cls[rep] == CLS_M, 0, within)
-    alt = cat.pool[src] if tot else np.zeros(0, np.uint8)
+    if layout == "aligned":
+        is_long = has_mut & (acontrib >= 32)
+        mut_dst = np.zeros(n, np.int64)
+        mut_dst[has_mut] = tasks[(first_slot + has_base)[has_mut], 2]
+        c16 = mut_dst & 15
+        short_c = np.where(is_long, 0, acontrib)
+        sh_excl = np.cumsum(short_c) - short_c
+        hidx = np.flatnonzero(hstart)
+        hof = np.cumsum(hstart) - 1  # index of each site's haplotype among the non-empty ones
+        sh_rel = sh_excl - sh_excl[hidx][hof]
+        short_tot = np.bincount(hap, weights=short_c, minlength=n_hap).astype(np.int64)
+        slot = np.where(is_long, (c16 + acontrib + 15) & ~15, 0)
+        sl_excl = np.cumsum(slot) - slot
+        sl_rel = sl_excl - sl_excl[hidx][hof]
+        a_new = np.where(is_long, ((short_tot[hap] + 15) & ~15) + sl_rel + c16, sh_rel)
+        alt_per_hap = ((short_tot + 15) & ~15) + np.bincount(hap, weights=slot, minlength=n_hap).astype(np.int64)
+        tasks[(first_slot + has_base)[has_mut], 0] = (a_new + (cls == CLS_M))[has_mut]
+        alt_base = np.zeros(n_hap + 1, np.uint64)
+        np.cumsum(alt_per_hap, out=alt_base[1:])
+        alt = np.full(int(alt_base[-1]), ord("."), np.uint8)
+        if tot:
+            alt[alt_base[:-1].astype(np.int64)[hap[rep]] + a_new[rep] + within] = cat.pool[src]
+    else:
+        alt_per_hap = np.bincount(hap, weights=acontrib, minlength=n_hap).astype(np.int64)
+        alt_base = np.zeros(n_hap + 1, np.uint64)
+        np.cumsum(alt_per_hap, out=alt_base[1:])
+        alt = cat.pool[src] if tot else np.zeros(0, np.uint8)
 
     # ---- annotations: (start,end) of every altered transcript on its haplotype's result tape = (g_start, +g_len)
 

@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         }
 #pragma unroll
         for (int w = 0; w < LWW; ++w) reinterpret_cast<uint32_t*>(lead)[lane * LWW + w] = 0u;
-        if (p.tma_mode) fence_async_smem();  // the prefill must be ordered before TMA loads land in the same bytes
+        fence_async_smem();  // the prefill must be ordered before TMA loads land in the same bytes
         __syncwarp();
         bool tma_used = false;
 
@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             uint32_t v1 = 0;    // end (exclusive) of the fully covered vector range, in vectors
             uint32_t tma_bytes = 0, tma_dst = 0;  // fully covered range served by a TMA bulk copy from a replica
             const uint8_t* tma_src = nullptr;
+            bool tma_alt = false;  // alteration payloads are read once (evict_first), reference runs are re-read (evict_last)
             bool has_lead = false, onT = false, onH = false, onM = false;
             int pvh = 0, pvt = 0, pa1 = 0, pb2 = 16;
             if (tr < t_hi) {
@@ -491,7 +492,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     const int vh = s >> 4, vt = (e - 1) >> 4;
                     const int v0b = (s + 15) & ~15, v1b = e & ~15;
                     if (v1b > v0b) {
-                        if (p.tma_mode && raw.w == 0u) {
+                        if ((p0 & 15) == 0) {
+                            // source and destination are in phase: a plain aligned TMA bulk copy straight from the
+                            // source tape (any stream; this is what the aligned producer layout arranges)
+                            tma_src = reinterpret_cast<const uint8_t*>(p0 + v0b);
+                            tma_alt = raw.w != 0u;
+                            tma_dst = (uint32_t)v0b;
+                            tma_bytes = (uint32_t)(v1b - v0b);
+                        } else if (p.tma_mode && raw.w == 0u) {
                             const long long q = p0 - (long long)p.ref;  // ref offset of tile byte 0
                             // replica r = (-q) mod 16 holds this run at the same 16-byte phase as the output
                             const uint32_t r = (uint32_t)(-q) & 15u;
@@ -518,14 +526,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 }
             }
             // TMA bulk loads first (they take the longest), the register-path pieces overlap with them
-            if (p.tma_mode) {  // warp-uniform
+            {
                 const uint32_t total = __reduce_add_sync(0xffffffffu, tma_bytes);
                 if (total) {
                     if (lane == 0) mbar_expect_tx(mbar, total);
                     __syncwarp();
                     if (tma_bytes) {
                         if (kHints)
-                            bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar, pol_keep);
+                            bulk_load_g2s(tile + tma_dst, tma_src, tma_bytes, mbar, tma_alt ? pol_stream : pol_keep);
                         else
                             bulk_load_g2s_nohint(tile + tma_dst, tma_src, tma_bytes, mbar);
                     }
