@@ -1,0 +1,215 @@
+// v2p_host.hpp -- C++17 host-side mirror of the reference's engine interface, over the C ABI (v2p_engine.h).
+//
+// The reference's host is Rust; its toolchain is not available in this image, so this header is what the host side
+// above the boundary looks like in a compiled language, with the reference's own names and argument meaning:
+//
+//   v2p::Engine / Engine::from_str     src/data_structures/InternalRep/engines.rs:15-30
+//   v2p::Task                          .../task.rs:2-19                 {exe_code, start_pos, length, start_pos_res}
+//   v2p::GIR  / GIR::execute(Engine)   .../gir.rs:15-46, :197-241       consumes the representation, returns
+//                                                                       (res_array, annotation); GPU arm -> C ABI
+//   v2p::HaplotypeBatch                .../haplotype_instruction.rs:75-158  get_g_rep's concat + re-index loop
+//                                      (update_task :140-158), generalised to MANY haplotypes per launch and to the
+//                                      B200 layouts (shared proteome tape, phase-aligned result slots)
+//
+// Errors: where the reference panics (task.rs:44/48, haplotype_instruction.rs:154, gir.rs:223) this throws
+// v2p::EngineError carrying the ABI status and the offending haplotype/task.  ST and MT are the caller's CPU engines
+// (gir.rs:201-235): GIR::execute refuses them, it never computes on the host.
+#ifndef V2P_HOST_HPP
+#define V2P_HOST_HPP
+
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "v2p_engine.h"
+
+namespace v2p {
+
+struct EngineError : std::runtime_error {
+    int status;
+    uint64_t bad_hap, bad_task;
+    EngineError(int st, const std::string& msg, uint64_t h = 0, uint64_t t = 0)
+        : std::runtime_error(msg + " (status " + std::to_string(st) + ")"), status(st), bad_hap(h), bad_task(t) {}
+};
+
+// engines.rs:15
+enum class Engine { ST = V2P_ENGINE_ST, MT = V2P_ENGINE_MT, GPU = V2P_ENGINE_GPU };
+
+// engines.rs:17-30 -- Err(format!("{} is not a supported engine", name)) becomes an exception
+inline Engine engine_from_str(const std::string& name) {
+    int kind = -1;
+    if (v2p_engine_from_str(name.c_str(), &kind) != V2P_OK) throw EngineError(V2P_ERR_BAD_ENGINE, name + " is not a supported engine");
+    return static_cast<Engine>(kind);
+}
+
+// task.rs:2-9
+struct Task {
+    uint8_t exe_code;
+    uint64_t start_pos, length, start_pos_res;
+    Task(uint8_t c, uint64_t sp, uint64_t len, uint64_t spr) : exe_code(c), start_pos(sp), length(len), start_pos_res(spr) {}
+    uint64_t get_length() const { return length; }
+    uint64_t get_start_pos_res() const { return start_pos_res; }
+    uint8_t get_stream() const { return exe_code; }
+    void shift_start_pos_stream(uint64_t n) { start_pos += n; }  // task.rs:103-107
+    void shift_start_pos_res(uint64_t n) { start_pos_res += n; }  // task.rs:108-112
+};
+
+using Annotation = std::map<std::string, std::pair<uint64_t, uint64_t>>;  // HashMap<String,(usize,usize)>
+
+// One engine context (one per GPU); RAII over v2p_engine_create / v2p_engine_destroy.
+class Context {
+public:
+    explicit Context(int cuda_device = 0) {
+        if (v2p_engine_create(cuda_device, &e_) != V2P_OK)
+            throw EngineError(V2P_ERR_CUDA, "no usable CUDA device: the GPU engine has no CPU fallback");
+    }
+    ~Context() { v2p_engine_destroy(e_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    v2p_engine* get() const { return e_; }
+    std::string last_error() const { return v2p_last_error(e_); }
+    void set_reference(const std::string& proteome_tape, uint32_t flags = 0) {
+        int st = v2p_engine_set_reference(e_, reinterpret_cast<const uint8_t*>(proteome_tape.data()), proteome_tape.size(), flags);
+        if (st != V2P_OK) throw EngineError(st, last_error());
+    }
+
+private:
+    v2p_engine* e_ = nullptr;
+};
+
+// gir.rs:15-23.  Tapes are UTF-32 (Rust `char`) like the reference's Vec<char>.
+class GIR {
+public:
+    GIR(std::vector<Task> g_rep, Annotation annotation, std::u32string alt_stream, std::u32string ref_stream,
+        std::u32string res_array)
+        : g_rep_(std::move(g_rep)), annotation_(std::move(annotation)), alt_(std::move(alt_stream)),
+          ref_(std::move(ref_stream)), res_(std::move(res_array)) {}
+    const std::vector<Task>& get_tasks() const { return g_rep_; }
+    const Annotation& get_annotation() const { return annotation_; }
+    uint64_t get_results_max() const {  // gir.rs:157-168
+        uint64_t m = 0;
+        for (const auto& kv : annotation_) m = kv.second.second > m ? kv.second.second : m;
+        return m;
+    }
+    // gir.rs:197-241: consumes self; `validate` is the DEBUG_GPU / DEBUG_CPU_EXEC contiguity check (gir.rs:203-229)
+    std::pair<std::u32string, Annotation> execute(Engine engine, Context& ctx, bool validate = false) && {
+        if (engine != Engine::GPU)
+            throw EngineError(V2P_ERR_NOT_GPU_ENGINE, "ST/MT engines are the caller's CPU path (gir.rs:201-235)");
+        // gir.rs:283-299 consume_and_produce_produce_content: four usize arrays + three char tapes
+        const size_t n = g_rep_.size();
+        std::vector<uint64_t> code(n), sp(n), len(n), spr(n);
+        for (size_t i = 0; i < n; ++i) {
+            code[i] = g_rep_[i].exe_code, sp[i] = g_rep_[i].start_pos, len[i] = g_rep_[i].length, spr[i] = g_rep_[i].start_pos_res;
+        }
+        uint64_t bad = 0;
+        int st = v2p_gir_execute(ctx.get(), V2P_ENGINE_GPU, n, code.data(), sp.data(), len.data(), spr.data(),
+                                 reinterpret_cast<const uint32_t*>(ref_.data()), ref_.size(),
+                                 reinterpret_cast<const uint32_t*>(alt_.data()), alt_.size(),
+                                 reinterpret_cast<uint32_t*>(&res_[0]), res_.size(), validate ? V2P_FLAG_VALIDATE : 0u, &bad);
+        if (st != V2P_OK) throw EngineError(st, ctx.last_error(), 0, bad);
+        return {std::move(res_), std::move(annotation_)};
+    }
+
+private:
+    std::vector<Task> g_rep_;
+    Annotation annotation_;
+    std::u32string alt_, ref_, res_;
+};
+
+// Many haplotypes per launch: HaplotypeInstruction::get_g_rep's concat loop (haplotype_instruction.rs:94-133),
+// writing straight into the packed batch layout of v2p_execute_batch.
+class HaplotypeBatch {
+public:
+    enum class RefLayout { PerHaplotype, SharedProteome };  // haplotype_instruction.rs:118  vs  registered tape
+    explicit HaplotypeBatch(RefLayout layout = RefLayout::PerHaplotype, bool aligned_slots = false)
+        : layout_(layout), aligned_(aligned_slots) {
+        if (aligned_ && layout_ != RefLayout::SharedProteome) throw std::invalid_argument("aligned slots need the shared proteome tape");
+    }
+
+    void begin_haplotype() {  // ref_counter = alt_counter = res_counter = 0  (haplotype_instruction.rs:91)
+        task_begin_.push_back(tasks_.size());
+        alt_base_.push_back(alt_.size());
+        out_base_.push_back(out_size_);
+        ref_base_.push_back(ref_.size());
+        annotations_.emplace_back();
+        ref_counter_ = alt_counter_ = res_counter_ = 0;
+    }
+
+    // One transcript's GIR (TranscriptInstruction::get_g_rep output): tasks relative to the transcript, its alt
+    // stream, its reference sequence (PerHaplotype) or its offset in the registered proteome (SharedProteome),
+    // and the size of its result array (compute_expected_results_array_size).
+    void add_transcript(const std::string& name, const std::vector<Task>& tasks, const std::string& alt_stream,
+                        const std::string& ref_stream, uint64_t proteome_offset, uint64_t res_len) {
+        if (task_begin_.empty()) throw std::logic_error("begin_haplotype() first");
+        uint64_t res_start = res_counter_, slot = res_len;
+        if (aligned_ && res_len) {  // result in phase with the proteome tape inside a 16-byte-multiple slot
+            const uint64_t c = proteome_offset & 15u;  // res_counter_ is a multiple of 16 here by construction
+            res_start = res_counter_ + c;
+            slot = (c + res_len + 15u) & ~uint64_t(15);
+        }
+        const uint64_t ref_shift = layout_ == RefLayout::PerHaplotype ? ref_counter_ : proteome_offset;
+        for (const Task& t : tasks) {  // update_task, haplotype_instruction.rs:140-158
+            uint64_t src;
+            if (t.exe_code == 0) src = t.start_pos + ref_shift;
+            else if (t.exe_code == 1) src = t.start_pos + alt_counter_;
+            else throw EngineError(V2P_ERR_BAD_STREAM, "Unsupported Stream code", task_begin_.size() - 1, tasks_.size() - task_begin_.back());
+            const uint64_t dst = t.start_pos_res + res_start;
+            if (src > 0xFFFFFFFFull || dst > 0xFFFFFFFFull || t.length > 0xFFFFFFFFull)
+                throw std::length_error("haplotype tape beyond 4 GiB");
+            tasks_.push_back(v2p_task16{(uint32_t)src, (uint32_t)t.length, (uint32_t)dst, (uint32_t)t.exe_code});
+        }
+        alt_.append(alt_stream);
+        if (layout_ == RefLayout::PerHaplotype) ref_.append(ref_stream);
+        annotations_.back()[name] = {res_start, res_start + res_len};  // haplotype_instruction.rs:120-125
+        ref_counter_ += ref_stream.size();
+        alt_counter_ += alt_stream.size();
+        res_counter_ += slot;
+        out_size_ += slot;
+    }
+
+    size_t n_haplotypes() const { return task_begin_.size(); }
+    const std::vector<v2p_task16>& tasks() const { return tasks_; }
+    const Annotation& annotation(size_t h) const { return annotations_[h]; }
+
+    // Executes every haplotype (n_hap x GIR::execute in one launch group); returns the concatenated result tapes.
+    // result(h) = out.substr(out_base(h), out_base(h+1)-out_base(h)); slice it by annotation(h) like SequenceTape::get_seq.
+    std::string execute(Engine engine, Context& ctx, bool validate = false) {
+        if (engine != Engine::GPU)
+            throw EngineError(V2P_ERR_NOT_GPU_ENGINE, "ST/MT engines are the caller's CPU path (gir.rs:201-235)");
+        const size_t H = task_begin_.size();
+        std::vector<uint64_t> tb(task_begin_), ab(alt_base_), ob(out_base_), rb(ref_base_);
+        tb.push_back(tasks_.size()), ab.push_back(alt_.size()), ob.push_back(out_size_), rb.push_back(ref_.size());
+        std::string out(out_size_, '\0');
+        v2p_batch b{};
+        b.task_begin = tb.data(), b.tasks = tasks_.data();
+        if (layout_ == RefLayout::PerHaplotype) {
+            b.ref = reinterpret_cast<const uint8_t*>(ref_.data());
+            b.ref_base = rb.data();
+            b.n_ref = ref_.size();
+        }  // SharedProteome: ref == NULL -> the tape registered with Context::set_reference
+        b.alt = reinterpret_cast<const uint8_t*>(alt_.data()), b.alt_base = ab.data();
+        b.out = reinterpret_cast<uint8_t*>(&out[0]), b.out_base = ob.data();
+        b.n_hap = H;
+        v2p_result r{};
+        int st = v2p_execute_batch(ctx.get(), &b, validate ? V2P_FLAG_VALIDATE : 0u, &r, nullptr);
+        if (st != V2P_OK) throw EngineError(st, ctx.last_error(), r.bad_hap, r.bad_task);
+        out_base_final_ = ob;
+        return out;
+    }
+    uint64_t out_base(size_t h) const { return out_base_final_.at(h); }
+
+private:
+    RefLayout layout_;
+    bool aligned_;
+    std::vector<v2p_task16> tasks_;
+    std::vector<uint64_t> task_begin_, alt_base_, out_base_, ref_base_, out_base_final_;
+    std::string alt_, ref_;
+    std::vector<Annotation> annotations_;
+    uint64_t ref_counter_ = 0, alt_counter_ = 0, res_counter_ = 0, out_size_ = 0;
+};
+
+}  // namespace v2p
+#endif  // V2P_HOST_HPP
