@@ -393,6 +393,18 @@ def main():
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     copy_avg_ms = float(np.mean(copy_ms))
     achieved = b_alg / (copy_avg_ms * 1e-3) / 1e9
+    # the kernel must WRITE every residue once: measure this GPU's write-only ceiling (torch fill_, best of 5) beside it
+    wbuf = d_out[: min(n_out, 8 << 30)]
+    wbest = 1e9
+    for _ in range(6):
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        wbuf.fill_(46)
+        w1.record()
+        torch.cuda.synchronize()
+        wbest = min(wbest, w0.elapsed_time(w1))
+    write_peak = wbuf.numel() / (wbest * 1e-3) / 1e9
+    write_rate = n_out / (copy_avg_ms * 1e-3) / 1e9
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath) and not args.fasta_image:
@@ -430,7 +442,10 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_copy_tiles", "peak_source": peak_src,
                      "alg_bytes_per_launch": b_alg, "kernel_ms": copy_avg_ms, "launch_group_ms": float(np.mean(group_ms)),
-                     "kernel_share_of_step": copy_avg_ms / ms_per_step},
+                     "kernel_share_of_step": copy_avg_ms / ms_per_step,
+                     "write_only": {"achieved_gbs": write_rate, "peak_gbs": write_peak, "frac": write_rate / write_peak,
+                                    "note": "result-tape bytes written / kernel time vs torch fill_ on the same GPU: the "
+                                            "hard floor of this path is one DRAM write per residue"}},
         "cpu_baseline": cpu, "parity": parity, "gen_seconds": round(t_gen, 1),
     }
     print(json.dumps(line))
