@@ -381,3 +381,49 @@ def test_fasta_file_image_on_device(gpu_engine):
         image = img[int(fb.out_base[2 * s]):int(fb.out_base[2 * s + 2])]
         recs = sorted(C.fasta_records(prot, b, plain, 2 * s, 1) + C.fasta_records(prot, b, plain, 2 * s + 1, 2))
         assert C.parse_fasta_image(image) == recs and (len(image) == 0 or image[0] == ord(">"))
+
+
+def test_concurrent_callers_share_one_context(gpu_engine):
+    """GIR::execute is called from many rayon workers at once (parts/exec.rs:36-39): concurrent host threads on ONE
+    context must each get their own haplotype's result (the context serialises them internally)."""
+    import threading
+
+    cohort = load_golden("cohort_a.json")
+    per_hap = cohort_haplotype_csqs(cohort)
+    girs = [hap_gir(c, cohort["refs"]) for _, c in sorted(per_hap.items())][:16]
+    want = [taskgen.execute_tasks(g.tasks, g.ref, g.alt, g.res_len) for g in girs]
+    got = [None] * len(girs)
+    errs = []
+
+    def worker(i):
+        try:
+            for _ in range(3):
+                res, _ = GIR(girs[i].tasks, girs[i].annotation, girs[i].alt, girs[i].ref, "." * girs[i].res_len).execute(
+                    Engine.GPU, gpu_engine)
+                got[i] = tape_to_str(res)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(girs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs and got == want
+
+
+def test_pinned_host_allocator_roundtrip(gpu_engine):
+    import ctypes as C
+
+    lib = L.load()
+    p = C.c_void_p()
+    assert lib.v2p_host_alloc(C.byref(p), 1 << 20) == 0 and p.value
+    buf = (C.c_uint8 * (1 << 20)).from_address(p.value)
+    out = np.frombuffer(buf, dtype=np.uint8)
+    b = random_batch(77, 4, 50000)
+    n = int(b["out_base"][-1])
+    assert n <= out.size
+    got, _ = gpu_engine.execute_batch(b["task_begin"], b["tasks"], b["ref"], b["alt"], b["alt_base"], b["out_base"], out=out[:n])
+    st, _, _, want = oracle_batch(b)
+    assert st == 0 and np.array_equal(got, want)
+    assert lib.v2p_host_free(p) == 0
