@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
     __syncthreads();
     if (p.status->bad_args) return;
     const uint4* __restrict__ tk = reinterpret_cast<const uint4*>(p.tasks);
+    // the CTA's first haplotype, kept in registers for the whole chunk
+    const uint64_t c_h = sh[0], c_tb0 = sh[1], c_tb1 = sh[2], c_o0 = sh[3], c_nres = sh[4] - sh[3], c_nalt = sh[5], c_nref = sh[6];
     constexpr int U = 4;  // tasks per thread whose loads are issued together
     for (int it0 = 0; it0 < kPlanIters; it0 += U) {
         uint4 raw[U], prv[U];
@@ -166,11 +168,11 @@ __global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
             const uint4 pr = prv[u];
             const uint64_t t = tr + p.task_origin;
             // bases of the owning haplotype: the CTA's first one (staged), else the next one, else a search
-            uint64_t h = sh[0], tb0 = sh[1], o0 = sh[3], n_res = sh[4] - sh[3], n_alt = sh[5], n_ref = sh[6];
-            if (t >= sh[2]) {
+            uint64_t h = c_h, tb0 = c_tb0, o0 = c_o0, n_res = c_nres, n_alt = c_nalt, n_ref = c_nref;
+            if (t >= c_tb1) {
                 h = h + 1;
                 if (h + 1 > p.n_hap || t >= __ldg(p.task_begin + h + 1) || t < __ldg(p.task_begin + h))
-                    h = upper_bound_u64(p.task_begin, sh[0] + 1, p.n_hap + 1, t) - 1;
+                    h = upper_bound_u64(p.task_begin, c_h + 1, p.n_hap + 1, t) - 1;
                 tb0 = __ldg(p.task_begin + h);
                 o0 = __ldg(p.out_base + h);
                 n_res = __ldg(p.out_base + h + 1) - o0;
