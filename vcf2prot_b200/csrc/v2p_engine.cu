@@ -157,11 +157,7 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     kp.tile_hap = (uint32_t*)sc.tile_hap.p;
     kp.status = (DevStatus*)sc.status.p;
     if (ev_start) CUDA_TRY(e, cudaEventRecord(ev_start, s));
-    // Fused plan (batch calls): lb[] by per-tile search, every task validated inside the copy kernel -- no pass over
-    // the task array besides the copy itself.  The SoA call keeps the separate k_plan_tasks pass: it may have to
-    // preserve the caller's result tape (keep_out), so nothing may be written before the tasks are known to be valid.
-    kp.fused_plan = kp.keep_out ? 0 : 1;
-    if (!kp.fused_plan) CUDA_TRY(e, cudaMemsetAsync(kp.lb, 0xFF, (kp.n_tiles + 1) * sizeof(uint32_t), s));
+    CUDA_TRY(e, cudaMemsetAsync(kp.lb, 0xFF, (kp.n_tiles + 1) * sizeof(uint32_t), s));
     if (init_status) {
         k_init_status<<<1, 1, 0, s>>>(kp.status);
         e->launches++;
@@ -169,10 +165,12 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     if (kp.n_hap) {
         k_plan_haps<<<(unsigned)((kp.n_hap + 255) / 256), 256, 0, s>>>(kp);
         e->launches++;
-        k_plan_tiles<<<(unsigned)((kp.n_tiles + 1 + 255) / 256), 256, 0, s>>>(kp);
-        e->launches++;
+        if (kp.n_tiles) {
+            k_plan_tiles<<<(unsigned)((kp.n_tiles + 255) / 256), 256, 0, s>>>(kp);
+            e->launches++;
+        }
     }
-    if (kp.n_tasks && !kp.fused_plan) {
+    if (kp.n_tasks) {
         k_plan_tasks<<<(unsigned)((kp.n_tasks + kPlanChunk - 1) / kPlanChunk), 256, 0, s>>>(kp);
         e->launches++;
     }
@@ -235,20 +233,6 @@ bool needs_serial(const DevStatus& st) {
     return !st.bad_args && st.err_key == ~0ull && st.gap_key == ~0ull && st.unsorted;
 }
 
-// Fused-plan batches only learn "not sorted by destination" from the copy kernel, whose task coverage is then not
-// guaranteed: before the serial-order kernel may touch memory, every task goes through the full validation pass.
-int revalidate(v2p_engine* e, cudaStream_t s, KParams kp, DevStatus* h_status) {
-    kp.fused_plan = 0;
-    k_init_status<<<1, 1, 0, s>>>(kp.status);
-    k_plan_haps<<<(unsigned)((kp.n_hap + 255) / 256), 256, 0, s>>>(kp);
-    if (kp.n_tasks) k_plan_tasks<<<(unsigned)((kp.n_tasks + kPlanChunk - 1) / kPlanChunk), 256, 0, s>>>(kp);
-    e->launches += 3;
-    CUDA_TRY(e, cudaGetLastError());
-    CUDA_TRY(e, cudaMemcpyAsync(h_status, kp.status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(e, cudaStreamSynchronize(s));
-    return V2P_OK;
-}
-
 // serial-order fallback, launched only after the plan reported unsorted/overlapping tasks
 int launch_serial(v2p_engine* e, cudaStream_t s, const KParams& kp) {
     unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(kp.n_hap, 1), (uint64_t)e->sm_count * 8);
@@ -308,10 +292,6 @@ int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
     if (cudaEventSynchronize(ev->ev_done) != cudaSuccess)
         return finish(fail(e, V2P_ERR_CUDA, "launch group failed: %s", cudaGetErrorString(cudaGetLastError())));
     const DevStatus& st = *ev->h_status;
-    if (needs_serial(st) && ev->kp.fused_plan) {
-        int rc = revalidate(e, ev->stream, ev->kp, ev->h_status);
-        if (rc) return finish(rc);
-    }
     if (needs_serial(st)) {
         int rc = launch_serial(e, ev->stream, ev->kp);
         if (rc) return finish(rc);
@@ -667,7 +647,6 @@ int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, co
     rc = launch_group(e, s, e->sc, kp, nullptr, nullptr, e->h_status, /*init_status=*/false, nullptr);
     if (rc) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(s));
-    if (needs_serial(*e->h_status) && kp.fused_plan && (rc = revalidate(e, s, kp, e->h_status))) return rc;
     if (needs_serial(*e->h_status)) {
         if ((rc = launch_serial(e, s, kp))) return rc;
         CUDA_TRY(e, cudaStreamSynchronize(s));

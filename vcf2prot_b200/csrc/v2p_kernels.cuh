@@ -58,7 +58,6 @@ struct KParams {
     uint32_t fill_word;  // 0x2E2E2E2E for 1-byte residues, 0x0000002E for UTF-32 units
     int keep_out;        // 1: uncovered bytes keep the caller's content (soa call without FILL_DOT)
     int validate;        // V2P_FLAG_VALIDATE
-    int fused_plan;      // 1: lb[] comes from k_plan_tiles' search and every task is validated inside k_copy_tiles
     DevStatus* status;
 };
 
@@ -109,41 +108,15 @@ __global__ void k_plan_haps(KParams p) {
     if (bad) atomicExch(&p.status->bad_args, 1u);
 }
 
-// One thread per output tile: the haplotype that owns the tile's first byte (binary search over out_base) and, in
-// fused-plan mode, lb[k] = first task whose global destination is >= the tile's first byte (binary search over the
-// haplotype's dst_off column).  The search result is only meaningful for task arrays sorted by destination; that
-// property is verified for every consecutive pair of tasks by k_copy_tiles itself (which also checks that lb[] is
-// monotone, i.e. that the tiles' task ranges cover every task), and a violation routes the batch to k_serial.
+// One thread per output tile: the haplotype that owns the tile's first byte (binary search over out_base).
 __global__ void k_plan_tiles(KParams p) {
     uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (k > p.n_tiles) return;
-    if (k == p.n_tiles) {
-        if (p.fused_plan) p.lb[k] = (uint32_t)p.n_tasks;
-        return;
-    }
+    if (k >= p.n_tiles) return;
     const uint64_t x = (k << p.tile_shift) + p.out_origin;
     uint64_t h = upper_bound_u64(p.out_base, 0, p.n_hap + 1, x);  // first h with out_base[h] > x
     h = h ? h - 1 : 0;
     if (h >= p.n_hap) h = p.n_hap - 1;
     p.tile_hap[k] = (uint32_t)h;
-    if (!p.fused_plan) return;
-    if (p.status->bad_args) {
-        p.lb[k] = 0u;
-        return;
-    }
-    const uint64_t want = x - __ldg(p.out_base + h);  // haplotype-relative destination of the tile's first byte
-    uint64_t lo = __ldg(p.task_begin + h) - p.task_origin, hi = __ldg(p.task_begin + h + 1) - p.task_origin;
-    if (hi > p.n_tasks) hi = p.n_tasks;
-    if (lo > hi) lo = hi;
-    const uint32_t* dst_col = reinterpret_cast<const uint32_t*>(p.tasks) + 2;  // v2p_task16::dst_off
-    while (lo < hi) {  // first task of the haplotype with dst_off >= want
-        const uint64_t mid = (lo + hi) >> 1;
-        if ((uint64_t)__ldg(dst_col + 4 * mid) < want)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    p.lb[k] = (uint32_t)lo;
 }
 
 // One thread per task (kPlanChunk tasks per CTA): everything the reference would panic on, plus lb[]
@@ -390,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
     constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4, 8 or 16)
     constexpr int LWW = LW / 4;     // ... as 32-bit words
-    constexpr int STRIDE = TILE + NV + 16 + 576;  // tile | lead[] | mbarrier | staged tasks (32 x 16 B) + bases (8 x 8 B)
+    constexpr int STRIDE = TILE + NV + 16 + 576;  // tile | lead[] | mbarrier | staged tasks (32 x 16 B) + bases (5 x 8 B)
     static_assert(LW == 4 || LW == 8 || LW == 16, "TILE must be 2048, 4096 or 8192");
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -427,18 +400,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         }
     };
     const uint32_t n_tasks32 = (uint32_t)p.n_tasks;  // < 2^32 - 1 (checked by the host)
-    auto first_task = [&](uint32_t lo, uint64_t kk) -> uint32_t {
+    auto first_task = [&](uint32_t lo) -> uint32_t {
         const uint32_t t = min(lo, n_tasks32);
-        // the task before may extend into the tile; tile 0 starts from task 0 so that every task index is visited
-        return (t > 0u && kk > 0) ? t - 1u : 0u;
+        return t > 0u ? t - 1u : 0u;  // the task before may extend into the tile
     };
     // stage(): cp.async the first 32 tasks of a tile and its haplotype's five bases into this warp's staging area
-    // lane j < 8 fetches base j of a haplotype: task_begin[h], [h+1], out_base[h], [h+1], alt_base[h], [h+1], ref_base[h], [h+1]
-    const uint64_t* const base_arr = lane < 2 ? p.task_begin : lane < 4 ? p.out_base : lane < 6 ? p.alt_base : p.ref_base;
-    const bool base_on = lane < 8 && base_arr != nullptr;
-    const uint32_t base_add = lane & 1u;
-    auto stage = [&](uint32_t lo, uint32_t hi, uint32_t hp, uint64_t kk) {
-        const uint32_t tr = first_task(lo, kk) + lane;
+    // lane j < 5 fetches base j of a haplotype: task_begin[h], task_begin[h+1], out_base[h], alt_base[h], ref_base[h]
+    const uint64_t* const base_arr = lane < 2 ? p.task_begin : lane == 2 ? p.out_base : lane == 3 ? p.alt_base : p.ref_base;
+    const bool base_on = lane < 5 && base_arr != nullptr;
+    const uint32_t base_add = lane == 1 ? 1u : 0u;
+    auto stage = [&](uint32_t lo, uint32_t hi, uint32_t hp) {
+        const uint32_t tr = first_task(lo) + lane;
         if (tr < min(hi, n_tasks32)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
         if (base_on) cp_async8(st_bases + lane, base_arr + hp + base_add);
         cp_async_commit();
@@ -447,27 +419,24 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     uint32_t c_lo, c_hi, c_hap, n_lo, n_hi, n_hap;
     load_meta(k, c_lo, c_hi, c_hap);
     load_meta(k + n_warps, n_lo, n_hi, n_hap);
-    if (k < p.n_tiles) stage(c_lo, c_hi, c_hap, k);
+    if (k < p.n_tiles) stage(c_lo, c_hi, c_hap);
     for (; k < p.n_tiles; k += n_warps) {
         const uint64_t tile_start = k * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
-        const uint32_t t_lo = first_task(c_lo, k);
+        const uint32_t t_lo = first_task(c_lo);
         const uint32_t t_hi = min(c_hi, n_tasks32);
         // this tile's tasks and bases were staged while the previous tile was being assembled
         cp_async_wait0();
         __syncwarp();
         const uint4 raw0 = st_tasks[lane];
         // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
-        const uint64_t hb_t0 = st_bases[0], hb_t1 = st_bases[1], hb_out = st_bases[2], hb_oute = st_bases[3];
-        const uint64_t hb_alt = st_bases[4], hb_alte = st_bases[5];
-        const uint64_t hb_ref = p.ref_base ? st_bases[6] : p.ref_origin;
-        const uint64_t hb_refe = p.ref_base ? st_bases[7] : p.ref_origin + p.n_ref;
-        if (p.fused_plan && c_lo > c_hi) atomicExch(&p.status->unsorted, 1u);  // lb[] not monotone: the search met unsorted tasks
+        const uint64_t hb_t0 = st_bases[0], hb_t1 = st_bases[1], hb_out = st_bases[2], hb_alt = st_bases[3];
+        const uint64_t hb_ref = p.ref_base ? st_bases[4] : p.ref_origin;
         __syncwarp();
         // advance the pipeline: stage the next tile (its metadata was fetched one tile ago), fetch metadata two ahead
         c_lo = n_lo, c_hi = n_hi, c_hap = n_hap;
-        if (k + n_warps < p.n_tiles) stage(c_lo, c_hi, c_hap, k + n_warps);
+        if (k + n_warps < p.n_tiles) stage(c_lo, c_hi, c_hap);
         load_meta(k + 2 * n_warps, n_lo, n_hi, n_hap);
 
         // the previous tile's bulk store must have finished READING shared memory before we overwrite it
@@ -506,51 +475,20 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             bool tma_alt = false;  // alteration payloads are read once (evict_first), reference runs are re-read (evict_last)
             bool has_lead = false, onT = false, onH = false, onM = false;
             int pvh = 0, pvt = 0, pa1 = 0, pb2 = 16;
-            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-            if (tr < t_hi) raw = tb == t_lo ? raw0 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
-            // the previous task's (dst_off, len) sits in the neighbouring lane (lane 0 fetches it when it must)
-            uint32_t pz = __shfl_up_sync(0xffffffffu, raw.z, 1), py = __shfl_up_sync(0xffffffffu, raw.y, 1);
             if (tr < t_hi) {
+                const uint4 raw = tb == t_lo ? raw0 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
                 const uint64_t t_abs = tr + p.task_origin;
-                uint64_t o_b = hb_out, a_b = hb_alt, r_b = hb_ref, tb0 = hb_t0;
-                uint64_t o_e = hb_oute, a_e = hb_alte, r_e = hb_refe;
+                uint64_t o_b = hb_out, a_b = hb_alt, r_b = hb_ref;
                 if (t_abs < hb_t0 || t_abs >= hb_t1) {  // another haplotype (tile spans a haplotype boundary)
                     const uint64_t h = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, t_abs) - 1;
-                    tb0 = __ldg(p.task_begin + h);
-                    o_b = __ldg(p.out_base + h), o_e = __ldg(p.out_base + h + 1);
-                    a_b = __ldg(p.alt_base + h), a_e = __ldg(p.alt_base + h + 1);
+                    o_b = __ldg(p.out_base + h);
+                    a_b = __ldg(p.alt_base + h);
                     r_b = p.ref_base ? __ldg(p.ref_base + h) : p.ref_origin;
-                    r_e = p.ref_base ? __ldg(p.ref_base + h + 1) : p.ref_origin + p.n_ref;
-                }
-                bool task_ok = true;
-                if (p.fused_plan) {
-                    // every reference panic, judged here because no separate plan pass looked at the tasks:
-                    // stream code (haplotype_instruction.rs:154), result / source slices (task.rs:44/48)
-                    const bool bad_stream = raw.w > 1u;
-                    const bool bad_res = (uint64_t)raw.z + raw.y > o_e - o_b;
-                    const bool bad_src = (uint64_t)raw.x + raw.y > (raw.w ? a_e - a_b : r_e - r_b);
-                    if (bad_stream | bad_res | bad_src) {
-                        atomicMin(&p.status->err_key, ((unsigned long long)tr << 8) |
-                                                          (bad_stream ? V2P_ERR_BAD_STREAM : bad_res ? V2P_ERR_RES_OOB : V2P_ERR_SRC_OOB));
-                        task_ok = false;
-                    }
-                    // order / contiguity against the previous task of the same haplotype (gir.rs:208); the pair
-                    // (first task of this tile's range, its predecessor) was checked by the tile before
-                    bool have_prev = lane > 0;
-                    if (lane == 0 && tb != t_lo) {  // later batch of the same tile: predecessor sits in the previous batch
-                        const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr - 1);
-                        pz = pr.z, py = pr.y, have_prev = true;
-                    }
-                    if (have_prev && t_abs > tb0) {
-                        const uint64_t pend = (uint64_t)pz + py;
-                        if (raw.z < pend) atomicExch(&p.status->unsorted, 1u);
-                        if (p.validate && raw.z != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
-                    }
                 }
                 const long long g = (long long)(o_b - p.out_origin + raw.z) - (long long)tile_start;
                 const long long ge = g + raw.y;
                 const int s = (int)max(g, 0ll), e = (int)min(ge, (long long)tile_len);
-                if (task_ok && e > s) {
+                if (e > s) {
                     const uint8_t* sb = raw.w ? p.alt + (a_b - p.alt_origin) : p.ref + (r_b - p.ref_origin);
                     p0 = (long long)(sb + raw.x) - g;
                     const int vh = s >> 4, vt = (e - 1) >> 4;
