@@ -1,0 +1,74 @@
+/*
+ * v2p_taskgen.h -- device-side Task generation: from per-haplotype variant-site lists
+ * to the packed batch v2p_execute_batch consumes, without the Task arrays ever crossing PCIe.
+ *
+ * What it replaces in the reference (host code there, and it stays available on the host here too):
+ *   TranscriptInstruction::get_g_rep / to_task / add_till_next_ins / add_last_instruction
+ *       src/data_structures/InternalRep/transcript_instructions.rs:335-427, :452-780   (Task emission rules)
+ *   HaplotypeInstruction::get_g_rep + update_task
+ *       src/data_structures/InternalRep/haplotype_instruction.rs:75-158                 (concatenate + re-index)
+ * for the seven csq classes the synthetic cohorts use (missense 'M', inframe_insertion 'I', inframe_deletion 'D',
+ * frameshift 'F', stop_gained 'G', stop_lost 'L', start_lost '0'); the host producer vcf2prot_b200/cohort.py is the
+ * bit-exact specification (it is itself checked tuple-for-tuple against the reference-pinned oracle).
+ *
+ * Input is what the host has after csq decoding and per-transcript grouping: a catalogue of variant sites sorted by
+ * (transcript, position) with their class and payload, and for every haplotype the ascending list of catalogue
+ * indices it carries (4 bytes per site instead of ~2.6 packed 16-byte tasks per site).
+ */
+#ifndef V2P_TASKGEN_H
+#define V2P_TASKGEN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "v2p_engine.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { V2P_CLS_M = 0, V2P_CLS_I = 1, V2P_CLS_D = 2, V2P_CLS_F = 3, V2P_CLS_G = 4, V2P_CLS_L = 5, V2P_CLS_0 = 6 };
+
+#define V2P_GEN_ALIGNED 0x1u /* phase-aligned result slots and long alteration payloads */
+
+typedef struct v2p_catalogue v2p_catalogue;
+
+/* Uploads the proteome index and the variant catalogue to `cuda_device` (host pointers).
+ *   tx_offsets[n_tx+1]  offset of every transcript in the proteome tape (tape registered with v2p_engine_set_reference)
+ *   per site i (sorted by (site_tx, site_pos), unique well-separated positions per transcript):
+ *     site_tx, site_pos (0-based; stop_lost: == transcript length; start_lost: 0), site_cls (V2P_CLS_*),
+ *     site_rlen (residues of the reference allele: deleted+anchor for 'D', else 1),
+ *     site_doff/site_dlen: the instruction data in `pool` (M: new residue; I: anchor+inserted; D: anchor;
+ *     F/L: new tail; G/0: empty)                                                                         */
+int v2p_catalogue_create(int cuda_device, uint64_t n_tx, const uint64_t* tx_offsets, uint64_t n_sites,
+                         const uint32_t* site_tx, const uint32_t* site_pos, const uint8_t* site_cls,
+                         const uint32_t* site_rlen, const uint64_t* site_doff, const uint32_t* site_dlen,
+                         const uint8_t* pool, uint64_t n_pool, v2p_catalogue** out);
+void v2p_catalogue_destroy(v2p_catalogue* c);
+const char* v2p_catalogue_last_error(v2p_catalogue* c);
+
+/* Result of one generation: a device-resident v2p_batch (ref == NULL: the registered proteome) plus the annotation
+ * table the consumer slices by (one row per altered transcript per haplotype, in tape order).  All pointers are
+ * device memory owned by the catalogue object and stay valid until the next v2p_generate_tasks / destroy.        */
+typedef struct {
+    v2p_batch batch;           /* pass to v2p_execute_batch with V2P_FLAG_DEVICE_PTRS; batch.out is allocated too */
+    uint64_t n_rows;           /* annotation rows                                                                */
+    const uint32_t* ann_hap;   /* haplotype of the row                                                            */
+    const uint32_t* ann_tx;    /* transcript                                                                      */
+    const uint64_t* ann_start; /* haplotype-relative [start, end) of its sequence on the result tape              */
+    const uint64_t* ann_end;
+    uint64_t n_sites;          /* selected sites consumed (those after a truncating variant emit nothing)         */
+    float gen_ms;              /* device time of the generation (CUDA events)                                     */
+} v2p_generated;
+
+/* site_begin[n_hap+1] / sites[site_begin[n_hap]]: host pointers; sites ascending inside each haplotype. */
+int v2p_generate_tasks(v2p_catalogue* c, uint64_t n_hap, const uint64_t* site_begin, const uint32_t* sites,
+                       uint32_t flags, v2p_generated* out);
+
+/* Test / debugging helper: device -> host copy of any array above. */
+int v2p_device_read(void* host_dst, const void* dev_src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2P_TASKGEN_H */

@@ -7,7 +7,7 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADER = os.path.join(ROOT, "include", "v2p_engine.h")
+HEADERS = [os.path.join(ROOT, "include", h) for h in ("v2p_engine.h", "v2p_taskgen.h")]
 
 
 @pytest.fixture(scope="module")
@@ -22,16 +22,18 @@ def lib():
 
 
 def header_functions():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(v2p_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for h in HEADERS:
+        src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names |= set(re.findall(r"\b(v2p_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_every_declared_symbol_is_exported(lib):
     from vcf2prot_b200 import _lib
 
     names = header_functions()
-    assert len(names) >= 14
+    assert len(names) >= 19
     for n in names:
         assert hasattr(lib, n), "libv2p_engine.so does not export %s" % n
         assert n in _lib.SYMBOLS, "ctypes binding lacks %s" % n
@@ -44,6 +46,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Task16) == 16
     assert C.sizeof(_lib.Batch) == 13 * 8
     assert C.sizeof(_lib.Result) == 32
+    assert C.sizeof(_lib.Generated) == 13 * 8 + 8 + 4 * 8 + 8 + 8
 
 
 def test_engine_from_str_contract(lib):

@@ -1,0 +1,61 @@
+"""GPU suite: the device-side Task generator is bit-exact against the host producer
+(vcf2prot_b200/cohort.py, itself pinned to the reference through the oracle) -- every output array -- and the batch it
+generates executes to the oracle's bytes."""
+import numpy as np
+import pytest
+
+from oracle import cengine
+from vcf2prot_b200 import cohort as C
+from vcf2prot_b200.taskgen import DeviceCatalogue, execute_generated
+
+pytestmark = pytest.mark.gpu
+
+RICH_MIX = (0.55, 0.10, 0.10, 0.08, 0.07, 0.05, 0.05)
+
+
+@pytest.fixture(scope="module")
+def world():
+    prot = C.make_proteome(seed=31, n_tx=400, mu=5.3, sigma=0.7, lo=30, hi=4000)
+    cat = C.make_catalogue(prot, 12000, seed=32, mix=RICH_MIX, fs_mean=30, fs_max=600, sl_max=120)
+    cat.af[:] = np.random.default_rng(5).choice([0.01, 0.05, 0.2, 0.5], size=cat.n)
+    dc = DeviceCatalogue(prot, cat, 0)
+    yield prot, cat, dc
+    dc.close()
+
+
+@pytest.mark.parametrize("aligned", [False, True])
+@pytest.mark.parametrize("seed,n_hap", [(1, 1), (2, 9), (3, 64)])
+def test_every_array_matches_the_host_producer(world, gpu_engine, aligned, seed, n_hap):
+    prot, cat, dc = world
+    hap, site = C.select_sites(cat, n_hap, np.random.default_rng(seed))
+    if n_hap == 9:  # haplotypes without any site in the middle and at the end
+        keep = ~np.isin(hap, (3, 8))
+        hap, site = hap[keep], site[keep]
+    want = C.build_batch(prot, cat, hap, site, n_hap, "global", "aligned" if aligned else "packed")
+    g = dc.generate(hap, site, n_hap, aligned)
+    b = g.batch
+    assert (b.n_hap, b.n_tasks, b.n_alt, b.n_out) == (n_hap, len(want.tasks), len(want.alt), want.n_residues)
+    assert np.array_equal(dc.read(b.task_begin, n_hap + 1, np.uint64), want.task_begin)
+    assert np.array_equal(dc.read(b.out_base, n_hap + 1, np.uint64), want.out_base)
+    assert np.array_equal(dc.read(b.alt_base, n_hap + 1, np.uint64), want.alt_base)
+    assert np.array_equal(dc.read(b.tasks, 4 * b.n_tasks, np.uint32).reshape(-1, 4), want.tasks)
+    assert np.array_equal(dc.read(b.alt, b.n_alt, np.uint8), want.alt)
+    assert g.n_rows == len(want.ann_hap)
+    assert np.array_equal(dc.read(g.ann_hap, g.n_rows, np.uint32), want.ann_hap)
+    assert np.array_equal(dc.read(g.ann_tx, g.n_rows, np.uint32), want.ann_tx)
+    assert np.array_equal(dc.read(g.ann_start, g.n_rows, np.uint64), want.ann_start)
+    assert np.array_equal(dc.read(g.ann_end, g.n_rows, np.uint64), want.ann_end)
+    # and the generated batch runs to the oracle's bytes, tasks never having existed on the host
+    gpu_engine.set_reference(prot.residues)
+    execute_generated(gpu_engine, g, validate=not aligned)
+    got = dc.read(b.out, b.n_out, np.uint8)
+    ref = np.zeros(want.n_residues, np.uint8)
+    assert cengine.batch_execute(want.task_begin, want.tasks, prot.residues, want.alt, want.alt_base, ref, want.out_base)[0] == 0
+    assert np.array_equal(got, ref)
+
+
+def test_no_sites_at_all(world, gpu_engine):
+    prot, cat, dc = world
+    g = dc.generate(np.zeros(0, np.int64), np.zeros(0, np.int64), 5, True)
+    assert (g.batch.n_tasks, g.batch.n_out, g.n_rows) == (0, 0, 0)
+    assert not dc.read(g.batch.task_begin, 6, np.uint64).any()

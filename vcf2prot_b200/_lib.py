@@ -14,6 +14,7 @@ ERR_NOT_CONTIGUOUS, ERR_NOT_GPU_ENGINE = 7, 9
 ENGINE_ST, ENGINE_MT, ENGINE_GPU = 0, 1, 2
 FLAG_FILL_DOT, FLAG_VALIDATE, FLAG_DEVICE_PTRS, FLAG_ASYNC = 1, 2, 4, 8
 REF_NO_TMA = 0x200
+GEN_ALIGNED = 1
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "BAD_ENGINE", 4: "BAD_STREAM", 5: "RES_OOB", 6: "SRC_OOB",
                 7: "NOT_CONTIGUOUS", 9: "NOT_GPU_ENGINE"}
@@ -34,7 +35,12 @@ class Result(C.Structure):
     _fields_ = [("status", C.c_int), ("bad_hap", C.c_uint64), ("bad_task", C.c_uint64), ("kernel_ms", C.c_float), ("copy_ms", C.c_float)]
 
 
-# every symbol include/v2p_engine.h declares: (restype, argtypes)
+class Generated(C.Structure):
+    _fields_ = [("batch", Batch), ("n_rows", C.c_uint64), ("ann_hap", C.c_void_p), ("ann_tx", C.c_void_p),
+                ("ann_start", C.c_void_p), ("ann_end", C.c_void_p), ("n_sites", C.c_uint64), ("gen_ms", C.c_float)]
+
+
+# every symbol include/*.h declares: (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
     "v2p_abi_version": (C.c_int, []),
@@ -54,6 +60,13 @@ SYMBOLS = {
     "v2p_engine_set_tuning": (C.c_int, [_P, C.c_int, C.c_int]),
     "v2p_engine_set_stream": (C.c_int, [_P, _P]),
     "v2p_engine_set_reference": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32]),
+    # include/v2p_taskgen.h
+    "v2p_catalogue_create": (C.c_int, [C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_uint64,
+                                       C.POINTER(_P)]),
+    "v2p_catalogue_destroy": (None, [_P]),
+    "v2p_catalogue_last_error": (C.c_char_p, [_P]),
+    "v2p_generate_tasks": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(Generated)]),
+    "v2p_device_read": (C.c_int, [_P, _P, C.c_size_t]),
 }
 
 _lib = None

@@ -1,0 +1,70 @@
+"""ctypes harness for the device-side Task generator (include/v2p_taskgen.h, csrc/v2p_taskgen.cu).
+
+DeviceCatalogue uploads a cohort.Catalogue once; generate() turns per-haplotype site lists into a device-resident
+batch that GpuEngine.execute_generated() runs without the Task arrays ever existing on the host."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .engine import EngineError, GpuEngine
+
+
+class DeviceCatalogue:
+    def __init__(self, prot, cat, device: int = 0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        self._keep = [np.ascontiguousarray(prot.offsets, np.uint64), np.ascontiguousarray(cat.t, np.uint32),
+                      np.ascontiguousarray(cat.p, np.uint32), np.ascontiguousarray(cat.cls, np.uint8),
+                      np.ascontiguousarray(cat.rlen, np.uint32), np.ascontiguousarray(cat.doff, np.uint64),
+                      np.ascontiguousarray(cat.dlen, np.uint32), np.ascontiguousarray(cat.pool, np.uint8)]
+        p = [a.ctypes.data_as(C.c_void_p) for a in self._keep]
+        st = self._lib.v2p_catalogue_create(device, prot.n_tx, p[0], cat.n, p[1], p[2], p[3], p[4], p[5], p[6], p[7],
+                                            len(cat.pool), C.byref(h))
+        if st:
+            raise EngineError(st, "v2p_catalogue_create failed")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.v2p_catalogue_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def generate(self, hap: np.ndarray, site: np.ndarray, n_hap: int, aligned: bool = True) -> L.Generated:
+        """(hap, site) pairs sorted by (hap, site) -- what cohort.select_sites returns."""
+        site_begin = np.zeros(n_hap + 1, np.uint64)
+        np.cumsum(np.bincount(hap, minlength=n_hap), out=site_begin[1:])
+        sites = np.ascontiguousarray(site, np.uint32)
+        g = L.Generated()
+        st = self._lib.v2p_generate_tasks(self._h, n_hap, site_begin.ctypes.data_as(C.c_void_p),
+                                          sites.ctypes.data_as(C.c_void_p), L.GEN_ALIGNED if aligned else 0, C.byref(g))
+        if st:
+            raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
+        return g
+
+    def read(self, dev_ptr, count: int, dtype) -> np.ndarray:
+        out = np.zeros(count, dtype)
+        if count:
+            st = self._lib.v2p_device_read(out.ctypes.data_as(C.c_void_p), C.c_void_p(dev_ptr), out.nbytes)
+            if st:
+                raise EngineError(st, "v2p_device_read failed")
+        return out
+
+
+def execute_generated(eng: GpuEngine, g: L.Generated, validate: bool = False) -> Tuple[float, float]:
+    """Run a generated (device-resident) batch; the result tape stays in g.batch.out.  -> (group_ms, copy_ms)"""
+    res = L.Result()
+    st = eng._lib.v2p_execute_batch(eng._h, C.byref(g.batch), L.FLAG_DEVICE_PTRS | (L.FLAG_VALIDATE if validate else 0),
+                                    C.byref(res), None)
+    if st:
+        raise EngineError(st, eng.last_error(), res.bad_hap, res.bad_task)
+    return float(res.kernel_ms), float(res.copy_ms)
