@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--fasta-image", action="store_true",
                     help="emit `>{transcript}_{hap}\\n{seq}\\n` framing as extra copy segments (packed layout only): "
                          "the result tape is the FASTA file image")
+    ap.add_argument("--no-taskgen", action="store_true", help="skip the device-side Task generation measurement")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
                     help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
     return ap.parse_args()
@@ -386,6 +387,28 @@ def main():
         if rb:
             cpu["reference_binary"] = rb
 
+    # ---- the same cohort's Task arrays generated ON the device from the per-haplotype site lists
+    taskgen = None
+    if world == 1 and not args.no_taskgen and not args.fasta_image and batch.kept_hap is not None:
+        from vcf2prot_b200.taskgen import DeviceCatalogue
+
+        dc = DeviceCatalogue(prot, cat, local_rank)
+        dc.generate(batch.kept_hap, batch.kept_site, n_hap, args.layout == "aligned")  # warm-up (allocations)
+        g = dc.generate(batch.kept_hap, batch.kept_site, n_hap, args.layout == "aligned")
+        same = (g.batch.n_tasks == n_tasks and g.batch.n_out == n_out and
+                bool(np.array_equal(dc.read(g.batch.tasks, 4 * min(n_tasks, 1 << 22), np.uint32).reshape(-1, 4),
+                                    batch.tasks[: min(n_tasks, 1 << 22)])) and
+                bool(np.array_equal(dc.read(g.batch.out_base, n_hap + 1, np.uint64), batch.out_base)))
+        if n_tasks > (1 << 22):  # and the tail of the task array
+            tail = dc.read(g.batch.tasks + 16 * (n_tasks - (1 << 20)), 4 << 20, np.uint32).reshape(-1, 4)
+            same = same and bool(np.array_equal(tail, batch.tasks[n_tasks - (1 << 20):]))
+        n_sites = int(len(batch.kept_site))
+        taskgen = {"gen_ms": g.gen_ms, "sites": n_sites, "tasks": n_tasks, "tasks_per_s": n_tasks / (g.gen_ms * 1e-3),
+                   "h2d_bytes": 4 * n_sites + 8 * (n_hap + 1), "h2d_bytes_if_tasks_were_uploaded": 16 * n_tasks + len(batch.alt),
+                   "equals_host_producer": same, "host_producer_seconds": round(t_gen, 1),
+                   "what": "v2p_generate_tasks: per-haplotype site lists -> packed Task batch on the GPU (incl. the H2D of the lists)"}
+        dc.close()
+
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
@@ -446,7 +469,7 @@ def main():
                      "write_only": {"achieved_gbs": write_rate, "peak_gbs": write_peak, "frac": write_rate / write_peak,
                                     "note": "result-tape bytes written / kernel time vs torch fill_ on the same GPU: the "
                                             "hard floor of this path is one DRAM write per residue"}},
-        "cpu_baseline": cpu, "parity": parity, "gen_seconds": round(t_gen, 1),
+        "cpu_baseline": cpu, "parity": parity, "taskgen": taskgen, "gen_seconds": round(t_gen, 1),
     }
     print(json.dumps(line))
     if world > 1:
