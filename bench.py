@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--fasta-image", action="store_true",
                     help="emit `>{transcript}_{hap}\\n{seq}\\n` framing as extra copy segments (packed layout only): "
                          "the result tape is the FASTA file image")
+    ap.add_argument("--maskdecode-samples", type=int, default=512,
+                    help="samples of the cohort whose FORMAT/BCSQ mask matrix is decoded on the device (0 = skip)")
     ap.add_argument("--no-taskgen", action="store_true", help="skip the device-side Task generation measurement")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
                     help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
@@ -407,6 +409,35 @@ def main():
                    "h2d_bytes": 4 * n_sites + 8 * (n_hap + 1), "h2d_bytes_if_tasks_were_uploaded": 16 * n_tasks + len(batch.alt),
                    "equals_host_producer": same, "host_producer_seconds": round(t_gen, 1),
                    "what": "v2p_generate_tasks: per-haplotype site lists -> packed Task batch on the GPU (incl. the H2D of the lists)"}
+        # ---- FORMAT/BCSQ bit-mask matrix -> per-haplotype site lists -> Task batch, on the device
+        md_samples = min(n_hap // 2, args.maskdecode_samples)
+        if md_samples > 0:
+            sel = batch.kept_hap < 2 * md_samples
+            mh, ms_ = batch.kept_hap[sel], batch.kept_site[sel]
+            rec = C.make_records(cat, 0x5EED0009, 1)
+            masks = C.encode_masks(rec, md_samples, mh, ms_)
+            d_masks = torch.from_numpy(masks.view(np.int32)).to(dev)
+            shape = masks.shape
+            lst = dc.sites_from_masks(masks, rec.csq_begin, rec.csq_site)  # host matrix: pageable H2D inside decode_ms
+            host_ms = lst.decode_ms
+            dc.sites_from_masks(d_masks.data_ptr(), rec.csq_begin, rec.csq_site, shape)
+            lst = dc.sites_from_masks(d_masks.data_ptr(), rec.csq_begin, rec.csq_site, shape)
+            want_begin = np.zeros(2 * md_samples + 1, np.uint64)
+            np.cumsum(np.bincount(mh, minlength=2 * md_samples), out=want_begin[1:])
+            ok = (lst.n_sites == len(ms_) and bool(np.array_equal(dc.read(lst.sites, lst.n_sites, np.uint32), ms_.astype(np.uint32)))
+                  and bool(np.array_equal(dc.read(lst.site_begin, 2 * md_samples + 1, np.uint64), want_begin)))
+            g2 = dc.generate_from_lists(lst, args.layout == "aligned")
+            n_t2 = int(batch.task_begin[2 * md_samples])
+            ok = ok and g2.batch.n_tasks == n_t2 and bool(np.array_equal(
+                dc.read(g2.batch.tasks, 4 * min(n_t2, 1 << 20), np.uint32).reshape(-1, 4), batch.tasks[: min(n_t2, 1 << 20)]))
+            cells = shape[0] * shape[1]
+            taskgen["maskdecode"] = {
+                "records": int(shape[0]), "samples": int(md_samples), "words_per_cell": int(shape[2]), "carrier_bits": int(len(ms_)),
+                "decode_ms": lst.decode_ms, "cells_per_s": cells / (lst.decode_ms * 1e-3),
+                "matrix_gbs": masks.nbytes * 2 / (lst.decode_ms * 1e-3) / 1e9, "decode_ms_from_pageable_host": host_ms,
+                "then_generate_ms": g2.gen_ms, "equals_host_lists_and_tasks": ok,
+                "what": "v2p_sites_from_masks (matrix resident in HBM; streamed twice) -> v2p_generate_tasks_from_lists"}
+            del d_masks
         dc.close()
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -65,6 +65,33 @@ typedef struct {
 int v2p_generate_tasks(v2p_catalogue* c, uint64_t n_hap, const uint64_t* site_begin, const uint32_t* sites,
                        uint32_t flags, v2p_generated* out);
 
+/* ---- genotype bit-masks -> per-haplotype site lists, on the device ------------------------------
+ * Replaces the reference's bit-mask decode and per-sample transpose -- its real wall-time hog (84 % of a run,
+ * SURVEY section 6): MaskDecoder.rs:95-153 (bit 2i of a FORMAT/BCSQ word -> haplotype 1 carries csq i, bit 2i+1 ->
+ * haplotype 2; several words: csq index = 15*word + i), vcf_ds.rs:126-295 (get_patient_fields / decode_back /
+ * extract_effects), then the per-transcript grouping + position sort + duplicate drop (vcf_tools.rs:82-96,
+ * vcf_ds.rs:442-479), which in catalogue terms is "ascending, duplicate-free site indices per haplotype".
+ *   masks[n_records][n_samples][words_per_cell]   the decimal FORMAT/BCSQ integers, row-major
+ *   csq_begin[n_records+1], csq_site[]            csq k of record r -> catalogue site (or -1: unsupported class)
+ * A mask bit that selects a csq the record does not have is an error (the reference indexes out of range there,
+ * vcf_ds.rs:287).  Output: device CSR lists for n_hap = 2*n_samples haplotypes (haplotype = 2*sample + {0,1}).  */
+typedef struct {
+    uint64_t n_hap, n_sites;
+    const uint64_t* site_begin; /* device, n_hap+1 */
+    const uint32_t* sites;      /* device, n_sites */
+    float decode_ms;            /* device time incl. the H2D of the mask matrix */
+} v2p_site_lists;
+
+/* flags: V2P_FLAG_DEVICE_PTRS -> `masks` is device memory (csq_begin / csq_site are always host pointers).
+ * Errors: V2P_ERR_SRC_OOB when a mask bit selects a csq beyond the record's count (err text names the record);
+ * the lists are owned by the catalogue object and stay valid until the next v2p_sites_from_masks / destroy.     */
+int v2p_sites_from_masks(v2p_catalogue* c, uint64_t n_records, uint64_t n_samples, uint32_t words_per_cell,
+                         const uint32_t* masks, const uint64_t* csq_begin, const int32_t* csq_site, uint32_t flags,
+                         v2p_site_lists* out);
+
+/* v2p_generate_tasks on device-resident lists (the output of v2p_sites_from_masks). */
+int v2p_generate_tasks_from_lists(v2p_catalogue* c, const v2p_site_lists* lists, uint32_t flags, v2p_generated* out);
+
 /* Test / debugging helper: device -> host copy of any array above. */
 int v2p_device_read(void* host_dst, const void* dev_src, size_t bytes);
 

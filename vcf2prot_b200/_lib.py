@@ -42,6 +42,11 @@ class Generated(C.Structure):
 
 # every symbol include/*.h declares: (restype, argtypes)
 _P = C.c_void_p
+class SiteLists(C.Structure):
+    _fields_ = [("n_hap", C.c_uint64), ("n_sites", C.c_uint64), ("site_begin", C.c_void_p), ("sites", C.c_void_p),
+                ("decode_ms", C.c_float)]
+
+
 SYMBOLS = {
     "v2p_abi_version": (C.c_int, []),
     "v2p_engine_from_str": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
@@ -66,6 +71,8 @@ SYMBOLS = {
     "v2p_catalogue_destroy": (None, [_P]),
     "v2p_catalogue_last_error": (C.c_char_p, [_P]),
     "v2p_generate_tasks": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(Generated)]),
+    "v2p_sites_from_masks": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint32, C.POINTER(SiteLists)]),
+    "v2p_generate_tasks_from_lists": (C.c_int, [_P, C.POINTER(SiteLists), C.c_uint32, C.POINTER(Generated)]),
     "v2p_device_read": (C.c_int, [_P, _P, C.c_size_t]),
 }
 

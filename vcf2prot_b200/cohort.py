@@ -209,6 +209,65 @@ class Batch:
         return int(self.out_base[-1])
 
 
+# ---- VCF-record view of a catalogue: the input side of v2p_sites_from_masks -------------------
+@dataclass
+class Records:
+    """Synthetic VCF records over a catalogue: record r lists csq entries csq_begin[r]..csq_begin[r+1]; entry k names
+    the catalogue site it stands for or -1 for a consequence class the tool drops (vcf_ds.rs:249,262).  site_rec /
+    site_k locate every catalogue site's entry; words = FORMAT/BCSQ integers per cell (MaskDecoder.rs:122-153)."""
+    csq_begin: np.ndarray  # u64 [n_rec+1]
+    csq_site: np.ndarray   # i32 [n_csq]
+    site_rec: np.ndarray   # i64 [cat.n]
+    site_k: np.ndarray     # i64 [cat.n]
+    words: int
+
+    @property
+    def n_rec(self) -> int:
+        return len(self.csq_begin) - 1
+
+
+def make_records(cat: Catalogue, seed: int, max_sites_per_record: int = 1, p_unsupported: float = 0.0,
+                 wide_every: int = 0) -> Records:
+    """Groups consecutive catalogue sites into records of 1..max_sites_per_record entries, sprinkles unsupported
+    entries between them, and makes every `wide_every`-th record wider than one 15-entry mask word."""
+    rng = np.random.default_rng(seed)
+    csq_begin, csq_site = [0], []
+    site_rec, site_k = np.zeros(cat.n, np.int64), np.zeros(cat.n, np.int64)
+    i = r = 0
+    while i < cat.n:
+        take = int(rng.integers(1, max_sites_per_record + 1))
+        if wide_every and r % wide_every == wide_every - 1:
+            take = int(rng.integers(16, 40))
+        entries = []
+        for s in range(i, min(i + take, cat.n)):
+            while p_unsupported and rng.random() < p_unsupported:
+                entries.append(-1)
+            site_rec[s], site_k[s] = r, len(entries)
+            entries.append(s)
+        i += take
+        csq_site.extend(entries)
+        csq_begin.append(len(csq_site))
+        r += 1
+    cb = np.asarray(csq_begin, np.uint64)
+    widest = int(np.diff(cb.astype(np.int64)).max()) if r else 1
+    words = 1 if widest <= 16 else (widest + 14) // 15
+    return Records(cb, np.asarray(csq_site, np.int32), site_rec, site_k, words)
+
+
+def encode_masks(rec: Records, n_samples: int, hap: np.ndarray, site: np.ndarray) -> np.ndarray:
+    """(haplotype, site) carrier pairs -> masks[n_rec, n_samples, words]: what bcftools csq writes into FORMAT/BCSQ
+    (bit 2k of the cell: haplotype 1 carries the record's csq k, bit 2k+1: haplotype 2; 15 csq per word when a
+    record needs several words, MaskDecoder.rs:122-153)."""
+    masks = np.zeros((rec.n_rec, n_samples, rec.words), np.uint32)
+    k = rec.site_k[site]
+    if rec.words == 1:
+        w, bit = np.zeros(len(k), np.int64), 2 * k + (hap & 1)
+    else:
+        w, bit = k // 15, 2 * (k % 15) + (hap & 1)
+    np.bitwise_or.at(masks, (rec.site_rec[site], hap >> 1, w), (np.uint32(1) << bit.astype(np.uint32)))
+    return masks
+
+
 def select_sites(cat: Catalogue, n_hap: int, rng: np.random.Generator) -> Tuple[np.ndarray, np.ndarray]:
     """Each haplotype carries site i with probability af[i].  Returns (hap, site), sorted by (hap, site)."""
     haps, sites = [], []

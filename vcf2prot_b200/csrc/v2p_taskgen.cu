@@ -16,7 +16,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 #include <new>
 #include <string>
 
@@ -238,6 +240,122 @@ __global__ void k_tg_emit_alt(Sel s, Cat c, Out o) {
     for (uint64_t w = 0; w < acon; ++w) dst[w] = src[cls == V2P_CLS_M ? 0 : w];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Genotype bit-masks -> per-haplotype site lists (MaskDecoder.rs:95-153 + the transpose of vcf_ds.rs:126-295).
+// The mask matrix is streamed twice (population count to size the key buffer, then the emit); everything after that
+// works on the set bits only: 64-bit keys (haplotype << site_bits | site), one radix sort over the significant bits,
+// duplicate drop, and a binary search per haplotype for the CSR offsets.
+struct MdCtr {
+    unsigned long long n_bits, cursor, bad_record, n_unique;
+};
+
+__device__ __forceinline__ uint4 md_load4(const uint32_t* m, uint64_t j, uint64_t n_words) {
+    if (j + 4 <= n_words) return __ldcs(reinterpret_cast<const uint4*>(m + j));
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (j < n_words) v.x = m[j];
+    if (j + 1 < n_words) v.y = m[j + 1];
+    if (j + 2 < n_words) v.z = m[j + 2];
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_md_count(const uint32_t* __restrict__ masks, uint64_t n_words, MdCtr* ctr) {
+    unsigned long long n = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    for (uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j < n_words; j += stride) {
+        const uint4 v = md_load4(masks, j, n_words);
+        n += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    n = __reduce_add_sync(0xffffffffu, (unsigned)n);  // <= 32 lanes * a few thousand words * 32 bits: fits 32 bits
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&ctr->n_bits, n);
+}
+
+struct MdArgs {
+    const uint32_t* masks;
+    uint64_t n_words, n_samples;
+    uint32_t W, site_bits;
+    const uint64_t* csq_begin;
+    const int32_t* csq_site;
+    uint64_t* keys;
+    MdCtr* ctr;
+};
+
+// one word of one cell: set bit b -> csq 15*w + (b >> 1) of the record, haplotype 2*sample + (b & 1)
+__device__ __forceinline__ unsigned md_word(const MdArgs& a, uint32_t word, uint64_t j, uint64_t* dst, bool write) {
+    if (!word) return 0;
+    const uint64_t cell = j / a.W;
+    const uint32_t w = (uint32_t)(j - cell * a.W);
+    const uint64_t r = cell / a.n_samples, smp = cell - r * a.n_samples;
+    const uint64_t c0 = a.csq_begin[r], nc = a.csq_begin[r + 1] - c0;
+    unsigned n = 0;
+    while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        const uint64_t k = 15ull * w + (b >> 1);
+        if (k >= nc) {
+            atomicMin(&a.ctr->bad_record, (unsigned long long)r);
+            continue;
+        }
+        const int32_t site = a.csq_site[c0 + k];
+        if (site < 0) continue;  // a consequence class the tool does not support: dropped, vcf_ds.rs:249,262
+        if (write) dst[n] = ((2 * smp + (b & 1)) << a.site_bits) | (uint32_t)site;
+        ++n;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256) k_md_emit(MdArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    const unsigned lane = threadIdx.x & 31;
+    // uniform trip count so the warp-wide scan below is always converged
+    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x * 4;
+    for (uint64_t base = first; base < a.n_words; base += stride) {
+        const uint64_t j = base + (uint64_t)threadIdx.x * 4;
+        const uint4 v = md_load4(a.masks, j, a.n_words);
+        const bool any = (v.x | v.y | v.z | v.w) != 0;
+        if (!__any_sync(0xffffffffu, any)) continue;
+        unsigned n = 0;
+        if (any)
+            n = md_word(a, v.x, j, nullptr, false) + md_word(a, v.y, j + 1, nullptr, false) +
+                md_word(a, v.z, j + 2, nullptr, false) + md_word(a, v.w, j + 3, nullptr, false);
+        unsigned incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (!tot) continue;
+        unsigned long long wb = 0;
+        if (lane == 31) wb = atomicAdd(&a.ctr->cursor, (unsigned long long)tot);
+        wb = __shfl_sync(0xffffffffu, wb, 31);
+        if (n) {
+            uint64_t* dst = a.keys + wb + (incl - n);
+            dst += md_word(a, v.x, j, dst, true);
+            dst += md_word(a, v.y, j + 1, dst, true);
+            dst += md_word(a, v.z, j + 2, dst, true);
+            md_word(a, v.w, j + 3, dst, true);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_md_csr(const uint64_t* __restrict__ keys, const MdCtr* ctr, uint64_t n_hap,
+                                                uint32_t site_bits, uint64_t* site_begin, uint32_t* sites) {
+    const uint64_t n = ctr->n_unique;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sites[i] = (uint32_t)(keys[i] & ((1ull << site_bits) - 1));
+    if (i <= n_hap) {  // first key of haplotype >= i
+        const uint64_t want = i << site_bits;
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (keys[mid] < want) lo = mid + 1;
+            else hi = mid;
+        }
+        site_begin[i] = lo;
+    }
+}
+
 }  // namespace
 
 struct v2p_catalogue {
@@ -251,6 +369,8 @@ struct v2p_catalogue {
     Buf sites, site_begin, site_hap, flags, scan_in[6], scan_out[6], cub_tmp, totals;
     Buf g_first, g_len, g_slot, g_slot_x, g_hap, g_tx, ann_start, ann_end;
     Buf tasks, task_begin, alt_base, out_base, alt_per_hap, short_tot, mut_dst, alt, out;
+    // mask decode (v2p_sites_from_masks)
+    Buf md_masks, md_csq_begin, md_csq_site, md_keys[2], md_uniq, md_begin, md_sites, md_ctr;
 };
 
 namespace {
@@ -299,6 +419,9 @@ int xsum(v2p_catalogue* c, const uint64_t* in, uint64_t* out, uint64_t n) {
 
 inline unsigned blocks(uint64_t n) { return (unsigned)((n + 255) / 256); }
 
+int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const uint64_t* d_site_begin, const uint32_t* d_sites,
+                       uint32_t flags, v2p_generated* out);
+
 }  // namespace
 
 extern "C" {
@@ -339,7 +462,8 @@ void v2p_catalogue_destroy(v2p_catalogue* c) {
     Buf* all[] = {&c->tx_off, &c->tx, &c->pos, &c->rlen, &c->dlen, &c->cls, &c->doff, &c->pool, &c->sites, &c->site_begin,
                   &c->site_hap, &c->flags, &c->cub_tmp, &c->totals, &c->g_first, &c->g_len, &c->g_slot, &c->g_slot_x, &c->g_hap,
                   &c->g_tx, &c->ann_start, &c->ann_end, &c->tasks, &c->task_begin, &c->alt_base, &c->out_base, &c->alt_per_hap,
-                  &c->short_tot, &c->mut_dst, &c->alt, &c->out};
+                  &c->short_tot, &c->mut_dst, &c->alt, &c->out, &c->md_masks, &c->md_csq_begin, &c->md_csq_site, &c->md_keys[0],
+                  &c->md_keys[1], &c->md_uniq, &c->md_begin, &c->md_sites, &c->md_ctr};
     for (Buf* b : all)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 6; ++i) {
@@ -369,11 +493,113 @@ int v2p_generate_tasks(v2p_catalogue* c, uint64_t n_hap, const uint64_t* site_be
     if (n_sel && !sites) return cfail(c, V2P_ERR_INVALID_ARG, "sites is NULL");
     for (uint64_t h = 0; h < n_hap; ++h)
         if (site_begin[h + 1] < site_begin[h]) return cfail(c, V2P_ERR_INVALID_ARG, "site_begin not monotone");
+    int rc;
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    if ((rc = upload(c, c->sites, sites, n_sel * 4)) || (rc = upload(c, c->site_begin, site_begin, (n_hap + 1) * 8))) return rc;
+    return generate_on_device(c, n_hap, n_sel, (const uint64_t*)c->site_begin.p, (const uint32_t*)c->sites.p, flags, out);
+}
+
+int v2p_sites_from_masks(v2p_catalogue* c, uint64_t n_records, uint64_t n_samples, uint32_t words_per_cell,
+                         const uint32_t* masks, const uint64_t* csq_begin, const int32_t* csq_site, uint32_t flags,
+                         v2p_site_lists* out) {
+    if (!c || !out || !csq_begin || !words_per_cell || csq_begin[0] != 0) return V2P_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    c->err.clear();
+    const uint64_t n_words = n_records * n_samples * words_per_cell, n_hap = 2 * n_samples, n_csq = csq_begin[n_records];
+    if ((n_words && !masks) || (n_csq && !csq_site)) return cfail(c, V2P_ERR_INVALID_ARG, "masks / csq_site is NULL");
+    if (n_hap >> 31) return cfail(c, V2P_ERR_INVALID_ARG, "more than 2^30 samples");
+    for (uint64_t r = 0; r < n_records; ++r)
+        if (csq_begin[r + 1] < csq_begin[r]) return cfail(c, V2P_ERR_INVALID_ARG, "csq_begin not monotone");
+    for (uint64_t k = 0; k < n_csq; ++k)
+        if (csq_site[k] >= 0 && (uint64_t)csq_site[k] >= c->n_sites)
+            return cfail(c, V2P_ERR_INVALID_ARG, "csq_site[%llu] = %d is not a catalogue site", (unsigned long long)k, csq_site[k]);
+    CU(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     int rc;
     CU(c, cudaEventRecord(c->ev0, st));
-    if ((rc = upload(c, c->sites, sites, n_sel * 4)) || (rc = upload(c, c->site_begin, site_begin, (n_hap + 1) * 8)) ||
-        (rc = need(c, c->site_hap, n_sel * 4 + 16)) || (rc = need(c, c->flags, n_sel + 16)) || (rc = need(c, c->mut_dst, n_sel * 8 + 16)) ||
+    const uint32_t* d_masks = masks;
+    if (!(flags & V2P_FLAG_DEVICE_PTRS)) {
+        if ((rc = upload(c, c->md_masks, masks, n_words * 4))) return rc;
+        d_masks = (const uint32_t*)c->md_masks.p;
+    } else if ((uintptr_t)masks & 15) {
+        return cfail(c, V2P_ERR_INVALID_ARG, "device mask matrix must be 16-byte aligned");
+    }
+    if ((rc = upload(c, c->md_csq_begin, csq_begin, (n_records + 1) * 8)) || (rc = upload(c, c->md_csq_site, csq_site, n_csq * 4)) ||
+        (rc = need(c, c->md_ctr, sizeof(MdCtr))) || (rc = need(c, c->md_begin, (n_hap + 1) * 8)))
+        return rc;
+    MdCtr* ctr = (MdCtr*)c->md_ctr.p;
+    MdCtr h{0, 0, ~0ull, 0};
+    CU(c, cudaMemcpyAsync(ctr, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_words + 1023) / 1024 + 1, (uint64_t)sms * 16);
+    if (n_words) k_md_count<<<grid, 256, 0, st>>>(d_masks, n_words, ctr);
+    CU(c, cudaMemcpyAsync(&h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    const uint64_t cap = h.n_bits;  // upper bound of the keys: every set bit
+    uint32_t site_bits = 1, hap_bits = 1;
+    while ((1ull << site_bits) < c->n_sites) ++site_bits;
+    while ((1ull << hap_bits) < n_hap + 1) ++hap_bits;
+    if ((rc = need(c, c->md_keys[0], cap * 8 + 16)) || (rc = need(c, c->md_keys[1], cap * 8 + 16)) ||
+        (rc = need(c, c->md_uniq, cap * 8 + 16)) || (rc = need(c, c->md_sites, cap * 4 + 16)))
+        return rc;
+    uint64_t n_unique = 0;
+    if (cap) {
+        MdArgs a{d_masks, n_words, n_samples, words_per_cell, site_bits, (const uint64_t*)c->md_csq_begin.p,
+                 (const int32_t*)c->md_csq_site.p, (uint64_t*)c->md_keys[0].p, ctr};
+        k_md_emit<<<grid, 256, 0, st>>>(a);
+        CU(c, cudaMemcpyAsync(&h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        if (h.bad_record != ~0ull)
+            return cfail(c, V2P_ERR_SRC_OOB, "record %llu: a mask bit selects a consequence beyond the record's %llu (vcf_ds.rs:287)",
+                         h.bad_record, (unsigned long long)(csq_begin[h.bad_record + 1] - csq_begin[h.bad_record]));
+        const uint64_t n_keys = h.cursor;
+        if (n_keys) {
+            cub::DoubleBuffer<uint64_t> db((uint64_t*)c->md_keys[0].p, (uint64_t*)c->md_keys[1].p);
+            size_t tmp = 0;
+            CU(c, cub::DeviceRadixSort::SortKeys(nullptr, tmp, db, (int64_t)n_keys, 0, (int)(site_bits + hap_bits), st));
+            if ((rc = need(c, c->cub_tmp, tmp))) return rc;
+            CU(c, cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp, db, (int64_t)n_keys, 0, (int)(site_bits + hap_bits), st));
+            CU(c, cub::DeviceSelect::Unique(nullptr, tmp, db.Current(), (uint64_t*)c->md_uniq.p, &ctr->n_unique, (int64_t)n_keys, st));
+            if ((rc = need(c, c->cub_tmp, tmp))) return rc;
+            CU(c, cub::DeviceSelect::Unique(c->cub_tmp.p, tmp, db.Current(), (uint64_t*)c->md_uniq.p, &ctr->n_unique, (int64_t)n_keys, st));
+            CU(c, cudaMemcpyAsync(&h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaStreamSynchronize(st));
+            n_unique = h.n_unique;
+        }
+    }
+    k_md_csr<<<blocks(std::max<uint64_t>(n_unique, n_hap + 1)), 256, 0, st>>>((const uint64_t*)c->md_uniq.p, ctr, n_hap, site_bits,
+                                                                             (uint64_t*)c->md_begin.p, (uint32_t*)c->md_sites.p);
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev1, st));
+    CU(c, cudaStreamSynchronize(st));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    out->n_hap = n_hap, out->n_sites = n_unique;
+    out->site_begin = (const uint64_t*)c->md_begin.p, out->sites = (const uint32_t*)c->md_sites.p;
+    out->decode_ms = ms;
+    return V2P_OK;
+}
+
+int v2p_generate_tasks_from_lists(v2p_catalogue* c, const v2p_site_lists* lists, uint32_t flags, v2p_generated* out) {
+    if (!c || !out || !lists || (lists->n_hap && !lists->site_begin)) return V2P_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    c->err.clear();
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    return generate_on_device(c, lists->n_hap, lists->n_sites, lists->site_begin, lists->sites, flags, out);
+}
+
+}  // extern "C"
+
+namespace {
+
+// site_begin / sites are device pointers here; c->ev0 has been recorded by the caller
+int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const uint64_t* d_site_begin, const uint32_t* d_sites,
+                       uint32_t flags, v2p_generated* out) {
+    cudaStream_t st = c->stream;
+    int rc;
+    if ((rc = need(c, c->site_hap, n_sel * 4 + 16)) || (rc = need(c, c->flags, n_sel + 16)) || (rc = need(c, c->mut_dst, n_sel * 8 + 16)) ||
         (rc = need(c, c->totals, 64)))
         return rc;
     for (int i = 0; i < 6; ++i)
@@ -382,7 +608,7 @@ int v2p_generate_tasks(v2p_catalogue* c, uint64_t n_hap, const uint64_t* site_be
             (const uint32_t*)c->dlen.p, (const uint8_t*)c->cls.p, (const uint64_t*)c->doff.p, (const uint8_t*)c->pool.p};
     Sel s{};
     s.n_sel = n_sel, s.n_hap = n_hap;
-    s.sites = (const uint32_t*)c->sites.p, s.site_begin = (const uint64_t*)c->site_begin.p;
+    s.sites = d_sites, s.site_begin = d_site_begin;
     s.site_hap = (uint32_t*)c->site_hap.p, s.flags = (uint8_t*)c->flags.p;
     uint64_t** ins[6] = {&s.cnt, &s.slen, &s.acon, &s.newg, &s.shortc, &s.slotl};
     uint64_t** outs[6] = {&s.task_x, &s.l_x, &s.a_x, &s.g_x, &s.sh_x, &s.sl_x};
@@ -470,4 +696,5 @@ int v2p_generate_tasks(v2p_catalogue* c, uint64_t n_hap, const uint64_t* site_be
     return V2P_OK;
 }
 
-}  // extern "C"
+}  // namespace
+

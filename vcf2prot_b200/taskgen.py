@@ -51,6 +51,34 @@ class DeviceCatalogue:
             raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
         return g
 
+    def sites_from_masks(self, masks, csq_begin: np.ndarray, csq_site: np.ndarray, shape=None) -> L.SiteLists:
+        """masks[n_records, n_samples, W] (the decimal FORMAT/BCSQ words) -> device CSR site lists per haplotype
+        (MaskDecoder.rs:95-153 + the per-sample transpose, vcf_ds.rs:126-295).  `masks` is a numpy array, or a device
+        pointer (int) together with shape=(n_records, n_samples, W)."""
+        flags = 0
+        if isinstance(masks, np.ndarray):
+            masks = np.ascontiguousarray(masks, np.uint32)
+            n_rec, n_samp, w = masks.shape
+            mp = masks.ctypes.data_as(C.c_void_p)
+        else:
+            n_rec, n_samp, w = shape
+            mp, flags = C.c_void_p(int(masks)), L.FLAG_DEVICE_PTRS
+        cb = np.ascontiguousarray(csq_begin, np.uint64)
+        cs = np.ascontiguousarray(csq_site, np.int32)
+        out = L.SiteLists()
+        st = self._lib.v2p_sites_from_masks(self._h, n_rec, n_samp, w, mp, cb.ctypes.data_as(C.c_void_p),
+                                            cs.ctypes.data_as(C.c_void_p), flags, C.byref(out))
+        if st:
+            raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
+        return out
+
+    def generate_from_lists(self, lists: L.SiteLists, aligned: bool = True) -> L.Generated:
+        g = L.Generated()
+        st = self._lib.v2p_generate_tasks_from_lists(self._h, C.byref(lists), L.GEN_ALIGNED if aligned else 0, C.byref(g))
+        if st:
+            raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
+        return g
+
     def read(self, dev_ptr, count: int, dtype) -> np.ndarray:
         out = np.zeros(count, dtype)
         if count:
