@@ -392,6 +392,7 @@ def main():
     # ---- the same cohort's Task arrays generated ON the device from the per-haplotype site lists
     taskgen = None
     if world == 1 and not args.no_taskgen and not args.fasta_image and batch.kept_hap is not None:
+        from vcf2prot_b200 import cohort as C
         from vcf2prot_b200.taskgen import DeviceCatalogue
 
         dc = DeviceCatalogue(prot, cat, local_rank)
