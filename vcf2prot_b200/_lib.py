@@ -47,6 +47,11 @@ class SiteLists(C.Structure):
                 ("decode_ms", C.c_float)]
 
 
+class GzipResult(C.Structure):
+    _fields_ = [("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("n_chunks", C.c_uint64), ("n_stored_chunks", C.c_uint64),
+                ("ms", C.c_float)]
+
+
 SYMBOLS = {
     "v2p_abi_version": (C.c_int, []),
     "v2p_engine_from_str": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
@@ -74,6 +79,11 @@ SYMBOLS = {
     "v2p_sites_from_masks": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint32, C.POINTER(SiteLists)]),
     "v2p_generate_tasks_from_lists": (C.c_int, [_P, C.POINTER(SiteLists), C.c_uint32, C.POINTER(Generated)]),
     "v2p_device_read": (C.c_int, [_P, _P, C.c_size_t]),
+    "v2p_gzip_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "v2p_gzip_destroy": (None, [_P]),
+    "v2p_gzip_last_error": (C.c_char_p, [_P]),
+    "v2p_gzip_bound": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "v2p_gzip_files": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint64, _P, C.c_uint32, C.POINTER(GzipResult)]),
 }
 
 _lib = None
