@@ -108,8 +108,10 @@ def code_lengths(freq: Sequence[int], limit: int = 15) -> List[int]:
 
 
 def header_ops(lens: Sequence[int]) -> List[Tuple[int, int, int]]:
-    """The 257 literal/length lengths + 1 distance length (0) as code-length symbols: (symbol, extra value, extra bits)."""
-    seq = list(lens) + [0]
+    """The 257 literal/length lengths + 1 distance length (0) as code-length symbols: (symbol, extra value, extra bits).
+    Lengths of the 256 byte values are run-length coded (one run per device thread group); the end-of-block length and
+    the zero distance length follow as two plain symbols."""
+    seq = list(lens[:256])
     ops, i = [], 0
     while i < len(seq):
         v, r = seq[i], 1
@@ -133,7 +135,7 @@ def header_ops(lens: Sequence[int]) -> List[Tuple[int, int, int]]:
                 ops.append((16, t - 3, 2))
                 r -= t
             ops.extend([(v, 0, 0)] * r)
-    return ops
+    return ops + [(lens[256], 0, 0), (0, 0, 0)]
 
 
 def encode_chunk(data: bytes) -> bytes:

@@ -36,7 +36,9 @@ __constant__ uint8_t c_cl_code[19] = {0, 11, 27, 7, 8, 4, 12, 2, 10, 6, 14, 1, 9
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 __device__ uint32_t g_crc_tab[256];
-__device__ uint32_t g_xp8[40];  // x^(8 * 2^j) mod P, reflected
+__device__ uint32_t g_xp8[40];   // x^(8 * 2^j) mod P, reflected
+__device__ uint32_t g_x64[256];  // x^(8 * 64 * k): a CRC moved past k whole pieces
+__device__ uint32_t g_xb[65];    // x^(8 * m),  m = 0..64
 
 // a*b mod P, reflected representation (bit 31 is x^0)
 __device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {
@@ -61,11 +63,19 @@ __global__ void k_gz_init() {
     uint32_t c = (uint32_t)t;
     for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? POLY : 0u);
     g_crc_tab[t] = c;
+    uint32_t x8 = 0x80000000u >> 8, xb = 0x80000000u, x64;  // x^8, then x^(8t) by t multiplications
+    for (int k = 0; k < t && k < 65; ++k) xb = gf_mul(xb, x8);
+    if (t < 65) g_xb[t] = xb;
+    x64 = x8;
+    for (int k = 0; k < 6; ++k) x64 = gf_mul(x64, x64);  // x^(8*64)
+    uint32_t v = 0x80000000u;
+    for (int k = 0; k < t; ++k) v = gf_mul(v, x64);
+    g_x64[t] = v;
     if (t == 0) {
-        uint32_t v = 0x80000000u >> 8;  // x^8
+        uint32_t sq = x8;
         for (int j = 0; j < 40; ++j) {
-            g_xp8[j] = v;
-            v = gf_mul(v, v);
+            g_xp8[j] = sq;
+            sq = gf_mul(sq, sq);
         }
     }
 }
@@ -196,61 +206,92 @@ __device__ void build_lengths(Tree& t, uint8_t* lens) {
         for (uint32_t r = 0; r < t.num[l]; ++r) lens[t.sym[i++]] = (uint8_t)l;
 }
 
-// The block header after the 3 block-type bits: HLIT=257, HDIST=1, HCLEN=19, the fixed code-length code, then the 257
-// literal/length lengths and the single (unused, zero) distance length as run-length coded code-length symbols.
+// ---- block header ---------------------------------------------------------------------------------------------------
+// After the 3 block-type bits: HLIT=257, HDIST=1, HCLEN=19, the fixed code-length code (74 bits so far), then the code
+// lengths as code-length symbols: the 256 byte values run-length coded -- one thread per run, so both the size and
+// the bits come out of a block-wide scan instead of a serial walk -- then the end-of-block length and the single
+// (unused, zero) distance length as two plain symbols.
+constexpr uint32_t HDR_FIXED_BITS = 3 + 5 + 5 + 4 + 19 * 3;
+
 struct BitSink {
-    uint32_t* words;  // nullptr: count only
+    uint32_t* words;
     uint32_t pos;
     __device__ __forceinline__ void put(uint32_t v, uint32_t nbits) {
-        if (words) {
-            const uint32_t w = pos >> 5, sh = pos & 31;
-            const uint64_t x = (uint64_t)v << sh;
-            atomicOr(&words[w], (uint32_t)x);
-            if (sh + nbits > 32) atomicOr(&words[w + 1], (uint32_t)(x >> 32));
-        }
+        const uint32_t w = pos >> 5, sh = pos & 31;
+        const uint64_t x = (uint64_t)v << sh;
+        atomicOr(&words[w], (uint32_t)x);
+        if (sh + nbits > 32) atomicOr(&words[w + 1], (uint32_t)(x >> 32));
         pos += nbits;
     }
     __device__ __forceinline__ void cl(uint32_t s, uint32_t xv, uint32_t xb) {
-        put(c_cl_code[s], c_cl_len[s]);
-        if (xb) put(xv, xb);
+        put(c_cl_code[s] | xv << c_cl_len[s], c_cl_len[s] + xb);
     }
 };
 
-__device__ void emit_header(const uint8_t* lens, BitSink& o) {
-    o.put(0, 1);   // BFINAL
-    o.put(2, 2);   // dynamic Huffman
-    o.put(0, 5);   // HLIT  - 257
-    o.put(0, 5);   // HDIST - 1
-    o.put(15, 4);  // HCLEN - 4
-    for (int i = 0; i < 19; ++i) o.put(c_cl_len[c_cl_order[i]], 3);
-    int i = 0;
-    while (i < 258) {
-        const uint32_t v = i < 257 ? lens[i] : 0;
-        int r = 1;
-        while (i + r < 258 && (i + r < 257 ? lens[i + r] : 0) == v) ++r;
-        i += r;
-        if (v == 0) {
-            while (r >= 11) {
-                const int t = min(r, 138);
-                o.cl(18, t - 11, 7);
-                r -= t;
-            }
-            if (r >= 3) {
-                o.cl(17, r - 3, 3);
-                r = 0;
-            }
-            for (; r > 0; --r) o.cl(0, 0, 0);
-        } else {
-            o.cl(v, 0, 0);
-            --r;
-            while (r >= 3) {
-                const int t = min(r, 6);
-                o.cl(16, t - 3, 2);
-                r -= t;
-            }
-            for (; r > 0; --r) o.cl(v, 0, 0);
-        }
+__device__ __forceinline__ uint32_t run_bits(uint32_t v, uint32_t r) {
+    if (v == 0) {
+        const uint32_t k = r / 138, rem = r % 138;
+        return k * (c_cl_len[18] + 7u) + (rem >= 11 ? c_cl_len[18] + 7u : rem >= 3 ? c_cl_len[17] + 3u : rem * c_cl_len[0]);
     }
+    const uint32_t q = r - 1, k = q / 6, rem = q % 6, lv = c_cl_len[v];
+    return lv + k * (c_cl_len[16] + 2u) + (rem >= 3 ? c_cl_len[16] + 2u : rem * lv);
+}
+
+__device__ void emit_run(BitSink& o, uint32_t v, uint32_t r) {
+    if (v == 0) {
+        while (r >= 11) {
+            const uint32_t t = min(r, 138u);
+            o.cl(18, t - 11, 7);
+            r -= t;
+        }
+        if (r >= 3) {
+            o.cl(17, r - 3, 3);
+            r = 0;
+        }
+        for (; r > 0; --r) o.cl(0, 0, 0);
+    } else {
+        o.cl(v, 0, 0);
+        --r;
+        while (r >= 3) {
+            const uint32_t t = min(r, 6u);
+            o.cl(16, t - 3, 2);
+            r -= t;
+        }
+        for (; r > 0; --r) o.cl(v, 0, 0);
+    }
+}
+
+// thread t < 256 looks at byte value t: is it the first of a run of equal code lengths, and how long is the run.
+// s_mask[8] must hold the ballots of `start` (one word per warp) and be visible (barrier) before the call.
+__device__ __forceinline__ uint32_t run_length(const uint32_t* s_mask, int t) {
+    int w = t >> 5;
+    const int lane = t & 31;
+    uint32_t m = lane == 31 ? 0u : s_mask[w] & (~0u << (lane + 1));
+    while (!m && ++w < NT / 32) m = s_mask[w];
+    return (m ? w * 32 + __ffs(m) - 1 : 256) - t;
+}
+
+// block-wide exclusive scan of one value per thread (NT threads); two barriers; *total = sum over the block
+__device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* s_scan, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    __syncthreads();  // s_scan free
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        const uint32_t x = s_scan[w];
+        before += w < warp ? x : 0u;
+        tot += x;
+    }
+    *total = tot;
+    return before + incl - v;
 }
 
 // ---- pass 1 ---------------------------------------------------------------------------------------------------------
@@ -258,11 +299,12 @@ __global__ void __launch_bounds__(NT) k_gz_plan(GzArgs a) {
     __shared__ __align__(16) uint32_t s_in[CH / 4 + 8];
     __shared__ uint32_t s_hist[NT / 32][260];
     __shared__ uint32_t s_tab[256];
-    __shared__ uint32_t s_key[260];
+    __shared__ uint32_t s_used[260];
     __shared__ uint8_t s_lens[LENS_STRIDE];
     __shared__ Tree s_tree;
     __shared__ ChunkPos s_pos;
-    __shared__ uint32_t s_red[NT / 32];
+    __shared__ uint32_t s_red[NT / 32], s_mask[NT / 32], s_cnt[NT / 32], s_scan[NT / 32];
+    __shared__ uint32_t s_last_crc;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     s_tab[t] = g_crc_tab[t];
 
@@ -282,8 +324,9 @@ __global__ void __launch_bounds__(NT) k_gz_plan(GzArgs a) {
         load_chunk(s_in, a, p.begin, p.n);
         __syncthreads();
 
-        // this thread's piece: histogram + CRC-32, then its share of the chunk CRC
-        const int my = max(0, min(PIECE, (int)p.n - t * PIECE));
+        // my piece: histogram + CRC-32; the chunk CRC is  x^(8m) * XOR_t x^(8*64*(np-2-t)) * crc_t  ^  crc_last
+        // (np pieces, the last one m bytes long): one GF(2) multiplication per thread
+        const int np = (int)(p.n + PIECE - 1) / PIECE, my = max(0, min(PIECE, (int)p.n - t * PIECE));
         uint32_t crc = 0xFFFFFFFFu;
         for (int k = 0; k * 4 < my; ++k) {
             uint32_t wd = s_in[t * (PIECE / 4) + k];
@@ -294,53 +337,68 @@ __global__ void __launch_bounds__(NT) k_gz_plan(GzArgs a) {
                 crc = s_tab[(crc ^ byte) & 255u] ^ (crc >> 8);
             }
         }
-        crc = my ? ~crc : 0u;
-        uint32_t part = my ? gf_mul(x_pow_8n((uint64_t)(p.n - t * PIECE - my)), crc) : 0u;
+        crc = ~crc;
+        uint32_t part = t < np - 1 ? gf_mul(g_x64[np - 2 - t], crc) : 0u;
+        if (t == np - 1) s_last_crc = crc;
 #pragma unroll
         for (int d = 16; d; d >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, d);
         if (lane == 0) s_red[warp] = part;
         __syncthreads();
 
-        // frequencies and the sort key (frequency, symbol); symbol 256 (end of block) occurs once
+        // frequencies; the used symbols compacted (symbol 256, end of block, occurs once and goes last)
         uint32_t f = 0;
+#pragma unroll
         for (int w = 0; w < NT / 32; ++w) f += s_hist[w][t];
-        s_key[t] = f ? (f << 9 | (uint32_t)t) : 0xFFFFFFFFu;
-        if (t == 0) s_key[256] = (1u << 9) | 256u;
+        const uint32_t key = f << 9 | (uint32_t)t;  // sort key (frequency, symbol)
+        const uint32_t um = __ballot_sync(0xffffffffu, f != 0);
+        if (lane == 0) s_cnt[warp] = __popc(um);
         __syncthreads();
-        {
-            int n_used = 0;
-            uint32_t rank = 0, rank256 = 0;
-            const uint32_t mine = s_key[t];
-            for (int j = 0; j < 257; ++j) {
-                const uint32_t k = s_key[j];
-                n_used += k != 0xFFFFFFFFu;
-                rank += k < mine;
-                rank256 += k < ((1u << 9) | 256u);
+        int n_used = 1, at = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) {
+            const int x = (int)s_cnt[w];
+            at += w < warp ? x : 0;
+            n_used += x;
+        }
+        if (f) s_used[at + __popc(um & ((1u << lane) - 1u))] = key;
+        if (t == 0) s_used[n_used - 1] = 1u << 9 | 256u;
+        __syncthreads();
+        {  // rank among the used symbols = position in the sorted leaf list
+            const uint32_t eob = 1u << 9 | 256u;
+            int rank = 0, rank_eob = 0;
+            for (int j = 0; j < n_used; ++j) {
+                const uint32_t k = s_used[j];
+                rank += k < key;
+                rank_eob += k < eob;
             }
-            if (mine != 0xFFFFFFFFu) s_tree.sym[rank] = (uint16_t)t, s_tree.w[rank] = mine >> 9;
-            if (t == 0) s_tree.sym[rank256] = 256, s_tree.w[rank256] = 1, s_tree.n = n_used;
+            if (f) s_tree.sym[rank] = (uint16_t)t, s_tree.w[rank] = f;
+            if (t == 0) s_tree.sym[rank_eob] = 256, s_tree.w[rank_eob] = 1, s_tree.n = n_used;
         }
         __syncthreads();
         if (t == 0) {
             build_lengths(s_tree, s_lens);
-            BitSink hs{nullptr, 0};
-            emit_header(s_lens, hs);
-            s_key[258] = hs.pos;
             uint32_t c32 = 0;
+#pragma unroll
             for (int w = 0; w < NT / 32; ++w) c32 ^= s_red[w];
-            a.ccrc[c] = c32;
+            const uint32_t m = p.n - (uint32_t)(np - 1) * PIECE;
+            a.ccrc[c] = gf_mul(g_xb[m], c32) ^ s_last_crc;
         }
         __syncthreads();
-        // payload bits = sum f * len (+ the end-of-block code)
-        uint32_t bits = f * s_lens[t] + (t == 0 ? s_lens[256] : 0);
+        // header bits (one thread per run of equal lengths) + payload bits, reduced over the block
+        const uint32_t mylen = s_lens[t];
+        const bool start = t == 0 || s_lens[t - 1] != mylen;
+        const uint32_t sm = __ballot_sync(0xffffffffu, start);
+        if (lane == 0) s_mask[warp] = sm;
+        __syncthreads();
+        uint32_t bits = f * mylen + (start ? run_bits(mylen, run_length(s_mask, t)) : 0u);
 #pragma unroll
         for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
-        __syncthreads();  // s_red reuse
-        if (lane == 0) s_red[warp] = bits;
+        if (lane == 0) s_scan[warp] = bits;
         __syncthreads();
         if (t == 0) {
-            uint32_t tot = s_key[258];
-            for (int w = 0; w < NT / 32; ++w) tot += s_red[w];
+            uint32_t tot = HDR_FIXED_BITS + c_cl_len[s_lens[256]] + c_cl_len[0] + s_lens[256];
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) tot += s_scan[w];
             const uint32_t dyn = (tot + 3 + 7) / 8 + 4;  // + empty stored block header, aligned, 00 00 FF FF
             const bool stored = dyn >= p.n + 5;
             s_lens[260] = stored;
@@ -378,15 +436,16 @@ __global__ void __launch_bounds__(128) k_gz_files(GzArgs a) {
 }
 
 // ---- pass 2 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_gz_encode(GzArgs a) {
+__global__ void __launch_bounds__(NT, 4) k_gz_encode(GzArgs a) {
     __shared__ __align__(16) uint32_t s_in[CH / 4 + 8];
     __shared__ uint32_t s_out[CH / 4 + 16];
     __shared__ uint32_t s_code[260];  // reversed code | length << 16
     __shared__ uint8_t s_lens[LENS_STRIDE];
-    __shared__ uint32_t s_next[16];
-    __shared__ uint32_t s_scan[NT / 32];
+    __shared__ uint16_t s_usym[260];
+    __shared__ uint32_t s_next[16], s_lcnt[16];
+    __shared__ uint32_t s_scan[NT / 32], s_mask[NT / 32], s_cnt[NT / 32];
     __shared__ ChunkPos s_pos;
-    __shared__ uint32_t s_hdr_end, s_bytes;
+    __shared__ uint32_t s_bytes;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
     for (uint64_t c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
@@ -394,6 +453,7 @@ __global__ void __launch_bounds__(NT) k_gz_encode(GzArgs a) {
         if (t == 0) s_pos = locate(a, c);
         for (int i = t; i < LENS_STRIDE; i += NT) s_lens[i] = a.lens[c * LENS_STRIDE + i];
         for (int i = t; i < CH / 4 + 16; i += NT) s_out[i] = 0;
+        if (t < 16) s_lcnt[t] = 0;
         __syncthreads();
         const ChunkPos p = s_pos;
         if (p.n == 0) continue;
@@ -410,79 +470,91 @@ __global__ void __launch_bounds__(NT) k_gz_encode(GzArgs a) {
             continue;
         }
         const uint32_t dph = (uint32_t)((uintptr_t)dst & 3u);  // s_out word 0 <-> the aligned word holding dst[0]
-        if (t == 0) {  // first code of every length (RFC 1951 3.2.2)
-            uint32_t cnt[16];
-            for (int l = 0; l < 16; ++l) cnt[l] = 0;
-            for (int s = 0; s < 257; ++s) cnt[s_lens[s]]++;
-            cnt[0] = 0;
+        const uint32_t mylen = s_lens[t], eoblen = s_lens[256];
+        const bool start = t == 0 || s_lens[t - 1] != mylen;
+        const uint32_t sm = __ballot_sync(0xffffffffu, start), um = __ballot_sync(0xffffffffu, mylen != 0);
+        if (lane == 0) s_mask[warp] = sm, s_cnt[warp] = __popc(um);
+        if (mylen) atomicAdd(&s_lcnt[mylen], 1u);
+        if (t == 0) atomicAdd(&s_lcnt[eoblen], 1u);
+        __syncthreads();
+        // used byte values in symbol order (for the canonical codes); first code of every length (RFC 1951 3.2.2)
+        int n_used = 1, at = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) {
+            const int x = (int)s_cnt[w];
+            at += w < warp ? x : 0;
+            n_used += x;
+        }
+        at += __popc(um & ((1u << lane) - 1u));
+        if (mylen) s_usym[at] = (uint16_t)t;
+        if (t == 0) {
             uint32_t code = 0;
             for (int l = 1; l < 16; ++l) {
-                code = (code + cnt[l - 1]) << 1;
+                code = (code + (l > 1 ? s_lcnt[l - 1] : 0u)) << 1;
                 s_next[l] = code;
             }
-        } else if (t == 32) {
-            BitSink hs{s_out, dph * 8};
-            emit_header(s_lens, hs);
-            s_hdr_end = hs.pos;
         }
-        __syncthreads();
-        for (int s = t; s < 257; s += NT) {
-            const uint32_t l = s_lens[s];
-            uint32_t code = 0;
-            if (l) {
-                uint32_t before = 0;
-                for (int j = 0; j < s; ++j) before += s_lens[j] == l;
-                code = __brev(s_next[l] + before) >> (32 - l);
-            }
-            s_code[s] = code | l << 16;
+        const uint32_t run = start ? run_length(s_mask, t) : 0u;
+        uint32_t hdr_total;
+        const uint32_t hdr_at = block_scan(start ? run_bits(mylen, run) : 0u, s_scan, &hdr_total);  // barriers inside
+        const uint32_t hdr0 = dph * 8;
+        if (start) {
+            BitSink o{s_out, hdr0 + HDR_FIXED_BITS + hdr_at};
+            emit_run(o, mylen, run);
+        }
+        if (t == 32) {
+            BitSink o{s_out, hdr0};
+            o.put(0u | 2u << 1, 3);               // not final, dynamic Huffman
+            o.put(0u | 0u << 5 | 15u << 10, 14);  // HLIT - 257, HDIST - 1, HCLEN - 4
+            for (int i = 0; i < 19; ++i) o.put(c_cl_len[c_cl_order[i]], 3);
+            o.pos = hdr0 + HDR_FIXED_BITS + hdr_total;
+            o.cl(eoblen, 0, 0);
+            o.cl(0, 0, 0);
+        }
+        const uint32_t data0 = hdr0 + HDR_FIXED_BITS + hdr_total + c_cl_len[eoblen] + c_cl_len[0];
+        if (mylen) {
+            uint32_t before = 0;
+            for (int j = 0; j < at; ++j) before += s_lens[s_usym[j]] == mylen;
+            s_code[t] = (__brev(s_next[mylen] + before) >> (32 - mylen)) | mylen << 16;
+        } else {
+            s_code[t] = 0;
+        }
+        if (t == 0) {  // end of block is the last symbol of its length
+            uint32_t before = 0;
+            for (int j = 0; j < n_used - 1; ++j) before += s_lens[s_usym[j]] == eoblen;
+            s_code[256] = (__brev(s_next[eoblen] + before) >> (32 - eoblen)) | eoblen << 16;
         }
         __syncthreads();
         // bits of my piece, block-wide exclusive scan, then pack
         const int my = max(0, min(PIECE, (int)p.n - t * PIECE));
-        uint32_t wd[PIECE / 4];
         uint32_t bits = 0;
-#pragma unroll
-        for (int k = 0; k < PIECE / 4; ++k) {
-            wd[k] = s_in[t * (PIECE / 4) + k];
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (k * 4 + b < my) bits += s_code[(wd[k] >> (8 * b)) & 255u] >> 16;
+        for (int k = 0; k * 4 < my; ++k) {
+            const uint32_t wd = s_in[t * (PIECE / 4) + k];
+            const int nb = min(4, my - k * 4);
+            for (int b = 0; b < nb; ++b) bits += s_code[(wd >> (8 * b)) & 255u] >> 16;
         }
-        uint32_t incl = bits;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-        for (int w = 0; w < NT / 32; ++w) {
-            before += w < warp ? s_scan[w] : 0;
-            total += s_scan[w];
-        }
-        uint32_t pos = s_hdr_end + before + incl - bits;
+        uint32_t total;
+        uint32_t pos = data0 + block_scan(bits, s_scan, &total);
         {
             uint64_t acc = 0;
             uint32_t have = pos & 31, word = pos >> 5;  // acc holds `have` bits below the next code
-#pragma unroll
-            for (int k = 0; k < PIECE / 4; ++k) {
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (k * 4 + b < my) {
-                        const uint32_t cl = s_code[(wd[k] >> (8 * b)) & 255u];
-                        acc |= (uint64_t)(cl & 0xFFFFu) << have;
-                        have += cl >> 16;
-                        if (have >= 32) {
-                            atomicOr(&s_out[word++], (uint32_t)acc);
-                            acc >>= 32, have -= 32;
-                        }
+            for (int k = 0; k * 4 < my; ++k) {
+                const uint32_t wd = s_in[t * (PIECE / 4) + k];
+                const int nb = min(4, my - k * 4);
+                for (int b = 0; b < nb; ++b) {
+                    const uint32_t cl = s_code[(wd >> (8 * b)) & 255u];
+                    acc |= (uint64_t)(cl & 0xFFFFu) << have;
+                    have += cl >> 16;
+                    if (have >= 32) {
+                        atomicOr(&s_out[word++], (uint32_t)acc);
+                        acc >>= 32, have -= 32;
                     }
+                }
             }
-            if (have && acc) atomicOr(&s_out[word], (uint32_t)acc);
+            if (acc) atomicOr(&s_out[word], (uint32_t)acc);
         }
         if (t == 0) {  // end of block, empty stored block (3 zero bits), pad to a byte, 00 00 FF FF
-            BitSink o{s_out, s_hdr_end + total};
+            BitSink o{s_out, data0 + total};
             o.put(s_code[256] & 0xFFFFu, s_code[256] >> 16);
             o.pos = (o.pos + 3 + 7) & ~7u;
             o.pos += 16;
