@@ -1,12 +1,15 @@
 #!/usr/bin/env python
-"""Summarise an ncu report's source page per CUDA line: usage  profiles_tool.py report.ncu-rep [topN]"""
+"""Summarise an ncu report's source page per CUDA line: usage  ncu_lines.py report.ncu-rep [topN] [kernel-name]"""
 import csv, subprocess, sys
 rep=sys.argv[1]; top=int(sys.argv[2]) if len(sys.argv)>2 else 25
-txt=subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass'],stdout=subprocess.PIPE,stderr=subprocess.DEVNULL,text=True).stdout
+cmd=['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass']
+if len(sys.argv)>3: cmd+=['--kernel-name',sys.argv[3]]
+txt=subprocess.run(cmd,stdout=subprocess.PIPE,stderr=subprocess.DEVNULL,text=True).stdout
 rows=list(csv.reader(txt.splitlines()))
 h=None; lines=[]
 for r in rows:
     if r and r[0]=='Line No' and len(r)>5:
+        if '# Samples' not in r: h=None; continue
         h=r; S=h.index('# Samples'); I=h.index('Instructions Executed'); continue
     if h and len(r)==len(h) and r[0] not in ('','Line No'):
         try: lines.append((int(r[0]),r[1],int(r[S] or 0),int(r[I] or 0)))

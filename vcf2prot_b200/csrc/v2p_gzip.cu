@@ -35,7 +35,7 @@ __constant__ uint8_t c_cl_len[19] = {4, 5, 5, 5, 4, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5
 __constant__ uint8_t c_cl_code[19] = {0, 11, 27, 7, 8, 4, 12, 2, 10, 6, 14, 1, 9, 23, 15, 31, 5, 13, 3};
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-__device__ uint32_t g_crc_tab[256];
+__device__ uint32_t g_crc_tab[4][256];  // slicing-by-4: [k][b] = CRC of byte b followed by k zero bytes
 __device__ uint32_t g_xp8[40];   // x^(8 * 2^j) mod P, reflected
 __device__ uint32_t g_x64[256];  // x^(8 * 64 * k): a CRC moved past k whole pieces
 __device__ uint32_t g_xb[65];    // x^(8 * m),  m = 0..64
@@ -62,7 +62,12 @@ __global__ void k_gz_init() {
     const int t = threadIdx.x;
     uint32_t c = (uint32_t)t;
     for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? POLY : 0u);
-    g_crc_tab[t] = c;
+    g_crc_tab[0][t] = c;
+    __syncthreads();
+    for (int k = 1; k < 4; ++k) {
+        c = (c >> 8) ^ g_crc_tab[0][c & 255u];
+        g_crc_tab[k][t] = c;
+    }
     uint32_t x8 = 0x80000000u >> 8, xb = 0x80000000u, x64;  // x^8, then x^(8t) by t multiplications
     for (int k = 0; k < t && k < 65; ++k) xb = gf_mul(xb, x8);
     if (t < 65) g_xb[t] = xb;
@@ -298,7 +303,7 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* s_scan, uin
 __global__ void __launch_bounds__(NT) k_gz_plan(GzArgs a) {
     __shared__ __align__(16) uint32_t s_in[CH / 4 + 8];
     __shared__ uint32_t s_hist[NT / 32][260];
-    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_tab[4][256];
     __shared__ uint32_t s_used[260];
     __shared__ uint8_t s_lens[LENS_STRIDE];
     __shared__ Tree s_tree;
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(NT) k_gz_plan(GzArgs a) {
     __shared__ uint32_t s_red[NT / 32], s_mask[NT / 32], s_cnt[NT / 32], s_scan[NT / 32];
     __shared__ uint32_t s_last_crc;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    s_tab[t] = g_crc_tab[t];
+    for (int k = 0; k < 4; ++k) s_tab[k][t] = g_crc_tab[k][t];
 
     for (uint64_t c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
         __syncthreads();  // previous iteration done with shared memory
@@ -328,13 +333,33 @@ __global__ void __launch_bounds__(NT) k_gz_plan(GzArgs a) {
         // (np pieces, the last one m bytes long): one GF(2) multiplication per thread
         const int np = (int)(p.n + PIECE - 1) / PIECE, my = max(0, min(PIECE, (int)p.n - t * PIECE));
         uint32_t crc = 0xFFFFFFFFu;
-        for (int k = 0; k * 4 < my; ++k) {
-            uint32_t wd = s_in[t * (PIECE / 4) + k];
-            const int nb = min(4, my - k * 4);
-            for (int b = 0; b < nb; ++b, wd >>= 8) {
-                const uint32_t byte = wd & 255u;
-                atomicAdd(&s_hist[warp][byte], 1u);
-                crc = s_tab[(crc ^ byte) & 255u] ^ (crc >> 8);
+        uint32_t* hist = s_hist[warp];
+        if (my == PIECE) {  // whole piece: 16-byte shared loads, four bytes of CRC per step
+            const uint4* pv = reinterpret_cast<const uint4*>(s_in + t * (PIECE / 4));
+#pragma unroll
+            for (int q = 0; q < PIECE / 16; ++q) {
+                const uint4 v = pv[q];
+                const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t wd = wds[k];
+                    atomicAdd(&hist[wd & 255u], 1u);
+                    atomicAdd(&hist[(wd >> 8) & 255u], 1u);
+                    atomicAdd(&hist[(wd >> 16) & 255u], 1u);
+                    atomicAdd(&hist[wd >> 24], 1u);
+                    crc ^= wd;
+                    crc = s_tab[3][crc & 255u] ^ s_tab[2][(crc >> 8) & 255u] ^ s_tab[1][(crc >> 16) & 255u] ^ s_tab[0][crc >> 24];
+                }
+            }
+        } else {
+            for (int k = 0; k * 4 < my; ++k) {
+                uint32_t wd = s_in[t * (PIECE / 4) + k];
+                const int nb = min(4, my - k * 4);
+                for (int b = 0; b < nb; ++b, wd >>= 8) {
+                    const uint32_t byte = wd & 255u;
+                    atomicAdd(&hist[byte], 1u);
+                    crc = s_tab[0][(crc ^ byte) & 255u] ^ (crc >> 8);
+                }
             }
         }
         crc = ~crc;
@@ -528,26 +553,61 @@ __global__ void __launch_bounds__(NT, 4) k_gz_encode(GzArgs a) {
         // bits of my piece, block-wide exclusive scan, then pack
         const int my = max(0, min(PIECE, (int)p.n - t * PIECE));
         uint32_t bits = 0;
-        for (int k = 0; k * 4 < my; ++k) {
-            const uint32_t wd = s_in[t * (PIECE / 4) + k];
-            const int nb = min(4, my - k * 4);
-            for (int b = 0; b < nb; ++b) bits += s_code[(wd >> (8 * b)) & 255u] >> 16;
+        const uint4* pv = reinterpret_cast<const uint4*>(s_in + t * (PIECE / 4));
+        if (my == PIECE) {
+#pragma unroll
+            for (int q = 0; q < PIECE / 16; ++q) {
+                const uint4 v = pv[q];
+                const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    bits += (s_code[wds[k] & 255u] >> 16) + (s_code[(wds[k] >> 8) & 255u] >> 16) +
+                            (s_code[(wds[k] >> 16) & 255u] >> 16) + (s_code[wds[k] >> 24] >> 16);
+            }
+        } else {
+            for (int k = 0; k * 4 < my; ++k) {
+                const uint32_t wd = s_in[t * (PIECE / 4) + k];
+                const int nb = min(4, my - k * 4);
+                for (int b = 0; b < nb; ++b) bits += s_code[(wd >> (8 * b)) & 255u] >> 16;
+            }
         }
         uint32_t total;
         uint32_t pos = data0 + block_scan(bits, s_scan, &total);
         {
             uint64_t acc = 0;
             uint32_t have = pos & 31, word = pos >> 5;  // acc holds `have` bits below the next code
-            for (int k = 0; k * 4 < my; ++k) {
-                const uint32_t wd = s_in[t * (PIECE / 4) + k];
-                const int nb = min(4, my - k * 4);
-                for (int b = 0; b < nb; ++b) {
-                    const uint32_t cl = s_code[(wd >> (8 * b)) & 255u];
-                    acc |= (uint64_t)(cl & 0xFFFFu) << have;
-                    have += cl >> 16;
-                    if (have >= 32) {
-                        atomicOr(&s_out[word++], (uint32_t)acc);
-                        acc >>= 32, have -= 32;
+            if (my == PIECE) {
+#pragma unroll
+                for (int q = 0; q < PIECE / 16; ++q) {
+                    const uint4 v = pv[q];
+                    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {  // two codes (<= 30 bits) per 64-bit insert
+                            const uint32_t c0 = s_code[(wds[k] >> (16 * h)) & 255u], c1 = s_code[(wds[k] >> (16 * h + 8)) & 255u];
+                            const uint32_t l0 = c0 >> 16;
+                            acc |= (uint64_t)((c0 & 0xFFFFu) | (c1 & 0xFFFFu) << l0) << have;
+                            have += l0 + (c1 >> 16);
+                            if (have >= 32) {
+                                atomicOr(&s_out[word++], (uint32_t)acc);
+                                acc >>= 32, have -= 32;
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int k = 0; k * 4 < my; ++k) {
+                    const uint32_t wd = s_in[t * (PIECE / 4) + k];
+                    const int nb = min(4, my - k * 4);
+                    for (int b = 0; b < nb; ++b) {
+                        const uint32_t cl = s_code[(wd >> (8 * b)) & 255u];
+                        acc |= (uint64_t)(cl & 0xFFFFu) << have;
+                        have += cl >> 16;
+                        if (have >= 32) {
+                            atomicOr(&s_out[word++], (uint32_t)acc);
+                            acc >>= 32, have -= 32;
+                        }
                     }
                 }
             }
