@@ -128,6 +128,30 @@ __device__ __forceinline__ void load_chunk(uint32_t* s_in, const GzArgs& a, uint
     const uint4* base = reinterpret_cast<const uint4*>(src - ph);
     const uint8_t* lo = a.in + a.in_lo;
     const uint8_t* hi = a.in + a.in_hi;
+    if (n == CH && src - ph >= lo && src + CH + 16 <= hi) {  // whole chunk inside the buffer: all loads in flight at once
+        const uint32_t wsh = ph >> 2, bsh = (ph & 3u) * 8;
+        uint4 x[CH / 16 / NT], y[CH / 16 / NT];
+#pragma unroll
+        for (int u = 0; u < CH / 16 / NT; ++u) {
+            x[u] = __ldcs(base + threadIdx.x + u * NT);
+            y[u] = __ldcs(base + threadIdx.x + u * NT + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < CH / 16 / NT; ++u) {
+            const uint32_t q[8] = {x[u].x, x[u].y, x[u].z, x[u].w, y[u].x, y[u].y, y[u].z, y[u].w};
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t a0 = 0, a1 = 0;
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (wsh == (uint32_t)m) a0 = q[k + m], a1 = q[k + m + 1 < 8 ? k + m + 1 : 7];
+                w[k] = __funnelshift_r(a0, a1, bsh);
+            }
+            *reinterpret_cast<uint4*>(s_in + (threadIdx.x + u * NT) * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return;
+    }
     for (uint32_t v = threadIdx.x; v * 16 < n; v += NT) {
         const uint8_t* g0 = reinterpret_cast<const uint8_t*>(base + v);
         uint32_t w[4];
@@ -161,54 +185,76 @@ __device__ __forceinline__ void load_chunk(uint32_t* s_in, const GzArgs& a, uint
 struct Tree {
     uint32_t w[2 * 257];
     uint16_t parent[2 * 257];
-    uint8_t depth[2 * 257];
     uint16_t sym[260];
     uint32_t num[16];
     int n;
 };
 
-// Length-limited Huffman lengths, one thread.  Leaves are sorted by (frequency, symbol); two-queue merge, leaf first on
-// ties; depths above 15 folded back by the Kraft-sum repair; the rarest symbols get the longest lengths.
-__device__ void build_lengths(Tree& t, uint8_t* lens) {
+// Length-limited Huffman lengths, by one warp.  Leaves are sorted by (frequency, symbol); two-queue merge, leaf first
+// on ties (lane 0, queue heads kept in registers); leaf depths by walking up, one leaf per lane; depths above 15 folded
+// back by the Kraft-sum repair; the rarest symbols get the longest lengths.
+__device__ void build_lengths(Tree& t, uint8_t* lens, int lane) {
     const int n = t.n;
     if (n == 1) {
-        lens[t.sym[0]] = 1;
+        if (lane == 0) lens[t.sym[0]] = 1;
         return;
     }
-    int li = 0, ii = n;
-    for (int k = n; k < 2 * n - 1; ++k) {
-        uint32_t sum = 0;
-        for (int r = 0; r < 2; ++r) {
-            int pick;
-            if (li < n && (ii >= k || t.w[li] <= t.w[ii])) pick = li++;
-            else pick = ii++;
-            sum += t.w[pick];
-            t.parent[pick] = (uint16_t)k;
-        }
-        t.w[k] = sum;
-    }
-    for (int l = 0; l < 16; ++l) t.num[l] = 0;
-    t.depth[2 * n - 2] = 0;
-    for (int k = 2 * n - 3; k >= 0; --k) {
-        const int d = t.depth[t.parent[k]] + 1;
-        t.depth[k] = (uint8_t)min(d, 255);
-        if (k < n) t.num[min(d, 15)]++;
-    }
-    uint32_t total = 0;
-    for (int l = 1; l <= 15; ++l) total += t.num[l] << (15 - l);
-    while (total > (1u << 15)) {
-        t.num[15]--;
-        for (int l = 14; l >= 1; --l)
-            if (t.num[l]) {
-                t.num[l]--;
-                t.num[l + 1] += 2;
-                break;
+    if (lane == 0) {
+        constexpr uint32_t NONE = 0xFFFFFFFFu;
+        int li = 0, ii = n;
+        uint32_t wl = t.w[0], wl2 = n > 1 ? t.w[1] : NONE, wi = NONE;
+        for (int k = n; k < 2 * n - 1; ++k) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (li < n && (ii >= k || wl <= wi)) {
+                    sum += wl;
+                    t.parent[li++] = (uint16_t)k;
+                    wl = wl2;
+                    wl2 = li + 1 < n ? t.w[li + 1] : NONE;
+                } else {
+                    sum += wi;
+                    t.parent[ii++] = (uint16_t)k;
+                    wi = ii < k ? t.w[ii] : NONE;
+                }
             }
-        --total;
+            t.w[k] = sum;
+            if (ii == k) wi = sum;  // the new node is the head of the (otherwise empty) internal queue
+        }
     }
-    int i = 0;
-    for (int l = 15; l >= 1; --l)
-        for (uint32_t r = 0; r < t.num[l]; ++r) lens[t.sym[i++]] = (uint8_t)l;
+    if (lane < 16) t.num[lane] = 0;
+    __syncwarp();
+    const int root = 2 * n - 2;
+    for (int i = lane; i < n; i += 32) {
+        int d = 0;
+        for (int k = i; k != root; k = t.parent[k]) ++d;
+        atomicAdd(&t.num[min(d, 15)], 1u);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t total = 0;
+        for (int l = 1; l <= 15; ++l) total += t.num[l] << (15 - l);
+        while (total > (1u << 15)) {
+            t.num[15]--;
+            for (int l = 14; l >= 1; --l)
+                if (t.num[l]) {
+                    t.num[l]--;
+                    t.num[l + 1] += 2;
+                    break;
+                }
+            --total;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {  // leaf i (ascending frequency): lengths are handed out longest first
+        uint32_t acc = 0;
+        int l = 15;
+        for (; l > 1; --l) {
+            acc += t.num[l];
+            if ((uint32_t)i < acc) break;
+        }
+        lens[t.sym[i]] = (uint8_t)l;
+    }
 }
 
 // ---- block header ---------------------------------------------------------------------------------------------------
@@ -400,8 +446,8 @@ __global__ void __launch_bounds__(NT) k_gz_plan(GzArgs a) {
             if (t == 0) s_tree.sym[rank_eob] = 256, s_tree.w[rank_eob] = 1, s_tree.n = n_used;
         }
         __syncthreads();
-        if (t == 0) {
-            build_lengths(s_tree, s_lens);
+        if (warp == 0) build_lengths(s_tree, s_lens, lane);
+        if (t == 32) {
             uint32_t c32 = 0;
 #pragma unroll
             for (int w = 0; w < NT / 32; ++w) c32 ^= s_red[w];
