@@ -346,7 +346,7 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* s_scan, uin
 }
 
 // ---- pass 1 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_gz_plan(GzArgs a) {
+__global__ void __launch_bounds__(NT, 6) k_gz_plan(GzArgs a) {
     __shared__ __align__(16) uint32_t s_in[CH / 4 + 8];
     __shared__ uint32_t s_hist[NT / 32][260];
     __shared__ uint32_t s_tab[4][256];
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(128) k_gz_files(GzArgs a) {
 }
 
 // ---- pass 2 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 4) k_gz_encode(GzArgs a) {
+__global__ void __launch_bounds__(NT, 5) k_gz_encode(GzArgs a) {
     __shared__ __align__(16) uint32_t s_in[CH / 4 + 8];
     __shared__ uint32_t s_out[CH / 4 + 16];
     __shared__ uint32_t s_code[260];  // reversed code | length << 16
