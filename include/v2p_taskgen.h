@@ -30,6 +30,12 @@ extern "C" {
 enum { V2P_CLS_M = 0, V2P_CLS_I = 1, V2P_CLS_D = 2, V2P_CLS_F = 3, V2P_CLS_G = 4, V2P_CLS_L = 5, V2P_CLS_0 = 6 };
 
 #define V2P_GEN_ALIGNED 0x1u /* phase-aligned result slots and long alteration payloads */
+#define V2P_GEN_FASTA 0x2u   /* record framing as copy segments: every transcript's tasks are wrapped
+                              * in a header task `>{name}_{1|2}\n` and a newline task, both fed from a name tape appended
+                              * to the haplotype's alt tape, so the result tape IS the .fasta text of
+                              * write_altered_only (personalized_genome.rs:97,107); haplotype = 2*sample + (hap-1).
+                              * Packed layout only; needs v2p_catalogue_set_names.  ann_start/ann_end then bracket the
+                              * sequence between header and newline. Twin: cohort.py::fasta_image.                      */
 
 typedef struct v2p_catalogue v2p_catalogue;
 
@@ -45,6 +51,9 @@ int v2p_catalogue_create(int cuda_device, uint64_t n_tx, const uint64_t* tx_offs
                          const uint32_t* site_rlen, const uint64_t* site_doff, const uint32_t* site_dlen,
                          const uint8_t* pool, uint64_t n_pool, v2p_catalogue** out);
 void v2p_catalogue_destroy(v2p_catalogue* c);
+
+/* Transcript names for V2P_GEN_FASTA: name t = names[name_off[t] .. name_off[t+1]) (host pointers, copied). */
+int v2p_catalogue_set_names(v2p_catalogue* c, const uint64_t* name_off, const uint8_t* names);
 const char* v2p_catalogue_last_error(v2p_catalogue* c);
 
 /* Result of one generation: a device-resident v2p_batch (ref == NULL: the registered proteome) plus the annotation

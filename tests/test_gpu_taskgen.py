@@ -59,3 +59,62 @@ def test_no_sites_at_all(world, gpu_engine):
     g = dc.generate(np.zeros(0, np.int64), np.zeros(0, np.int64), 5, True)
     assert (g.batch.n_tasks, g.batch.n_out, g.n_rows) == (0, 0, 0)
     assert not dc.read(g.batch.task_begin, 6, np.uint64).any()
+
+
+def _variable_names(prot, seed):
+    """Names of 1..24 bytes (one empty) so that every header length differs."""
+    rng = np.random.default_rng(seed)
+    nlen = rng.integers(1, 25, prot.n_tx)
+    nlen[7] = 0
+    off = np.zeros(prot.n_tx + 1, np.uint64)
+    np.cumsum(nlen, out=off[1:])
+    pool = rng.choice(np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789.-", np.uint8), int(off[-1]))
+    return off, pool
+
+
+@pytest.mark.parametrize("names", ["default", "variable"])
+@pytest.mark.parametrize("seed,n_hap", [(4, 2), (5, 10), (6, 64)])
+def test_fasta_framing_matches_the_host_producer(world, gpu_engine, names, seed, n_hap):
+    """V2P_GEN_FASTA: header/newline segments and the name tape come out exactly as cohort.fasta_image builds them
+    (itself checked record for record against the reference binary, tests/test_cohort_taskgen.py), and the executed
+    tape is the .fasta text of every sample."""
+    prot, cat, dc = world
+    nm = C.default_names(prot) if names == "default" else _variable_names(prot, seed)
+    dc.set_names(*nm)
+    hap, site = C.select_sites(cat, n_hap, np.random.default_rng(seed))
+    if n_hap == 10:  # haplotypes without any site: first, middle, last
+        keep = ~np.isin(hap, (0, 4, 9))
+        hap, site = hap[keep], site[keep]
+    want = C.fasta_image(prot, C.build_batch(prot, cat, hap, site, n_hap, "global", "packed"), nm)
+    g = dc.generate(hap, site, n_hap, aligned=False, fasta=True)
+    b = g.batch
+    assert (b.n_hap, b.n_tasks, b.n_alt, b.n_out) == (n_hap, len(want.tasks), len(want.alt), want.n_residues)
+    assert np.array_equal(dc.read(b.task_begin, n_hap + 1, np.uint64), want.task_begin)
+    assert np.array_equal(dc.read(b.out_base, n_hap + 1, np.uint64), want.out_base)
+    assert np.array_equal(dc.read(b.alt_base, n_hap + 1, np.uint64), want.alt_base)
+    assert np.array_equal(dc.read(b.tasks, 4 * b.n_tasks, np.uint32).reshape(-1, 4), want.tasks)
+    assert np.array_equal(dc.read(b.alt, b.n_alt, np.uint8), want.alt)
+    assert np.array_equal(dc.read(g.ann_start, g.n_rows, np.uint64), want.ann_start)
+    assert np.array_equal(dc.read(g.ann_end, g.n_rows, np.uint64), want.ann_end)
+    gpu_engine.set_reference(prot.residues)
+    execute_generated(gpu_engine, g, validate=True)  # a file image has no gaps: gir.rs:208 holds
+    got = dc.read(b.out, b.n_out, np.uint8)
+    ref = np.zeros(want.n_residues, np.uint8)
+    assert cengine.batch_execute(want.task_begin, want.tasks, prot.residues, want.alt, want.alt_base, ref, want.out_base)[0] == 0
+    assert np.array_equal(got, ref)
+    if names == "default":  # the text parses back into the records the consumer contract gives
+        plain = C.build_batch(prot, cat, hap, site, n_hap, "global", "packed")
+        tape = np.zeros(plain.n_residues, np.uint8)
+        assert cengine.batch_execute(plain.task_begin, plain.tasks, prot.residues, plain.alt, plain.alt_base, tape, plain.out_base)[0] == 0
+        for h in (0, n_hap - 1):
+            image = got[int(want.out_base[h]):int(want.out_base[h + 1])]
+            assert C.parse_fasta_image(image) == sorted(C.fasta_records(prot, plain, tape, h, 1 + (h & 1)))
+
+
+def test_fasta_flag_errors(world):
+    prot, cat, dc = world
+    from vcf2prot_b200.engine import EngineError
+    dc.set_names(*C.default_names(prot))
+    hap, site = C.select_sites(cat, 2, np.random.default_rng(1))
+    with pytest.raises(EngineError):  # a file image cannot contain pad bytes
+        dc.generate(hap, site, 2, aligned=True, fasta=True)

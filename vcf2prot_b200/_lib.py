@@ -14,7 +14,7 @@ ERR_NOT_CONTIGUOUS, ERR_NOT_GPU_ENGINE = 7, 9
 ENGINE_ST, ENGINE_MT, ENGINE_GPU = 0, 1, 2
 FLAG_FILL_DOT, FLAG_VALIDATE, FLAG_DEVICE_PTRS, FLAG_ASYNC = 1, 2, 4, 8
 REF_NO_TMA = 0x200
-GEN_ALIGNED = 1
+GEN_ALIGNED, GEN_FASTA = 1, 2
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "BAD_ENGINE", 4: "BAD_STREAM", 5: "RES_OOB", 6: "SRC_OOB",
                 7: "NOT_CONTIGUOUS", 9: "NOT_GPU_ENGINE"}
@@ -74,6 +74,7 @@ SYMBOLS = {
     "v2p_catalogue_create": (C.c_int, [C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_uint64,
                                        C.POINTER(_P)]),
     "v2p_catalogue_destroy": (None, [_P]),
+    "v2p_catalogue_set_names": (C.c_int, [_P, _P, _P]),
     "v2p_catalogue_last_error": (C.c_char_p, [_P]),
     "v2p_generate_tasks": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(Generated)]),
     "v2p_sites_from_masks": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint32, C.POINTER(SiteLists)]),

@@ -503,38 +503,54 @@ def fasta_records(prot: Proteome, batch: Batch, out: np.ndarray, h: int, hap_lab
     return recs
 
 
-def fasta_image(prot: Proteome, b: Batch) -> Batch:
+def default_names(prot: Proteome) -> Tuple[np.ndarray, np.ndarray]:
+    """Transcript names as a (name_off[n_tx+1], pool) tape: `ENST%011d` (Proteome.name)."""
+    n = prot.n_tx
+    pool = np.zeros((n, 15), np.uint8)
+    pool[:, 0:4] = np.frombuffer(b"ENST", np.uint8)
+    pool[:, 4:15] = (np.arange(n)[:, None] // 10 ** np.arange(10, -1, -1)[None, :]) % 10 + ord("0")
+    return (15 * np.arange(n + 1)).astype(np.uint64), pool.reshape(-1)
+
+
+def fasta_image(prot: Proteome, b: Batch, names: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Batch:
     """SURVEY 8(f) rank 1 -- FASTA record formatting on the device, with NO new kernel: the record framing of
     `write_altered_only` (personalized_genome.rs:97,107: `>{transcript}_{1|2}\n{seq}\n`) becomes two more copy
-    segments per transcript, fed from a name tape appended to the haplotype's alt tape:
+    segments per transcript, fed from a name tape appended to the haplotype's alt tape (one entry
+    `>{name}_{1|2}\n\n` of len(name)+5 bytes per record, at offset e behind the alteration bytes):
 
-        header task  (1, n_alt + 20*j,      19, record start)      ">ENST00000000042_1\n"
+        header task  (1, n_alt + e,               len(name)+4, record start)      ">ENST00000000042_1\n"
         ... the transcript's own tasks, shifted ...
-        newline task (1, n_alt + 20*j + 19,  1, after the sequence)
+        newline task (1, n_alt + e + len(name)+4, 1,           after the sequence)
 
     so haplotype h's result tape IS the text of its records and `out[out_base[2s] : out_base[2s+2]]` is sample s's
     .fasta file image (hap-1 records, then hap-2 records; the reference's own record order is HashMap-random).
-    Needs the packed layout (a file image cannot contain pad bytes) and haplotype index = 2*sample + (hap-1)."""
+    Needs the packed layout (a file image cannot contain pad bytes) and haplotype index = 2*sample + (hap-1).
+    `names` = (name_off[n_tx+1], pool) gives the transcript names (default: Proteome.name)."""
     if b.ref_base is not None or b.ann_ntasks is None:
         raise ValueError("fasta_image needs a global-ref batch built by build_batch")
+    name_off, name_pool = default_names(prot) if names is None else names
+    name_off = np.asarray(name_off).astype(np.int64)
     G, n_hap, n_old = len(b.ann_hap), b.n_hap, len(b.tasks)
     c = b.ann_ntasks
+    nlen = (name_off[1:] - name_off[:-1])[b.ann_tx]  # name length of every record
+    elen = nlen + 5                                    # its entry on the name tape
     gstart = np.cumsum(c) - c
     gid_of_task = np.repeat(np.arange(G), c)
     new_idx = np.arange(n_old) + 2 * gid_of_task + 1
     hdr_idx = gstart + 2 * np.arange(G)
     nl_idx = gstart + c + 2 * np.arange(G) + 1
-    # j = index of the group inside its haplotype
+    # e = offset of the record's entry inside its haplotype's name tape
     hfirst = np.ones(G, bool)
     hfirst[1:] = b.ann_hap[1:] != b.ann_hap[:-1]
-    j = np.arange(G) - np.flatnonzero(hfirst)[np.cumsum(hfirst) - 1] if G else np.zeros(0, np.int64)
+    e_excl = np.cumsum(elen) - elen
+    e = e_excl - e_excl[np.flatnonzero(hfirst)[np.cumsum(hfirst) - 1]] if G else np.zeros(0, np.int64)
     n_alt_h = (b.alt_base[1:] - b.alt_base[:-1]).astype(np.int64)
     tasks = np.zeros((n_old + 2 * G, 4), np.uint32)
     tasks[new_idx] = b.tasks
-    tasks[hdr_idx, 0] = n_alt_h[b.ann_hap] + 20 * j
-    tasks[hdr_idx, 1] = 19
+    tasks[hdr_idx, 0] = n_alt_h[b.ann_hap] + e
+    tasks[hdr_idx, 1] = nlen + 4
     tasks[hdr_idx, 3] = 1
-    tasks[nl_idx, 0] = n_alt_h[b.ann_hap] + 20 * j + 19
+    tasks[nl_idx, 0] = n_alt_h[b.ann_hap] + e + nlen + 4
     tasks[nl_idx, 1] = 1
     tasks[nl_idx, 3] = 1
     # destinations: running sum of lengths inside each haplotype, in the new order
@@ -552,25 +568,26 @@ def fasta_image(prot: Proteome, b: Batch) -> Batch:
     tasks[:, 2] = l_excl - hap_l0[task_hap]
     out_base = np.zeros(n_hap + 1, np.uint64)
     np.cumsum(np.bincount(task_hap, weights=ln, minlength=n_hap).astype(np.int64), out=out_base[1:])
-    # name tape: 20 bytes per transcript appended behind the haplotype's alteration bytes
-    groups_per_hap = np.bincount(b.ann_hap, minlength=n_hap)
+    # name tape: one entry per record appended behind the haplotype's alteration bytes
+    names_per_hap = np.bincount(b.ann_hap, weights=elen, minlength=n_hap).astype(np.int64)
     alt_base = np.zeros(n_hap + 1, np.uint64)
-    np.cumsum(n_alt_h + 20 * groups_per_hap, out=alt_base[1:])
+    np.cumsum(n_alt_h + names_per_hap, out=alt_base[1:])
     alt = np.zeros(int(alt_base[-1]), np.uint8)
     old_pos = np.arange(len(b.alt)) + (alt_base[:-1].astype(np.int64) - b.alt_base[:-1].astype(np.int64))[
         np.repeat(np.arange(n_hap), n_alt_h)]
     alt[old_pos] = b.alt
-    names = np.zeros((G, 20), np.uint8)
-    names[:, 0] = ord(">")
-    names[:, 1:5] = np.frombuffer(b"ENST", np.uint8)
-    names[:, 5:16] = (b.ann_tx[:, None] // 10 ** np.arange(10, -1, -1)[None, :]) % 10 + ord("0")
-    names[:, 16] = ord("_")
-    names[:, 17] = ord("1") + (b.ann_hap & 1)
-    names[:, 18] = ord("\n")
-    names[:, 19] = ord("\n")
-    base = alt_base[:-1].astype(np.int64)[b.ann_hap] + n_alt_h[b.ann_hap] + 20 * j
-    alt[(base[:, None] + np.arange(20)[None, :]).reshape(-1)] = names.reshape(-1)
-    seq_start = tasks[hdr_idx, 2].astype(np.int64) + 19
+    base = alt_base[:-1].astype(np.int64)[b.ann_hap] + n_alt_h[b.ann_hap] + e
+    alt[base] = ord(">")
+    tot = int(nlen.sum())
+    if tot:  # the name bytes of every record, gathered from the pool
+        rec_of = np.repeat(np.arange(G), nlen)
+        within = np.arange(tot) - np.repeat(np.cumsum(nlen) - nlen, nlen)
+        alt[base[rec_of] + 1 + within] = np.asarray(name_pool, np.uint8)[name_off[b.ann_tx][rec_of] + within]
+    alt[base + 1 + nlen] = ord("_")
+    alt[base + 2 + nlen] = ord("1") + (b.ann_hap & 1)
+    alt[base + 3 + nlen] = ord("\n")
+    alt[base + 4 + nlen] = ord("\n")
+    seq_start = tasks[hdr_idx, 2].astype(np.int64) + nlen + 4
     return Batch(task_begin, tasks, alt, alt_base, out_base, None, b.ref, b.ann_hap, b.ann_tx, seq_start,
                  seq_start + (b.ann_end - b.ann_start), b.kept_hap, b.kept_site, c + 2)
 

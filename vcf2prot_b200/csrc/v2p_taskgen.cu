@@ -37,6 +37,8 @@ struct Cat {  // device views
     const uint8_t* cls;
     const uint64_t* doff;
     const uint8_t* pool;
+    const uint64_t* name_off;  // FASTA framing (V2P_GEN_FASTA): transcript names, name_off[n_tx+1] into `names`
+    const uint8_t* names;
 };
 
 struct Sel {  // one generation
@@ -48,6 +50,8 @@ struct Sel {  // one generation
     uint64_t *cnt, *slen, *acon, *newg, *shortc, *slotl;              // scan inputs  (n_sel+1, last = 0)
     uint64_t *task_x, *l_x, *a_x, *g_x, *sh_x, *sl_x;                  // exclusive scans
     int aligned;
+    int fasta;  // V2P_GEN_FASTA: `>{name}_{1|2}\n` / `\n` segments around every transcript (packed layout); shortc/sh_x then
+                // carry the name-tape entry lengths (len(name)+5 per record) instead of the short-payload sizes
 };
 
 __device__ __forceinline__ bool is_trunc(uint8_t c) { return c == V2P_CLS_F || c == V2P_CLS_G || c == V2P_CLS_L || c == V2P_CLS_0; }
@@ -113,6 +117,12 @@ __global__ void k_tg_classify(Sel s, Cat c) {
         acon = k.acontrib;
         const bool is_long = s.aligned && k.has_mut && acon >= 32;
         shortc = is_long ? 0 : acon;
+        if (s.fasta) {  // record framing (personalized_genome.rs:97,107): header before the first task, '\n' after the last
+            const uint64_t nlen = c.name_off[t + 1] - c.name_off[t];
+            cnt += (newg ? 1 : 0) + (lastg ? 1 : 0);
+            slen += (newg ? nlen + 4 : 0) + (lastg ? 1 : 0);
+            shortc = newg ? nlen + 5 : 0;
+        }
         fl = 1u | (newg ? 2u : 0u) | (lastg ? 4u : 0u) | (is_long ? 8u : 0u);
     }
     s.flags[j] = fl;
@@ -164,7 +174,7 @@ __global__ void k_tg_hap_bases(Sel s, Grp g, Out o) {
     const uint64_t j = s.site_begin[h];
     o.task_begin[h] = s.task_x[j];
     o.out_base[h] = g.g_slot_x[s.g_x[j]];
-    if (!s.aligned) o.alt_base[h] = s.a_x[j];
+    if (!s.aligned) o.alt_base[h] = s.a_x[j] + (s.fasta ? s.sh_x[j] : 0);  // FASTA: + the name-tape entries before
 }
 
 __global__ void k_tg_emit_tasks(Sel s, Cat c, Grp g, Out o) {
@@ -179,9 +189,16 @@ __global__ void k_tg_emit_tasks(Sel s, Cat c, Grp g, Out o) {
     const uint64_t G0 = s.g_x[s.site_begin[h]];
     const uint64_t c16tx = c.tx_off[t] & 15u;
     const uint64_t g_start = g.g_slot_x[gi] - g.g_slot_x[G0] + ((s.aligned && g.g_len[gi]) ? c16tx : 0);
+    // FASTA framing: this record's entry `>{name}_{1|2}\n\n` on the name tape behind the haplotype's alteration bytes
+    const uint64_t nlen = s.fasta ? c.name_off[t + 1] - c.name_off[t] : 0;
+    uint64_t name_src = 0;
+    if (s.fasta) {
+        const uint64_t j0 = s.site_begin[h], j1 = s.site_begin[h + 1];
+        name_src = (s.a_x[j1] - s.a_x[j0]) + (s.sh_x[g.g_first[gi]] - s.sh_x[j0]);
+    }
     if (newg) {
-        g.ann_start[gi] = g_start;
-        g.ann_end[gi] = g_start + g.g_len[gi];
+        g.ann_start[gi] = g_start + (s.fasta ? nlen + 4 : 0);
+        g.ann_end[gi] = g_start + g.g_len[gi] - (s.fasta ? 1 : 0);
     }
     const uint64_t Lr = c.tx_off[t + 1] - c.tx_off[t];
     const uint64_t p_next = lastg ? Lr : c.pos[s.sites[j + 1]];
@@ -189,6 +206,10 @@ __global__ void k_tg_emit_tasks(Sel s, Cat c, Grp g, Out o) {
     uint64_t dst = g_start + (s.l_x[j] - s.l_x[g.g_first[gi]]);
     uint64_t slot = s.task_x[j];
     const uint64_t ref0 = c.tx_off[t];
+    if (s.fasta && newg) {
+        o.tasks[slot++] = v2p_task16{(uint32_t)name_src, (uint32_t)(nlen + 4), (uint32_t)dst, 1u};
+        dst += nlen + 4;
+    }
     if (k.has_base) {
         o.tasks[slot++] = v2p_task16{(uint32_t)ref0, (uint32_t)k.base_len, (uint32_t)dst, 0u};
         dst += k.base_len;
@@ -199,7 +220,11 @@ __global__ void k_tg_emit_tasks(Sel s, Cat c, Grp g, Out o) {
         if (fl & 8u) s.slotl[j] = ((dst & 15u) + k.acontrib + 15u) & ~uint64_t(15);
         dst += k.mut_len;
     }
-    if (k.has_fol) o.tasks[slot++] = v2p_task16{(uint32_t)(ref0 + k.fol_start), (uint32_t)k.fol_len, (uint32_t)dst, 0u};
+    if (k.has_fol) {
+        o.tasks[slot++] = v2p_task16{(uint32_t)(ref0 + k.fol_start), (uint32_t)k.fol_len, (uint32_t)dst, 0u};
+        dst += k.fol_len;
+    }
+    if (s.fasta && lastg) o.tasks[slot] = v2p_task16{(uint32_t)(name_src + nlen + 4), 1u, (uint32_t)dst, 1u};
 }
 
 __global__ void k_tg_alt_sizes(Sel s, Out o) {  // aligned layout: [short payloads | pad to 16 | long slots] per haplotype
@@ -221,9 +246,20 @@ __global__ void k_tg_emit_alt(Sel s, Cat c, Out o) {
     const uint8_t fl = s.flags[j];
     if (!(fl & 1u)) return;
     const uint64_t acon = s.acon[j];
-    if (!acon) return;
     const uint32_t h = s.site_hap[j], si = s.sites[j];
     const uint64_t j0 = s.site_begin[h];
+    if (s.fasta && (fl & 2u)) {  // the record's name-tape entry: '>' name '_' {1|2} '\n' '\n'
+        const uint32_t t = c.tx[si];
+        const uint64_t n0 = c.name_off[t], nlen = c.name_off[t + 1] - n0;
+        uint8_t* d = o.alt + o.alt_base[h] + (s.a_x[s.site_begin[h + 1]] - s.a_x[j0]) + (s.sh_x[j] - s.sh_x[j0]);
+        d[0] = '>';
+        for (uint64_t w = 0; w < nlen; ++w) d[1 + w] = c.names[n0 + w];
+        d[1 + nlen] = '_';
+        d[2 + nlen] = (uint8_t)('1' + (h & 1u));
+        d[3 + nlen] = '\n';
+        d[4 + nlen] = '\n';
+    }
+    if (!acon) return;
     const uint8_t cls = c.cls[si];
     uint64_t a_new;
     if (!s.aligned) a_new = s.a_x[j] - s.a_x[j0];
@@ -233,7 +269,8 @@ __global__ void k_tg_emit_alt(Sel s, Cat c, Out o) {
     const bool has_mut = cls == V2P_CLS_M || cls == V2P_CLS_I || cls == V2P_CLS_D || cls == V2P_CLS_F || cls == V2P_CLS_L;
     if (has_mut) {
         const bool has_base = (fl & 2u) && cls != V2P_CLS_0;
-        o.tasks[s.task_x[j] + (has_base ? 1 : 0)].src_off = (uint32_t)(a_new + (cls == V2P_CLS_M ? 1 : 0));
+        const uint64_t slot = s.task_x[j] + (has_base ? 1 : 0) + ((s.fasta && (fl & 2u)) ? 1 : 0);
+        o.tasks[slot].src_off = (uint32_t)(a_new + (cls == V2P_CLS_M ? 1 : 0));
     }
     uint8_t* dst = o.alt + o.alt_base[h] + a_new;
     const uint8_t* src = c.pool + c.doff[si];
@@ -365,6 +402,8 @@ struct v2p_catalogue {
     std::string err;
     uint64_t n_tx = 0, n_sites = 0;
     Buf tx_off, tx, pos, rlen, dlen, cls, doff, pool;
+    Buf name_off, names;  // v2p_catalogue_set_names
+    bool has_names = false;
     // per-generation buffers
     Buf sites, site_begin, site_hap, flags, scan_in[6], scan_out[6], cub_tmp, totals;
     Buf g_first, g_len, g_slot, g_slot_x, g_hap, g_tx, ann_start, ann_end;
@@ -459,7 +498,8 @@ void v2p_catalogue_destroy(v2p_catalogue* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    Buf* all[] = {&c->tx_off, &c->tx, &c->pos, &c->rlen, &c->dlen, &c->cls, &c->doff, &c->pool, &c->sites, &c->site_begin,
+    Buf* all[] = {&c->name_off, &c->names,
+                  &c->tx_off, &c->tx, &c->pos, &c->rlen, &c->dlen, &c->cls, &c->doff, &c->pool, &c->sites, &c->site_begin,
                   &c->site_hap, &c->flags, &c->cub_tmp, &c->totals, &c->g_first, &c->g_len, &c->g_slot, &c->g_slot_x, &c->g_hap,
                   &c->g_tx, &c->ann_start, &c->ann_end, &c->tasks, &c->task_begin, &c->alt_base, &c->out_base, &c->alt_per_hap,
                   &c->short_tot, &c->mut_dst, &c->alt, &c->out, &c->md_masks, &c->md_csq_begin, &c->md_csq_site, &c->md_keys[0],
@@ -477,6 +517,22 @@ void v2p_catalogue_destroy(v2p_catalogue* c) {
 }
 
 const char* v2p_catalogue_last_error(v2p_catalogue* c) { return c ? c->err.c_str() : "catalogue is NULL"; }
+
+int v2p_catalogue_set_names(v2p_catalogue* c, const uint64_t* name_off, const uint8_t* names) {
+    if (!c || !name_off) return V2P_ERR_INVALID_ARG;
+    c->err.clear();
+    c->has_names = false;
+    if (name_off[0] != 0) return cfail(c, V2P_ERR_INVALID_ARG, "name_off[0] must be 0");
+    for (uint64_t t = 0; t < c->n_tx; ++t)
+        if (name_off[t + 1] < name_off[t]) return cfail(c, V2P_ERR_INVALID_ARG, "name_off not monotone");
+    if (name_off[c->n_tx] && !names) return cfail(c, V2P_ERR_INVALID_ARG, "names is NULL");
+    CU(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload(c, c->name_off, name_off, (c->n_tx + 1) * 8)) || (rc = upload(c, c->names, names, name_off[c->n_tx]))) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->has_names = true;
+    return V2P_OK;
+}
 
 int v2p_device_read(void* host_dst, const void* dev_src, size_t bytes) {
     if (!bytes) return V2P_OK;
@@ -604,8 +660,13 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
         return rc;
     for (int i = 0; i < 6; ++i)
         if ((rc = need(c, c->scan_in[i], (n_sel + 1) * 8)) || (rc = need(c, c->scan_out[i], (n_sel + 1) * 8))) return rc;
+    const bool fasta = (flags & V2P_GEN_FASTA) != 0;
+    if (fasta && (flags & V2P_GEN_ALIGNED))
+        return cfail(c, V2P_ERR_INVALID_ARG, "V2P_GEN_FASTA needs the packed layout (a file image cannot contain pad bytes)");
+    if (fasta && !c->has_names) return cfail(c, V2P_ERR_INVALID_ARG, "V2P_GEN_FASTA needs v2p_catalogue_set_names first");
     Cat cat{(const uint64_t*)c->tx_off.p, (const uint32_t*)c->tx.p, (const uint32_t*)c->pos.p, (const uint32_t*)c->rlen.p,
-            (const uint32_t*)c->dlen.p, (const uint8_t*)c->cls.p, (const uint64_t*)c->doff.p, (const uint8_t*)c->pool.p};
+            (const uint32_t*)c->dlen.p, (const uint8_t*)c->cls.p, (const uint64_t*)c->doff.p, (const uint8_t*)c->pool.p,
+            (const uint64_t*)c->name_off.p, (const uint8_t*)c->names.p};
     Sel s{};
     s.n_sel = n_sel, s.n_hap = n_hap;
     s.sites = d_sites, s.site_begin = d_site_begin;
@@ -614,6 +675,7 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
     uint64_t** outs[6] = {&s.task_x, &s.l_x, &s.a_x, &s.g_x, &s.sh_x, &s.sl_x};
     for (int i = 0; i < 6; ++i) *ins[i] = (uint64_t*)c->scan_in[i].p, *outs[i] = (uint64_t*)c->scan_out[i].p;
     s.aligned = (flags & V2P_GEN_ALIGNED) ? 1 : 0;
+    s.fasta = fasta ? 1 : 0;
 
     for (int i = 0; i < 6; ++i)  // sentinel entry [n_sel] of every scan input
         CU(c, cudaMemsetAsync((char*)c->scan_in[i].p + n_sel * 8, 0, 8, st));
@@ -653,7 +715,7 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
     if ((rc = xsum(c, g.g_slot, g.g_slot_x, n_groups + 1))) return rc;
     k_tg_hap_bases<<<blocks(n_hap + 1), 256, 0, st>>>(s, g, o);
     if (n_sel) k_tg_emit_tasks<<<blocks(n_sel), 256, 0, st>>>(s, cat, g, o);
-    uint64_t n_alt = 0, n_out = 0;
+    uint64_t n_alt = 0, n_out = 0, n_names = 0;
     if (s.aligned) {
         if ((rc = xsum(c, s.slotl, s.sl_x, n_sel + 1))) return rc;
         k_tg_alt_sizes<<<blocks(n_hap + 1), 256, 0, st>>>(s, o);
@@ -661,9 +723,11 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
         CU(c, cudaMemcpyAsync(&n_alt, o.alt_base + n_hap, 8, cudaMemcpyDeviceToHost, st));
     } else {
         CU(c, cudaMemcpyAsync(&n_alt, s.a_x + n_sel, 8, cudaMemcpyDeviceToHost, st));
+        if (fasta) CU(c, cudaMemcpyAsync(&n_names, s.sh_x + n_sel, 8, cudaMemcpyDeviceToHost, st));
     }
     CU(c, cudaMemcpyAsync(&n_out, g.g_slot_x + n_groups, 8, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
+    n_alt += n_names;
     if ((rc = need(c, c->alt, n_alt + 64)) || (rc = need(c, c->out, n_out + 64))) return rc;
     o.alt = (uint8_t*)c->alt.p;
     CU(c, cudaMemsetAsync(o.alt, '.', n_alt + 16, st));

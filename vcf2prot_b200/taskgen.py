@@ -39,14 +39,26 @@ class DeviceCatalogue:
         except Exception:
             pass
 
-    def generate(self, hap: np.ndarray, site: np.ndarray, n_hap: int, aligned: bool = True) -> L.Generated:
-        """(hap, site) pairs sorted by (hap, site) -- what cohort.select_sites returns."""
+    def set_names(self, name_off: np.ndarray, pool: np.ndarray) -> None:
+        """Transcript names for fasta=True generations (cohort.default_names gives the synthetic ones)."""
+        no, pl = np.ascontiguousarray(name_off, np.uint64), np.ascontiguousarray(pool, np.uint8)
+        st = self._lib.v2p_catalogue_set_names(self._h, no.ctypes.data_as(C.c_void_p), pl.ctypes.data_as(C.c_void_p))
+        if st:
+            raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
+
+    @staticmethod
+    def _flags(aligned: bool, fasta: bool) -> int:
+        return (L.GEN_ALIGNED if aligned else 0) | (L.GEN_FASTA if fasta else 0)
+
+    def generate(self, hap: np.ndarray, site: np.ndarray, n_hap: int, aligned: bool = True, fasta: bool = False) -> L.Generated:
+        """(hap, site) pairs sorted by (hap, site) -- what cohort.select_sites returns.  fasta=True: the result tape is
+        the .fasta text (V2P_GEN_FASTA; packed layout only, set_names first)."""
         site_begin = np.zeros(n_hap + 1, np.uint64)
         np.cumsum(np.bincount(hap, minlength=n_hap), out=site_begin[1:])
         sites = np.ascontiguousarray(site, np.uint32)
         g = L.Generated()
         st = self._lib.v2p_generate_tasks(self._h, n_hap, site_begin.ctypes.data_as(C.c_void_p),
-                                          sites.ctypes.data_as(C.c_void_p), L.GEN_ALIGNED if aligned else 0, C.byref(g))
+                                          sites.ctypes.data_as(C.c_void_p), self._flags(aligned, fasta), C.byref(g))
         if st:
             raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
         return g
@@ -72,9 +84,9 @@ class DeviceCatalogue:
             raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
         return out
 
-    def generate_from_lists(self, lists: L.SiteLists, aligned: bool = True) -> L.Generated:
+    def generate_from_lists(self, lists: L.SiteLists, aligned: bool = True, fasta: bool = False) -> L.Generated:
         g = L.Generated()
-        st = self._lib.v2p_generate_tasks_from_lists(self._h, C.byref(lists), L.GEN_ALIGNED if aligned else 0, C.byref(g))
+        st = self._lib.v2p_generate_tasks_from_lists(self._h, C.byref(lists), self._flags(aligned, fasta), C.byref(g))
         if st:
             raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
         return g
