@@ -68,6 +68,8 @@ void v2p_engine_destroy(v2p_engine* e);
 /* Message of the last failure on this context ("" if none).  Valid until the next call on `e`. */
 const char* v2p_last_error(v2p_engine* e);
 int v2p_abi_version(void);
+/* CUDA device ordinal the context was created on. */
+int v2p_engine_device(v2p_engine* e);
 
 /* Pinned host memory for tapes / task arrays so H2D/D2H run at PCIe rate (optional helper). */
 int v2p_host_alloc(void** ptr, size_t bytes);

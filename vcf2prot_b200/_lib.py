@@ -52,8 +52,20 @@ class GzipResult(C.Structure):
                 ("ms", C.c_float)]
 
 
+class PipelineResult(C.Structure):
+    _fields_ = [("n_samples", C.c_uint64), ("n_chunks", C.c_uint64), ("n_sites", C.c_uint64), ("n_tasks", C.c_uint64),
+                ("n_records", C.c_uint64), ("image_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("decode_ms", C.c_float), ("gen_ms", C.c_float), ("exec_ms", C.c_float), ("gzip_ms", C.c_float),
+                ("wall_s", C.c_double)]
+
+
+# int sink(void* user, uint64_t first_sample, uint64_t n_samples, const uint8_t* data, const uint64_t* file_begin)
+FILE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64))
+PIPE_GZIP = 1
+
 SYMBOLS = {
     "v2p_abi_version": (C.c_int, []),
+    "v2p_engine_device": (C.c_int, [_P]),
     "v2p_engine_from_str": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "v2p_engine_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "v2p_engine_destroy": (None, [_P]),
@@ -85,6 +97,14 @@ SYMBOLS = {
     "v2p_gzip_last_error": (C.c_char_p, [_P]),
     "v2p_gzip_bound": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "v2p_gzip_files": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint64, _P, C.c_uint32, C.POINTER(GzipResult)]),
+    # include/v2p_pipeline.h
+    "v2p_pipeline_create": (C.c_int, [_P, C.POINTER(_P), C.c_uint32, C.POINTER(_P)]),
+    "v2p_pipeline_destroy": (None, [_P]),
+    "v2p_pipeline_last_error": (C.c_char_p, [_P]),
+    "v2p_pipeline_run_lists": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint64, _P, FILE_SINK, _P,
+                                         C.POINTER(PipelineResult)]),
+    "v2p_pipeline_run_masks": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         _P, C.c_uint64, _P, FILE_SINK, _P, C.POINTER(PipelineResult)]),
 }
 
 _lib = None

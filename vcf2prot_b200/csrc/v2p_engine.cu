@@ -326,6 +326,8 @@ extern "C" {
 
 int v2p_abi_version(void) { return V2P_ABI_VERSION; }
 
+int v2p_engine_device(v2p_engine* e) { return e ? e->device : -1; }
+
 int v2p_engine_from_str(const char* s, int* engine_kind) {
     if (!s || !engine_kind) return V2P_ERR_INVALID_ARG;
     if (!strcmp(s, "st") || !strcmp(s, "ST")) return *engine_kind = V2P_ENGINE_ST, V2P_OK;

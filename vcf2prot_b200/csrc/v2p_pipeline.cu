@@ -1,0 +1,307 @@
+// v2p_pipeline.cu -- site lists / bit-masks -> per-sample .fasta(.gz) file images in host memory (include/v2p_pipeline.h).
+//
+// Host-side sequencing only: every byte is produced by the kernels behind v2p_generate_tasks (V2P_GEN_FASTA),
+// v2p_execute_batch and v2p_gzip_files; this file chains them per chunk of samples through the public C ABI and
+// overlaps each chunk's copy-back with the next chunk's kernels (one copy stream + one event per lane).  It stands
+// where the reference loops over probands on rayon threads (parts/exec.rs:27-41) and writes one file per proband
+// (parts/io.rs:45-57, personalized_genome.rs:72-117).  No CPU fallback: any stage that fails fails the call.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "v2p_pipeline.h"
+
+namespace {
+
+struct Lane {
+    v2p_catalogue* cat = nullptr;  // borrowed
+    v2p_gzip* gz = nullptr;        // owned
+    cudaStream_t copy = nullptr;
+    cudaEvent_t landed = nullptr;
+    void* d_gz = nullptr;  // compressed chunk (device)
+    size_t d_gz_cap = 0;
+    void* d_begin = nullptr;  // rebased site_begin of the chunk (mask entry point)
+    size_t d_begin_cap = 0;
+    uint8_t* h_buf = nullptr;  // pinned staging (sink mode)
+    size_t h_cap = 0;
+    // the chunk in flight
+    bool pending = false;
+    uint64_t first_sample = 0, n = 0;
+    const uint8_t* h_data = nullptr;
+    std::vector<uint64_t> fb_rel;
+};
+
+}  // namespace
+
+struct v2p_pipeline {
+    v2p_engine* eng = nullptr;
+    int device = 0;
+    uint32_t n_lanes = 0;
+    Lane lanes[V2P_PIPE_MAX_LANES];
+    std::string err;
+};
+
+namespace {
+
+int pfail(v2p_pipeline* p, int code, const char* fmt, ...) {
+    char buf[640];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (p) p->err = buf;
+    return code;
+}
+#define PCU(p, call)                                                                                                   \
+    do {                                                                                                               \
+        cudaError_t _st = (call);                                                                                      \
+        if (_st != cudaSuccess)                                                                                        \
+            return pfail((p), V2P_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__); \
+    } while (0)
+
+int grow_dev(v2p_pipeline* p, void*& ptr, size_t& cap, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    if (cap >= bytes) return V2P_OK;
+    if (ptr) PCU(p, cudaFree(ptr));
+    ptr = nullptr, cap = 0;
+    PCU(p, cudaMalloc(&ptr, bytes + bytes / 8));
+    cap = bytes + bytes / 8;
+    return V2P_OK;
+}
+
+int grow_host(v2p_pipeline* p, Lane& l, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 4096);
+    if (l.h_cap >= bytes) return V2P_OK;
+    if (l.h_buf) PCU(p, cudaFreeHost(l.h_buf));
+    l.h_buf = nullptr, l.h_cap = 0;
+    PCU(p, cudaMallocHost((void**)&l.h_buf, bytes + bytes / 8));
+    l.h_cap = bytes + bytes / 8;
+    return V2P_OK;
+}
+
+// the chunk's bytes have landed: hand them to the sink (chunks retire in sample order, lanes rotate)
+int retire(v2p_pipeline* p, Lane& l, v2p_file_sink sink, void* user) {
+    if (!l.pending) return V2P_OK;
+    l.pending = false;
+    PCU(p, cudaEventSynchronize(l.landed));
+    if (sink && sink(user, l.first_sample, l.n, l.h_data, l.fb_rel.data()) != 0)
+        return pfail(p, V2P_ERR_INVALID_ARG, "the file sink stopped the run at sample %llu", (unsigned long long)l.first_sample);
+    return V2P_OK;
+}
+
+// What differs between the two entry points: how chunk [h0,h1) gets its Task batch.
+struct ListSource {
+    const uint64_t* site_begin;  // host, n_hap+1 (absolute indices into `sites`)
+    const uint32_t* h_sites;     // host lists, or
+    const uint32_t* d_sites;     // device lists (mask entry point)
+};
+
+int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chunk_samples, uint32_t flags, uint8_t* out,
+        uint64_t out_capacity, uint64_t* file_begin, v2p_file_sink sink, void* user, v2p_pipeline_result* res) {
+    if (!out && !sink) return pfail(p, V2P_ERR_INVALID_ARG, "neither an output buffer nor a sink was given");
+    if (out && !file_begin) return pfail(p, V2P_ERR_INVALID_ARG, "file_begin is NULL");
+    if (!chunk_samples) chunk_samples = 128;
+    const bool gzip = (flags & V2P_PIPE_GZIP) != 0;
+    PCU(p, cudaSetDevice(p->device));
+    for (uint32_t i = 0; i < p->n_lanes; ++i) p->lanes[i].pending = false;
+    uint64_t total = 0;
+    if (file_begin) file_begin[0] = 0;
+    std::vector<uint64_t> sb, hb;
+    uint64_t ci = 0;
+    int rc = V2P_OK;
+    for (uint64_t s0 = 0; s0 < n_samples && rc == V2P_OK; s0 += chunk_samples, ++ci) {
+        const uint64_t ns = std::min<uint64_t>(chunk_samples, n_samples - s0), h0 = 2 * s0, nh = 2 * ns;
+        Lane& l = p->lanes[ci % p->n_lanes];
+        if ((rc = retire(p, l, sink, user))) break;
+        // ---- Task batch of the chunk, generated on the device with the record framing in it
+        sb.resize(nh + 1);
+        for (uint64_t h = 0; h <= nh; ++h) sb[h] = src.site_begin[h0 + h] - src.site_begin[h0];
+        v2p_generated g;
+        if (src.h_sites) {
+            rc = v2p_generate_tasks(l.cat, nh, sb.data(), src.h_sites + src.site_begin[h0], V2P_GEN_FASTA, &g);
+            res->h2d_bytes += sb[nh] * 4 + (nh + 1) * 8;
+        } else {
+            if ((rc = grow_dev(p, l.d_begin, l.d_begin_cap, (nh + 1) * 8))) break;
+            PCU(p, cudaMemcpy(l.d_begin, sb.data(), (nh + 1) * 8, cudaMemcpyHostToDevice));
+            v2p_site_lists lists;
+            memset(&lists, 0, sizeof lists);
+            lists.n_hap = nh, lists.n_sites = sb[nh];
+            lists.site_begin = (const uint64_t*)l.d_begin, lists.sites = src.d_sites + src.site_begin[h0];
+            rc = v2p_generate_tasks_from_lists(l.cat, &lists, V2P_GEN_FASTA, &g);
+            res->h2d_bytes += (nh + 1) * 8;
+        }
+        if (rc) {
+            pfail(p, rc, "task generation failed at sample %llu: %s", (unsigned long long)s0, v2p_catalogue_last_error(l.cat));
+            break;
+        }
+        // ---- the hot path: every haplotype's result tape == its FASTA text
+        v2p_result er;
+        if ((rc = v2p_execute_batch(p->eng, &g.batch, V2P_FLAG_DEVICE_PTRS, &er, nullptr))) {
+            pfail(p, rc, "execution failed at sample %llu (haplotype %llu task %llu): %s", (unsigned long long)s0,
+                  (unsigned long long)er.bad_hap, (unsigned long long)er.bad_task, v2p_last_error(p->eng));
+            break;
+        }
+        // ---- file bounds: sample s owns haplotypes 2s, 2s+1
+        hb.resize(nh + 1);
+        PCU(p, cudaMemcpy(hb.data(), g.batch.out_base, (nh + 1) * 8, cudaMemcpyDeviceToHost));
+        l.fb_rel.resize(ns + 1);
+        for (uint64_t s = 0; s <= ns; ++s) l.fb_rel[s] = hb[2 * s];
+        const uint8_t* d_src = g.batch.out;
+        uint64_t bytes = g.batch.n_out;
+        if (gzip) {
+            const uint64_t cap = v2p_gzip_bound(g.batch.n_out, ns);
+            if ((rc = grow_dev(p, l.d_gz, l.d_gz_cap, cap))) break;
+            std::vector<uint64_t> fb_abs(l.fb_rel);
+            v2p_gzip_result zr;
+            if ((rc = v2p_gzip_files(l.gz, g.batch.out, fb_abs.data(), ns, (uint8_t*)l.d_gz, cap, l.fb_rel.data(),
+                                     V2P_FLAG_DEVICE_PTRS, &zr))) {
+                pfail(p, rc, "gzip failed at sample %llu: %s", (unsigned long long)s0, v2p_gzip_last_error(l.gz));
+                break;
+            }
+            res->gzip_ms += zr.ms;
+            d_src = (const uint8_t*)l.d_gz;
+            bytes = l.fb_rel[ns];
+        }
+        // ---- copy-back on the lane's own stream: overlaps the next chunk's kernels
+        uint8_t* h_dst;
+        if (out) {
+            if (total + bytes > out_capacity) {
+                rc = pfail(p, V2P_ERR_RES_OOB, "output needs more than %llu bytes (at sample %llu)", (unsigned long long)out_capacity,
+                           (unsigned long long)s0);
+                break;
+            }
+            h_dst = out + total;
+        } else {
+            if ((rc = grow_host(p, l, bytes))) break;
+            h_dst = l.h_buf;
+        }
+        if (bytes) PCU(p, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, l.copy));
+        PCU(p, cudaEventRecord(l.landed, l.copy));
+        l.pending = true, l.first_sample = s0, l.n = ns, l.h_data = h_dst;
+        if (file_begin)
+            for (uint64_t s = 1; s <= ns; ++s) file_begin[s0 + s] = total + l.fb_rel[s];
+        total += bytes;
+        res->n_sites += g.n_sites, res->n_tasks += g.batch.n_tasks, res->n_records += g.n_rows;
+        res->image_bytes += g.batch.n_out, res->out_bytes += bytes;
+        res->gen_ms += g.gen_ms, res->exec_ms += er.kernel_ms;
+        res->n_chunks++;
+    }
+    // drain in order: the oldest chunk sits in the lane the next chunk would have taken
+    for (uint32_t k = 0; k < p->n_lanes; ++k) {
+        Lane& l = p->lanes[(ci + k) % p->n_lanes];
+        if (rc == V2P_OK) rc = retire(p, l, sink, user);
+        else if (l.pending) cudaEventSynchronize(l.landed), l.pending = false;
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int v2p_pipeline_create(v2p_engine* e, v2p_catalogue* const* lanes, uint32_t n_lanes, v2p_pipeline** out) {
+    if (!out) return V2P_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!e || !lanes || n_lanes < 1 || n_lanes > V2P_PIPE_MAX_LANES) return V2P_ERR_INVALID_ARG;
+    for (uint32_t i = 0; i < n_lanes; ++i) {
+        if (!lanes[i]) return V2P_ERR_INVALID_ARG;
+        for (uint32_t k = 0; k < i; ++k)
+            if (lanes[k] == lanes[i]) return V2P_ERR_INVALID_ARG;  // a lane owns the buffers of a chunk in flight
+    }
+    v2p_pipeline* p = new (std::nothrow) v2p_pipeline();
+    if (!p) return V2P_ERR_INVALID_ARG;
+    p->eng = e;
+    p->device = v2p_engine_device(e);
+    p->n_lanes = n_lanes;
+    bool ok = cudaSetDevice(p->device) == cudaSuccess;
+    for (uint32_t i = 0; ok && i < n_lanes; ++i) {
+        Lane& l = p->lanes[i];
+        l.cat = lanes[i];
+        ok = v2p_gzip_create(p->device, &l.gz) == V2P_OK &&
+             cudaStreamCreateWithFlags(&l.copy, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&l.landed, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
+        v2p_pipeline_destroy(p);
+        return V2P_ERR_CUDA;
+    }
+    *out = p;
+    return V2P_OK;
+}
+
+void v2p_pipeline_destroy(v2p_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (uint32_t i = 0; i < p->n_lanes; ++i) {
+        Lane& l = p->lanes[i];
+        if (l.copy) cudaStreamSynchronize(l.copy), cudaStreamDestroy(l.copy);
+        if (l.landed) cudaEventDestroy(l.landed);
+        if (l.gz) v2p_gzip_destroy(l.gz);
+        if (l.d_gz) cudaFree(l.d_gz);
+        if (l.d_begin) cudaFree(l.d_begin);
+        if (l.h_buf) cudaFreeHost(l.h_buf);
+    }
+    delete p;
+}
+
+const char* v2p_pipeline_last_error(v2p_pipeline* p) { return p ? p->err.c_str() : "pipeline is NULL"; }
+
+int v2p_pipeline_run_lists(v2p_pipeline* p, uint64_t n_samples, const uint64_t* site_begin, const uint32_t* sites,
+                           uint32_t chunk_samples, uint32_t flags, uint8_t* out, uint64_t out_capacity, uint64_t* file_begin,
+                           v2p_file_sink sink, void* user, v2p_pipeline_result* res) {
+    if (!p) return V2P_ERR_INVALID_ARG;
+    p->err.clear();
+    v2p_pipeline_result local;
+    memset(&local, 0, sizeof local);
+    if (!site_begin || site_begin[0] != 0) return pfail(p, V2P_ERR_INVALID_ARG, "site_begin is NULL or does not start at 0");
+    for (uint64_t h = 0; h < 2 * n_samples; ++h)
+        if (site_begin[h + 1] < site_begin[h]) return pfail(p, V2P_ERR_INVALID_ARG, "site_begin not monotone at haplotype %llu", (unsigned long long)h);
+    if (site_begin[2 * n_samples] && !sites) return pfail(p, V2P_ERR_INVALID_ARG, "sites is NULL");
+    const auto t0 = std::chrono::steady_clock::now();
+    local.n_samples = n_samples;
+    ListSource src{site_begin, sites ? sites : reinterpret_cast<const uint32_t*>(site_begin), nullptr};
+    const int rc = run(p, n_samples, src, chunk_samples, flags, out, out_capacity, file_begin, sink, user, &local);
+    local.wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (res) *res = local;
+    return rc;
+}
+
+int v2p_pipeline_run_masks(v2p_pipeline* p, uint64_t n_records, uint64_t n_samples, uint32_t words_per_cell,
+                           const uint32_t* masks, const uint64_t* csq_begin, const int32_t* csq_site, uint32_t mask_flags,
+                           uint32_t chunk_samples, uint32_t flags, uint8_t* out, uint64_t out_capacity, uint64_t* file_begin,
+                           v2p_file_sink sink, void* user, v2p_pipeline_result* res) {
+    if (!p) return V2P_ERR_INVALID_ARG;
+    p->err.clear();
+    v2p_pipeline_result local;
+    memset(&local, 0, sizeof local);
+    const auto t0 = std::chrono::steady_clock::now();
+    local.n_samples = n_samples;
+    // the whole matrix is decoded once, by the last lane's catalogue object (the lists live in its md_* buffers, which no
+    // generation touches); the chunks read them in place
+    v2p_catalogue* dec = p->lanes[p->n_lanes - 1].cat;
+    v2p_site_lists lists;
+    int rc = v2p_sites_from_masks(dec, n_records, n_samples, words_per_cell, masks, csq_begin, csq_site, mask_flags, &lists);
+    if (rc) {
+        pfail(p, rc, "mask decode failed: %s", v2p_catalogue_last_error(dec));
+    } else {
+        local.decode_ms = lists.decode_ms;
+        if (!(mask_flags & V2P_FLAG_DEVICE_PTRS)) local.h2d_bytes += n_records * n_samples * words_per_cell * 4;
+        std::vector<uint64_t> sb(2 * n_samples + 1);
+        PCU(p, cudaSetDevice(p->device));
+        PCU(p, cudaMemcpy(sb.data(), lists.site_begin, sb.size() * 8, cudaMemcpyDeviceToHost));
+        ListSource src{sb.data(), nullptr, lists.sites};
+        rc = run(p, n_samples, src, chunk_samples, flags, out, out_capacity, file_begin, sink, user, &local);
+    }
+    local.wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (res) *res = local;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+"""ctypes harness for the whole-cohort pipeline (include/v2p_pipeline.h, csrc/v2p_pipeline.cu): per-haplotype site
+lists (or the FORMAT/BCSQ mask matrix) in, per-sample .fasta / .fasta.gz file images out, everything in between on
+the device -- what parts/exec.rs:27-41 + parts/io.rs:45-57 do per proband in the reference."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .engine import EngineError, GpuEngine
+from .taskgen import DeviceCatalogue
+
+
+class DevicePipeline:
+    """`eng` must have the proteome registered.  One DeviceCatalogue per lane (chunk in flight) is created here."""
+
+    def __init__(self, eng: GpuEngine, prot, cat, names=None, lanes: int = 2, device: int = 0):
+        from . import cohort
+
+        self._lib = L.load()
+        self._eng = eng
+        self._cats = [DeviceCatalogue(prot, cat, device) for _ in range(lanes)]
+        nm = cohort.default_names(prot) if names is None else names
+        for c in self._cats:
+            c.set_names(*nm)
+        arr = (C.c_void_p * lanes)(*[c._h for c in self._cats])
+        h = C.c_void_p()
+        st = self._lib.v2p_pipeline_create(eng._h, arr, lanes, C.byref(h))
+        if st:
+            raise EngineError(st, "v2p_pipeline_create failed")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.v2p_pipeline_destroy(self._h)
+            self._h = None
+            for c in self._cats:
+                c.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self) -> str:
+        return (self._lib.v2p_pipeline_last_error(self._h) or b"").decode()
+
+    @staticmethod
+    def _sink(fn: Optional[Callable]):
+        if fn is None:
+            return L.FILE_SINK(), None
+
+        def cb(_user, first, n, data, fb):
+            try:
+                begins = np.ctypeslib.as_array(fb, shape=(n + 1,))
+                view = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), shape=(max(int(begins[n]), 1),))
+                return int(fn(int(first), int(n), view[: int(begins[n])], begins) or 0)
+            except Exception:  # never unwind through the C frame
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        return L.FILE_SINK(cb), cb
+
+    def _dest(self, out, n_samples):
+        if out is None:
+            return None, 0, None, None
+        fb = np.zeros(n_samples + 1, np.uint64)
+        return out.ctypes.data_as(C.c_void_p), out.nbytes, fb.ctypes.data_as(C.c_void_p), fb
+
+    def run_lists(self, site_begin: np.ndarray, sites: np.ndarray, n_samples: int, chunk_samples: int = 128, gzip: bool = False,
+                  out: Optional[np.ndarray] = None, sink: Optional[Callable] = None) -> Tuple[Optional[np.ndarray], L.PipelineResult]:
+        """site_begin[2*n_samples+1], sites: the cohort's CSR site lists.  Either `out` (uint8 host array; returns the
+        file_begin offsets into it) or `sink(first_sample, n, data, file_begin)` called per chunk in sample order."""
+        sb, st_ = np.ascontiguousarray(site_begin, np.uint64), np.ascontiguousarray(sites, np.uint32)
+        op, cap, fbp, fb = self._dest(out, n_samples)
+        cb, keep = self._sink(sink)
+        res = L.PipelineResult()
+        st = self._lib.v2p_pipeline_run_lists(self._h, n_samples, sb.ctypes.data_as(C.c_void_p), st_.ctypes.data_as(C.c_void_p),
+                                              chunk_samples, L.PIPE_GZIP if gzip else 0, op, cap, fbp, cb, None, C.byref(res))
+        del keep
+        if st:
+            raise EngineError(st, self._err())
+        return fb, res
+
+    def run_masks(self, masks, csq_begin: np.ndarray, csq_site: np.ndarray, shape=None, chunk_samples: int = 128, gzip: bool = False,
+                  out: Optional[np.ndarray] = None, sink: Optional[Callable] = None) -> Tuple[Optional[np.ndarray], L.PipelineResult]:
+        """masks[n_records, n_samples, W]: numpy array, or a device pointer (int) with shape=(n_records, n_samples, W)."""
+        mflags = 0
+        if isinstance(masks, np.ndarray):
+            masks = np.ascontiguousarray(masks, np.uint32)
+            n_rec, n_samp, w = masks.shape
+            mp = masks.ctypes.data_as(C.c_void_p)
+        else:
+            n_rec, n_samp, w = shape
+            mp, mflags = C.c_void_p(int(masks)), L.FLAG_DEVICE_PTRS
+        cbeg, csite = np.ascontiguousarray(csq_begin, np.uint64), np.ascontiguousarray(csq_site, np.int32)
+        op, cap, fbp, fb = self._dest(out, n_samp)
+        cb, keep = self._sink(sink)
+        res = L.PipelineResult()
+        st = self._lib.v2p_pipeline_run_masks(self._h, n_rec, n_samp, w, mp, cbeg.ctypes.data_as(C.c_void_p),
+                                              csite.ctypes.data_as(C.c_void_p), mflags, chunk_samples, L.PIPE_GZIP if gzip else 0,
+                                              op, cap, fbp, cb, None, C.byref(res))
+        del keep
+        if st:
+            raise EngineError(st, self._err())
+        return fb, res
+
+
+def csr_lists(hap: np.ndarray, site: np.ndarray, n_hap: int) -> Tuple[np.ndarray, np.ndarray]:
+    """(hap, site) pairs sorted by (hap, site) -> (site_begin[n_hap+1], sites)."""
+    site_begin = np.zeros(n_hap + 1, np.uint64)
+    np.cumsum(np.bincount(hap, minlength=n_hap), out=site_begin[1:])
+    return site_begin, np.ascontiguousarray(site, np.uint32)
