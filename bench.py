@@ -68,6 +68,10 @@ def parse_args():
     ap.add_argument("--gzip-samples", type=int, default=256,
                     help="samples whose FASTA file image is gzip-compressed on the device (0 = skip)")
     ap.add_argument("--no-taskgen", action="store_true", help="skip the device-side Task generation measurement")
+    ap.add_argument("--pipeline-samples", type=int, default=-1,
+                    help="samples run through v2p_pipeline_run_lists (site lists -> .fasta / .fasta.gz images in pinned host "
+                         "memory); -1 = the whole cohort, 0 = skip")
+    ap.add_argument("--pipeline-chunk", type=int, default=128, help="samples per pipeline chunk")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
                     help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
     return ap.parse_args()
@@ -282,6 +286,69 @@ def gzip_measure(args, prot, cat, eng, dev, local_rank, torch):
             "d2h_ms_if_uncompressed": d2h_ms * res.in_bytes / max(1, res.out_bytes), "inflates_to_the_image": bool(ok),
             "cpu_zlib9_one_core": {"mbs": len(one) / t_z9 / 1e6, "ratio": len(one) / z9, "sample_bytes": len(one)},
             "what": "v2p_gzip_files, device -> device: one gzip member per sample file, 16 KiB dynamic-Huffman chunks"}
+
+
+def oracle_file_text(batch, prot, s: int) -> bytes:
+    """Sample s's .fasta text from the ORACLE's tapes (hap-1 records, then hap-2 records, tape order)."""
+    from oracle import cengine
+    from vcf2prot_b200 import cohort as C
+
+    h0, h1 = 2 * s, 2 * s + 2
+    t0, t1 = int(batch.task_begin[h0]), int(batch.task_begin[h1])
+    a0, a1 = int(batch.alt_base[h0]), int(batch.alt_base[h1])
+    o0, o1 = int(batch.out_base[h0]), int(batch.out_base[h1])
+    tape = np.zeros(o1 - o0, np.uint8)
+    rebase = lambda a, x: (a[h0:h1 + 1] - np.uint64(x)).astype(np.uint64)
+    st, _, _ = cengine.batch_execute(rebase(batch.task_begin, t0), batch.tasks[t0:t1], prot.residues, batch.alt[a0:a1],
+                                     rebase(batch.alt_base, a0), tape, rebase(batch.out_base, o0))
+    assert st == 0
+    txt = []
+    for k in (0, 1):
+        base = int(batch.out_base[h0 + k]) - o0
+        lo, hi = np.searchsorted(batch.ann_hap, [h0 + k, h0 + k + 1])
+        for r in range(lo, hi):
+            seq = tape[base + int(batch.ann_start[r]): base + int(batch.ann_end[r])].tobytes()
+            txt.append(b">" + prot.name(int(batch.ann_tx[r])).encode() + b"_%d\n" % (k + 1) + seq + b"\n")
+    return b"".join(txt)
+
+
+def pipeline_measure(args, prot, cat, batch, eng, local_rank):
+    """v2p_pipeline_run_lists on the timed cohort: the per-haplotype site lists go up (4 B/site), every sample's .fasta
+    (then .fasta.gz) image lands in the pipeline's pinned ring and is handed to a sink; tasks, tapes and images never
+    exist on the host.  First and last file are compared with the oracle's text."""
+    import zlib
+
+    from vcf2prot_b200.pipeline import DevicePipeline, csr_lists
+
+    ns = batch.n_hap // 2 if args.pipeline_samples < 0 else min(args.pipeline_samples, batch.n_hap // 2)
+    sel = batch.kept_hap < 2 * ns
+    sb, sites = csr_lists(batch.kept_hap[sel], batch.kept_site[sel], 2 * ns)
+    n_res = int((batch.ann_end - batch.ann_start)[batch.ann_hap < 2 * ns].sum())
+    want_first, want_last = oracle_file_text(batch, prot, 0), oracle_file_text(batch, prot, ns - 1)
+    pipe = DevicePipeline(eng, prot, cat, lanes=2, device=local_rank)
+    out = {"samples": ns, "chunk_samples": args.pipeline_chunk, "lanes": 2, "residues": n_res,
+           "api": "v2p_pipeline_run_lists (host site lists in, file images to a sink through the pipeline's pinned ring)"}
+    warm = min(ns, 2 * args.pipeline_chunk)
+    for gz in (False, True):
+        got = {}
+
+        def sink(first, n, data, begins):
+            if first == 0:
+                got["first"] = bytes(data[: int(begins[1])])
+            if first + n == ns:
+                got["last"] = bytes(data[int(begins[n - 1]): int(begins[n])])
+            return 0
+
+        pipe.run_lists(sb[: 2 * warm + 1], sites[: int(sb[2 * warm])], warm, args.pipeline_chunk, gz, sink=lambda *a: 0)  # allocations
+        _, r = pipe.run_lists(sb, sites, ns, args.pipeline_chunk, gz, sink=sink)
+        un = (lambda b: zlib.decompress(b, wbits=31)) if gz else (lambda b: b)
+        out["fasta_gz" if gz else "fasta"] = {
+            "residues_per_s": n_res / r.wall_s, "wall_s": r.wall_s, "h2d_bytes": int(r.h2d_bytes), "d2h_bytes": int(r.out_bytes),
+            "image_bytes": int(r.image_bytes), "records": int(r.n_records), "tasks": int(r.n_tasks), "chunks": int(r.n_chunks),
+            "gen_ms": r.gen_ms, "exec_ms": r.exec_ms, "gzip_ms": r.gzip_ms,
+            "first_and_last_file_equal_oracle_text": bool(un(got["first"]) == want_first and un(got["last"]) == want_last)}
+    pipe.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -500,6 +567,12 @@ def main():
     if world == 1 and args.gzip_samples > 0 and not args.no_registered_ref:
         gzip_line = gzip_measure(args, prot, cat, eng, dev, local_rank, torch)
 
+    # ---- all of it behind one call: site lists -> .fasta / .fasta.gz images in pinned host memory
+    pipeline_line = None
+    if (world == 1 and args.pipeline_samples != 0 and not args.no_registered_ref and not args.fasta_image and
+            batch.kept_hap is not None and not args.no_cpu_baseline):
+        pipeline_line = pipeline_measure(args, prot, cat, batch, eng, local_rank)
+
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
@@ -560,7 +633,7 @@ def main():
                      "write_only": {"achieved_gbs": write_rate, "peak_gbs": write_peak, "frac": write_rate / write_peak,
                                     "note": "result-tape bytes written / kernel time vs torch fill_ on the same GPU: the "
                                             "hard floor of this path is one DRAM write per residue"}},
-        "cpu_baseline": cpu, "parity": parity, "taskgen": taskgen, "gzip": gzip_line, "gen_seconds": round(t_gen, 1),
+        "cpu_baseline": cpu, "parity": parity, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
     }
     print(json.dumps(line))
     if world > 1:

@@ -21,6 +21,7 @@
 
 #include "v2p_engine.h"
 #include "v2p_kernels.cuh"
+#include "v2p_mapped.cuh"
 
 using namespace v2p;
 
@@ -187,8 +188,11 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     }
     if (ev_stop) CUDA_TRY(e, cudaEventRecord(ev_stop, s));
     CUDA_TRY(e, cudaGetLastError());
-    // status rides the stream right behind the kernels, so a later launch cannot overwrite it first
-    CUDA_TRY(e, cudaMemcpyAsync(h_status, kp.status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    // status rides the stream right behind the kernels, so a later launch cannot overwrite it first; it is stored
+    // into mapped pinned memory by a kernel (v2p_mapped.cuh) so it never queues behind a result tape on the copy engine
+    static_assert(sizeof(DevStatus) == 24, "DevStatus is published as three 8-byte words");
+    CUDA_TRY(e, publish_words(reinterpret_cast<unsigned long long*>(h_status), kp.status, 3, s));
+    e->launches++;
     return V2P_OK;
 }
 
@@ -272,7 +276,7 @@ v2p_event* acquire_event(v2p_engine* e) {
     if (cudaEventCreate(&ev->ev_start) != cudaSuccess || cudaEventCreate(&ev->ev_stop) != cudaSuccess ||
         cudaEventCreate(&ev->ev_copy) != cudaSuccess ||
         cudaEventCreateWithFlags(&ev->ev_done, cudaEventDisableTiming) != cudaSuccess ||
-        cudaMallocHost((void**)&ev->h_status, sizeof(DevStatus)) != cudaSuccess) {
+        cudaHostAlloc((void**)&ev->h_status, sizeof(DevStatus), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         free_event(ev);
         return nullptr;
     }
@@ -347,7 +351,7 @@ int v2p_engine_create(int cuda_device, v2p_engine** out) {
     cudaDeviceProp prop;
     bool ok = cudaSetDevice(cuda_device) == cudaSuccess && cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaMallocHost((void**)&e->h_status, sizeof(DevStatus)) == cudaSuccess;
+              cudaHostAlloc((void**)&e->h_status, sizeof(DevStatus), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
     for (int i = 0; ok && i < kSlots; ++i)
         ok = cudaStreamCreateWithFlags(&e->slots[i].stream, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "v2p_gzip.h"
+#include "v2p_mapped.cuh"
 
 namespace {
 
@@ -693,6 +694,7 @@ struct v2p_gzip {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     Buf file_begin, chunk_first, lens, csize, ccrc, coff, out_begin, ctr, cub_tmp, in_stage, out_stage;
+    v2p::MappedBuf pub;  // totals and per-file offsets come back through mapped pinned memory (v2p_mapped.cuh)
 };
 
 namespace {
@@ -758,6 +760,7 @@ void v2p_gzip_destroy(v2p_gzip* z) {
                   &z->in_stage, &z->out_stage};
     for (Buf* b : all)
         if (b->p) cudaFree(b->p);
+    z->pub.release();
     if (z->ev0) cudaEventDestroy(z->ev0);
     if (z->ev1) cudaEventDestroy(z->ev1);
     if (z->stream) cudaStreamDestroy(z->stream);
@@ -821,11 +824,15 @@ int v2p_gzip_files(v2p_gzip* z, const uint8_t* in, const uint64_t* file_begin, u
     ZCU(z, cub::DeviceScan::ExclusiveSum(nullptr, tmp, a.csize, (uint64_t*)z->coff.p, (int64_t)(n_chunks + 1), st));
     if ((rc = zneed(z, z->cub_tmp, tmp))) return rc;
     ZCU(z, cub::DeviceScan::ExclusiveSum(z->cub_tmp.p, tmp, a.csize, (uint64_t*)z->coff.p, (int64_t)(n_chunks + 1), st));
-    uint64_t total = 0;
-    unsigned long long n_stored = 0;
-    ZCU(z, cudaMemcpyAsync(&total, (const uint64_t*)z->coff.p + n_chunks, 8, cudaMemcpyDeviceToHost, st));
-    ZCU(z, cudaMemcpyAsync(&n_stored, z->ctr.p, 8, cudaMemcpyDeviceToHost, st));
+    ZCU(z, z->pub.reserve(n_files + 1 + 8));
+    {
+        v2p::PubList pl{};
+        pl.src[0] = (const unsigned long long*)z->coff.p + n_chunks, pl.src[1] = (const unsigned long long*)z->ctr.p, pl.n = 2;
+        v2p::k_publish_list<<<1, 32, 0, st>>>(z->pub.p, pl);
+    }
     ZCU(z, cudaStreamSynchronize(st));
+    const uint64_t total = z->pub.p[0];
+    const unsigned long long n_stored = z->pub.p[1];
     if (total > out_capacity)
         return zfail(z, V2P_ERR_RES_OOB, "output needs %llu bytes, capacity is %llu (v2p_gzip_bound gives a safe size)",
                      (unsigned long long)total, (unsigned long long)out_capacity);
@@ -838,10 +845,11 @@ int v2p_gzip_files(v2p_gzip* z, const uint8_t* in, const uint64_t* file_begin, u
     k_gz_files<<<(unsigned)((n_files + 1 + 127) / 128), 128, 0, st>>>(a);
     k_gz_encode<<<grid, NT, 0, st>>>(a);
     ZCU(z, cudaGetLastError());
-    ZCU(z, cudaMemcpyAsync(out_begin, z->out_begin.p, (n_files + 1) * 8, cudaMemcpyDeviceToHost, st));
+    ZCU(z, v2p::publish_words(z->pub.p + 8, z->out_begin.p, n_files + 1, st));
     if (!dev && total) ZCU(z, cudaMemcpyAsync(out, a.out, total, cudaMemcpyDeviceToHost, st));
     ZCU(z, cudaEventRecord(z->ev1, st));
     ZCU(z, cudaStreamSynchronize(st));
+    memcpy(out_begin, z->pub.p + 8, (n_files + 1) * 8);
     float ms = 0;
     ZCU(z, cudaEventElapsedTime(&ms, z->ev0, z->ev1));
     if (res) res->in_bytes = in_bytes, res->out_bytes = total, res->n_chunks = n_chunks, res->n_stored_chunks = n_stored, res->ms = ms;

@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "v2p_mapped.cuh"
 #include "v2p_pipeline.h"
 
 namespace {
@@ -29,6 +30,7 @@ struct Lane {
     size_t d_gz_cap = 0;
     void* d_begin = nullptr;  // rebased site_begin of the chunk (mask entry point)
     size_t d_begin_cap = 0;
+    v2p::MappedBuf pub;        // out_base of the chunk, published by a kernel (v2p_mapped.cuh)
     uint8_t* h_buf = nullptr;  // pinned staging (sink mode)
     size_t h_cap = 0;
     // the chunk in flight
@@ -44,6 +46,7 @@ struct v2p_pipeline {
     v2p_engine* eng = nullptr;
     int device = 0;
     uint32_t n_lanes = 0;
+    cudaStream_t aux = nullptr;  // small kernels of the pipeline itself (never behind a copy-back)
     Lane lanes[V2P_PIPE_MAX_LANES];
     std::string err;
 };
@@ -113,7 +116,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
     for (uint32_t i = 0; i < p->n_lanes; ++i) p->lanes[i].pending = false;
     uint64_t total = 0;
     if (file_begin) file_begin[0] = 0;
-    std::vector<uint64_t> sb, hb;
+    std::vector<uint64_t> sb;
     uint64_t ci = 0;
     int rc = V2P_OK;
     for (uint64_t s0 = 0; s0 < n_samples && rc == V2P_OK; s0 += chunk_samples, ++ci) {
@@ -149,10 +152,11 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
             break;
         }
         // ---- file bounds: sample s owns haplotypes 2s, 2s+1
-        hb.resize(nh + 1);
-        PCU(p, cudaMemcpy(hb.data(), g.batch.out_base, (nh + 1) * 8, cudaMemcpyDeviceToHost));
+        PCU(p, l.pub.reserve(nh + 1));
+        PCU(p, v2p::publish_words(l.pub.p, g.batch.out_base, nh + 1, p->aux));
+        PCU(p, cudaStreamSynchronize(p->aux));
         l.fb_rel.resize(ns + 1);
-        for (uint64_t s = 0; s <= ns; ++s) l.fb_rel[s] = hb[2 * s];
+        for (uint64_t s = 0; s <= ns; ++s) l.fb_rel[s] = l.pub.p[2 * s];
         const uint8_t* d_src = g.batch.out;
         uint64_t bytes = g.batch.n_out;
         if (gzip) {
@@ -220,7 +224,7 @@ int v2p_pipeline_create(v2p_engine* e, v2p_catalogue* const* lanes, uint32_t n_l
     p->eng = e;
     p->device = v2p_engine_device(e);
     p->n_lanes = n_lanes;
-    bool ok = cudaSetDevice(p->device) == cudaSuccess;
+    bool ok = cudaSetDevice(p->device) == cudaSuccess && cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking) == cudaSuccess;
     for (uint32_t i = 0; ok && i < n_lanes; ++i) {
         Lane& l = p->lanes[i];
         l.cat = lanes[i];
@@ -247,7 +251,9 @@ void v2p_pipeline_destroy(v2p_pipeline* p) {
         if (l.d_gz) cudaFree(l.d_gz);
         if (l.d_begin) cudaFree(l.d_begin);
         if (l.h_buf) cudaFreeHost(l.h_buf);
+        l.pub.release();
     }
+    if (p->aux) cudaStreamDestroy(p->aux);
     delete p;
 }
 

@@ -22,6 +22,7 @@
 #include <new>
 #include <string>
 
+#include "v2p_mapped.cuh"
 #include "v2p_taskgen.h"
 
 namespace {
@@ -402,6 +403,7 @@ struct v2p_catalogue {
     std::string err;
     uint64_t n_tx = 0, n_sites = 0;
     Buf tx_off, tx, pos, rlen, dlen, cls, doff, pool;
+    v2p::MappedBuf pub;   // totals come back through mapped pinned memory, not the copy engine (v2p_mapped.cuh)
     Buf name_off, names;  // v2p_catalogue_set_names
     bool has_names = false;
     // per-generation buffers
@@ -510,6 +512,7 @@ void v2p_catalogue_destroy(v2p_catalogue* c) {
         if (c->scan_in[i].p) cudaFree(c->scan_in[i].p);
         if (c->scan_out[i].p) cudaFree(c->scan_out[i].p);
     }
+    c->pub.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -590,8 +593,16 @@ int v2p_sites_from_masks(v2p_catalogue* c, uint64_t n_records, uint64_t n_sample
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const unsigned grid = (unsigned)std::min<uint64_t>((n_words + 1023) / 1024 + 1, (uint64_t)sms * 16);
     if (n_words) k_md_count<<<grid, 256, 0, st>>>(d_masks, n_words, ctr);
-    CU(c, cudaMemcpyAsync(&h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaStreamSynchronize(st));
+    static_assert(sizeof(MdCtr) == 32, "MdCtr is published as four 8-byte words");
+    CU(c, c->pub.reserve(64));
+    auto fetch_ctr = [&]() -> cudaError_t {  // counters -> mapped pinned memory -> h
+        cudaError_t e1 = v2p::publish_words(c->pub.p, ctr, 4, st);
+        if (e1 != cudaSuccess) return e1;
+        e1 = cudaStreamSynchronize(st);
+        memcpy(&h, c->pub.p, sizeof h);
+        return e1;
+    };
+    CU(c, fetch_ctr());
     const uint64_t cap = h.n_bits;  // upper bound of the keys: every set bit
     uint32_t site_bits = 1, hap_bits = 1;
     while ((1ull << site_bits) < c->n_sites) ++site_bits;
@@ -604,8 +615,7 @@ int v2p_sites_from_masks(v2p_catalogue* c, uint64_t n_records, uint64_t n_sample
         MdArgs a{d_masks, n_words, n_samples, words_per_cell, site_bits, (const uint64_t*)c->md_csq_begin.p,
                  (const int32_t*)c->md_csq_site.p, (uint64_t*)c->md_keys[0].p, ctr};
         k_md_emit<<<grid, 256, 0, st>>>(a);
-        CU(c, cudaMemcpyAsync(&h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
-        CU(c, cudaStreamSynchronize(st));
+        CU(c, fetch_ctr());
         if (h.bad_record != ~0ull)
             return cfail(c, V2P_ERR_SRC_OOB, "record %llu: a mask bit selects a consequence beyond the record's %llu (vcf_ds.rs:287)",
                          h.bad_record, (unsigned long long)(csq_begin[h.bad_record + 1] - csq_begin[h.bad_record]));
@@ -619,8 +629,7 @@ int v2p_sites_from_masks(v2p_catalogue* c, uint64_t n_records, uint64_t n_sample
             CU(c, cub::DeviceSelect::Unique(nullptr, tmp, db.Current(), (uint64_t*)c->md_uniq.p, &ctr->n_unique, (int64_t)n_keys, st));
             if ((rc = need(c, c->cub_tmp, tmp))) return rc;
             CU(c, cub::DeviceSelect::Unique(c->cub_tmp.p, tmp, db.Current(), (uint64_t*)c->md_uniq.p, &ctr->n_unique, (int64_t)n_keys, st));
-            CU(c, cudaMemcpyAsync(&h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
-            CU(c, cudaStreamSynchronize(st));
+            CU(c, fetch_ctr());
             n_unique = h.n_unique;
         }
     }
@@ -686,11 +695,14 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
     for (int i = 0; i < 5; ++i)
         if ((rc = xsum(c, *ins[i], *outs[i], n_sel + 1))) return rc;
     // totals: n_tasks, n_groups
-    uint64_t tot[2];
-    CU(c, cudaMemcpyAsync(&tot[0], s.task_x + n_sel, 8, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaMemcpyAsync(&tot[1], s.g_x + n_sel, 8, cudaMemcpyDeviceToHost, st));
+    CU(c, c->pub.reserve(64));
+    {
+        v2p::PubList pl{};
+        pl.src[0] = (const unsigned long long*)(s.task_x + n_sel), pl.src[1] = (const unsigned long long*)(s.g_x + n_sel), pl.n = 2;
+        v2p::k_publish_list<<<1, 32, 0, st>>>(c->pub.p, pl);
+    }
     CU(c, cudaStreamSynchronize(st));
-    const uint64_t n_tasks = tot[0], n_groups = tot[1];
+    const uint64_t n_tasks = c->pub.p[0], n_groups = c->pub.p[1];
 
     Grp g{};
     g.n_groups = n_groups;
@@ -715,19 +727,21 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
     if ((rc = xsum(c, g.g_slot, g.g_slot_x, n_groups + 1))) return rc;
     k_tg_hap_bases<<<blocks(n_hap + 1), 256, 0, st>>>(s, g, o);
     if (n_sel) k_tg_emit_tasks<<<blocks(n_sel), 256, 0, st>>>(s, cat, g, o);
-    uint64_t n_alt = 0, n_out = 0, n_names = 0;
+    v2p::PubList pl{};
     if (s.aligned) {
         if ((rc = xsum(c, s.slotl, s.sl_x, n_sel + 1))) return rc;
         k_tg_alt_sizes<<<blocks(n_hap + 1), 256, 0, st>>>(s, o);
         if ((rc = xsum(c, o.alt_per_hap, o.alt_base, n_hap + 1))) return rc;
-        CU(c, cudaMemcpyAsync(&n_alt, o.alt_base + n_hap, 8, cudaMemcpyDeviceToHost, st));
+        pl.src[0] = (const unsigned long long*)(o.alt_base + n_hap);
     } else {
-        CU(c, cudaMemcpyAsync(&n_alt, s.a_x + n_sel, 8, cudaMemcpyDeviceToHost, st));
-        if (fasta) CU(c, cudaMemcpyAsync(&n_names, s.sh_x + n_sel, 8, cudaMemcpyDeviceToHost, st));
+        pl.src[0] = (const unsigned long long*)(s.a_x + n_sel);
     }
-    CU(c, cudaMemcpyAsync(&n_out, g.g_slot_x + n_groups, 8, cudaMemcpyDeviceToHost, st));
+    pl.src[1] = (const unsigned long long*)(g.g_slot_x + n_groups);
+    pl.src[2] = (const unsigned long long*)(s.sh_x + n_sel);  // FASTA: bytes of the name tape
+    pl.n = 3;
+    v2p::k_publish_list<<<1, 32, 0, st>>>(c->pub.p, pl);
     CU(c, cudaStreamSynchronize(st));
-    n_alt += n_names;
+    const uint64_t n_out = c->pub.p[1], n_alt = c->pub.p[0] + (fasta ? c->pub.p[2] : 0);
     if ((rc = need(c, c->alt, n_alt + 64)) || (rc = need(c, c->out, n_out + 64))) return rc;
     o.alt = (uint8_t*)c->alt.p;
     CU(c, cudaMemsetAsync(o.alt, '.', n_alt + 16, st));
