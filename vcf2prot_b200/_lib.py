@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libv2p_engine.so")
+LIB_PATH = os.environ.get("V2P_ENGINE_LIB") or os.path.join(HERE, "libv2p_engine.so")  # env: kernel A/B builds
 
 V2P_OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_BAD_ENGINE, ERR_BAD_STREAM, ERR_RES_OOB, ERR_SRC_OOB = 1, 2, 3, 4, 5, 6

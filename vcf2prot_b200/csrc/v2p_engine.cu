@@ -33,7 +33,7 @@ struct DevBuf {
 };
 
 struct Scratch {  // per-stream planning scratch
-    DevBuf lb, tile_hap, status;
+    DevBuf lb, tile_hap, chunk_hap, status;
 };
 
 constexpr int kSlots = 3;
@@ -154,6 +154,9 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     if ((rc = reserve(e, sc.lb, (kp.n_tiles + 1) * sizeof(uint32_t)))) return rc;
     if ((rc = reserve(e, sc.tile_hap, std::max<uint64_t>(kp.n_tiles, 1) * sizeof(uint32_t)))) return rc;
     if ((rc = reserve(e, sc.status, sizeof(DevStatus)))) return rc;
+    const uint64_t n_chunks = (kp.n_tasks + kPlanWarpTasks - 1) / kPlanWarpTasks;
+    if ((rc = reserve(e, sc.chunk_hap, std::max<uint64_t>(n_chunks, 1) * sizeof(uint32_t)))) return rc;
+    kp.chunk_hap = (uint32_t*)sc.chunk_hap.p;
     kp.lb = (uint32_t*)sc.lb.p;
     kp.tile_hap = (uint32_t*)sc.tile_hap.p;
     kp.status = (DevStatus*)sc.status.p;
@@ -166,8 +169,8 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     if (kp.n_hap) {
         k_plan_haps<<<(unsigned)((kp.n_hap + 255) / 256), 256, 0, s>>>(kp);
         e->launches++;
-        if (kp.n_tiles) {
-            k_plan_tiles<<<(unsigned)((kp.n_tiles + 255) / 256), 256, 0, s>>>(kp);
+        if (kp.n_tiles || n_chunks) {
+            k_plan_tiles<<<(unsigned)((std::max(kp.n_tiles, n_chunks) + 255) / 256), 256, 0, s>>>(kp);
             e->launches++;
         }
     }
@@ -367,11 +370,11 @@ void v2p_engine_destroy(v2p_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&e->sc.lb,     &e->sc.tile_hap, &e->sc.status, &e->d_soa[0], &e->d_soa[1],  &e->d_soa[2], &e->d_soa[3],
+    DevBuf* bufs[] = {&e->sc.chunk_hap, &e->sc.lb,     &e->sc.tile_hap, &e->sc.status, &e->d_soa[0], &e->d_soa[1],  &e->d_soa[2], &e->d_soa[3],
                       &e->soa_tasks, &e->soa_ref,     &e->soa_alt,   &e->soa_out,  &e->soa_bases, &e->ref_rep};
     for (DevBuf* b : bufs) release(*b);
     for (Slot& sl : e->slots) {
-        DevBuf* sb[] = {&sl.sc.lb,      &sl.sc.tile_hap, &sl.sc.status,  &sl.d_tasks, &sl.d_task_begin, &sl.d_ref,
+        DevBuf* sb[] = {&sl.sc.chunk_hap, &sl.sc.lb,      &sl.sc.tile_hap, &sl.sc.status,  &sl.d_tasks, &sl.d_task_begin, &sl.d_ref,
                         &sl.d_ref_base, &sl.d_alt,       &sl.d_alt_base, &sl.d_out,   &sl.d_out_base};
         for (DevBuf* b : sb) release(*b);
         if (sl.stream) cudaStreamDestroy(sl.stream);

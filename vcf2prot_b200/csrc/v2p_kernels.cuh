@@ -52,6 +52,7 @@ struct KParams {
     uint64_t task_origin, ref_origin, alt_origin, out_origin;
     uint32_t* lb;        // n_tiles+1
     uint32_t* tile_hap;  // n_tiles
+    uint32_t* chunk_hap;  // haplotype of the first task of every k_plan_tasks warp (kPlanWarpTasks tasks each)
     uint64_t n_tiles;
     uint32_t tile_bytes;
     uint32_t tile_shift;  // log2(tile_bytes)
@@ -108,109 +109,150 @@ __global__ void k_plan_haps(KParams p) {
     if (bad) atomicExch(&p.status->bad_args, 1u);
 }
 
-// One thread per output tile: the haplotype that owns the tile's first byte (binary search over out_base).
-__global__ void k_plan_tiles(KParams p) {
-    uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (k >= p.n_tiles) return;
-    const uint64_t x = (k << p.tile_shift) + p.out_origin;
-    uint64_t h = upper_bound_u64(p.out_base, 0, p.n_hap + 1, x);  // first h with out_base[h] > x
-    h = h ? h - 1 : 0;
-    if (h >= p.n_hap) h = p.n_hap - 1;
-    p.tile_hap[k] = (uint32_t)h;
+// One lane per task; every warp owns kPlanWarpTasks CONSECUTIVE tasks: everything the reference would panic on, plus
+// lb[] (tile -> first task).  All task arithmetic is launch-relative and 32-bit (n_tasks < 2^32-2, checked by the host;
+// a tile index fits 32 bits for any tape that fits HBM).  The owning haplotype's bases are warp-uniform registers that
+// advance with the warp's position (a haplotype is ~20k tasks; the haplotype of every warp's first task comes from
+// k_plan_tiles, so no warp starts with a dependent-load binary search); only a sub-iteration that straddles a
+// haplotype boundary or the end of the range takes the per-lane lookup.  The previous task's (dst, len, tile) reaches
+// a lane by ONE rotate shuffle per value: lane 31 contributes what it held in the previous sub-iteration.
+__device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
+constexpr int kPlanU = 4;                       // sub-iterations whose loads are issued together
+constexpr int kPlanWarpTasks = 32 * 16;         // consecutive tasks per warp
+constexpr int kPlanChunk = kPlanWarpTasks * 8;  // ... per 256-thread CTA
+
+struct PlanHap {  // bases of one haplotype, launch-relative
+    uint32_t tb0, tb1;  // its tasks [tb0, tb1)
+    uint64_t orel;      // start of its result tape
+    uint64_t n_res, n_alt, n_ref;
+};
+
+__device__ __forceinline__ PlanHap plan_hap_load(const KParams& p, uint64_t h) {
+    PlanHap c;
+    c.tb0 = (uint32_t)(__ldg(p.task_begin + h) - p.task_origin);
+    c.tb1 = (uint32_t)min(__ldg(p.task_begin + h + 1) - p.task_origin, p.n_tasks);
+    const uint64_t o0 = __ldg(p.out_base + h);
+    c.orel = o0 - p.out_origin;
+    c.n_res = __ldg(p.out_base + h + 1) - o0;
+    c.n_alt = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
+    c.n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
+    return c;
+}
+__device__ __forceinline__ PlanHap plan_hap_of(const KParams& p, uint32_t tr) {
+    return plan_hap_load(p, upper_bound_u64(p.task_begin, 0, p.n_hap + 1, tr + p.task_origin) - 1);
 }
 
-// One thread per task (kPlanChunk tasks per CTA): everything the reference would panic on, plus lb[]
-// (tile -> first task).  A CTA's tasks almost always sit inside one haplotype: that haplotype is found once per
-// CTA (binary search by thread 0) and its bases are staged in shared memory.
-constexpr int kPlanIters = 16;
-constexpr int kPlanChunk = 256 * kPlanIters;
-
-__global__ void __launch_bounds__(256) k_plan_tasks(KParams p) {
-    __shared__ uint64_t sh[8];  // h0, task_begin[h0], task_begin[h0+1], out_base[h0], out_base[h0+1], n_alt(h0), n_ref(h0)
-    const uint64_t tfirst = blockIdx.x * (uint64_t)kPlanChunk;
-    if (threadIdx.x == 0) {
-        const uint64_t h0 = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, tfirst + p.task_origin) - 1;
-        sh[0] = h0;
-        sh[1] = p.task_begin[h0];
-        sh[2] = p.task_begin[h0 + 1];
-        sh[3] = p.out_base[h0];
-        sh[4] = p.out_base[h0 + 1];
-        sh[5] = p.alt_base[h0 + 1] - p.alt_base[h0];
-        sh[6] = p.ref_base ? p.ref_base[h0 + 1] - p.ref_base[h0] : p.n_ref;
+// One thread per output tile: the haplotype that owns the tile's first byte (binary search over out_base);
+// and one thread per k_plan_tasks warp: the haplotype of its first task (binary search over task_begin).
+__global__ void k_plan_tiles(KParams p) {
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (k < p.n_tiles) {
+        const uint64_t x = (k << p.tile_shift) + p.out_origin;
+        uint64_t h = upper_bound_u64(p.out_base, 0, p.n_hap + 1, x);  // first h with out_base[h] > x
+        h = h ? h - 1 : 0;
+        if (h >= p.n_hap) h = p.n_hap - 1;
+        p.tile_hap[k] = (uint32_t)h;
     }
-    __syncthreads();
+    const uint64_t t = k * kPlanWarpTasks;
+    if (t < p.n_tasks) {
+        uint64_t h = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, t + p.task_origin);
+        h = h ? h - 1 : 0;  // task_begin[0] > origin is reported by k_plan_haps (bad_args)
+        if (h >= p.n_hap) h = p.n_hap - 1;
+        p.chunk_hap[k] = (uint32_t)h;
+    }
+}
+
+// One task of the plan (lane-private): m = bases of its haplotype; (kprev, p_dst, p_len) = the task in front of it.
+__device__ __forceinline__ void plan_one(const KParams& p, const PlanHap& m, const uint4 raw, const uint32_t tr,
+                                         const uint32_t kt, const uint32_t kprev, const uint32_t p_dst,
+                                         const uint32_t p_len) {
+    const uint32_t src = raw.x, len = raw.y, dst = raw.z, stream = raw.w;
+    // every reference panic, one predicate each (error paths are cold)
+    const bool bad_stream = stream > 1u;                                           // haplotype_instruction.rs:154
+    const bool bad_res = (uint64_t)dst + len > m.n_res;                            // task.rs:44/48 (result slice)
+    const bool bad_src = (uint64_t)src + len > (stream == 0 ? m.n_ref : m.n_alt);  // task.rs:44/48 (source slice)
+    if (bad_stream | bad_res | bad_src) {
+        const unsigned long long key = (unsigned long long)tr << 8;
+        atomicMin(&p.status->err_key, key | (bad_stream ? V2P_ERR_BAD_STREAM : bad_res ? V2P_ERR_RES_OOB : V2P_ERR_SRC_OOB));
+        return;
+    }
+    if (tr != m.tb0) {  // previous task is in the same haplotype: gir.rs:208 contiguity + sortedness
+        const uint64_t pend = (uint64_t)p_dst + p_len;
+        if (dst < pend) {
+            atomicExch(&p.status->unsorted, 1u);
+            return;
+        }
+        if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
+    }
+    // only tasks that start a new tile (or follow whole tiles of '.') write lb[]; kt <= n_tiles after the checks above,
+    // and kprev == ~0 (task 0) wraps to tile 0
+    if (kt != kprev) p.lb[kprev + 1u] = tr;
+    if (kt - kprev > 1u && kt != kprev)
+        for (uint32_t k = kprev + 2u; k <= kt; ++k) p.lb[k] = tr;
+}
+
+#ifndef V2P_PLAN_MINB
+#define V2P_PLAN_MINB 4
+#endif
+__global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t wid = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t first64 = wid * kPlanWarpTasks;
+    if (first64 >= p.n_tasks) return;
     if (p.status->bad_args) return;
+    const uint32_t first = (uint32_t)first64;
+    const uint32_t end = (uint32_t)min(first64 + kPlanWarpTasks, p.n_tasks);
     const uint4* __restrict__ tk = reinterpret_cast<const uint4*>(p.tasks);
-    // the CTA's first haplotype, kept in registers for the whole chunk
-    const uint64_t c_h = sh[0], c_tb0 = sh[1], c_tb1 = sh[2], c_o0 = sh[3], c_nres = sh[4] - sh[3], c_nalt = sh[5], c_nref = sh[6];
-    constexpr int U = 4;  // tasks per thread whose loads are issued together
-    for (int it0 = 0; it0 < kPlanIters; it0 += U) {
-        uint4 raw[U], prv[U];
+    const uint32_t rot = (lane + 31u) & 31u;
+
+    uint4 raw[kPlanU];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t tr = tfirst + (uint64_t)(it0 + u) * 256 + threadIdx.x;
-            raw[u] = tr < p.n_tasks ? __ldg(tk + tr) : make_uint4(0u, 0u, 0u, 0u);
+    for (int u = 0; u < kPlanU; ++u) {  // the first loads go out before the haplotype bases are known
+        const uint32_t tr = first + 32 * u + lane;
+        raw[u] = tr < end ? __ldg(tk + tr) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    PlanHap c = plan_hap_load(p, __ldg(p.chunk_hap + wid));  // warp-uniform
+    // what lane 31 "held before": the task in front of this warp's range (its tile, dst, len)
+    uint32_t o_kt = 0xFFFFFFFFu, o_dst = 0u, o_len = 0u;  // first == 0: lb[0 .. tile of task 0] = 0
+    if (first > 0) {
+        const uint4 pt = __ldg(tk + first - 1);
+        const uint64_t porel = first - 1 >= c.tb0 ? c.orel : plan_hap_of(p, first - 1).orel;
+        o_kt = (uint32_t)((porel + pt.z) >> p.tile_shift);
+        o_dst = pt.z, o_len = pt.y;
+    }
+
+    for (uint32_t base = first; base < end; base += 32 * kPlanU) {
+        if (base != first) {
+#pragma unroll
+            for (int u = 0; u < kPlanU; ++u) {
+                const uint32_t tr = base + 32 * u + lane;
+                raw[u] = tr < end ? __ldg(tk + tr) : make_uint4(0u, 0u, 0u, 0u);
+            }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            // the previous task sits in the neighbouring lane, except for lane 0
-            const uint64_t tr = tfirst + (uint64_t)(it0 + u) * 256 + threadIdx.x;
-            prv[u].x = __shfl_up_sync(0xffffffffu, raw[u].x, 1);
-            prv[u].y = __shfl_up_sync(0xffffffffu, raw[u].y, 1);
-            prv[u].z = __shfl_up_sync(0xffffffffu, raw[u].z, 1);
-            prv[u].w = 0u;
-            if ((threadIdx.x & 31) == 0 && tr > 0 && tr < p.n_tasks) prv[u] = __ldg(tk + tr - 1);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t tr = tfirst + (uint64_t)(it0 + u) * 256 + threadIdx.x;  // launch-relative task index
-            if (tr >= p.n_tasks) continue;
-            const uint4 pr = prv[u];
-            const uint64_t t = tr + p.task_origin;
-            // bases of the owning haplotype: the CTA's first one (staged), else the next one, else a search
-            uint64_t h = c_h, tb0 = c_tb0, o0 = c_o0, n_res = c_nres, n_alt = c_nalt, n_ref = c_nref;
-            if (t >= c_tb1) {
-                h = h + 1;
-                if (h + 1 > p.n_hap || t >= __ldg(p.task_begin + h + 1) || t < __ldg(p.task_begin + h))
-                    h = upper_bound_u64(p.task_begin, c_h + 1, p.n_hap + 1, t) - 1;
-                tb0 = __ldg(p.task_begin + h);
-                o0 = __ldg(p.out_base + h);
-                n_res = __ldg(p.out_base + h + 1) - o0;
-                n_alt = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
-                n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
-            }
-            const uint32_t src = raw[u].x, len = raw[u].y, dst = raw[u].z, stream = raw[u].w;
-            // every reference panic, one predicate each (error paths are cold)
-            const bool bad_stream = stream > 1u;                                              // haplotype_instruction.rs:154
-            const bool bad_res = (uint64_t)dst + len > n_res;                                 // task.rs:44/48 (result slice)
-            const bool bad_src = (uint64_t)src + len > (stream == 0 ? n_ref : n_alt);         // task.rs:44/48 (source slice)
-            if (bad_stream | bad_res | bad_src) {
-                const unsigned long long key = (unsigned long long)tr << 8;
-                atomicMin(&p.status->err_key,
-                          key | (bad_stream ? V2P_ERR_BAD_STREAM : bad_res ? V2P_ERR_RES_OOB : V2P_ERR_SRC_OOB));
-                continue;
-            }
-            const uint64_t orel = o0 - p.out_origin;               // launch-relative start of the haplotype's tape
-            const uint64_t kt = (orel + dst) >> p.tile_shift;      // tile in which this task starts
-            uint64_t kprev;                                        // tile in which the previous task starts (+1 = first lb to write)
-            if (t > tb0) {  // previous task is in the same haplotype: gir.rs:208 contiguity + sortedness
-                const uint64_t pend = (uint64_t)pr.z + pr.y;
-                if (dst < pend) {
-                    atomicExch(&p.status->unsorted, 1u);
-                    continue;
-                }
-                if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
-                kprev = (orel + pr.z) >> p.tile_shift;
-            } else if (tr == 0) {
-                kprev = ~0ull;  // so that lb[0..kt] = 0
-            } else {  // first task of a haplotype: the previous task belongs to the last non-empty haplotype before
-                uint64_t hp = h;
-                while (hp > 0 && __ldg(p.task_begin + hp) > t - 1) --hp;
-                kprev = (__ldg(p.out_base + hp) - p.out_origin + pr.z) >> p.tile_shift;
-            }
-            if (kt != kprev) {  // only tasks that start a new tile (or follow whole tiles of '.') write lb[]
-                const uint64_t k_hi = min(kt, p.n_tiles);
-                for (uint64_t k = kprev + 1; k <= k_hi; ++k) p.lb[k] = (uint32_t)tr;
+        for (int u = 0; u < kPlanU; ++u) {
+            const uint32_t t0 = base + 32 * u;  // warp-uniform
+            if (t0 >= end) break;
+            if (t0 >= c.tb1) c = plan_hap_of(p, t0);  // the warp moved into another haplotype
+            const uint32_t tr = t0 + lane;
+            const uint32_t len = raw[u].y, dst = raw[u].z;
+            const bool whole = t0 + 32u <= min(c.tb1, end);  // warp-uniform: all 32 tasks exist and belong to c
+            if (whole) {
+                const uint32_t kt = (uint32_t)((c.orel + dst) >> p.tile_shift);  // tile in which this task starts
+                const uint32_t kprev = __shfl_sync(0xffffffffu, lane == 31u ? o_kt : kt, rot);
+                const uint32_t p_dst = __shfl_sync(0xffffffffu, lane == 31u ? o_dst : dst, rot);
+                const uint32_t p_len = __shfl_sync(0xffffffffu, lane == 31u ? o_len : len, rot);
+                o_kt = kt, o_dst = dst, o_len = len;
+                plan_one(p, c, raw[u], tr, kt, kprev, p_dst, p_len);
+            } else {  // a haplotype boundary or the end of the range inside these 32 tasks: per-lane bases
+                PlanHap m = c;
+                if (tr >= c.tb1 && tr < end) m = plan_hap_of(p, tr);
+                const uint32_t kt = (uint32_t)((m.orel + dst) >> p.tile_shift);
+                const uint32_t kprev = __shfl_sync(0xffffffffu, lane == 31u ? o_kt : kt, rot);
+                const uint32_t p_dst = __shfl_sync(0xffffffffu, lane == 31u ? o_dst : dst, rot);
+                const uint32_t p_len = __shfl_sync(0xffffffffu, lane == 31u ? o_len : len, rot);
+                o_kt = kt, o_dst = dst, o_len = len;
+                if (tr < end) plan_one(p, m, raw[u], tr, kt, kprev, p_dst, p_len);
             }
         }
     }
@@ -249,7 +291,6 @@ __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
