@@ -72,6 +72,8 @@ def parse_args():
                     help="samples run through v2p_pipeline_run_lists (site lists -> .fasta / .fasta.gz images in pinned host "
                          "memory); -1 = the whole cohort, 0 = skip")
     ap.add_argument("--pipeline-chunk", type=int, default=128, help="samples per pipeline chunk")
+    ap.add_argument("--written-samples", type=int, default=256,
+                    help="samples whose files the pipeline also WRITES, {tmpdir}/{proband}.fasta and .fasta.gz (0 = skip)")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
                     help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
     return ap.parse_args()
@@ -312,7 +314,7 @@ def oracle_file_text(batch, prot, s: int) -> bytes:
     return b"".join(txt)
 
 
-def pipeline_measure(args, prot, cat, batch, eng, local_rank):
+def pipeline_measure(args, prot, cat, batch, eng, local_rank, barrier, shard, dev):
     """v2p_pipeline_run_lists on the timed cohort: the per-haplotype site lists go up (4 B/site), every sample's .fasta
     (then .fasta.gz) image lands in the pipeline's pinned ring and is handed to a sink; tasks, tapes and images never
     exist on the host.  First and last file are compared with the oracle's text."""
@@ -340,13 +342,40 @@ def pipeline_measure(args, prot, cat, batch, eng, local_rank):
             return 0
 
         pipe.run_lists(sb[: 2 * warm + 1], sites[: int(sb[2 * warm])], warm, args.pipeline_chunk, gz, sink=lambda *a: 0)  # allocations
+        barrier()
         _, r = pipe.run_lists(sb, sites, ns, args.pipeline_chunk, gz, sink=sink)
         un = (lambda b: zlib.decompress(b, wbits=31)) if gz else (lambda b: b)
+        wall = shard.max_over_ranks(r.wall_s, dev)  # all ranks run their own sample range at once (weak scaling)
         out["fasta_gz" if gz else "fasta"] = {
-            "residues_per_s": n_res / r.wall_s, "wall_s": r.wall_s, "h2d_bytes": int(r.h2d_bytes), "d2h_bytes": int(r.out_bytes),
+            "residues_per_s": shard.sum_over_ranks(n_res, dev) / wall, "wall_s": wall, "h2d_bytes": int(r.h2d_bytes), "d2h_bytes": int(r.out_bytes),
             "image_bytes": int(r.image_bytes), "records": int(r.n_records), "tasks": int(r.n_tasks), "chunks": int(r.n_chunks),
             "gen_ms": r.gen_ms, "exec_ms": r.exec_ms, "gzip_ms": r.gzip_ms,
             "first_and_last_file_equal_oracle_text": bool(un(got["first"]) == want_first and un(got["last"]) == want_last)}
+    # ---- and onto the file system: {tmpdir}/{proband}.fasta[.gz] through the native directory writer (rank 0 only)
+    nw = min(args.written_samples, ns)
+    if nw > 0 and int(os.environ.get("RANK", "0")) == 0:
+        import shutil
+        import tempfile
+
+        from vcf2prot_b200.pipeline import DirWriter
+
+        n_res_w = int((batch.ann_end - batch.ann_start)[batch.ann_hap < 2 * nw].sum())
+        names = ["S%06d" % i for i in range(nw)]
+        out["written"] = {"samples": nw, "residues": n_res_w, "writer_threads": 8,
+                          "what": "v2p_pipeline_run_lists -> v2p_dir_writer_sink: write(2) of the file images, one file per proband"}
+        for gz in (False, True):
+            tmpdir = tempfile.mkdtemp(prefix="v2p_written_")
+            try:
+                w = DirWriter(tmpdir, names, compressed=gz, threads=8)
+                _, r = pipe.run_lists(sb[: 2 * nw + 1], sites[: int(sb[2 * nw])], nw, args.pipeline_chunk, gz, sink=w)
+                one = open(os.path.join(tmpdir, names[0] + (".fasta.gz" if gz else ".fasta")), "rb").read()
+                ok = (zlib.decompress(one, wbits=31) if gz else one) == want_first and w.files_written == nw
+                out["written"]["fasta_gz" if gz else "fasta"] = {
+                    "residues_per_s": n_res_w / r.wall_s, "wall_s": r.wall_s, "bytes": w.bytes_written, "files": w.files_written,
+                    "file_gbs": w.bytes_written / r.wall_s / 1e9, "first_file_equals_oracle_text": bool(ok)}
+                w.close()
+            finally:
+                shutil.rmtree(tmpdir, ignore_errors=True)
     pipe.close()
     return out
 
@@ -479,6 +508,12 @@ def main():
     h_last = h_outs[(len(chunks) - 1) % depth]
     e2e_matches_device = bool(np.array_equal(h_last[:o1 - o0], d_out[o0:o1].cpu().numpy())) if args.e2e_steps > 0 else None
 
+    # ---- all of it behind one call: site lists -> .fasta / .fasta.gz images in pinned host memory (every rank its range)
+    pipeline_line = None
+    if (args.pipeline_samples != 0 and not args.no_registered_ref and not args.fasta_image and
+            batch.kept_hap is not None and not args.no_cpu_baseline):
+        pipeline_line = pipeline_measure(args, prot, cat, batch, eng, local_rank, barrier, shard, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -566,12 +601,6 @@ def main():
     gzip_line = None
     if world == 1 and args.gzip_samples > 0 and not args.no_registered_ref:
         gzip_line = gzip_measure(args, prot, cat, eng, dev, local_rank, torch)
-
-    # ---- all of it behind one call: site lists -> .fasta / .fasta.gz images in pinned host memory
-    pipeline_line = None
-    if (world == 1 and args.pipeline_samples != 0 and not args.no_registered_ref and not args.fasta_image and
-            batch.kept_hap is not None and not args.no_cpu_baseline):
-        pipeline_line = pipeline_measure(args, prot, cat, batch, eng, local_rank)
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):

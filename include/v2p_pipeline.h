@@ -74,6 +74,21 @@ int v2p_pipeline_run_masks(v2p_pipeline* p, uint64_t n_records, uint64_t n_sampl
                            uint64_t out_capacity, uint64_t* file_begin, v2p_file_sink sink, void* user,
                            v2p_pipeline_result* res);
 
+/* ---- a ready-made sink: the reference's writer ------------------------------------------------------------------
+ * parts/io.rs:35-57 + personalized_genome.rs:74-84: one file per proband, `{out_dir}/{proband}.fasta` or
+ * `{out_dir}/{proband}.fasta.gz`, created/truncated.  The bytes are the pipeline's file images, written as they are
+ * (plain write(2) from `threads` host threads per chunk; nothing is formatted or compressed on the host).
+ * Use:  v2p_pipeline_run_lists(..., out = NULL, ..., v2p_dir_writer_sink, writer, &res).                         */
+typedef struct v2p_dir_writer v2p_dir_writer;
+int v2p_dir_writer_create(const char* out_dir, const char* const* proband_names, uint64_t n_probands, int compressed,
+                          uint32_t threads, v2p_dir_writer** out);
+int v2p_dir_writer_sink(void* writer, uint64_t first_sample, uint64_t n_samples, const uint8_t* data,
+                        const uint64_t* file_begin); /* a v2p_file_sink */
+uint64_t v2p_dir_writer_bytes(v2p_dir_writer* w);  /* bytes written so far */
+uint64_t v2p_dir_writer_files(v2p_dir_writer* w);  /* files written so far */
+const char* v2p_dir_writer_last_error(v2p_dir_writer* w);
+void v2p_dir_writer_destroy(v2p_dir_writer* w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,3 +93,29 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert not pat.search(txt), "%s reaches into the oracle" % fn
+
+
+def test_dir_writer_sink_writes_one_file_per_proband(lib, tmp_path):
+    """The ready-made sink of include/v2p_pipeline.h is host code (parts/io.rs:35-57 naming): no GPU needed."""
+    import numpy as np
+
+    from vcf2prot_b200.pipeline import DirWriter
+
+    names = ["HG%05d" % i for i in range(7)]
+    w = DirWriter(str(tmp_path), names, compressed=False, threads=3)
+    data = np.frombuffer(b">T_1\nMEDL\n>T_2\nMEDK\n" + b"" + b">U_1\n\n", np.uint8).copy()
+    fb = np.array([0, 10, 20, 20, 26], np.uint64)  # third file is empty
+    rc = lib.v2p_dir_writer_sink(w._h, 2, 4, data.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert rc == 0 and w.files_written == 4 and w.bytes_written == 26
+    assert (tmp_path / "HG00002.fasta").read_bytes() == b">T_1\nMEDL\n"
+    assert (tmp_path / "HG00003.fasta").read_bytes() == b">T_2\nMEDK\n"
+    assert (tmp_path / "HG00004.fasta").read_bytes() == b""
+    assert (tmp_path / "HG00005.fasta").read_bytes() == b">U_1\n\n"
+    assert not (tmp_path / "HG00000.fasta").exists()
+    # a chunk beyond the proband list, and an unwritable directory, stop the run (non-zero)
+    assert lib.v2p_dir_writer_sink(w._h, 5, 4, data.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.POINTER(C.c_uint64))) != 0
+    w.close()
+    w2 = DirWriter(str(tmp_path / "missing_dir"), names, compressed=True)
+    assert lib.v2p_dir_writer_sink(w2._h, 0, 4, data.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.POINTER(C.c_uint64))) != 0
+    assert "missing_dir" in w2.last_error() and ".fasta.gz" in w2.last_error()
+    w2.close()

@@ -126,3 +126,27 @@ def test_pipeline_errors(world, gpu_engine):
     fb, _ = pipe.run_lists(sb, sites, 4, 2, False, out=np.zeros(1 << 22, np.uint8))
     assert fb[-1] > 0
     pipe.close()
+
+
+@pytest.mark.parametrize("gzip", [False, True])
+def test_files_on_disk_through_the_native_writer(world, gpu_engine, tmp_path, gzip):
+    """lists -> `{out_dir}/{proband}.fasta[.gz]` (parts/io.rs:35-57), no Python between the GPU and the file system."""
+    from vcf2prot_b200.pipeline import DirWriter
+
+    prot, cat = world
+    n_samples = 23
+    hap, site = cohort_sites(cat, n_samples, 11, drop=(6, 7))
+    want, _ = oracle_files(prot, cat, hap, site, n_samples)
+    gpu_engine.set_reference(prot.residues)
+    pipe = DevicePipeline(gpu_engine, prot, cat, lanes=2)
+    names = ["NA%05d" % (7 * i) for i in range(n_samples)]
+    w = DirWriter(str(tmp_path), names, compressed=gzip, threads=4)
+    sb, sites = csr_lists(hap, site, 2 * n_samples)
+    _, res = pipe.run_lists(sb, sites, n_samples, 5, gzip, sink=w)
+    assert w.files_written == n_samples and w.bytes_written == res.out_bytes
+    for s, name in enumerate(names):
+        raw = (tmp_path / (name + (".fasta.gz" if gzip else ".fasta"))).read_bytes()
+        assert (zlib.decompress(raw, wbits=31) if gzip else raw) == want[s], name
+    assert want[3] == b"" and (tmp_path / ("NA00021" + (".fasta.gz" if gzip else ".fasta"))).exists()
+    w.close()
+    pipe.close()

@@ -103,6 +103,12 @@ SYMBOLS = {
     "v2p_pipeline_last_error": (C.c_char_p, [_P]),
     "v2p_pipeline_run_lists": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint64, _P, FILE_SINK, _P,
                                          C.POINTER(PipelineResult)]),
+    "v2p_dir_writer_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_uint64, C.c_int, C.c_uint32, C.POINTER(_P)]),
+    "v2p_dir_writer_sink": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, C.POINTER(C.c_uint64)]),
+    "v2p_dir_writer_bytes": (C.c_uint64, [_P]),
+    "v2p_dir_writer_files": (C.c_uint64, [_P]),
+    "v2p_dir_writer_last_error": (C.c_char_p, [_P]),
+    "v2p_dir_writer_destroy": (None, [_P]),
     "v2p_pipeline_run_masks": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _P, C.c_uint64, _P, FILE_SINK, _P, C.POINTER(PipelineResult)]),
 }

@@ -6,8 +6,14 @@
 // where the reference loops over probands on rayon threads (parts/exec.rs:27-41) and writes one file per proband
 // (parts/io.rs:45-57, personalized_genome.rs:72-117).  No CPU fallback: any stage that fails fails the call.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <mutex>
+#include <thread>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -309,5 +315,79 @@ int v2p_pipeline_run_masks(v2p_pipeline* p, uint64_t n_records, uint64_t n_sampl
     if (res) *res = local;
     return rc;
 }
+
+// ---- directory writer (parts/io.rs:35-57, personalized_genome.rs:74-84) ----------------------------------------------
+struct v2p_dir_writer {
+    std::string dir, suffix, err;
+    std::vector<std::string> names;
+    unsigned threads = 4;
+    std::atomic<uint64_t> bytes{0}, files{0};
+    std::mutex mu;
+};
+
+int v2p_dir_writer_create(const char* out_dir, const char* const* proband_names, uint64_t n_probands, int compressed,
+                          uint32_t threads, v2p_dir_writer** out) {
+    if (!out) return V2P_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!out_dir || (n_probands && !proband_names)) return V2P_ERR_INVALID_ARG;
+    v2p_dir_writer* w = new (std::nothrow) v2p_dir_writer();
+    if (!w) return V2P_ERR_INVALID_ARG;
+    w->dir = out_dir;
+    w->suffix = compressed ? ".fasta.gz" : ".fasta";
+    w->threads = std::max<uint32_t>(1, std::min<uint32_t>(threads ? threads : 4, 64));
+    for (uint64_t i = 0; i < n_probands; ++i) {
+        if (!proband_names[i]) {
+            delete w;
+            return V2P_ERR_INVALID_ARG;
+        }
+        w->names.emplace_back(proband_names[i]);
+    }
+    *out = w;
+    return V2P_OK;
+}
+
+int v2p_dir_writer_sink(void* writer, uint64_t first_sample, uint64_t n_samples, const uint8_t* data, const uint64_t* file_begin) {
+    v2p_dir_writer* w = static_cast<v2p_dir_writer*>(writer);
+    if (!w || !file_begin || first_sample + n_samples > w->names.size()) {
+        if (w) w->err = "chunk beyond the proband list";
+        return 1;
+    }
+    std::atomic<int> failed{0};
+    auto work = [&](unsigned k, unsigned stride) {
+        for (uint64_t i = k; i < n_samples && !failed.load(std::memory_order_relaxed); i += stride) {
+            const std::string path = w->dir + "/" + w->names[first_sample + i] + w->suffix;
+            const int fd = ::open(path.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+            const uint8_t* ptr = data + file_begin[i];
+            uint64_t left = file_begin[i + 1] - file_begin[i];
+            bool ok = fd >= 0;
+            while (ok && left) {
+                const ssize_t n = ::write(fd, ptr, (size_t)std::min<uint64_t>(left, 1u << 30));
+                if (n < 0 && errno == EINTR) continue;
+                if (n <= 0) ok = false;
+                else ptr += n, left -= (uint64_t)n;
+            }
+            if (fd >= 0 && ::close(fd) != 0) ok = false;
+            if (!ok) {
+                std::lock_guard<std::mutex> g(w->mu);
+                w->err = "could not create/write " + path + ": " + std::strerror(errno);
+                failed.store(1);
+                return;
+            }
+            w->bytes += file_begin[i + 1] - file_begin[i];
+            w->files += 1;
+        }
+    };
+    const unsigned T = (unsigned)std::min<uint64_t>(w->threads, std::max<uint64_t>(n_samples, 1));
+    std::vector<std::thread> pool;
+    for (unsigned k = 1; k < T; ++k) pool.emplace_back(work, k, T);
+    work(0, T);
+    for (std::thread& t : pool) t.join();
+    return failed.load();
+}
+
+uint64_t v2p_dir_writer_bytes(v2p_dir_writer* w) { return w ? w->bytes.load() : 0; }
+uint64_t v2p_dir_writer_files(v2p_dir_writer* w) { return w ? w->files.load() : 0; }
+const char* v2p_dir_writer_last_error(v2p_dir_writer* w) { return w ? w->err.c_str() : "writer is NULL"; }
+void v2p_dir_writer_destroy(v2p_dir_writer* w) { delete w; }
 
 }  // extern "C"

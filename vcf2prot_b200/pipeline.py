@@ -13,6 +13,42 @@ from .engine import EngineError, GpuEngine
 from .taskgen import DeviceCatalogue
 
 
+class DirWriter:
+    """The reference's writer as a native sink (parts/io.rs:35-57): `{out_dir}/{proband}.fasta[.gz]`, one per sample."""
+
+    def __init__(self, out_dir: str, proband_names: List[str], compressed: bool, threads: int = 8):
+        self._lib = L.load()
+        arr = (C.c_char_p * len(proband_names))(*[n.encode() for n in proband_names])
+        h = C.c_void_p()
+        st = self._lib.v2p_dir_writer_create(out_dir.encode(), arr, len(proband_names), int(compressed), threads, C.byref(h))
+        if st:
+            raise EngineError(st, "v2p_dir_writer_create failed")
+        self._h = h
+        self.sink = L.FILE_SINK(C.cast(self._lib.v2p_dir_writer_sink, C.c_void_p).value)
+
+    @property
+    def bytes_written(self) -> int:
+        return int(self._lib.v2p_dir_writer_bytes(self._h))
+
+    @property
+    def files_written(self) -> int:
+        return int(self._lib.v2p_dir_writer_files(self._h))
+
+    def last_error(self) -> str:
+        return (self._lib.v2p_dir_writer_last_error(self._h) or b"").decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.v2p_dir_writer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DevicePipeline:
     """`eng` must have the proteome registered.  One DeviceCatalogue per lane (chunk in flight) is created here."""
 
@@ -49,9 +85,12 @@ class DevicePipeline:
         return (self._lib.v2p_pipeline_last_error(self._h) or b"").decode()
 
     @staticmethod
-    def _sink(fn: Optional[Callable]):
+    def _sink(fn):
+        """-> (function pointer, user pointer, object to keep alive)"""
         if fn is None:
-            return L.FILE_SINK(), None
+            return L.FILE_SINK(), None, None
+        if isinstance(fn, DirWriter):  # native sink, no Python in the loop
+            return fn.sink, fn._h, fn
 
         def cb(_user, first, n, data, fb):
             try:
@@ -64,7 +103,7 @@ class DevicePipeline:
                 traceback.print_exc()
                 return 1
 
-        return L.FILE_SINK(cb), cb
+        return L.FILE_SINK(cb), None, cb
 
     def _dest(self, out, n_samples):
         if out is None:
@@ -78,10 +117,10 @@ class DevicePipeline:
         file_begin offsets into it) or `sink(first_sample, n, data, file_begin)` called per chunk in sample order."""
         sb, st_ = np.ascontiguousarray(site_begin, np.uint64), np.ascontiguousarray(sites, np.uint32)
         op, cap, fbp, fb = self._dest(out, n_samples)
-        cb, keep = self._sink(sink)
+        cb, user, keep = self._sink(sink)
         res = L.PipelineResult()
         st = self._lib.v2p_pipeline_run_lists(self._h, n_samples, sb.ctypes.data_as(C.c_void_p), st_.ctypes.data_as(C.c_void_p),
-                                              chunk_samples, L.PIPE_GZIP if gzip else 0, op, cap, fbp, cb, None, C.byref(res))
+                                              chunk_samples, L.PIPE_GZIP if gzip else 0, op, cap, fbp, cb, user, C.byref(res))
         del keep
         if st:
             raise EngineError(st, self._err())
@@ -100,11 +139,11 @@ class DevicePipeline:
             mp, mflags = C.c_void_p(int(masks)), L.FLAG_DEVICE_PTRS
         cbeg, csite = np.ascontiguousarray(csq_begin, np.uint64), np.ascontiguousarray(csq_site, np.int32)
         op, cap, fbp, fb = self._dest(out, n_samp)
-        cb, keep = self._sink(sink)
+        cb, user, keep = self._sink(sink)
         res = L.PipelineResult()
         st = self._lib.v2p_pipeline_run_masks(self._h, n_rec, n_samp, w, mp, cbeg.ctypes.data_as(C.c_void_p),
                                               csite.ctypes.data_as(C.c_void_p), mflags, chunk_samples, L.PIPE_GZIP if gzip else 0,
-                                              op, cap, fbp, cb, None, C.byref(res))
+                                              op, cap, fbp, cb, user, C.byref(res))
         del keep
         if st:
             raise EngineError(st, self._err())
