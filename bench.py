@@ -435,8 +435,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    dkw = {"aligned_layout": args.layout == "aligned"}  # the producer's hint (V2P_FLAG_ALIGNED_LAYOUT)
     for _ in range(max(args.warmup, 3)):
-        eng.execute_batch_device(*dargs)
+        eng.execute_batch_device(*dargs, **dkw)
     barrier()
 
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
@@ -452,7 +453,7 @@ def main():
     with torch.cuda.stream(side):
         ev0.record()
         for _ in range(args.steps):
-            group_ms.append(eng.execute_batch_device(*dargs))
+            group_ms.append(eng.execute_batch_device(*dargs, **dkw))
             copy_ms.append(eng.last_copy_ms)
         ev1.record()
     barrier()
@@ -486,7 +487,7 @@ def main():
         pending = []
         for i, (a, b) in enumerate(chunks):
             ev = eng.execute_hap_range(a, b, h_task_begin, h_tasks, None if not args.no_registered_ref else h_ref, h_alt,
-                                       h_alt_base, h_out_base, h_outs[i % depth], wait=False)
+                                       h_alt_base, h_out_base, h_outs[i % depth], wait=False, **dkw)
             pending.append(ev)
             if len(pending) >= depth:
                 eng.wait_event(pending.pop(0))

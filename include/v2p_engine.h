@@ -56,6 +56,11 @@ int v2p_engine_from_str(const char* s, int* engine_kind);
 #define V2P_FLAG_VALIDATE 0x2u    /* run the gir.rs:203-229 contiguity check; report first bad index, copy nothing */
 #define V2P_FLAG_DEVICE_PTRS 0x4u /* batch call: every data pointer is device memory on the engine's GPU  */
 #define V2P_FLAG_ASYNC 0x8u       /* batch call: enqueue and return; completion + status via v2p_event_wait */
+#define V2P_FLAG_ALIGNED_LAYOUT 0x10u /* batch call, performance hint only (results never depend on it): the producer
+                                     placed every transcript's result in phase (mod 16) with its source in the
+                                     reference tape (v2p::HaplotypeBatch aligned layout, V2P_GEN_ALIGNED), so tiles
+                                     are processed in tape order instead of the haplotype-interleaved order that keeps
+                                     the replicas of the reference resident in L2 for the reference's own layout */
 
 /* ---- lifecycle --------------------------------------------------------------------------------- */
 typedef struct v2p_engine v2p_engine;

@@ -117,6 +117,53 @@ def test_random_batches_bit_exact(gpu_engine, variant, seed, n_hap, mean_res):
         gpu_engine.set_tuning(-1, 0)
 
 
+@pytest.mark.parametrize("variant", [0, 8])
+@pytest.mark.parametrize("seed,n_hap,mean_res", [(61, 2, 50_000), (62, 97, 40_000), (63, 500, 9_000), (64, 33, 400_000)])
+def test_tile_order_never_changes_results(gpu_engine, variant, seed, n_hap, mean_res):
+    """The haplotype-interleaved tile order (default) and tape order (V2P_FLAG_ALIGNED_LAYOUT hint) are schedules of
+    the same tiles: both give the oracle's bytes, with ragged haplotypes (exponential lengths leave most slots of the
+    order table empty) and empty ones."""
+    gpu_engine.set_tuning(variant, 0)
+    try:
+        b = random_batch(seed, n_hap, mean_res, n_ref=150_001, empty_hap_prob=0.15)
+        st, _, _, want = oracle_batch(b)
+        assert st == 0
+        gpu_engine.set_reference(b["ref"], "replicas")
+        for hint in (False, True):
+            out, _ = gpu_engine.execute_batch(b["task_begin"], b["tasks"], None, b["alt"], b["alt_base"], b["out_base"],
+                                              aligned_layout=hint)
+            assert np.array_equal(out, want), hint
+            out, _ = gpu_engine.execute_batch(b["task_begin"], b["tasks"], b["ref"], b["alt"], b["alt_base"], b["out_base"],
+                                              aligned_layout=hint)
+            assert np.array_equal(out, want), hint
+    finally:
+        gpu_engine.set_tuning(-1, 0)
+
+
+def test_tile_order_falls_back_when_haplotypes_are_wildly_uneven(gpu_engine):
+    """One 6 MB haplotype among 400 of a few bytes: the order table (max tiles per haplotype x haplotypes) would be
+    ~100x the tile count, so the plan keeps tape order -- same bytes."""
+    rng = np.random.default_rng(7)
+    ref = rng.integers(65, 91, size=70_000, dtype=np.uint8)
+    n_hap, big = 401, 200
+    rows, tb, ob = [], [0], [0]
+    for h in range(n_hap):
+        n = 6_000_000 if h == big else int(rng.integers(0, 40))
+        pos = 0
+        while pos < n:
+            ln = min(int(rng.integers(1, 60_000)), n - pos)
+            rows.append((int(rng.integers(0, len(ref) - ln + 1)), ln, pos, 0))
+            pos += ln
+        tb.append(len(rows))
+        ob.append(ob[-1] + n)
+    u = lambda x: np.asarray(x, dtype=np.uint64)
+    b = dict(task_begin=u(tb), tasks=np.asarray(rows, np.uint32).reshape(-1, 4), ref=ref, alt=np.zeros(0, np.uint8),
+             alt_base=u([0] * (n_hap + 1)), out_base=u(ob), ref_base=None)
+    out, _ = gpu_batch(gpu_engine, b)
+    st, _, _, want = oracle_batch(b)
+    assert st == 0 and np.array_equal(out, want)
+
+
 @pytest.mark.parametrize("mode", ["replicas", "plain"])
 @pytest.mark.parametrize("variant", [0, 2, 4, 5, 7, 8])
 @pytest.mark.parametrize("seed,n_hap,mean_res", [(51, 5, 400), (52, 30, 30000), (53, 4, 2_000_000)])

@@ -12,7 +12,7 @@ V2P_OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_BAD_ENGINE, ERR_BAD_STREAM, ERR_RES_OOB, ERR_SRC_OOB = 1, 2, 3, 4, 5, 6
 ERR_NOT_CONTIGUOUS, ERR_NOT_GPU_ENGINE = 7, 9
 ENGINE_ST, ENGINE_MT, ENGINE_GPU = 0, 1, 2
-FLAG_FILL_DOT, FLAG_VALIDATE, FLAG_DEVICE_PTRS, FLAG_ASYNC = 1, 2, 4, 8
+FLAG_FILL_DOT, FLAG_VALIDATE, FLAG_DEVICE_PTRS, FLAG_ASYNC, FLAG_ALIGNED_LAYOUT = 1, 2, 4, 8, 16
 REF_NO_TMA = 0x200
 GEN_ALIGNED, GEN_FASTA = 1, 2
 

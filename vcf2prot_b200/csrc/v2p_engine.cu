@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -33,7 +34,7 @@ struct DevBuf {
 };
 
 struct Scratch {  // per-stream planning scratch
-    DevBuf lb, tile_hap, chunk_hap, status;
+    DevBuf lb, tile_hap, chunk_hap, order, status;
 };
 
 constexpr int kSlots = 3;
@@ -80,6 +81,9 @@ struct v2p_engine {
     uint64_t rep_stride = 0, reg_n_ref = 0;
     bool has_ref = false;
     int ref_tma_mode = 0;  // 1: 16 replicas + TMA bulk copies (default), 0: register path only
+    int order_gshift = 2;  // interleave groups of 2^2 consecutive tiles (measured best: profiles/r1);
+                           // env V2P_TILE_ORDER=tape: tiles in tape order; =gN: groups of 2^N tiles (A/B knobs)
+    bool tape_order = false;
 };
 
 namespace {
@@ -124,26 +128,28 @@ void release(DevBuf& b) {
 struct CopyVariant {
     int tile;
     int ctas_per_sm;
-    void (*fn)(const KParams);
+    void (*fn)(const KParams);     // tiles in tape order
+    void (*fn_il)(const KParams);  // haplotype-interleaved tile order (FLAGS | 2)
 };
+#define V2P_VARIANT(T, G, M, F) k_copy_tiles<T, G, M, F>, k_copy_tiles<T, G, M, (F) | 2>
 const CopyVariant kVariants[] = {
-    {4096, 4, k_copy_tiles<4096, 2, 4, 1>},  // 0: 4 KiB tiles, 4 CTAs/SM (64 regs), L2 hints  [default]
-    {4096, 4, k_copy_tiles<4096, 2, 4, 0>},  // 1: no L2 hints
-    {4096, 4, k_copy_tiles<4096, 1, 4, 1>},  // 2: one vector in flight per lane
-    {4096, 5, k_copy_tiles<4096, 2, 5, 1>},  // 3: 5 CTAs/SM (48 regs)
-    {4096, 6, k_copy_tiles<4096, 1, 6, 1>},  // 4: 6 CTAs/SM (40 regs)
-    {4096, 3, k_copy_tiles<4096, 4, 3, 1>},  // 5: 3 CTAs/SM (80 regs), 4 vectors in flight
-    {2048, 6, k_copy_tiles<2048, 2, 6, 1>},  // 6: 2 KiB tiles, 6 CTAs/SM
-    {2048, 8, k_copy_tiles<2048, 1, 8, 1>},  // 7: 2 KiB tiles, 8 CTAs/SM (32 regs)
-    {8192, 3, k_copy_tiles<8192, 2, 3, 1>},  // 8: 8 KiB tiles, 3 CTAs/SM (80 regs)
-    {8192, 2, k_copy_tiles<8192, 4, 2, 1>},  // 9: 8 KiB tiles, 2 CTAs/SM
+    {4096, 4, V2P_VARIANT(4096, 2, 4, 1)},  // 0: 4 KiB tiles, 4 CTAs/SM (64 regs), L2 hints  [default without replicas]
+    {4096, 4, V2P_VARIANT(4096, 2, 4, 0)},  // 1: no L2 hints
+    {4096, 4, V2P_VARIANT(4096, 1, 4, 1)},  // 2: one vector in flight per lane
+    {4096, 5, V2P_VARIANT(4096, 2, 5, 1)},  // 3: 5 CTAs/SM (48 regs)
+    {4096, 6, V2P_VARIANT(4096, 1, 6, 1)},  // 4: 6 CTAs/SM (40 regs)
+    {4096, 3, V2P_VARIANT(4096, 4, 3, 1)},  // 5: 3 CTAs/SM (80 regs), 4 vectors in flight
+    {2048, 6, V2P_VARIANT(2048, 2, 6, 1)},  // 6: 2 KiB tiles, 6 CTAs/SM
+    {2048, 8, V2P_VARIANT(2048, 1, 8, 1)},  // 7: 2 KiB tiles, 8 CTAs/SM (32 regs)
+    {8192, 3, V2P_VARIANT(8192, 2, 3, 1)},  // 8: 8 KiB tiles, 3 CTAs/SM (80 regs)  [default with replicas]
+    {8192, 2, V2P_VARIANT(8192, 4, 2, 1)},  // 9: 8 KiB tiles, 2 CTAs/SM
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 constexpr int kAutoTma = 8, kAutoPlain = 0;  // measured best per path (profiles/r1)
 
 // plan + copy on stream s.  kp.{lb,tile_hap,status,n_tiles,tile_bytes} are filled here.
 int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEvent_t ev_start, cudaEvent_t ev_stop,
-                 DevStatus* h_status, bool init_status, cudaEvent_t ev_copy) {
+                 DevStatus* h_status, bool init_status, cudaEvent_t ev_copy, bool aligned_layout) {
     const CopyVariant& cv = kVariants[e->variant >= 0 ? e->variant : (kp.tma_mode ? kAutoTma : kAutoPlain)];
     const int T = cv.tile;
     kp.tile_bytes = (uint32_t)T;
@@ -157,11 +163,26 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     const uint64_t n_chunks = (kp.n_tasks + kPlanWarpTasks - 1) / kPlanWarpTasks;
     if ((rc = reserve(e, sc.chunk_hap, std::max<uint64_t>(n_chunks, 1) * sizeof(uint32_t)))) return rc;
     kp.chunk_hap = (uint32_t*)sc.chunk_hap.p;
+    // tile order: 16-byte header (s_max) + one slot per (tile rank within its haplotype, haplotype)
+    if (kp.n_tiles >= 0xFFF00000ull) return fail(e, V2P_ERR_INVALID_ARG, "more than 2^32 tiles in one launch");
+    // tape order = identity over n_tiles (n_hap "1"): the cap then only has to hold the identity
+    // Tile order: haplotype-interleaved unless the caller says the layout is phase-aligned
+    // (V2P_FLAG_ALIGNED_LAYOUT: every run then comes from the one plain tape and tape order is ~3 % faster).
+    const bool interleave = !aligned_layout && !e->tape_order && kp.n_hap > 1;
+    kp.order_gshift = (uint32_t)e->order_gshift;
+    const uint64_t order_cap =
+        interleave ? std::min<uint64_t>(2 * kp.n_tiles + ((kp.n_hap + 64) << kp.order_gshift), 0xFFF00000ull) : 0;
+    if ((rc = reserve(e, sc.order, 16 + order_cap * sizeof(uint32_t)))) return rc;
+    kp.order_hdr = (uint32_t*)sc.order.p;
+    kp.order = kp.order_hdr + 4;
+    kp.order_cap = order_cap;
     kp.lb = (uint32_t*)sc.lb.p;
     kp.tile_hap = (uint32_t*)sc.tile_hap.p;
     kp.status = (DevStatus*)sc.status.p;
     if (ev_start) CUDA_TRY(e, cudaEventRecord(ev_start, s));
     CUDA_TRY(e, cudaMemsetAsync(kp.lb, 0xFF, (kp.n_tiles + 1) * sizeof(uint32_t), s));
+    CUDA_TRY(e, cudaMemsetAsync(kp.order_hdr, 0, 16, s));
+    if (order_cap) CUDA_TRY(e, cudaMemsetAsync(kp.order, 0xFF, order_cap * sizeof(uint32_t), s));
     if (init_status) {
         k_init_status<<<1, 1, 0, s>>>(kp.status);
         e->launches++;
@@ -184,9 +205,9 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
         size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + 16 + 576) + 17 * 16;
-        if (smem > 48 * 1024)
-            CUDA_TRY(e, cudaFuncSetAttribute(cv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cv.fn<<<grid, kThreads, smem, s>>>(kp);
+        void (*fn)(const KParams) = interleave ? cv.fn_il : cv.fn;
+        if (smem > 48 * 1024) CUDA_TRY(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<grid, kThreads, smem, s>>>(kp);
         e->launches++;
     }
     if (ev_stop) CUDA_TRY(e, cudaEventRecord(ev_stop, s));
@@ -362,6 +383,9 @@ int v2p_engine_create(int cuda_device, v2p_engine** out) {
         return V2P_ERR_CUDA;
     }
     e->sm_count = prop.multiProcessorCount;
+    const char* ord = getenv("V2P_TILE_ORDER");
+    e->tape_order = ord && !strcmp(ord, "tape");
+    if (ord && ord[0] == 'g' && ord[1] >= '0' && ord[1] <= '6') e->order_gshift = ord[1] - '0';
     *out = e;
     return V2P_OK;
 }
@@ -370,11 +394,11 @@ void v2p_engine_destroy(v2p_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&e->sc.chunk_hap, &e->sc.lb,     &e->sc.tile_hap, &e->sc.status, &e->d_soa[0], &e->d_soa[1],  &e->d_soa[2], &e->d_soa[3],
+    DevBuf* bufs[] = {&e->sc.order, &e->sc.chunk_hap, &e->sc.lb,     &e->sc.tile_hap, &e->sc.status, &e->d_soa[0], &e->d_soa[1],  &e->d_soa[2], &e->d_soa[3],
                       &e->soa_tasks, &e->soa_ref,     &e->soa_alt,   &e->soa_out,  &e->soa_bases, &e->ref_rep};
     for (DevBuf* b : bufs) release(*b);
     for (Slot& sl : e->slots) {
-        DevBuf* sb[] = {&sl.sc.chunk_hap, &sl.sc.lb,      &sl.sc.tile_hap, &sl.sc.status,  &sl.d_tasks, &sl.d_task_begin, &sl.d_ref,
+        DevBuf* sb[] = {&sl.sc.order, &sl.sc.chunk_hap, &sl.sc.lb,      &sl.sc.tile_hap, &sl.sc.status,  &sl.d_tasks, &sl.d_task_begin, &sl.d_ref,
                         &sl.d_ref_base, &sl.d_alt,       &sl.d_alt_base, &sl.d_out,   &sl.d_out_base};
         for (DevBuf* b : sb) release(*b);
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -564,7 +588,8 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
         kp.tma_mode = e->ref_tma_mode;
     }
     ev->stream = s;
-    rc = launch_group(e, s, *sc, kp, ev->ev_start, ev->ev_stop, ev->h_status, true, ev->ev_copy);
+    rc = launch_group(e, s, *sc, kp, ev->ev_start, ev->ev_stop, ev->h_status, true, ev->ev_copy,
+                      (flags & V2P_FLAG_ALIGNED_LAYOUT) != 0);
     if (rc) return bail(rc);
     // host mode: the copy-back is enqueued right away (a batch that needs the serial-order kernel repeats it later)
     if (ev->slot && ev->out_bytes &&
@@ -653,7 +678,7 @@ int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, co
             (const uint64_t*)e->d_soa[3].p, n_ref, n_alt, n_res, 4u, kp.validate, (v2p_task16*)e->soa_tasks.p, kp.status);
         e->launches++;
     }
-    rc = launch_group(e, s, e->sc, kp, nullptr, nullptr, e->h_status, /*init_status=*/false, nullptr);
+    rc = launch_group(e, s, e->sc, kp, nullptr, nullptr, e->h_status, /*init_status=*/false, nullptr, false);
     if (rc) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(s));
     if (needs_serial(*e->h_status)) {

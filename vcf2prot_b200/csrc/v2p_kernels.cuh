@@ -53,6 +53,13 @@ struct KParams {
     uint32_t* lb;        // n_tiles+1
     uint32_t* tile_hap;  // n_tiles
     uint32_t* chunk_hap;  // haplotype of the first task of every k_plan_tasks warp (kPlanWarpTasks tasks each)
+    // Tile processing order (see k_copy_tiles): order_hdr[0] = s_max = most tile GROUPS (2^order_gshift consecutive
+    // tiles) any haplotype owns (k_plan_haps); order[((g * n_hap + h) << gshift) + i] = tile i of group g of haplotype h,
+    // or ~0 (k_plan_tiles).  When that does not fit order_cap (wildly uneven haplotypes) order[] is the identity.
+    uint32_t* order_hdr;
+    uint32_t* order;
+    uint64_t order_cap;
+    uint32_t order_gshift;
     uint64_t n_tiles;
     uint32_t tile_bytes;
     uint32_t tile_shift;  // log2(tile_bytes)
@@ -107,6 +114,18 @@ __global__ void k_plan_haps(KParams p) {
         if (p.ref_base) bad |= p.ref_base[h + 1] - p.ref_origin != p.n_ref;
     }
     if (bad) atomicExch(&p.status->bad_args, 1u);
+    // tiles whose first byte lies in this haplotype's tape: ceil(o1/T) - ceil(o0/T), in groups; the maximum sizes the order
+    const uint64_t T1 = (uint64_t)p.tile_bytes - 1;
+    const uint64_t nt = bad ? 0 : ((o1 - p.out_origin + T1) >> p.tile_shift) - ((o0 - p.out_origin + T1) >> p.tile_shift);
+    uint32_t s = (uint32_t)((nt + (1u << p.order_gshift) - 1) >> p.order_gshift);
+    s = __reduce_max_sync(__activemask(), s);
+    if ((threadIdx.x & 31) == 0 && s) atomicMax(p.order_hdr, s);
+}
+
+// slots of the haplotype-interleaved tile order, or 0 when it does not fit (then order[] is the identity over n_tiles)
+__device__ __forceinline__ uint64_t tile_order_slots(const KParams& p, uint32_t s_max) {
+    const uint64_t n = ((uint64_t)s_max * p.n_hap) << p.order_gshift;
+    return (p.n_hap > 1 && n <= p.order_cap) ? n : 0;
 }
 
 // One lane per task; every warp owns kPlanWarpTasks CONSECUTIVE tasks: everything the reference would panic on, plus
@@ -152,6 +171,14 @@ __global__ void k_plan_tiles(KParams p) {
         h = h ? h - 1 : 0;
         if (h >= p.n_hap) h = p.n_hap - 1;
         p.tile_hap[k] = (uint32_t)h;
+        if (tile_order_slots(p, p.order_hdr[0])) {  // slot of this tile in the haplotype-interleaved order
+            const uint64_t first = (__ldg(p.out_base + h) - p.out_origin + p.tile_bytes - 1) >> p.tile_shift;
+            const uint64_t c = k - first, gm = (1u << p.order_gshift) - 1;
+            const uint64_t idx = (((c >> p.order_gshift) * p.n_hap + h) << p.order_gshift) + (c & gm);
+            if (idx < p.order_cap) p.order[idx] = (uint32_t)k;  // (always, unless the base arrays are inconsistent)
+        } else if (k < p.order_cap) {
+            p.order[k] = (uint32_t)k;
+        }
     }
     const uint64_t t = k * kPlanWarpTasks;
     if (t < p.n_tasks) {
@@ -397,10 +424,11 @@ __device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const ui
 
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
 // parallelism); MINB: CTAs per SM the register allocation is held to.
-// FLAGS: 1 = L2 cache-policy hints.
+// FLAGS: 1 = L2 cache-policy hints; 2 = haplotype-interleaved tile order (see below).
 template <int TILE, int G, int MINB, int FLAGS>
 __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) {
     constexpr bool kHints = (FLAGS & 1) != 0;
+    constexpr bool kOrder = (FLAGS & 2) != 0;
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
     constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4, 8 or 16)
     constexpr int LWW = LW / 4;     // ... as 32-bit words
@@ -429,16 +457,31 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     const uint4 fillv = make_uint4(p.fill_word, p.fill_word, p.fill_word, p.fill_word);
 
-    // Software pipeline over this warp's tiles: metadata (lb[k], lb[k+1], tile_hap[k]) is fetched two tiles ahead,
-    // the first batch of tasks and the owning haplotype's bases one tile ahead, so that a tile starts with its
+    // Processing order (FLAGS & 2).  A warp's successive tiles are NOT neighbours on the tape: slot
+    // ((g * n_hap + h) << gshift) + i is tile i of group g of haplotype h, so the ~3.5k warps in flight sit at the same
+    // relative position of ~3.5k different haplotypes.  Every haplotype's tape follows the proteome's transcript order,
+    // so at any moment the whole GPU reads one narrow band of the proteome (times 16 replicas) -- it stays in L2 however
+    // large the replica set is -- instead of sweeping all 171 MB of it once per ~9 haplotypes.  Slots without a tile
+    // (shorter haplotypes) hold ~0.  Without the flag, slots are tiles in tape order (phase-aligned layouts, whose
+    // runs come from the one plain tape, gain nothing from the interleave).
+    uint64_t n_slots = p.n_tiles;
+    if constexpr (kOrder) {
+        const uint64_t ns = tile_order_slots(p, __ldg(p.order_hdr));
+        if (ns) n_slots = ns;  // else order[] is the identity over n_tiles
+    }
+    // Software pipeline over this warp's slots: metadata (tile, lb[k], lb[k+1], tile_hap[k]) is fetched two slots ahead,
+    // the first batch of tasks and the owning haplotype's bases one ahead, so that a tile starts with its
     // dependent loads already landed.
-    auto load_meta = [&](uint64_t kk, uint32_t& lo, uint32_t& hi, uint32_t& hp) {
+    auto load_meta = [&](uint64_t kk, uint32_t& lo, uint32_t& hi, uint32_t& hp) {  // kk: tile (~0 / past the end: none)
         lo = hi = hp = 0;
         if (kk < p.n_tiles) {
             lo = __ldg(p.lb + kk);
             hi = __ldg(p.lb + kk + 1);
             hp = __ldg(p.tile_hap + kk);
         }
+    };
+    auto tile_of_slot = [&](uint64_t slot) -> uint32_t {  // interleaved order only; ~0 = no tile
+        return slot < n_slots ? __ldg(p.order + slot) : 0xFFFFFFFFu;
     };
     const uint32_t n_tasks32 = (uint32_t)p.n_tasks;  // < 2^32 - 1 (checked by the host)
     auto first_task = [&](uint32_t lo) -> uint32_t {
@@ -456,13 +499,24 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         if (base_on) cp_async8(st_bases + lane, base_arr + hp + base_add);
         cp_async_commit();
     };
+    // k: this warp's tile (tape order) or slot (interleaved order; then t0/t1/t2 are the tiles of slots k, k + n_warps,
+    // k + 2 n_warps -- the slot -> tile entry is fetched three ahead, its metadata two ahead, its tasks one ahead)
     uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
     uint32_t c_lo, c_hi, c_hap, n_lo, n_hi, n_hap;
-    load_meta(k, c_lo, c_hi, c_hap);
-    load_meta(k + n_warps, n_lo, n_hi, n_hap);
-    if (k < p.n_tiles) stage(c_lo, c_hi, c_hap);
-    for (; k < p.n_tiles; k += n_warps) {
-        const uint64_t tile_start = k * (uint64_t)TILE;
+    uint32_t t0 = 0xFFFFFFFFu, t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu;
+    if constexpr (kOrder) {
+        t0 = tile_of_slot(k), t1 = tile_of_slot(k + n_warps), t2 = tile_of_slot(k + 2 * n_warps);
+        load_meta(t0, c_lo, c_hi, c_hap);
+        load_meta(t1, n_lo, n_hi, n_hap);
+        if (t0 != 0xFFFFFFFFu) stage(c_lo, c_hi, c_hap);
+    } else {
+        load_meta(k, c_lo, c_hi, c_hap);
+        load_meta(k + n_warps, n_lo, n_hi, n_hap);
+        if (k < p.n_tiles) stage(c_lo, c_hi, c_hap);
+    }
+    for (; k < n_slots; k += n_warps) {
+        const uint32_t tile_no = t0;  // interleaved order: ~0 = an empty slot
+        const uint64_t tile_start = (kOrder ? (uint64_t)(tile_no == 0xFFFFFFFFu ? 0u : tile_no) : k) * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
         const uint32_t t_lo = first_task(c_lo);
@@ -475,10 +529,19 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         const uint64_t hb_t0 = st_bases[0], hb_t1 = st_bases[1], hb_out = st_bases[2], hb_alt = st_bases[3];
         const uint64_t hb_ref = p.ref_base ? st_bases[4] : p.ref_origin;
         __syncwarp();
-        // advance the pipeline: stage the next tile (its metadata was fetched one tile ago), fetch metadata two ahead
+        // advance the pipeline: stage the next tile (its metadata was fetched one slot ago), fetch metadata two ahead
         c_lo = n_lo, c_hi = n_hi, c_hap = n_hap;
-        if (k + n_warps < p.n_tiles) stage(c_lo, c_hi, c_hap);
-        load_meta(k + 2 * n_warps, n_lo, n_hi, n_hap);
+        if constexpr (kOrder) {
+            t0 = t1;
+            if (t0 != 0xFFFFFFFFu) stage(c_lo, c_hi, c_hap);
+            t1 = t2;
+            load_meta(t1, n_lo, n_hi, n_hap);
+            t2 = tile_of_slot(k + 3 * n_warps);
+            if (tile_no == 0xFFFFFFFFu) continue;  // an empty slot
+        } else {
+            if (k + n_warps < p.n_tiles) stage(c_lo, c_hi, c_hap);
+            load_meta(k + 2 * n_warps, n_lo, n_hi, n_hap);
+        }
 
         // the previous tile's bulk store must have finished READING shared memory before we overwrite it
         if (lane == 0) bulk_wait_read0();

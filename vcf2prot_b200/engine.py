@@ -165,8 +165,10 @@ class GpuEngine:
     # ------------------------------------------------------------------ (ii) batched native call
     def execute_batch(self, task_begin: np.ndarray, tasks: np.ndarray, ref: np.ndarray, alt: np.ndarray,
                       alt_base: np.ndarray, out_base: np.ndarray, ref_base: Optional[np.ndarray] = None,
-                      validate: bool = False, out: Optional[np.ndarray] = None) -> Tuple[np.ndarray, float]:
-        """Host (numpy) buffers in, host result tape out.  Returns (out u8[out_base[-1]-out_base[0]...], kernel_ms)."""
+                      validate: bool = False, out: Optional[np.ndarray] = None,
+                      aligned_layout: bool = False) -> Tuple[np.ndarray, float]:
+        """Host (numpy) buffers in, host result tape out.  Returns (out u8[out_base[-1]-out_base[0]...], kernel_ms).
+        aligned_layout: V2P_FLAG_ALIGNED_LAYOUT, a performance hint for phase-aligned producers (never changes results)."""
         task_begin = np.ascontiguousarray(task_begin, dtype=np.uint64)
         tasks = np.ascontiguousarray(tasks, dtype=np.uint32)
         ref = None if ref is None else np.ascontiguousarray(ref, dtype=np.uint8)
@@ -186,7 +188,8 @@ class GpuEngine:
         b.alt, b.alt_base, b.out, b.out_base = p(alt), p(alt_base), p(out), p(out_base)
         b.n_hap = max(n_hap, 0)
         res = L.Result()
-        st = self._lib.v2p_execute_batch(self._h, C.byref(b), L.FLAG_VALIDATE if validate else 0, C.byref(res), None)
+        flags = (L.FLAG_VALIDATE if validate else 0) | (L.FLAG_ALIGNED_LAYOUT if aligned_layout else 0)
+        st = self._lib.v2p_execute_batch(self._h, C.byref(b), flags, C.byref(res), None)
         if st != L.V2P_OK:
             raise EngineError(st, self.last_error(), res.bad_hap, res.bad_task)
         self.last_copy_ms = float(res.copy_ms)
@@ -194,7 +197,7 @@ class GpuEngine:
 
     def execute_hap_range(self, h0: int, h1: int, task_begin: np.ndarray, tasks: np.ndarray, ref: np.ndarray,
                           alt: np.ndarray, alt_base: np.ndarray, out_base: np.ndarray, out_chunk: np.ndarray,
-                          validate: bool = False, wait: bool = True):
+                          validate: bool = False, wait: bool = True, aligned_layout: bool = False):
         """Host-pointer call on haplotypes [h0,h1) of a larger host-resident cohort (the streaming shape: the
         caller's pinned staging buffer `out_chunk` receives just this range's result tapes).  The base arrays keep
         their cohort-absolute values; the library rebases on entry [0] of each slice."""
@@ -211,7 +214,7 @@ class GpuEngine:
         b.out = addr(out_chunk) - o0  # virtual base: out[o0] is out_chunk[0]
         b.n_hap = h1 - h0
         res = L.Result()
-        flags = L.FLAG_VALIDATE if validate else 0
+        flags = (L.FLAG_VALIDATE if validate else 0) | (L.FLAG_ALIGNED_LAYOUT if aligned_layout else 0)
         if not wait:  # returns an event; up to 3 host-pointer batches may be in flight (copy-back overlaps upload)
             ev = C.c_void_p()
             st = self._lib.v2p_execute_batch(self._h, C.byref(b), flags | L.FLAG_ASYNC, None, C.byref(ev))
@@ -225,7 +228,8 @@ class GpuEngine:
         return float(res.kernel_ms)
 
     def execute_batch_device(self, n_hap: int, task_begin, tasks, ref, alt, alt_base, out, out_base, n_tasks: int,
-                             n_alt: int, n_out: int, ref_base=None, validate: bool = False, wait: bool = True):
+                             n_alt: int, n_out: int, ref_base=None, validate: bool = False, wait: bool = True,
+                             aligned_layout: bool = False):
         """Device-resident buffers (torch CUDA tensors or raw device pointers).  Returns kernel_ms (wait=True)
         or an opaque event handle to pass to wait_event()."""
         ptr = lambda x: None if x is None else (x if isinstance(x, int) else x.data_ptr())
@@ -234,7 +238,7 @@ class GpuEngine:
         b.n_ref = int(ref.numel()) if hasattr(ref, "numel") else 0  # ref=None -> the registered reference
         b.alt, b.alt_base, b.out, b.out_base = ptr(alt), ptr(alt_base), ptr(out), ptr(out_base)
         b.n_hap, b.n_tasks, b.n_alt, b.n_out = n_hap, n_tasks, n_alt, n_out
-        flags = L.FLAG_DEVICE_PTRS | (L.FLAG_VALIDATE if validate else 0)
+        flags = L.FLAG_DEVICE_PTRS | (L.FLAG_VALIDATE if validate else 0) | (L.FLAG_ALIGNED_LAYOUT if aligned_layout else 0)
         res = L.Result()
         if wait:
             st = self._lib.v2p_execute_batch(self._h, C.byref(b), flags, C.byref(res), None)

@@ -100,11 +100,12 @@ class DeviceCatalogue:
         return out
 
 
-def execute_generated(eng: GpuEngine, g: L.Generated, validate: bool = False) -> Tuple[float, float]:
-    """Run a generated (device-resident) batch; the result tape stays in g.batch.out.  -> (group_ms, copy_ms)"""
+def execute_generated(eng: GpuEngine, g: L.Generated, validate: bool = False, aligned_layout: bool = False) -> Tuple[float, float]:
+    """Run a generated (device-resident) batch; the result tape stays in g.batch.out.  -> (group_ms, copy_ms)
+    aligned_layout: the batch was generated with aligned=True (V2P_FLAG_ALIGNED_LAYOUT hint)."""
     res = L.Result()
-    st = eng._lib.v2p_execute_batch(eng._h, C.byref(g.batch), L.FLAG_DEVICE_PTRS | (L.FLAG_VALIDATE if validate else 0),
-                                    C.byref(res), None)
+    flags = L.FLAG_DEVICE_PTRS | (L.FLAG_VALIDATE if validate else 0) | (L.FLAG_ALIGNED_LAYOUT if aligned_layout else 0)
+    st = eng._lib.v2p_execute_batch(eng._h, C.byref(g.batch), flags, C.byref(res), None)
     if st:
         raise EngineError(st, eng.last_error(), res.bad_hap, res.bad_task)
     return float(res.kernel_ms), float(res.copy_ms)
