@@ -55,9 +55,10 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=-1, help="copy-kernel variant (-1: engine's automatic choice)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--ref-mode", default="replicas", choices=["replicas", "plain"])
-    ap.add_argument("--layout", default="aligned", choices=["packed", "aligned"],
-                    help="result-tape layout: packed = the reference's (res_counter); aligned = transcripts in phase "
-                         "with the proteome tape (<=30 '.' pad bytes per transcript, never seen by the consumer)")
+    ap.add_argument("--layout", default="packed", choices=["packed", "aligned"],
+                    help="result-tape layout: packed = the reference's own (res_counter, haplotype_instruction.rs:132), "
+                         "what a drop-in caller hands over; aligned = transcripts in phase with the proteome tape (<=30 "
+                         "'.' pad bytes per transcript, never seen by the consumer) -- measured beside it (other_layout)")
     ap.add_argument("--no-registered-ref", action="store_true",
                     help="pass the proteome with every call (generic register path) instead of registering it once")
     ap.add_argument("--fasta-image", action="store_true",
@@ -548,6 +549,7 @@ def main():
 
     # ---- the same cohort's Task arrays generated ON the device from the per-haplotype site lists
     taskgen = None
+    other_line = None
     if world == 1 and not args.no_taskgen and not args.fasta_image and batch.kept_hap is not None:
         from vcf2prot_b200 import cohort as C
         from vcf2prot_b200.taskgen import DeviceCatalogue
@@ -567,6 +569,32 @@ def main():
                    "h2d_bytes": 4 * n_sites + 8 * (n_hap + 1), "h2d_bytes_if_tasks_were_uploaded": 16 * n_tasks + len(batch.alt),
                    "equals_host_producer": same, "host_producer_seconds": round(t_gen, 1),
                    "what": "v2p_generate_tasks: per-haplotype site lists -> packed Task batch on the GPU (incl. the H2D of the lists)"}
+        # ---- the same cohort in the OTHER result-tape layout, generated on the device and executed from there
+        other = "aligned" if args.layout == "packed" else "packed"
+        from vcf2prot_b200.taskgen import execute_generated
+
+        go = dc.generate(batch.kept_hap, batch.kept_site, n_hap, other == "aligned")
+        runs = [execute_generated(eng, go, aligned_layout=(other == "aligned")) for _ in range(3 + min(args.steps, 20))][3:]
+        o_group, o_copy = float(np.mean([r[0] for r in runs])), float(np.mean([r[1] for r in runs]))
+        # its records must be the primary layout's records (which the oracle checked): first and last haplotype
+        rec_ok = True
+        o_base = dc.read(go.batch.out_base, n_hap + 1, np.uint64)
+        rows_of = lambda h: np.searchsorted(batch.ann_hap, [h, h + 1])
+        for h in (0, n_hap - 1):
+            lo, hi = rows_of(h)
+            o_s = dc.read(go.ann_start + 8 * int(lo), int(hi - lo), np.uint64)
+            o_e = dc.read(go.ann_end + 8 * int(lo), int(hi - lo), np.uint64)
+            o_tape = dc.read(go.batch.out + int(o_base[h]), int(o_base[h + 1] - o_base[h]), np.uint8)
+            p_tape = d_out[int(batch.out_base[h]):int(batch.out_base[h + 1])].cpu().numpy()
+            for r in range(int(hi - lo)):
+                a, b_ = p_tape[int(batch.ann_start[lo + r]):int(batch.ann_end[lo + r])], o_tape[int(o_s[r]):int(o_e[r])]
+                rec_ok = rec_ok and a.shape == b_.shape and bool((a == b_).all())
+        n_alg_o = int(go.batch.n_out) + n_res + 16 * int(go.batch.n_tasks)  # written + read + tasks
+        other_line = {"layout": other, "value": n_res / (o_group * 1e-3), "ms_per_step": o_group, "kernel_ms": o_copy,
+                      "alg_gbs_kernel": n_alg_o / (o_copy * 1e-3) / 1e9, "result_tape_bytes": int(go.batch.n_out),
+                      "records_equal_primary_layout": bool(rec_ok),
+                      "what": "same cohort, Task batch generated on the device in the other layout (v2p_generate_tasks) and "
+                              "executed in place; per-call CUDA events, %d calls" % len(runs)}
         # ---- FORMAT/BCSQ bit-mask matrix -> per-haplotype site lists -> Task batch, on the device
         md_samples = min(n_hap // 2, args.maskdecode_samples)
         if md_samples > 0:
@@ -646,7 +674,8 @@ def main():
                    "haplotypes_per_gpu": n_hap, "tasks_per_gpu": n_tasks, "residues_per_gpu": n_res, "result_tape_bytes_per_gpu": n_out,
                    "mean_task_bytes": n_res / max(n_tasks, 1), "l2_policy": "inputs_larger_than_l2 (output %.1f GB, tasks %.2f GB "
                    "per step; the %.1f MB proteome is L2-resident by design)" % (n_out / 1e9, n_tasks * 16 / 1e9, len(batch.ref) / 1e6),
-                   "tile_variant": args.variant, "layout": args.layout, "fasta_image": bool(args.fasta_image), "reference_tape": "caller-supplied per call" if args.no_registered_ref else
+                   "tile_variant": args.variant, "layout": args.layout,
+                   "tile_order": "tape (V2P_FLAG_ALIGNED_LAYOUT)" if args.layout == "aligned" else "haplotype-interleaved", "fasta_image": bool(args.fasta_image), "reference_tape": "caller-supplied per call" if args.no_registered_ref else
                    "registered once (v2p_engine_set_reference, mode %s)" % args.ref_mode, "parallelism": "sample-sharded x%d, no collective" % world},
         "haplotypes_per_s": total_haps / (ms_per_step * 1e-3),
         "alg_gbs": total_alg / (ms_per_step * 1e-3) / 1e9,
@@ -663,7 +692,7 @@ def main():
                      "write_only": {"achieved_gbs": write_rate, "peak_gbs": write_peak, "frac": write_rate / write_peak,
                                     "note": "result-tape bytes written / kernel time vs torch fill_ on the same GPU: the "
                                             "hard floor of this path is one DRAM write per residue"}},
-        "cpu_baseline": cpu, "parity": parity, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
+        "cpu_baseline": cpu, "parity": parity, "other_layout": other_line, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
     }
     print(json.dumps(line))
     if world > 1:
