@@ -52,6 +52,34 @@ int v2p_catalogue_create(int cuda_device, uint64_t n_tx, const uint64_t* tx_offs
                          const uint8_t* pool, uint64_t n_pool, v2p_catalogue** out);
 void v2p_catalogue_destroy(v2p_catalogue* c);
 
+/* ---- the general catalogue: every instruction code of the reference --------------------------------------------------
+ * One entry per distinct mutation (csq record x transcript), sorted by (transcript, mutated position): the reference's
+ * `Instruction {code, pos_ref, pos_res, len, data}` (instruction.rs:6-16) as Instruction::from_mutation builds it
+ * (instruction.rs:64-1098) WITH validate_s_state taken as true, plus the two facts the device needs to redo that
+ * validation per haplotype (instruction.rs:1075-1098 -- it depends on which other mutations the haplotype carries):
+ *   V2P_INS_STAR         the consequence class is '*'-prefixed (its instruction is dropped when an earlier mutation of
+ *                        the same transcript on the same haplotype invalidates)
+ *   V2P_INS_INVALIDATES  mut_type is stop_gained / frameshift / *stop_gained, or inframe_insertion / inframe_deletion
+ *                        whose mutated amino-acid field is '*' or ends in '*'
+ * code 'E' = phi (unsupported / always invalid): dropped.  Per transcript on a haplotype the generator then restates
+ * from_alt_transcript's filter (transcript_instructions.rs:41-63), compute_expected_results_array_size (:214-321),
+ * get_g_rep / to_task / add_till_next_ins / add_last_instruction (:335-780) and HaplotypeInstruction::get_g_rep's
+ * concatenation (haplotype_instruction.rs:75-158), including its outcomes other than "tasks":
+ *   start_lost ('0'/'U')                 -> annotation row (s, s), no tasks
+ *   no supported mutation left           -> the transcript is absent
+ *   "... must be the last mutation" Err  -> the transcript is skipped; its expected size stays in the tape as trailing
+ *                                           '.' (the reference sizes the tape before the Err, haplotype_instruction.rs:78)
+ *   usize underflow / negative size      -> V2P_ERR_TASKGEN naming haplotype and transcript (the reference aborts)
+ * The rules are csrc/v2p_taskgen_rules.cuh (also compiled for the host by tests/cpp/taskgen_rules_test.cpp).
+ * Generations from this catalogue use the reference's packed layout (V2P_GEN_ALIGNED is refused); V2P_GEN_FASTA works. */
+#define V2P_INS_STAR 0x1u
+#define V2P_INS_INVALIDATES 0x2u
+int v2p_catalogue_create_ins(int cuda_device, uint64_t n_tx, const uint64_t* tx_offsets, uint64_t n_sites,
+                             const uint32_t* site_tx, const uint8_t* ins_code, const uint8_t* ins_flags,
+                             const uint32_t* ins_pos_ref, const uint32_t* ins_pos_res, const uint32_t* ins_len,
+                             const uint64_t* ins_doff, const uint32_t* ins_dlen, const uint8_t* pool, uint64_t n_pool,
+                             v2p_catalogue** out);
+
 /* Transcript names for V2P_GEN_FASTA: name t = names[name_off[t] .. name_off[t+1]) (host pointers, copied). */
 int v2p_catalogue_set_names(v2p_catalogue* c, const uint64_t* name_off, const uint8_t* names);
 const char* v2p_catalogue_last_error(v2p_catalogue* c);
@@ -68,6 +96,7 @@ typedef struct {
     const uint64_t* ann_end;
     uint64_t n_sites;          /* selected sites consumed (those after a truncating variant emit nothing)         */
     float gen_ms;              /* device time of the generation (CUDA events)                                     */
+    uint64_t n_skipped;        /* general catalogue: transcripts skipped by "must be the last mutation"           */
 } v2p_generated;
 
 /* site_begin[n_hap+1] / sites[site_begin[n_hap]]: host pointers; sites ascending inside each haplotype. */

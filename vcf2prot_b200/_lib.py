@@ -10,14 +10,14 @@ LIB_PATH = os.environ.get("V2P_ENGINE_LIB") or os.path.join(HERE, "libv2p_engine
 
 V2P_OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_BAD_ENGINE, ERR_BAD_STREAM, ERR_RES_OOB, ERR_SRC_OOB = 1, 2, 3, 4, 5, 6
-ERR_NOT_CONTIGUOUS, ERR_NOT_GPU_ENGINE = 7, 9
+ERR_NOT_CONTIGUOUS, ERR_NOT_GPU_ENGINE, ERR_TASKGEN = 7, 9, 10
 ENGINE_ST, ENGINE_MT, ENGINE_GPU = 0, 1, 2
 FLAG_FILL_DOT, FLAG_VALIDATE, FLAG_DEVICE_PTRS, FLAG_ASYNC, FLAG_ALIGNED_LAYOUT = 1, 2, 4, 8, 16
 REF_NO_TMA = 0x200
 GEN_ALIGNED, GEN_FASTA = 1, 2
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "BAD_ENGINE", 4: "BAD_STREAM", 5: "RES_OOB", 6: "SRC_OOB",
-                7: "NOT_CONTIGUOUS", 9: "NOT_GPU_ENGINE"}
+                7: "NOT_CONTIGUOUS", 9: "NOT_GPU_ENGINE", 10: "TASKGEN"}
 
 
 class Task16(C.Structure):
@@ -37,7 +37,8 @@ class Result(C.Structure):
 
 class Generated(C.Structure):
     _fields_ = [("batch", Batch), ("n_rows", C.c_uint64), ("ann_hap", C.c_void_p), ("ann_tx", C.c_void_p),
-                ("ann_start", C.c_void_p), ("ann_end", C.c_void_p), ("n_sites", C.c_uint64), ("gen_ms", C.c_float)]
+                ("ann_start", C.c_void_p), ("ann_end", C.c_void_p), ("n_sites", C.c_uint64), ("gen_ms", C.c_float),
+                ("n_skipped", C.c_uint64)]
 
 
 # every symbol include/*.h declares: (restype, argtypes)
@@ -85,6 +86,8 @@ SYMBOLS = {
     # include/v2p_taskgen.h
     "v2p_catalogue_create": (C.c_int, [C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_uint64,
                                        C.POINTER(_P)]),
+    "v2p_catalogue_create_ins": (C.c_int, [C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64,
+                                           C.POINTER(_P)]),
     "v2p_catalogue_destroy": (None, [_P]),
     "v2p_catalogue_set_names": (C.c_int, [_P, _P, _P]),
     "v2p_catalogue_last_error": (C.c_char_p, [_P]),

@@ -24,6 +24,7 @@
 
 #include "v2p_mapped.cuh"
 #include "v2p_taskgen.h"
+#include "v2p_taskgen_rules.cuh"
 
 namespace {
 
@@ -280,6 +281,162 @@ __global__ void k_tg_emit_alt(Sel s, Cat c, Out o) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
+// General catalogue (v2p_catalogue_create_ins): every instruction code, the reference's own outcomes.  One thread per
+// transcript-on-haplotype runs csrc/v2p_taskgen_rules.cuh twice: a counting pass (sizes, task and alteration-byte counts,
+// outcome), scans over the groups, then the emitting pass.
+struct InsCat {
+    const uint64_t* tx_off;
+    const uint32_t* tx;
+    const uint8_t *code, *flags;
+    const uint32_t *pos_ref, *pos_res, *len, *dlen;
+    const uint64_t* doff;
+    const uint8_t* pool;
+    const uint64_t* name_off;
+    const uint8_t* names;
+};
+
+struct InsGen {
+    uint64_t n_sel, n_hap, n_groups;
+    const uint32_t* sites;
+    const uint64_t* site_begin;
+    const uint32_t* site_hap;
+    uint64_t *newg, *g_x;  // per site (+ sentinel)
+    // per group (+ sentinel)
+    uint64_t *g_first, *g_size;
+    uint32_t *g_hap, *g_tx, *g_nsites;
+    uint8_t* g_status;
+    uint64_t *c_tasks, *c_alt, *c_name, *c_adv, *c_tape, *c_rows, *c_skip;  // scan inputs
+    uint64_t *x_tasks, *x_alt, *x_name, *x_adv, *x_tape, *x_rows, *x_skip;  // exclusive scans
+    unsigned long long* err;  // min group index the reference aborts on
+    int fasta;
+};
+
+__global__ void k_ti_mark(InsGen g, InsCat c) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j > g.n_sel) return;
+    if (j == g.n_sel) {
+        g.newg[j] = 0;
+        return;
+    }
+    const uint32_t h = g.site_hap[j];
+    g.newg[j] = (j == g.site_begin[h] || c.tx[g.sites[j - 1]] != c.tx[g.sites[j]]) ? 1 : 0;
+}
+
+struct InsGet {
+    const InsCat* c;
+    const uint32_t* sites;
+    uint64_t j0;
+    __device__ __forceinline__ v2p_rules::TgIns operator()(int i) const {
+        const uint32_t si = sites[j0 + i];
+        v2p_rules::TgIns t;
+        t.code = c->code[si], t.flags = c->flags[si];
+        t.pos_ref = c->pos_ref[si], t.pos_res = c->pos_res[si], t.len = c->len[si], t.dlen = c->dlen[si];
+        t.doff = c->doff[si];
+        return t;
+    }
+};
+
+__global__ void k_ti_count(InsGen g, InsCat c) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j == 0) {  // sentinels of the per-group scans
+        const uint64_t G = g.n_groups;
+        g.c_tasks[G] = g.c_alt[G] = g.c_name[G] = g.c_adv[G] = g.c_tape[G] = g.c_rows[G] = g.c_skip[G] = 0;
+        g.g_first[G] = g.n_sel;
+    }
+    if (j >= g.n_sel || !g.newg[j]) return;
+    const uint64_t gi = g.g_x[j];
+    const uint32_t h = g.site_hap[j], t = c.tx[g.sites[j]];
+    const uint64_t j1 = g.site_begin[h + 1];
+    uint64_t je = j + 1;
+    while (je < j1 && c.tx[g.sites[je]] == t) ++je;
+    const InsGet get{&c, g.sites, j};
+    v2p_rules::NullSink null;
+    const v2p_rules::TgSummary s = v2p_rules::tg_transcript(get, (int)(je - j), c.tx_off[t + 1] - c.tx_off[t], null);
+    if (s.status == v2p_rules::TG_PANIC) atomicMin(g.err, (unsigned long long)gi);
+    const bool row = s.status == v2p_rules::TG_OK || s.status == v2p_rules::TG_EMPTY;
+    const uint64_t adv = s.status == v2p_rules::TG_OK ? s.size : 0;
+    const uint64_t nlen = g.fasta ? c.name_off[t + 1] - c.name_off[t] : 0;
+    g.g_first[gi] = j, g.g_nsites[gi] = (uint32_t)(je - j), g.g_hap[gi] = h, g.g_tx[gi] = t;
+    g.g_status[gi] = (uint8_t)s.status, g.g_size[gi] = s.size;
+    g.c_tasks[gi] = s.n_tasks + ((g.fasta && row) ? 2 : 0);
+    g.c_alt[gi] = s.n_alt;
+    g.c_name[gi] = (g.fasta && row) ? nlen + 5 : 0;
+    g.c_rows[gi] = row ? 1 : 0;
+    g.c_skip[gi] = s.status == v2p_rules::TG_SKIPPED ? 1 : 0;
+    if (g.fasta) {  // a file image holds records only: header + sequence + newline per annotation row
+        g.c_adv[gi] = g.c_tape[gi] = row ? nlen + 4 + adv + 1 : 0;
+    } else {  // the tape was sized from every instruction set before any transcript could fail (haplotype_instruction.rs:78)
+        g.c_adv[gi] = adv;
+        g.c_tape[gi] = s.status == v2p_rules::TG_ABSENT ? 0 : s.size;
+    }
+}
+
+struct InsOut {
+    v2p_task16* tasks;
+    uint64_t *task_begin, *alt_base, *out_base;
+    uint8_t* alt;
+    uint32_t *ann_hap, *ann_tx;
+    uint64_t *ann_start, *ann_end;
+};
+
+__global__ void k_ti_hap_bases(InsGen g, InsOut o) {
+    uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (h > g.n_hap) return;
+    const uint64_t G0 = g.g_x[g.site_begin[h]];
+    o.task_begin[h] = g.x_tasks[G0];
+    o.alt_base[h] = g.x_alt[G0] + g.x_name[G0];
+    o.out_base[h] = g.x_tape[G0];
+}
+
+struct EmitSink {  // the rules' sink: writes tasks and alteration bytes in place
+    v2p_task16* tasks;     // next task slot
+    uint8_t* alt_bytes;    // next alteration byte of this transcript
+    const uint8_t* pool;
+    uint64_t ref0, alt0, dst0;  // proteome offset of the transcript; haplotype-relative offsets of its alt bytes / result
+    __device__ __forceinline__ void task(uint32_t stream, uint64_t src, uint64_t len, uint64_t dst) {
+        *tasks++ = v2p_task16{(uint32_t)((stream ? alt0 : ref0) + src), (uint32_t)len, (uint32_t)(dst0 + dst), stream};
+    }
+    __device__ __forceinline__ void alt(uint64_t doff, uint32_t dlen) {
+        for (uint32_t w = 0; w < dlen; ++w) alt_bytes[w] = pool[doff + w];
+        alt_bytes += dlen;
+    }
+};
+
+__global__ void k_ti_emit(InsGen g, InsCat c, InsOut o) {
+    uint64_t gi = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (gi >= g.n_groups) return;
+    const int status = g.g_status[gi];
+    if (status != v2p_rules::TG_OK && status != v2p_rules::TG_EMPTY) return;
+    const uint32_t h = g.g_hap[gi], t = g.g_tx[gi];
+    const uint64_t G0 = g.g_x[g.site_begin[h]], G1 = g.g_x[g.site_begin[h + 1]];
+    const uint64_t g_start = g.x_adv[gi] - g.x_adv[G0];
+    const uint64_t size = status == v2p_rules::TG_OK ? g.g_size[gi] : 0;
+    const uint64_t nlen = g.fasta ? c.name_off[t + 1] - c.name_off[t] : 0, hdr = g.fasta ? nlen + 4 : 0;
+    const uint64_t row = g.x_rows[gi];
+    o.ann_hap[row] = h, o.ann_tx[row] = t;
+    o.ann_start[row] = g_start + hdr, o.ann_end[row] = g_start + hdr + size;
+    v2p_task16* tk = o.tasks + g.x_tasks[gi];
+    const uint64_t alt_local = g.x_alt[gi] - g.x_alt[G0];
+    if (g.fasta) {  // `>{name}_{1|2}\n` before, `\n` after, both read from the name tape behind the alteration bytes
+        const uint64_t name_src = (g.x_alt[G1] - g.x_alt[G0]) + (g.x_name[gi] - g.x_name[G0]);
+        *tk++ = v2p_task16{(uint32_t)name_src, (uint32_t)hdr, (uint32_t)g_start, 1u};
+        o.tasks[g.x_tasks[gi + 1] - 1] = v2p_task16{(uint32_t)(name_src + hdr), 1u, (uint32_t)(g_start + hdr + size), 1u};
+        uint8_t* d = o.alt + o.alt_base[h] + name_src;
+        const uint64_t n0 = c.name_off[t];
+        d[0] = '>';
+        for (uint64_t w = 0; w < nlen; ++w) d[1 + w] = c.names[n0 + w];
+        d[1 + nlen] = '_';
+        d[2 + nlen] = (uint8_t)('1' + (h & 1u));
+        d[3 + nlen] = '\n';
+        d[4 + nlen] = '\n';
+    }
+    if (status != v2p_rules::TG_OK) return;
+    EmitSink sink{tk, o.alt + o.alt_base[h] + alt_local, c.pool, c.tx_off[t], alt_local, g_start + hdr};
+    const InsGet get{&c, g.sites, g.g_first[gi]};
+    v2p_rules::tg_transcript(get, (int)g.g_nsites[gi], c.tx_off[t + 1] - c.tx_off[t], sink);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Genotype bit-masks -> per-haplotype site lists (MaskDecoder.rs:95-153 + the transpose of vcf_ds.rs:126-295).
 // The mask matrix is streamed twice (population count to size the key buffer, then the emit); everything after that
 // works on the set bits only: 64-bit keys (haplotype << site_bits | site), one radix sort over the significant bits,
@@ -403,6 +560,9 @@ struct v2p_catalogue {
     std::string err;
     uint64_t n_tx = 0, n_sites = 0;
     Buf tx_off, tx, pos, rlen, dlen, cls, doff, pool;
+    bool is_ins = false;  // created by v2p_catalogue_create_ins (general rules) rather than the seven-class tables
+    Buf i_code, i_flags, i_pos_ref, i_pos_res, i_len;  // (+ tx, doff, dlen, pool shared with the class tables)
+    Buf gi_newg, gi_gx, gi_first, gi_size, gi_hap, gi_tx, gi_nsites, gi_status, gi_c[7], gi_x[7], gi_err;
     v2p::MappedBuf pub;   // totals come back through mapped pinned memory, not the copy engine (v2p_mapped.cuh)
     Buf name_off, names;  // v2p_catalogue_set_names
     bool has_names = false;
@@ -462,6 +622,8 @@ inline unsigned blocks(uint64_t n) { return (unsigned)((n + 255) / 256); }
 
 int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const uint64_t* d_site_begin, const uint32_t* d_sites,
                        uint32_t flags, v2p_generated* out);
+int generate_ins_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const uint64_t* d_site_begin,
+                           const uint32_t* d_sites, uint32_t flags, v2p_generated* out);
 
 }  // namespace
 
@@ -496,11 +658,50 @@ int v2p_catalogue_create(int cuda_device, uint64_t n_tx, const uint64_t* tx_offs
     return V2P_OK;
 }
 
+int v2p_catalogue_create_ins(int cuda_device, uint64_t n_tx, const uint64_t* tx_offsets, uint64_t n_sites,
+                             const uint32_t* site_tx, const uint8_t* ins_code, const uint8_t* ins_flags,
+                             const uint32_t* ins_pos_ref, const uint32_t* ins_pos_res, const uint32_t* ins_len,
+                             const uint64_t* ins_doff, const uint32_t* ins_dlen, const uint8_t* pool, uint64_t n_pool,
+                             v2p_catalogue** out) {
+    if (!out || !tx_offsets ||
+        (n_sites && (!site_tx || !ins_code || !ins_flags || !ins_pos_ref || !ins_pos_res || !ins_len || !ins_doff || !ins_dlen)))
+        return V2P_ERR_INVALID_ARG;
+    *out = nullptr;
+    for (uint64_t i = 0; i < n_sites; ++i)
+        if (site_tx[i] >= n_tx || ins_doff[i] + ins_dlen[i] > n_pool || (i && site_tx[i] < site_tx[i - 1])) return V2P_ERR_INVALID_ARG;
+    v2p_catalogue* c = new (std::nothrow) v2p_catalogue();
+    if (!c) return V2P_ERR_INVALID_ARG;
+    c->device = cuda_device;
+    c->is_ins = true;
+    if (cudaSetDevice(cuda_device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        delete c;
+        return V2P_ERR_CUDA;
+    }
+    c->n_tx = n_tx, c->n_sites = n_sites;
+    int rc = 0;
+    if ((rc = upload(c, c->tx_off, tx_offsets, (n_tx + 1) * 8)) || (rc = upload(c, c->tx, site_tx, n_sites * 4)) ||
+        (rc = upload(c, c->i_code, ins_code, n_sites)) || (rc = upload(c, c->i_flags, ins_flags, n_sites)) ||
+        (rc = upload(c, c->i_pos_ref, ins_pos_ref, n_sites * 4)) || (rc = upload(c, c->i_pos_res, ins_pos_res, n_sites * 4)) ||
+        (rc = upload(c, c->i_len, ins_len, n_sites * 4)) || (rc = upload(c, c->doff, ins_doff, n_sites * 8)) ||
+        (rc = upload(c, c->dlen, ins_dlen, n_sites * 4)) || (rc = upload(c, c->pool, pool, n_pool)) ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        v2p_catalogue_destroy(c);
+        return rc ? rc : V2P_ERR_CUDA;
+    }
+    *out = c;
+    return V2P_OK;
+}
+
 void v2p_catalogue_destroy(v2p_catalogue* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    Buf* all[] = {&c->name_off, &c->names,
+    Buf* all[] = {&c->i_code, &c->i_flags, &c->i_pos_ref, &c->i_pos_res, &c->i_len, &c->gi_newg, &c->gi_gx, &c->gi_first,
+                  &c->gi_size, &c->gi_hap, &c->gi_tx, &c->gi_nsites, &c->gi_status, &c->gi_err,
+                  &c->gi_c[0], &c->gi_c[1], &c->gi_c[2], &c->gi_c[3], &c->gi_c[4], &c->gi_c[5], &c->gi_c[6],
+                  &c->gi_x[0], &c->gi_x[1], &c->gi_x[2], &c->gi_x[3], &c->gi_x[4], &c->gi_x[5], &c->gi_x[6],
+                  &c->name_off, &c->names,
                   &c->tx_off, &c->tx, &c->pos, &c->rlen, &c->dlen, &c->cls, &c->doff, &c->pool, &c->sites, &c->site_begin,
                   &c->site_hap, &c->flags, &c->cub_tmp, &c->totals, &c->g_first, &c->g_len, &c->g_slot, &c->g_slot_x, &c->g_hap,
                   &c->g_tx, &c->ann_start, &c->ann_end, &c->tasks, &c->task_begin, &c->alt_base, &c->out_base, &c->alt_per_hap,
@@ -662,6 +863,7 @@ namespace {
 // site_begin / sites are device pointers here; c->ev0 has been recorded by the caller
 int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const uint64_t* d_site_begin, const uint32_t* d_sites,
                        uint32_t flags, v2p_generated* out) {
+    if (c->is_ins) return generate_ins_on_device(c, n_hap, n_sel, d_site_begin, d_sites, flags, out);
     cudaStream_t st = c->stream;
     int rc;
     if ((rc = need(c, c->site_hap, n_sel * 4 + 16)) || (rc = need(c, c->flags, n_sel + 16)) || (rc = need(c, c->mut_dst, n_sel * 8 + 16)) ||
@@ -774,5 +976,100 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
     return V2P_OK;
 }
 
-}  // namespace
+// General catalogue: site_begin / sites are device pointers; c->ev0 has been recorded by the caller.
+int generate_ins_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const uint64_t* d_site_begin,
+                           const uint32_t* d_sites, uint32_t flags, v2p_generated* out) {
+    cudaStream_t st = c->stream;
+    const bool fasta = (flags & V2P_GEN_FASTA) != 0;
+    if (flags & V2P_GEN_ALIGNED)
+        return cfail(c, V2P_ERR_INVALID_ARG, "the general catalogue generates the reference's packed layout only (no V2P_GEN_ALIGNED)");
+    if (fasta && !c->has_names) return cfail(c, V2P_ERR_INVALID_ARG, "V2P_GEN_FASTA needs v2p_catalogue_set_names first");
+    int rc;
+    if ((rc = need(c, c->site_hap, n_sel * 4 + 16)) || (rc = need(c, c->gi_newg, (n_sel + 1) * 8)) ||
+        (rc = need(c, c->gi_gx, (n_sel + 1) * 8)) || (rc = need(c, c->gi_err, 8)) || (rc = need(c, c->task_begin, (n_hap + 1) * 8)) ||
+        (rc = need(c, c->alt_base, (n_hap + 1) * 8)) || (rc = need(c, c->out_base, (n_hap + 1) * 8)))
+        return rc;
+    CU(c, c->pub.reserve(64));
+    InsCat cat{(const uint64_t*)c->tx_off.p, (const uint32_t*)c->tx.p, (const uint8_t*)c->i_code.p, (const uint8_t*)c->i_flags.p,
+               (const uint32_t*)c->i_pos_ref.p, (const uint32_t*)c->i_pos_res.p, (const uint32_t*)c->i_len.p,
+               (const uint32_t*)c->dlen.p, (const uint64_t*)c->doff.p, (const uint8_t*)c->pool.p,
+               (const uint64_t*)c->name_off.p, (const uint8_t*)c->names.p};
+    InsGen g{};
+    g.n_sel = n_sel, g.n_hap = n_hap, g.sites = d_sites, g.site_begin = d_site_begin;
+    g.site_hap = (const uint32_t*)c->site_hap.p;
+    g.newg = (uint64_t*)c->gi_newg.p, g.g_x = (uint64_t*)c->gi_gx.p;
+    g.err = (unsigned long long*)c->gi_err.p;
+    g.fasta = fasta ? 1 : 0;
+    CU(c, cudaMemsetAsync(g.err, 0xFF, 8, st));
+    if (n_sel) {
+        Sel sh{};
+        sh.n_sel = n_sel, sh.n_hap = n_hap, sh.site_begin = d_site_begin, sh.site_hap = (uint32_t*)c->site_hap.p;
+        k_tg_site_hap<<<blocks(n_sel), 256, 0, st>>>(sh);
+    }
+    k_ti_mark<<<blocks(n_sel + 1), 256, 0, st>>>(g, cat);
+    if ((rc = xsum(c, g.newg, g.g_x, n_sel + 1))) return rc;
+    {
+        v2p::PubList pl{};
+        pl.src[0] = (const unsigned long long*)(g.g_x + n_sel), pl.n = 1;
+        v2p::k_publish_list<<<1, 32, 0, st>>>(c->pub.p, pl);
+    }
+    CU(c, cudaStreamSynchronize(st));
+    const uint64_t G = c->pub.p[0];
+    g.n_groups = G;
+    if ((rc = need(c, c->gi_first, (G + 1) * 8)) || (rc = need(c, c->gi_size, (G + 1) * 8)) || (rc = need(c, c->gi_hap, (G + 1) * 4)) ||
+        (rc = need(c, c->gi_tx, (G + 1) * 4)) || (rc = need(c, c->gi_nsites, (G + 1) * 4)) || (rc = need(c, c->gi_status, G + 1)))
+        return rc;
+    for (int i = 0; i < 7; ++i)
+        if ((rc = need(c, c->gi_c[i], (G + 1) * 8)) || (rc = need(c, c->gi_x[i], (G + 1) * 8))) return rc;
+    g.g_first = (uint64_t*)c->gi_first.p, g.g_size = (uint64_t*)c->gi_size.p, g.g_hap = (uint32_t*)c->gi_hap.p;
+    g.g_tx = (uint32_t*)c->gi_tx.p, g.g_nsites = (uint32_t*)c->gi_nsites.p, g.g_status = (uint8_t*)c->gi_status.p;
+    uint64_t** cin[7] = {&g.c_tasks, &g.c_alt, &g.c_name, &g.c_adv, &g.c_tape, &g.c_rows, &g.c_skip};
+    uint64_t** cx[7] = {&g.x_tasks, &g.x_alt, &g.x_name, &g.x_adv, &g.x_tape, &g.x_rows, &g.x_skip};
+    for (int i = 0; i < 7; ++i) *cin[i] = (uint64_t*)c->gi_c[i].p, *cx[i] = (uint64_t*)c->gi_x[i].p;
+    k_ti_count<<<blocks(n_sel + 1), 256, 0, st>>>(g, cat);
+    for (int i = 0; i < 7; ++i)
+        if ((rc = xsum(c, *cin[i], *cx[i], G + 1))) return rc;
+    {
+        v2p::PubList pl{};
+        const uint64_t* tot[7] = {g.x_tasks + G, g.x_alt + G, g.x_name + G, g.x_tape + G, g.x_rows + G, g.x_skip + G, (const uint64_t*)g.err};
+        for (int i = 0; i < 7; ++i) pl.src[i] = (const unsigned long long*)tot[i];
+        pl.n = 7;
+        v2p::k_publish_list<<<1, 32, 0, st>>>(c->pub.p, pl);
+    }
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(st));
+    const uint64_t n_tasks = c->pub.p[0], n_alt = c->pub.p[1] + c->pub.p[2], n_out = c->pub.p[3], n_rows = c->pub.p[4],
+                   n_skip = c->pub.p[5], bad = c->pub.p[6];
+    if (bad != ~0ull) {  // name the transcript the reference aborts on
+        uint32_t hh = 0, tt = 0;
+        cudaMemcpy(&hh, g.g_hap + bad, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&tt, g.g_tx + bad, 4, cudaMemcpyDeviceToHost);
+        return cfail(c, V2P_ERR_TASKGEN,
+                     "haplotype %u transcript %u: the reference aborts while generating its tasks (usize underflow in "
+                     "add_till_next_ins / add_last_instruction, or a negative result size)", hh, tt);
+    }
+    if ((rc = need(c, c->tasks, (n_tasks + 1) * sizeof(v2p_task16))) || (rc = need(c, c->alt, n_alt + 64)) ||
+        (rc = need(c, c->out, n_out + 64)) || (rc = need(c, c->g_hap, (n_rows + 1) * 4)) || (rc = need(c, c->g_tx, (n_rows + 1) * 4)) ||
+        (rc = need(c, c->ann_start, (n_rows + 1) * 8)) || (rc = need(c, c->ann_end, (n_rows + 1) * 8)))
+        return rc;
+    InsOut o{(v2p_task16*)c->tasks.p, (uint64_t*)c->task_begin.p, (uint64_t*)c->alt_base.p, (uint64_t*)c->out_base.p,
+             (uint8_t*)c->alt.p, (uint32_t*)c->g_hap.p, (uint32_t*)c->g_tx.p, (uint64_t*)c->ann_start.p, (uint64_t*)c->ann_end.p};
+    k_ti_hap_bases<<<blocks(n_hap + 1), 256, 0, st>>>(g, o);
+    if (G) k_ti_emit<<<blocks(G), 256, 0, st>>>(g, cat, o);
+    CU(c, cudaEventRecord(c->ev1, st));
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    out->batch.task_begin = o.task_begin, out->batch.tasks = o.tasks;
+    out->batch.ref = nullptr, out->batch.ref_base = nullptr;
+    out->batch.alt = o.alt, out->batch.alt_base = o.alt_base;
+    out->batch.out = (uint8_t*)c->out.p, out->batch.out_base = o.out_base;
+    out->batch.n_hap = n_hap, out->batch.n_tasks = n_tasks, out->batch.n_alt = n_alt, out->batch.n_out = n_out;
+    out->n_rows = n_rows;
+    out->ann_hap = o.ann_hap, out->ann_tx = o.ann_tx, out->ann_start = o.ann_start, out->ann_end = o.ann_end;
+    out->n_sites = n_sel, out->gen_ms = ms, out->n_skipped = n_skip;
+    return V2P_OK;
+}
 
+}  // namespace

@@ -28,6 +28,37 @@ class DeviceCatalogue:
             raise EngineError(st, "v2p_catalogue_create failed")
         self._h = h
 
+    @classmethod
+    def from_instructions(cls, tx_offsets, site_tx, code, flags, pos_ref, pos_res, length, doff, dlen, pool, device: int = 0):
+        """The general catalogue (v2p_catalogue_create_ins): one reference `Instruction` per distinct mutation, sorted by
+        (transcript, mutated position), computed with validate_s_state taken as true, plus the V2P_INS_* flags."""
+        self = cls.__new__(cls)
+        self._lib = L.load()
+        arrs = [np.ascontiguousarray(tx_offsets, np.uint64), np.ascontiguousarray(site_tx, np.uint32),
+                np.ascontiguousarray(code, np.uint8), np.ascontiguousarray(flags, np.uint8),
+                np.ascontiguousarray(pos_ref, np.uint32), np.ascontiguousarray(pos_res, np.uint32),
+                np.ascontiguousarray(length, np.uint32), np.ascontiguousarray(doff, np.uint64),
+                np.ascontiguousarray(dlen, np.uint32), np.ascontiguousarray(pool, np.uint8)]
+        self._keep = arrs
+        p = [a.ctypes.data_as(C.c_void_p) for a in arrs]
+        h = C.c_void_p()
+        st = self._lib.v2p_catalogue_create_ins(device, len(arrs[0]) - 1, p[0], len(arrs[1]), p[1], p[2], p[3], p[4], p[5], p[6],
+                                                p[7], p[8], p[9], len(arrs[9]), C.byref(h))
+        if st:
+            raise EngineError(st, "v2p_catalogue_create_ins failed")
+        self._h = h
+        return self
+
+    def generate_lists(self, site_begin: np.ndarray, sites: np.ndarray, fasta: bool = False) -> L.Generated:
+        """CSR site lists (site_begin[n_hap+1], sites) -> generated batch, packed layout."""
+        sb, st_ = np.ascontiguousarray(site_begin, np.uint64), np.ascontiguousarray(sites, np.uint32)
+        g = L.Generated()
+        st = self._lib.v2p_generate_tasks(self._h, len(sb) - 1, sb.ctypes.data_as(C.c_void_p), st_.ctypes.data_as(C.c_void_p),
+                                          self._flags(False, fasta), C.byref(g))
+        if st:
+            raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
+        return g
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.v2p_catalogue_destroy(self._h)
