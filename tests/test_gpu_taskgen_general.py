@@ -221,3 +221,33 @@ def test_task_arrays_the_reference_panics_on_at_execution_are_rejected_by_the_en
         execute_generated(gpu_engine, g)
     assert ei.value.status in (L.ERR_RES_OOB, L.ERR_SRC_OOB) and ei.value.bad_hap == 0
     dc.close()
+
+
+@pytest.mark.parametrize("gzip", [False, True])
+def test_pipeline_over_the_general_catalogue(gpu_engine, gzip):
+    """csq-level cohort -> per-sample .fasta(.gz) through v2p_pipeline_run_lists with general catalogues as lanes."""
+    import zlib
+
+    from vcf2prot_b200.pipeline import DevicePipeline
+
+    w = random_world(51, n_hap=30)
+    name_off = (9 * np.arange(len(w.names) + 1)).astype(np.uint64)
+    cats = []
+    for _ in range(2):
+        dc = DeviceCatalogue.from_instructions(*w.cat_args)
+        dc.set_names(name_off, np.frombuffer("".join(w.names).encode(), np.uint8))
+        cats.append(dc)
+    gpu_engine.set_reference(w.tape)
+    pipe = DevicePipeline(gpu_engine, cats=cats)
+    out = np.zeros(1 << 20, np.uint8)
+    fb, res = pipe.run_lists(w.site_begin, w.sites, 15, 4, gzip, out=out)
+    ref_s = w.tape.tobytes().decode()
+    for s in range(15):
+        want = ""
+        for h in (2 * s, 2 * s + 1):
+            tasks, alt, ann, res_len, _ = w.oracle_hap(h)
+            tape = T.execute_tasks(tasks, ref_s, alt, res_len)
+            want += "".join(">%s_%d\n%s\n" % (w.names[t], 1 + (h & 1), tape[a:b]) for t, a, b in ann)
+        got = out[int(fb[s]):int(fb[s + 1])].tobytes()
+        assert (zlib.decompress(got, wbits=31) if gzip else got).decode() == want, s
+    pipe.close()
