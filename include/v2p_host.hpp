@@ -10,6 +10,10 @@
 //   v2p::HaplotypeBatch                .../haplotype_instruction.rs:75-158  get_g_rep's concat + re-index loop
 //                                      (update_task :140-158), generalised to MANY haplotypes per launch and to the
 //                                      B200 layouts (shared proteome tape, phase-aligned result slots)
+//   v2p::Instruction / InstructionCatalogue   .../instruction.rs:6-16   the host's Instruction values, uploaded once;
+//                                      Task generation then happens on the device (include/v2p_taskgen.h)
+//   v2p::Pipeline / v2p::DirWriter     parts/exec.rs:27-41 + parts/io.rs:35-57: every proband's haplotypes executed and
+//                                      written as {out_dir}/{proband}.fasta[.gz] (include/v2p_pipeline.h)
 //
 // Errors: where the reference panics (task.rs:44/48, haplotype_instruction.rs:154, gir.rs:223) this throws
 // v2p::EngineError carrying the ABI status and the offending haplotype/task.  ST and MT are the caller's CPU engines
@@ -25,6 +29,7 @@
 #include <vector>
 
 #include "v2p_engine.h"
+#include "v2p_pipeline.h"
 
 namespace v2p {
 
@@ -209,6 +214,110 @@ private:
     std::string alt_, ref_;
     std::vector<Annotation> annotations_;
     uint64_t ref_counter_ = 0, alt_counter_ = 0, res_counter_ = 0, out_size_ = 0;
+};
+
+// instruction.rs:6-16, as Instruction::from_mutation builds it with validate_s_state taken as true, plus the two facts
+// the device needs to redo that validation per haplotype (include/v2p_taskgen.h).
+struct Instruction {
+    uint32_t transcript;  // index into the proteome's transcript table
+    char code;
+    bool star;         // the consequence class is '*'-prefixed
+    bool invalidates;  // stop_gained / frameshift / *stop_gained / inframe ins-del whose mutated field is or ends in '*'
+    uint32_t pos_ref, pos_res, len;
+    std::string data;
+};
+
+// The general catalogue on one GPU: instructions sorted by (transcript, mutated position), transcript names for the
+// FASTA headers.  RAII over v2p_catalogue_create_ins / v2p_catalogue_destroy.
+class InstructionCatalogue {
+public:
+    InstructionCatalogue(int cuda_device, const std::vector<uint64_t>& tx_offsets, const std::vector<std::string>& tx_names,
+                         const std::vector<Instruction>& ins) {
+        std::vector<uint32_t> tx, pr, ps, ln, dl;
+        std::vector<uint8_t> code, flags;
+        std::vector<uint64_t> doff, name_off(1, 0);
+        std::string pool, names;
+        for (const Instruction& i : ins) {
+            tx.push_back(i.transcript), code.push_back((uint8_t)i.code);
+            flags.push_back((i.star ? V2P_INS_STAR : 0u) | (i.invalidates ? V2P_INS_INVALIDATES : 0u));
+            pr.push_back(i.pos_ref), ps.push_back(i.pos_res), ln.push_back(i.len);
+            doff.push_back(pool.size()), dl.push_back((uint32_t)i.data.size());
+            pool += i.data;
+        }
+        for (const std::string& n : tx_names) names += n, name_off.push_back(names.size());
+        int st = v2p_catalogue_create_ins(cuda_device, tx_offsets.size() - 1, tx_offsets.data(), ins.size(), tx.data(), code.data(),
+                                          flags.data(), pr.data(), ps.data(), ln.data(), doff.data(), dl.data(),
+                                          reinterpret_cast<const uint8_t*>(pool.data()), pool.size(), &c_);
+        if (st != V2P_OK) throw EngineError(st, "v2p_catalogue_create_ins failed");
+        st = v2p_catalogue_set_names(c_, name_off.data(), reinterpret_cast<const uint8_t*>(names.data()));
+        if (st != V2P_OK) {
+            const std::string msg = v2p_catalogue_last_error(c_);
+            v2p_catalogue_destroy(c_);
+            throw EngineError(st, msg);
+        }
+    }
+    ~InstructionCatalogue() { v2p_catalogue_destroy(c_); }
+    InstructionCatalogue(const InstructionCatalogue&) = delete;
+    InstructionCatalogue& operator=(const InstructionCatalogue&) = delete;
+    v2p_catalogue* get() const { return c_; }
+
+private:
+    v2p_catalogue* c_ = nullptr;
+};
+
+// parts/io.rs:35-57: {out_dir}/{proband}.fasta or .fasta.gz, one file per proband.
+class DirWriter {
+public:
+    DirWriter(const std::string& out_dir, const std::vector<std::string>& probands, bool write_compressed, unsigned threads = 4) {
+        std::vector<const char*> names;
+        for (const std::string& p : probands) names.push_back(p.c_str());
+        if (v2p_dir_writer_create(out_dir.c_str(), names.data(), names.size(), write_compressed ? 1 : 0, threads, &w_) != V2P_OK)
+            throw EngineError(V2P_ERR_INVALID_ARG, "v2p_dir_writer_create failed");
+    }
+    ~DirWriter() { v2p_dir_writer_destroy(w_); }
+    DirWriter(const DirWriter&) = delete;
+    DirWriter& operator=(const DirWriter&) = delete;
+    v2p_dir_writer* get() const { return w_; }
+    uint64_t files_written() const { return v2p_dir_writer_files(w_); }
+    uint64_t bytes_written() const { return v2p_dir_writer_bytes(w_); }
+
+private:
+    v2p_dir_writer* w_ = nullptr;
+};
+
+// parts/exec.rs:27-41 for Engine::GPU: every proband's two haplotypes, from their mutation lists to files.
+// `lanes`: one catalogue object per chunk in flight, built from the same instructions.
+class Pipeline {
+public:
+    Pipeline(Context& ctx, const std::vector<InstructionCatalogue*>& lanes) {
+        std::vector<v2p_catalogue*> raw;
+        for (InstructionCatalogue* c : lanes) raw.push_back(c->get());
+        if (v2p_pipeline_create(ctx.get(), raw.data(), (uint32_t)raw.size(), &p_) != V2P_OK)
+            throw EngineError(V2P_ERR_INVALID_ARG, "v2p_pipeline_create failed");
+    }
+    ~Pipeline() { v2p_pipeline_destroy(p_); }
+    Pipeline(const Pipeline&) = delete;
+    Pipeline& operator=(const Pipeline&) = delete;
+
+    // per_haplotype[2 * proband + (hap - 1)] = ascending catalogue indices of the mutations that haplotype carries
+    v2p_pipeline_result write(const std::vector<std::vector<uint32_t>>& per_haplotype, DirWriter& writer, bool write_compressed,
+                              uint32_t chunk_probands = 128) {
+        std::vector<uint64_t> begin(1, 0);
+        std::vector<uint32_t> sites;
+        for (const auto& l : per_haplotype) {
+            sites.insert(sites.end(), l.begin(), l.end());
+            begin.push_back(sites.size());
+        }
+        v2p_pipeline_result r{};
+        const int st = v2p_pipeline_run_lists(p_, per_haplotype.size() / 2, begin.data(), sites.data(), chunk_probands,
+                                              write_compressed ? V2P_PIPE_GZIP : 0u, nullptr, 0, nullptr, v2p_dir_writer_sink,
+                                              writer.get(), &r);
+        if (st != V2P_OK) throw EngineError(st, v2p_pipeline_last_error(p_));
+        return r;
+    }
+
+private:
+    v2p_pipeline* p_ = nullptr;
 };
 
 }  // namespace v2p

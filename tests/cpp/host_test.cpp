@@ -95,6 +95,33 @@ static std::vector<Case> load_cases(const char* path) {
     return out;
 }
 
+// The reference's own unit-test mutations (transcript_instructions.rs:884, :987, :1053, :1306) as two probands, from
+// Instruction values to {dir}/{proband}.fasta through the device generator, the engine and the native writer.
+static std::string slurp(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    return std::string((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+static void test_pipeline_writes_the_golden_records(v2p::Context& ctx, const std::string& dir) {
+    const std::string T = "MEDLGENTMVLSTLRSLNNFISQRVEGGSGLEELERGG";
+    ctx.set_reference(T);
+    // sorted by (transcript, mutated position): I and N share position 4 on different haplotypes
+    const std::vector<v2p::Instruction> ins = {
+        {0, 'I', false, false, 4, 4, 5, "GTEST"},             // inframe_insertion 5G>5GTEST        (test 5)
+        {0, 'N', true, false, 4, 4, 1, "H"},                  // *missense 5G>5H                    (test 1)
+        {0, 'F', false, true, 9, 9, 15, "VTESTFRAMESHIFT"},   // frameshift 10V>10VTESTFRAMESHIFT   (test 8)
+        {0, 'P', false, false, 37, 37, 0, ""},                // inframe_deletion&stop_retained 38*>38*  (test 20)
+    };
+    v2p::InstructionCatalogue lane0(0, {0, T.size()}, {"T"}, ins), lane1(0, {0, T.size()}, {"T"}, ins);
+    v2p::Pipeline pipe(ctx, {&lane0, &lane1});
+    v2p::DirWriter w(dir, {"HG1", "HG2", "HG3"}, false, 2);
+    const v2p_pipeline_result r = pipe.write({{1}, {2}, {0}, {3}, {}, {}}, w, false, 1);
+    CHECK(r.n_samples == 3 && r.n_chunks == 3 && r.n_records == 4 && w.files_written() == 3);
+    CHECK(slurp(dir + "/HG1.fasta") == ">T_1\nMEDLHENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVTESTFRAMESHIFT\n");
+    CHECK(slurp(dir + "/HG2.fasta") == ">T_1\nMEDLGTESTENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVLSTLRSLNNFISQRVEGGSGLEELERG.\n");
+    CHECK(slurp(dir + "/HG3.fasta").empty());
+}
+
 int main(int argc, char** argv) {
     test_engine_from_str();
     test_batch_reindexing();
@@ -134,6 +161,7 @@ int main(int argc, char** argv) {
                 CHECK(out.substr(hb.out_base(h) + se.first, se.second - se.first) == cases[i].expect);  // SequenceTape::get_seq
             }
     }
+    if (argc > 2) test_pipeline_writes_the_golden_records(ctx, argv[2]);
     std::printf("%s (%zu golden cases x 4 paths)\n", failures ? "FAILED" : "OK", cases.size());
     return failures ? 1 : 0;
 }

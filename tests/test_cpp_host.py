@@ -53,5 +53,8 @@ def test_cpp_host_builds_and_host_only_part_passes(binary):
 def test_cpp_host_golden_vectors_on_gpu(binary, tmp_path):
     cases = str(tmp_path / "cases.txt")
     assert write_cases(cases) >= 25
-    p = subprocess.run([binary, cases], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    outdir = tmp_path / "fasta"
+    outdir.mkdir()
+    p = subprocess.run([binary, cases, str(outdir)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert p.returncode == 0 and "OK" in p.stdout, p.stdout
+    assert sorted(f.name for f in outdir.iterdir()) == ["HG1.fasta", "HG2.fasta", "HG3.fasta"]
