@@ -29,8 +29,41 @@ for layout in ("aligned", "packed"):
     bb = C.synth_batch(prot, cat, 6, 7, layout=layout)
     want = np.zeros(bb.n_residues, np.uint8)
     assert cengine.batch_execute(bb.task_begin, bb.tasks, prot.residues, bb.alt, bb.alt_base, want, bb.out_base)[0] == 0
-    out, _ = eng.execute_batch(bb.task_begin, bb.tasks, None, bb.alt, bb.alt_base, bb.out_base)
-    ok &= bool(np.array_equal(out, want))
+    for hint in (False, True):  # interleaved tile order, then tape order (V2P_FLAG_ALIGNED_LAYOUT)
+        out, _ = eng.execute_batch(bb.task_begin, bb.tasks, None, bb.alt, bb.alt_base, bb.out_base, aligned_layout=hint)
+        ok &= bool(np.array_equal(out, want))
 res = eng.execute_soa([(0, 1, 1, 8), (0, 4, 1, 4), (0, 6, 2, 6)], "ABCFEFGH", "HGFEFCBA", "x" * 10, fill_dot=False)
 ok &= res.astype(np.uint8).tobytes() == b"xxxxExGHBx"
+# ---- the widened path: device task generation (class tables + FASTA framing, general catalogue), pipeline, gzip
+import zlib
+from tests.test_gpu_taskgen_general import random_world
+from vcf2prot_b200.pipeline import DevicePipeline, csr_lists
+from vcf2prot_b200.taskgen import DeviceCatalogue, execute_generated
+
+hap, site = C.select_sites(cat, 8, np.random.default_rng(3))
+plain = C.build_batch(prot, cat, hap, site, 8, "global", "packed")
+img = C.fasta_image(prot, plain)
+want = np.zeros(img.n_residues, np.uint8)
+assert cengine.batch_execute(img.task_begin, img.tasks, prot.residues, img.alt, img.alt_base, want, img.out_base)[0] == 0
+pipe = DevicePipeline(eng, prot, cat, lanes=2)
+sb, sites = csr_lists(hap, site, 8)
+for gz in (False, True):
+    out = np.zeros(len(want) + 4096, np.uint8)
+    fb, _ = pipe.run_lists(sb, sites, 4, 1, gz, out=out)
+    for s_ in range(4):
+        got = out[int(fb[s_]):int(fb[s_ + 1])].tobytes()
+        ok &= (zlib.decompress(got, wbits=31) if gz else got) == want[int(img.out_base[2 * s_]):int(img.out_base[2 * s_ + 2])].tobytes()
+pipe.close()
+w = random_world(11, n_tx=12, n_hap=10)
+dc = DeviceCatalogue.from_instructions(*w.cat_args)
+g = dc.generate_lists(w.site_begin, w.sites)
+eng.set_reference(w.tape)
+execute_generated(eng, g)
+tape = dc.read(g.batch.out, g.batch.n_out, np.uint8)
+ob = dc.read(g.batch.out_base, 11, np.uint64)
+from oracle import taskgen as T
+for h in range(10):
+    tasks, alt, ann, res_len, _ = w.oracle_hap(h)
+    ok &= tape[int(ob[h]):int(ob[h + 1])].tobytes().decode() == T.execute_tasks(tasks, w.tape.tobytes().decode(), alt, res_len)
+dc.close()
 print("SANITIZE_PROBE", "OK" if ok else "MISMATCH")
