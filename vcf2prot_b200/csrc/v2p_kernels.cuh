@@ -422,6 +422,8 @@ __device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const ui
     *dst = n;
 }
 
+constexpr int kLaneRunBytes = 512;  // out-of-phase runs up to this many fully covered bytes are copied by one lane
+
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
 // parallelism); MINB: CTAs per SM the register allocation is held to.
 // FLAGS: 1 = L2 cache-policy hints; 2 = haplotype-interleaved tile order (see below).
@@ -578,6 +580,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             const uint8_t* tma_src = nullptr;
             bool tma_alt = false;  // alteration payloads are read once (evict_first), reference runs are re-read (evict_last)
             bool has_lead = false, onT = false, onH = false, onM = false;
+            int lane_v0 = 0, lane_v1 = 0;  // fully covered vectors of a short out-of-phase run, copied by this lane
             int pvh = 0, pvt = 0, pa1 = 0, pb2 = 16;
             if (tr < t_hi) {
                 const uint4 raw = tb == t_lo ? raw0 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
@@ -612,6 +615,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                             tma_src = p.ref_rep + (uint64_t)r * p.rep_stride + (uint64_t)(q + v0b) + r;
                             tma_dst = (uint32_t)v0b;
                             tma_bytes = (uint32_t)(v1b - v0b);
+                        } else if (v1b - v0b <= kLaneRunBytes) {
+                            // a short out-of-phase run (an alteration payload, typically): this lane copies it alone,
+                            // below -- cheaper than waking the whole-tile owner scan for a few vectors
+                            lane_v0 = v0b >> 4, lane_v1 = v1b >> 4;
                         } else {
                             lead[v0b >> 4] = (uint8_t)(lane + 1);
                             v1 = (uint32_t)(v1b >> 4);
@@ -656,6 +663,21 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     const uint8_t* __restrict__ sp = reinterpret_cast<const uint8_t*>(p0) + (pvh << 4);
                     uint8_t* d = tile + (pvh << 4);
                     for (int j = pa1; j < pb2; ++j) d[j] = __ldg(sp + j);
+                }
+            }
+            if (lane_v1 > lane_v0) {  // four vectors per round: five aligned loads in flight, then realign + store
+                const unsigned long long sa = (unsigned long long)(p0 + (long long)lane_v0 * 16);
+                const uint32_t sh = (uint32_t)sa & 15u;  // != 0: in-phase runs went to the TMA unit
+                const uint4* ap = reinterpret_cast<const uint4*>(sa - sh);
+                uint4* const tv = reinterpret_cast<uint4*>(tile);
+                for (int v = lane_v0; v < lane_v1; v += 4, ap += 4) {
+                    const int n = lane_v1 - v;
+                    const uint4 c0 = __ldg(ap), c1 = __ldg(ap + 1);
+                    const uint4 c2 = n > 1 ? __ldg(ap + 2) : c1, c3 = n > 2 ? __ldg(ap + 3) : c1, c4 = n > 3 ? __ldg(ap + 4) : c1;
+                    tv[v] = realign16(c0, c1, sh);
+                    if (n > 1) tv[v + 1] = realign16(c1, c2, sh);
+                    if (n > 2) tv[v + 2] = realign16(c2, c3, sh);
+                    if (n > 3) tv[v + 3] = realign16(c3, c4, sh);
                 }
             }
             if (!__any_sync(0xffffffffu, has_lead)) continue;  // nothing for the register path in this batch
