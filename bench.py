@@ -595,6 +595,24 @@ def main():
                       "records_equal_primary_layout": bool(rec_ok),
                       "what": "same cohort, Task batch generated on the device in the other layout (v2p_generate_tasks) and "
                               "executed in place; per-call CUDA events, %d calls" % len(runs)}
+        # ---- the general catalogue (every instruction code; one thread per transcript) on the same lists
+        dg = DeviceCatalogue.from_instructions(*C.instruction_arrays(prot, cat), device=local_rank)
+        sb_all = np.zeros(n_hap + 1, np.uint64)
+        np.cumsum(np.bincount(batch.kept_hap, minlength=n_hap), out=sb_all[1:])
+        dg.generate_lists(sb_all, batch.kept_site)  # warm-up (allocations)
+        gg = dg.generate_lists(sb_all, batch.kept_site)
+        g_same = int(gg.batch.n_tasks) == (n_tasks if args.layout == "packed" else int(go.batch.n_tasks))
+        if args.layout == "packed":
+            m = min(n_tasks, 1 << 22)
+            g_same = (g_same and int(gg.batch.n_out) == n_out and
+                      bool(np.array_equal(dg.read(gg.batch.tasks, 4 * m, np.uint32).reshape(-1, 4), batch.tasks[:m])) and
+                      bool(np.array_equal(dg.read(gg.batch.tasks + 16 * (n_tasks - m), 4 * m, np.uint32).reshape(-1, 4), batch.tasks[n_tasks - m:])) and
+                      bool(np.array_equal(dg.read(gg.batch.out_base, n_hap + 1, np.uint64), batch.out_base)))
+        taskgen["general_catalogue"] = {"gen_ms": gg.gen_ms, "tasks_per_s": int(gg.batch.n_tasks) / (gg.gen_ms * 1e-3),
+                                        "equals_host_producer": bool(g_same), "skipped_transcripts": int(gg.n_skipped),
+                                        "what": "v2p_catalogue_create_ins + v2p_generate_tasks: the reference's Instruction values, "
+                                                "all 22 codes' rules, one thread per transcript-on-haplotype (packed layout)"}
+        dg.close()
         # ---- FORMAT/BCSQ bit-mask matrix -> per-haplotype site lists -> Task batch, on the device
         md_samples = min(n_hap // 2, args.maskdecode_samples)
         if md_samples > 0:

@@ -251,3 +251,34 @@ def test_pipeline_over_the_general_catalogue(gpu_engine, gzip):
         got = out[int(fb[s]):int(fb[s + 1])].tobytes()
         assert (zlib.decompress(got, wbits=31) if gzip else got).decode() == want, s
     pipe.close()
+
+
+@pytest.mark.parametrize("fasta", [False, True])
+def test_general_catalogue_equals_the_class_tables_on_a_synthetic_cohort(gpu_engine, fasta):
+    """Two implementations of the same rules -- one thread per site over class tables, one thread per transcript over
+    Instruction values -- give the same arrays on a cohort with all seven classes (packed layout, plain and FASTA)."""
+    from vcf2prot_b200 import cohort as C
+
+    prot = C.make_proteome(seed=71, n_tx=300, mu=5.3, sigma=0.7, lo=30, hi=3000)
+    cat = C.make_catalogue(prot, 8000, seed=72, mix=(0.55, 0.10, 0.10, 0.08, 0.07, 0.05, 0.05), fs_mean=30, fs_max=600, sl_max=120)
+    cat.af[:] = np.random.default_rng(8).choice([0.01, 0.05, 0.2, 0.5], size=cat.n)
+    hap, site = C.select_sites(cat, 50, np.random.default_rng(9))
+    kept = C.build_batch(prot, cat, hap, site, 50, "global", "packed")  # drops sites behind a truncating one (cohort rule)
+    hap, site = kept.kept_hap, kept.kept_site
+    a = DeviceCatalogue(prot, cat, 0)
+    b = DeviceCatalogue.from_instructions(*C.instruction_arrays(prot, cat))
+    for dc in (a, b):
+        dc.set_names(*C.default_names(prot))
+    ga = a.generate(hap, site, 50, aligned=False, fasta=fasta)
+    sb = np.zeros(51, np.uint64)
+    np.cumsum(np.bincount(hap, minlength=50), out=sb[1:])
+    gb = b.generate_lists(sb, site, fasta=fasta)
+    assert (ga.batch.n_tasks, ga.batch.n_alt, ga.batch.n_out, ga.n_rows) == (gb.batch.n_tasks, gb.batch.n_alt, gb.batch.n_out, gb.n_rows)
+    for f, n, dt in (("task_begin", 51, np.uint64), ("alt_base", 51, np.uint64), ("out_base", 51, np.uint64),
+                     ("tasks", 4 * ga.batch.n_tasks, np.uint32), ("alt", ga.batch.n_alt, np.uint8)):
+        assert np.array_equal(a.read(getattr(ga.batch, f), n, dt), b.read(getattr(gb.batch, f), n, dt)), f
+    for f, dt in (("ann_hap", np.uint32), ("ann_tx", np.uint32), ("ann_start", np.uint64), ("ann_end", np.uint64)):
+        assert np.array_equal(a.read(getattr(ga, f), ga.n_rows, dt), b.read(getattr(gb, f), gb.n_rows, dt)), f
+    assert gb.n_skipped == 0
+    a.close()
+    b.close()

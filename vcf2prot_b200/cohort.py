@@ -159,6 +159,18 @@ def make_catalogue(prot: Proteome, n_sites: int, seed: int, mix=MIX_C2, ins_max:
     return Catalogue(t, p, cls, rlen, doff, dlen, af.astype(np.float32), pool)
 
 
+def instruction_arrays(prot: Proteome, cat: Catalogue):
+    """The catalogue as reference `Instruction` values (instruction.rs:6-16) for the general device catalogue
+    (v2p_catalogue_create_ins / DeviceCatalogue.from_instructions): what Instruction::from_mutation yields for the seven
+    classes -- M: len 1; I: len = data length (anchor + inserted); D: len = deleted residues (ref allele - 1), data = anchor;
+    F / L: len = data length; G / 0: nothing -- plus the V2P_INS_INVALIDATES flag of frameshift and stop_gained
+    (instruction.rs:1083-1094).  -> positional arguments of DeviceCatalogue.from_instructions."""
+    code = np.frombuffer(b"MIDFGL0", np.uint8)[cat.cls]
+    length = np.select([cat.cls == CLS_M, cat.cls == CLS_D, (cat.cls == CLS_G) | (cat.cls == CLS_0)], [1, cat.rlen - 1, 0], cat.dlen)
+    flags = np.where((cat.cls == CLS_F) | (cat.cls == CLS_G), 2, 0).astype(np.uint8)
+    return (prot.offsets.astype(np.uint64), cat.t, code, flags, cat.p, cat.p, length, cat.doff, cat.dlen, cat.pool)
+
+
 def site_csq(prot: Proteome, cat: Catalogue, i: int) -> str:
     """The bcftools/csq string of site i (for the oracle / reference-binary side of the tests)."""
     t, p, c = int(cat.t[i]), int(cat.p[i]), int(cat.cls[i])
