@@ -32,6 +32,7 @@ typedef struct v2p_pipeline v2p_pipeline;
 
 #define V2P_PIPE_MAX_LANES 4
 #define V2P_PIPE_GZIP 0x1u /* deliver one gzip member per sample instead of the plain FASTA text */
+#define V2P_PIPE_SKIP_ABORTS 0x2u /* general catalogue lanes: V2P_GEN_SKIP_ABORTS (count, do not fail; v2p_taskgen.h) */
 
 /* `e`: engine with the proteome registered (v2p_engine_set_reference).  `lanes`: 1..4 catalogue objects created from
  * the SAME arrays, names set (v2p_catalogue_set_names); each lane owns the device buffers of one chunk in flight.
@@ -54,6 +55,8 @@ typedef struct {
     uint64_t h2d_bytes;                   /* site lists (or the mask matrix) uploaded                          */
     float decode_ms, gen_ms, exec_ms, gzip_ms; /* device time per stage, summed over chunks (CUDA events)     */
     double wall_s;                        /* host wall clock of the whole call                                 */
+    uint64_t n_skipped, n_aborted;        /* general catalogue: transcripts skipped ("must be the last mutation") and
+                                             left out where the reference would abort (V2P_PIPE_SKIP_ABORTS)    */
 } v2p_pipeline_result;
 
 /* Destination: either `out` (host memory, pinned for full PCIe rate; files are concatenated, file s =

@@ -72,6 +72,10 @@ void v2p_catalogue_destroy(v2p_catalogue* c);
  *   usize underflow / negative size      -> V2P_ERR_TASKGEN naming haplotype and transcript (the reference aborts)
  * The rules are csrc/v2p_taskgen_rules.cuh (also compiled for the host by tests/cpp/taskgen_rules_test.cpp).
  * Generations from this catalogue use the reference's packed layout (V2P_GEN_ALIGNED is refused); V2P_GEN_FASTA works. */
+#define V2P_GEN_SKIP_ABORTS 0x4u /* general catalogue: a transcript on which the reference would abort is left out (as if
+                                  * it carried no supported mutation) and counted in n_aborted, instead of failing the
+                                  * whole generation with V2P_ERR_TASKGEN -- one malformed record should not stop a
+                                  * 50,000-sample run; without the flag the behaviour is the reference's             */
 #define V2P_INS_STAR 0x1u
 #define V2P_INS_INVALIDATES 0x2u
 int v2p_catalogue_create_ins(int cuda_device, uint64_t n_tx, const uint64_t* tx_offsets, uint64_t n_sites,
@@ -97,6 +101,7 @@ typedef struct {
     uint64_t n_sites;          /* selected sites consumed (those after a truncating variant emit nothing)         */
     float gen_ms;              /* device time of the generation (CUDA events)                                     */
     uint64_t n_skipped;        /* general catalogue: transcripts skipped by "must be the last mutation"           */
+    uint64_t n_aborted;        /* general catalogue, V2P_GEN_SKIP_ABORTS: transcripts left out where the reference aborts */
 } v2p_generated;
 
 /* site_begin[n_hap+1] / sites[site_begin[n_hap]]: host pointers; sites ascending inside each haplotype. */

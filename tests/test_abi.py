@@ -46,7 +46,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Task16) == 16
     assert C.sizeof(_lib.Batch) == 13 * 8
     assert C.sizeof(_lib.Result) == 32
-    assert C.sizeof(_lib.Generated) == 13 * 8 + 8 + 4 * 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.Generated) == 13 * 8 + 8 + 4 * 8 + 8 + 8 + 8 + 8
 
 
 def test_engine_from_str_contract(lib):

@@ -282,3 +282,60 @@ def test_general_catalogue_equals_the_class_tables_on_a_synthetic_cohort(gpu_eng
     assert gb.n_skipped == 0
     a.close()
     b.close()
+
+
+def test_skip_aborts_leaves_the_transcript_out_and_counts_it(gpu_engine):
+    """V2P_GEN_SKIP_ABORTS: haplotypes that would stop the reference are generated without the offending transcripts;
+    every other transcript comes out as the oracle has it."""
+    bad = random_world(31, n_hap=6, want="gen_panic")
+    dc = DeviceCatalogue.from_instructions(*bad.cat_args)
+    g = dc.generate_lists(bad.site_begin, bad.sites, skip_aborts=True)
+    assert g.n_aborted >= 6
+    rows = list(zip(dc.read(g.ann_hap, g.n_rows, np.uint32), dc.read(g.ann_tx, g.n_rows, np.uint32),
+                    dc.read(g.ann_start, g.n_rows, np.uint64), dc.read(g.ann_end, g.n_rows, np.uint64)))
+    tb = dc.read(g.batch.task_begin, 7, np.uint64)
+    tasks = dc.read(g.batch.tasks, 4 * g.batch.n_tasks, np.uint32).reshape(-1, 4)
+    n_checked = 0
+    for h in range(6):
+        # per transcript: the oracle either aborts (then the device left it out) or gives the tasks the device emitted
+        want_rows, want_tasks, res_c, alt_c = [], [], 0, 0
+        for ti in T.haplotype_instructions(T.group_muts_per_transcript(bad.hap_csqs[h]), bad.refs):
+            try:
+                size = ti.expected_results_size()
+                gt = ti.get_g_rep(bad.refs)
+            except T.RefPanic:
+                continue
+            except T.TaskGenError:
+                res_c += 0
+                continue
+            t = bad.tx[ti.name]
+            want_tasks += [(c, sp + (int(bad.off[t]) if c == 0 else alt_c), ln, spr + res_c) for (c, sp, ln, spr) in gt.tasks]
+            want_rows.append((t, gt.annotation[0] + res_c, gt.annotation[1] + res_c))
+            alt_c += len(gt.alt)
+            res_c += gt.res_len
+        assert [(int(t), int(s), int(e)) for hh, t, s, e in rows if hh == h] == want_rows, h
+        assert [(int(s), int(a), int(l), int(d)) for a, l, d, s in tasks[int(tb[h]):int(tb[h + 1])]] == want_tasks, h
+        n_checked += len(want_rows)
+    assert n_checked > 0
+    dc.close()
+
+
+def test_pipeline_skip_aborts(gpu_engine):
+    from vcf2prot_b200.pipeline import DevicePipeline
+
+    bad = random_world(31, n_hap=6, want="gen_panic")
+    name_off = (9 * np.arange(len(bad.names) + 1)).astype(np.uint64)
+    cats = []
+    for _ in range(2):
+        dc = DeviceCatalogue.from_instructions(*bad.cat_args)
+        dc.set_names(name_off, np.frombuffer("".join(bad.names).encode(), np.uint8))
+        cats.append(dc)
+    gpu_engine.set_reference(bad.tape)
+    pipe = DevicePipeline(gpu_engine, cats=cats)
+    out = np.zeros(1 << 20, np.uint8)
+    with pytest.raises(EngineError) as ei:  # the reference's behaviour: the run stops
+        pipe.run_lists(bad.site_begin, bad.sites, 3, 2, False, out=out)
+    assert ei.value.status == L.ERR_TASKGEN
+    fb, res = pipe.run_lists(bad.site_begin, bad.sites, 3, 2, False, out=out, skip_aborts=True)
+    assert res.n_aborted >= 6 and res.n_records == out[: int(fb[-1])].tobytes().count(b">")
+    pipe.close()

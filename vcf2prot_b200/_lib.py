@@ -14,7 +14,7 @@ ERR_NOT_CONTIGUOUS, ERR_NOT_GPU_ENGINE, ERR_TASKGEN = 7, 9, 10
 ENGINE_ST, ENGINE_MT, ENGINE_GPU = 0, 1, 2
 FLAG_FILL_DOT, FLAG_VALIDATE, FLAG_DEVICE_PTRS, FLAG_ASYNC, FLAG_ALIGNED_LAYOUT = 1, 2, 4, 8, 16
 REF_NO_TMA = 0x200
-GEN_ALIGNED, GEN_FASTA = 1, 2
+GEN_ALIGNED, GEN_FASTA, GEN_SKIP_ABORTS = 1, 2, 4
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "BAD_ENGINE", 4: "BAD_STREAM", 5: "RES_OOB", 6: "SRC_OOB",
                 7: "NOT_CONTIGUOUS", 9: "NOT_GPU_ENGINE", 10: "TASKGEN"}
@@ -38,7 +38,7 @@ class Result(C.Structure):
 class Generated(C.Structure):
     _fields_ = [("batch", Batch), ("n_rows", C.c_uint64), ("ann_hap", C.c_void_p), ("ann_tx", C.c_void_p),
                 ("ann_start", C.c_void_p), ("ann_end", C.c_void_p), ("n_sites", C.c_uint64), ("gen_ms", C.c_float),
-                ("n_skipped", C.c_uint64)]
+                ("n_skipped", C.c_uint64), ("n_aborted", C.c_uint64)]
 
 
 # every symbol include/*.h declares: (restype, argtypes)
@@ -57,12 +57,12 @@ class PipelineResult(C.Structure):
     _fields_ = [("n_samples", C.c_uint64), ("n_chunks", C.c_uint64), ("n_sites", C.c_uint64), ("n_tasks", C.c_uint64),
                 ("n_records", C.c_uint64), ("image_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("decode_ms", C.c_float), ("gen_ms", C.c_float), ("exec_ms", C.c_float), ("gzip_ms", C.c_float),
-                ("wall_s", C.c_double)]
+                ("wall_s", C.c_double), ("n_skipped", C.c_uint64), ("n_aborted", C.c_uint64)]
 
 
 # int sink(void* user, uint64_t first_sample, uint64_t n_samples, const uint8_t* data, const uint64_t* file_begin)
 FILE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64))
-PIPE_GZIP = 1
+PIPE_GZIP, PIPE_SKIP_ABORTS = 1, 2
 
 SYMBOLS = {
     "v2p_abi_version": (C.c_int, []),

@@ -118,6 +118,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
     if (out && !file_begin) return pfail(p, V2P_ERR_INVALID_ARG, "file_begin is NULL");
     if (!chunk_samples) chunk_samples = 128;
     const bool gzip = (flags & V2P_PIPE_GZIP) != 0;
+    const uint32_t gen_flags = V2P_GEN_FASTA | ((flags & V2P_PIPE_SKIP_ABORTS) ? V2P_GEN_SKIP_ABORTS : 0u);
     PCU(p, cudaSetDevice(p->device));
     for (uint32_t i = 0; i < p->n_lanes; ++i) p->lanes[i].pending = false;
     uint64_t total = 0;
@@ -134,7 +135,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
         for (uint64_t h = 0; h <= nh; ++h) sb[h] = src.site_begin[h0 + h] - src.site_begin[h0];
         v2p_generated g;
         if (src.h_sites) {
-            rc = v2p_generate_tasks(l.cat, nh, sb.data(), src.h_sites + src.site_begin[h0], V2P_GEN_FASTA, &g);
+            rc = v2p_generate_tasks(l.cat, nh, sb.data(), src.h_sites + src.site_begin[h0], gen_flags, &g);
             res->h2d_bytes += sb[nh] * 4 + (nh + 1) * 8;
         } else {
             if ((rc = grow_dev(p, l.d_begin, l.d_begin_cap, (nh + 1) * 8))) break;
@@ -143,7 +144,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
             memset(&lists, 0, sizeof lists);
             lists.n_hap = nh, lists.n_sites = sb[nh];
             lists.site_begin = (const uint64_t*)l.d_begin, lists.sites = src.d_sites + src.site_begin[h0];
-            rc = v2p_generate_tasks_from_lists(l.cat, &lists, V2P_GEN_FASTA, &g);
+            rc = v2p_generate_tasks_from_lists(l.cat, &lists, gen_flags, &g);
             res->h2d_bytes += (nh + 1) * 8;
         }
         if (rc) {
@@ -201,6 +202,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
         res->n_sites += g.n_sites, res->n_tasks += g.batch.n_tasks, res->n_records += g.n_rows;
         res->image_bytes += g.batch.n_out, res->out_bytes += bytes;
         res->gen_ms += g.gen_ms, res->exec_ms += er.kernel_ms;
+        res->n_skipped += g.n_skipped, res->n_aborted += g.n_aborted;
         res->n_chunks++;
     }
     // drain in order: the oldest chunk sits in the lane the next chunk would have taken

@@ -307,8 +307,8 @@ struct InsGen {
     uint8_t* g_status;
     uint64_t *c_tasks, *c_alt, *c_name, *c_adv, *c_tape, *c_rows, *c_skip;  // scan inputs
     uint64_t *x_tasks, *x_alt, *x_name, *x_adv, *x_tape, *x_rows, *x_skip;  // exclusive scans
-    unsigned long long* err;  // min group index the reference aborts on
-    int fasta;
+    unsigned long long* err;  // [0] min group index the reference aborts on, [1] how many such groups
+    int fasta, skip_aborts;
 };
 
 __global__ void k_ti_mark(InsGen g, InsCat c) {
@@ -351,8 +351,12 @@ __global__ void k_ti_count(InsGen g, InsCat c) {
     while (je < j1 && c.tx[g.sites[je]] == t) ++je;
     const InsGet get{&c, g.sites, j};
     v2p_rules::NullSink null;
-    const v2p_rules::TgSummary s = v2p_rules::tg_transcript(get, (int)(je - j), c.tx_off[t + 1] - c.tx_off[t], null);
-    if (s.status == v2p_rules::TG_PANIC) atomicMin(g.err, (unsigned long long)gi);
+    v2p_rules::TgSummary s = v2p_rules::tg_transcript(get, (int)(je - j), c.tx_off[t + 1] - c.tx_off[t], null);
+    if (s.status == v2p_rules::TG_PANIC) {
+        atomicMin(g.err, (unsigned long long)gi);
+        atomicAdd(g.err + 1, 1ull);
+        if (g.skip_aborts) s = v2p_rules::TgSummary{v2p_rules::TG_ABSENT, 0, 0, 0};  // V2P_GEN_SKIP_ABORTS
+    }
     const bool row = s.status == v2p_rules::TG_OK || s.status == v2p_rules::TG_EMPTY;
     const uint64_t adv = s.status == v2p_rules::TG_OK ? s.size : 0;
     const uint64_t nlen = g.fasta ? c.name_off[t + 1] - c.name_off[t] : 0;
@@ -986,7 +990,7 @@ int generate_ins_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, con
     if (fasta && !c->has_names) return cfail(c, V2P_ERR_INVALID_ARG, "V2P_GEN_FASTA needs v2p_catalogue_set_names first");
     int rc;
     if ((rc = need(c, c->site_hap, n_sel * 4 + 16)) || (rc = need(c, c->gi_newg, (n_sel + 1) * 8)) ||
-        (rc = need(c, c->gi_gx, (n_sel + 1) * 8)) || (rc = need(c, c->gi_err, 8)) || (rc = need(c, c->task_begin, (n_hap + 1) * 8)) ||
+        (rc = need(c, c->gi_gx, (n_sel + 1) * 8)) || (rc = need(c, c->gi_err, 16)) || (rc = need(c, c->task_begin, (n_hap + 1) * 8)) ||
         (rc = need(c, c->alt_base, (n_hap + 1) * 8)) || (rc = need(c, c->out_base, (n_hap + 1) * 8)))
         return rc;
     CU(c, c->pub.reserve(64));
@@ -1000,7 +1004,9 @@ int generate_ins_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, con
     g.newg = (uint64_t*)c->gi_newg.p, g.g_x = (uint64_t*)c->gi_gx.p;
     g.err = (unsigned long long*)c->gi_err.p;
     g.fasta = fasta ? 1 : 0;
+    g.skip_aborts = (flags & V2P_GEN_SKIP_ABORTS) ? 1 : 0;
     CU(c, cudaMemsetAsync(g.err, 0xFF, 8, st));
+    CU(c, cudaMemsetAsync(g.err + 1, 0, 8, st));
     if (n_sel) {
         Sel sh{};
         sh.n_sel = n_sel, sh.n_hap = n_hap, sh.site_begin = d_site_begin, sh.site_hap = (uint32_t*)c->site_hap.p;
@@ -1031,16 +1037,17 @@ int generate_ins_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, con
         if ((rc = xsum(c, *cin[i], *cx[i], G + 1))) return rc;
     {
         v2p::PubList pl{};
-        const uint64_t* tot[7] = {g.x_tasks + G, g.x_alt + G, g.x_name + G, g.x_tape + G, g.x_rows + G, g.x_skip + G, (const uint64_t*)g.err};
-        for (int i = 0; i < 7; ++i) pl.src[i] = (const unsigned long long*)tot[i];
-        pl.n = 7;
+        const uint64_t* tot[8] = {g.x_tasks + G, g.x_alt + G, g.x_name + G, g.x_tape + G, g.x_rows + G, g.x_skip + G,
+                                  (const uint64_t*)g.err, (const uint64_t*)(g.err + 1)};
+        for (int i = 0; i < 8; ++i) pl.src[i] = (const unsigned long long*)tot[i];
+        pl.n = 8;
         v2p::k_publish_list<<<1, 32, 0, st>>>(c->pub.p, pl);
     }
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(st));
     const uint64_t n_tasks = c->pub.p[0], n_alt = c->pub.p[1] + c->pub.p[2], n_out = c->pub.p[3], n_rows = c->pub.p[4],
-                   n_skip = c->pub.p[5], bad = c->pub.p[6];
-    if (bad != ~0ull) {  // name the transcript the reference aborts on
+                   n_skip = c->pub.p[5], bad = c->pub.p[6], n_abort = c->pub.p[7];
+    if (bad != ~0ull && !g.skip_aborts) {  // name the transcript the reference aborts on
         uint32_t hh = 0, tt = 0;
         cudaMemcpy(&hh, g.g_hap + bad, 4, cudaMemcpyDeviceToHost);
         cudaMemcpy(&tt, g.g_tx + bad, 4, cudaMemcpyDeviceToHost);
@@ -1068,7 +1075,7 @@ int generate_ins_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, con
     out->batch.n_hap = n_hap, out->batch.n_tasks = n_tasks, out->batch.n_alt = n_alt, out->batch.n_out = n_out;
     out->n_rows = n_rows;
     out->ann_hap = o.ann_hap, out->ann_tx = o.ann_tx, out->ann_start = o.ann_start, out->ann_end = o.ann_end;
-    out->n_sites = n_sel, out->gen_ms = ms, out->n_skipped = n_skip;
+    out->n_sites = n_sel, out->gen_ms = ms, out->n_skipped = n_skip, out->n_aborted = n_abort;
     return V2P_OK;
 }
 

@@ -117,7 +117,8 @@ class DevicePipeline:
         return out.ctypes.data_as(C.c_void_p), out.nbytes, fb.ctypes.data_as(C.c_void_p), fb
 
     def run_lists(self, site_begin: np.ndarray, sites: np.ndarray, n_samples: int, chunk_samples: int = 128, gzip: bool = False,
-                  out: Optional[np.ndarray] = None, sink: Optional[Callable] = None) -> Tuple[Optional[np.ndarray], L.PipelineResult]:
+                  out: Optional[np.ndarray] = None, sink: Optional[Callable] = None,
+                  skip_aborts: bool = False) -> Tuple[Optional[np.ndarray], L.PipelineResult]:
         """site_begin[2*n_samples+1], sites: the cohort's CSR site lists.  Either `out` (uint8 host array; returns the
         file_begin offsets into it) or `sink(first_sample, n, data, file_begin)` called per chunk in sample order."""
         sb, st_ = np.ascontiguousarray(site_begin, np.uint64), np.ascontiguousarray(sites, np.uint32)
@@ -125,7 +126,8 @@ class DevicePipeline:
         cb, user, keep = self._sink(sink)
         res = L.PipelineResult()
         st = self._lib.v2p_pipeline_run_lists(self._h, n_samples, sb.ctypes.data_as(C.c_void_p), st_.ctypes.data_as(C.c_void_p),
-                                              chunk_samples, L.PIPE_GZIP if gzip else 0, op, cap, fbp, cb, user, C.byref(res))
+                                              chunk_samples, (L.PIPE_GZIP if gzip else 0) | (L.PIPE_SKIP_ABORTS if skip_aborts else 0),
+                                              op, cap, fbp, cb, user, C.byref(res))
         del keep
         if st:
             raise EngineError(st, self._err())

@@ -49,12 +49,13 @@ class DeviceCatalogue:
         self._h = h
         return self
 
-    def generate_lists(self, site_begin: np.ndarray, sites: np.ndarray, fasta: bool = False) -> L.Generated:
-        """CSR site lists (site_begin[n_hap+1], sites) -> generated batch, packed layout."""
+    def generate_lists(self, site_begin: np.ndarray, sites: np.ndarray, fasta: bool = False, skip_aborts: bool = False) -> L.Generated:
+        """CSR site lists (site_begin[n_hap+1], sites) -> generated batch, packed layout.  skip_aborts: leave out (and
+        count) transcripts the reference would abort on instead of raising V2P_ERR_TASKGEN."""
         sb, st_ = np.ascontiguousarray(site_begin, np.uint64), np.ascontiguousarray(sites, np.uint32)
         g = L.Generated()
         st = self._lib.v2p_generate_tasks(self._h, len(sb) - 1, sb.ctypes.data_as(C.c_void_p), st_.ctypes.data_as(C.c_void_p),
-                                          self._flags(False, fasta), C.byref(g))
+                                          self._flags(False, fasta) | (L.GEN_SKIP_ABORTS if skip_aborts else 0), C.byref(g))
         if st:
             raise EngineError(st, (self._lib.v2p_catalogue_last_error(self._h) or b"").decode())
         return g
