@@ -1,0 +1,113 @@
+"""CPU suite: the device generator's rules (csrc/v2p_taskgen_rules.cuh, host build) against the REFERENCE BINARY itself --
+not the oracle -- on seeded random cohorts over all 22 supported consequence classes: every FASTA record the reference's
+own prebuilt tool writes (oracle/_ref/vcf2prot, `-g st`) must be what the rules' tasks produce, and every transcript the
+rules skip / drop / leave empty must be absent / empty in its output.  The oracle only pre-filters mutation sets on which
+the reference aborts (one abort would end the whole run of the binary)."""
+import random
+import subprocess
+
+import pytest
+
+from oracle import refbin
+from oracle import taskgen as T
+from tests.test_taskgen_rules import AA, OK, EMPTY, case_text, random_csq, rules_binary, static_instruction  # noqa: F401
+
+pytestmark = pytest.mark.skipif(not refbin.available(), reason="oracle/_ref/vcf2prot not built (make -C oracle ref)")
+
+
+def safe_for_the_binary(csqs, refs):
+    """No abort anywhere in generation or execution (the oracle's view) -- otherwise the binary would die mid-run."""
+    try:
+        g = T.haplotype_g_rep(T.haplotype_instructions(T.group_muts_per_transcript(csqs), refs), refs)
+        T.sequence_tape_records(T.execute_tasks(g.tasks, g.ref, g.alt, g.res_len), g.annotation, 1)
+        return True
+    except T.RefPanic:
+        return False
+
+
+def random_cohort(seed, n_tx=40, n_samples=120):
+    rng = random.Random(seed)
+    refs = {"ENST%05d" % i: "M" + "".join(rng.choice(AA) for _ in range(rng.randint(11, 90))) for i in range(n_tx)}
+    pool = []
+    for name, seq in refs.items():
+        for _ in range(rng.randint(2, 6)):
+            c = random_csq(rng, name, len(seq))
+            try:
+                static_instruction(T.Mutation.from_csq(c))
+            except (T.TaskGenError, T.RefPanic):
+                continue
+            pool.append(c)
+    pool = sorted(set(pool))
+    haps = []
+    while len(haps) < 2 * n_samples:
+        csqs, used = [], set()
+        for c in rng.sample(pool, rng.randint(0, 10)):
+            m = T.Mutation.from_csq(c)
+            if (m.transcript_name, m.mut_pos) in used:
+                continue
+            used.add((m.transcript_name, m.mut_pos))
+            csqs.append(c)
+        if safe_for_the_binary(csqs, refs):
+            haps.append(csqs)
+    return refs, pool, haps
+
+
+def rules_records(binary, refs, csqs, hap_label):
+    """FASTA records of one haplotype from the rules' output alone."""
+    cases, muts_of = [], {}
+    for name, muts in T.group_muts_per_transcript(csqs):
+        muts_of[name] = muts
+        cases.append(case_text(name, muts, len(refs[name])))
+    if not cases:
+        return []
+    p = subprocess.run([binary], input="".join(cases), stdout=subprocess.PIPE, text=True, check=True)
+    recs, cur = [], None
+    blocks = {}
+    for line in p.stdout.splitlines():
+        f = line.split()
+        if f[0] == "RESULT":
+            cur = blocks[f[1]] = {"status": int(f[2]), "size": int(f[3]), "tasks": [], "alt": ""}
+        elif f[0] == "TASK":
+            cur["tasks"].append(tuple(int(x) for x in f[1:]))
+        elif f[0] == "ALT":
+            cur["alt"] = "" if f[1] == "-" else f[1]
+    # HaplotypeInstruction::get_g_rep (haplotype_instruction.rs:75-158): the tape is sized from every transcript that has
+    # instructions (skipped ones included), transcripts are laid down in name order, tasks run in that order on ONE tape
+    # (a transcript whose tasks overrun its own result spills into its neighbour, as in the reference)
+    SKIPPED = 3
+    tape_len = sum(b["size"] for b in blocks.values() if b["status"] in (OK, EMPTY, SKIPPED))
+    tape, res_c, ann = ["."] * tape_len, 0, []
+    for name in sorted(blocks):
+        b = blocks[name]
+        if b["status"] == EMPTY:
+            ann.append((name, res_c, res_c))
+        elif b["status"] == OK:
+            for (stream, src, ln, dst) in b["tasks"]:
+                seg = (b["alt"] if stream else refs[name])[src:src + ln]
+                assert len(seg) == ln and res_c + dst + ln <= tape_len, "the reference would abort here"
+                tape[res_c + dst:res_c + dst + ln] = seg
+            ann.append((name, res_c, res_c + b["size"]))
+            res_c += b["size"]
+    tape = "".join(tape)
+    return [("%s_%d" % (name, hap_label), tape[s_:e_]) for name, s_, e_ in ann]
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103, 104])
+def test_every_record_of_the_reference_binary(rules_binary, seed):
+    refs, pool, haps = random_cohort(seed)
+    n_samples = len(haps) // 2
+    samples = ["S%03d" % i for i in range(n_samples)]
+    records = []
+    for c in pool:  # one VCF record per distinct consequence; bit 0 -> haplotype 1, bit 1 -> haplotype 2
+        cells = [([0] if c in haps[2 * s] else [], [0] if c in haps[2 * s + 1] else []) for s in range(n_samples)]
+        if any(h1 or h2 for h1, h2 in cells):
+            records.append(([c], cells))
+    got, stdout, rc = refbin.run_reference(refbin.vcf_text(samples, records), refs, "st")
+    assert rc == 0, stdout[-2000:]
+    n_rec = n_empty = 0
+    for s, smp in enumerate(samples):
+        want = sorted(rules_records(rules_binary, refs, haps[2 * s], 1) + rules_records(rules_binary, refs, haps[2 * s + 1], 2))
+        assert [tuple(r) for r in got.get(smp, [])] == want, smp
+        n_rec += len(want)
+        n_empty += sum(1 for _, q in want if q == "")
+    assert n_rec > 400 and n_empty > 8
