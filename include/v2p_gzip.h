@@ -29,6 +29,7 @@ extern "C" {
 
 #define V2P_GZIP_CHUNK 16384u
 
+/* Threading: one call at a time per v2p_gzip object (it owns its scratch buffers); objects are independent. */
 typedef struct v2p_gzip v2p_gzip;
 
 int v2p_gzip_create(int cuda_device, v2p_gzip** out);

@@ -28,6 +28,8 @@
 extern "C" {
 #endif
 
+/* Threading: one v2p_pipeline_run_* at a time per pipeline object; the engine it borrows stays usable from other threads
+ * (its calls serialise on the engine's own lock).  The sink runs on the calling thread. */
 typedef struct v2p_pipeline v2p_pipeline;
 
 #define V2P_PIPE_MAX_LANES 4

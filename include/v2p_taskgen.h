@@ -37,6 +37,9 @@ enum { V2P_CLS_M = 0, V2P_CLS_I = 1, V2P_CLS_D = 2, V2P_CLS_F = 3, V2P_CLS_G = 4
                               * Packed layout only; needs v2p_catalogue_set_names.  ann_start/ann_end then bracket the
                               * sequence between header and newline. Twin: cohort.py::fasta_image.                      */
 
+/* Threading: a catalogue object owns the device buffers of ONE generation at a time -- calls on the same object must not
+ * overlap (use one object per concurrent caller / pipeline lane; the uploaded tables are small).  Objects on different
+ * GPUs, or different objects on one GPU, are independent. */
 typedef struct v2p_catalogue v2p_catalogue;
 
 /* Uploads the proteome index and the variant catalogue to `cuda_device` (host pointers).
