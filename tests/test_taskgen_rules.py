@@ -162,3 +162,26 @@ def test_random_mutation_sets_over_all_classes(rules_binary, seed):
             cases.append((key, T.alt_transcript(key, csqs), refs))
     hist = run_cases(rules_binary, cases)
     assert hist[OK] > 300 and hist[SKIPPED] > 20 and hist[ABSENT] > 5, hist
+
+
+def test_reference_task_builder_unit_tests(rules_binary):
+    """transcript_instructions.rs:806-882 (test_get_task_from_frameshift / _stop_gained / _stop_lost / _inframe_insersion):
+    the exact Task tuples and alt-tape contents those tests assert, produced here from whole transcripts (so the frameshift
+    task starts where ITS base task ends, 39, not at the hand-set 30 of the unit test)."""
+    def run(csq_aa, typ, ref_len):
+        name = "ENST00000000001"
+        m = T.Mutation.from_csq("%s|GENE|%s|protein_coding|-|%s|1C>T" % (typ, name, csq_aa))
+        p = subprocess.run([rules_binary], input=case_text(name, [m], ref_len), stdout=subprocess.PIPE, text=True, check=True)
+        tasks = [tuple(int(x) for x in l.split()[1:]) for l in p.stdout.splitlines() if l.startswith("TASK")]
+        alt = [l.split()[1] for l in p.stdout.splitlines() if l.startswith("ALT")]
+        return tasks, (alt[0] if alt and alt[0] != "-" else "")
+
+    tasks, alt = run("40VGLHFWTM*>40VDSTFGQC", "frameshift", 48)
+    assert tasks == [(0, 0, 39, 0), (1, 0, 8, 39)] and alt == "VDSTFGQC"  # :806-822  Task::new(1, 0, 8, <end of the base task>)
+    tasks, alt = run("40VGLHFWTM*>40*", "stop_gained", 48)
+    assert tasks == [(0, 0, 39, 0)] and alt == ""                        # :824-840  phi (2,0,0,0): nothing is pushed
+    tasks, alt = run("489*>489S", "stop_lost", 488)
+    assert tasks == [(0, 0, 488, 0), (1, 0, 1, 488)] and alt == "S"      # :842-861
+    tasks, alt = run("125Y>125YRR", "inframe_insertion", 300)
+    assert tasks[:2] == [(0, 0, 124, 0), (1, 0, 3, 124)] and alt == "YRR"  # :863-882
+    assert tasks[2] == (0, 125, 175, 127)
