@@ -216,6 +216,42 @@ private:
     uint64_t ref_counter_ = 0, alt_counter_ = 0, res_counter_ = 0, out_size_ = 0;
 };
 
+// sequence_tape.rs:9-117 -- the consumer of a haplotype's result tape: sequences annotated head to tail on one string.
+// The engine never sees it; it is here so that a C++ host slices results exactly as the reference does.
+class SequenceTape {
+public:
+    // sequence_tape.rs:33-41: Err("Bad Tape Encountered ...") when an annotation ends beyond the tape
+    SequenceTape(std::string seq_str, Annotation annotations) : seq_(std::move(seq_str)), ann_(std::move(annotations)) {
+        const uint64_t mx = get_max_index(ann_);
+        if (mx > seq_.size())
+            throw std::invalid_argument("Bad Tape Encountered, the provided maximum index is " + std::to_string(mx) +
+                                        " while tape length is " + std::to_string(seq_.size()));
+    }
+    const Annotation& get_annotation() const { return ann_; }
+    // sequence_tape.rs:77-89
+    std::string get_seq(const std::string& seq_name) const {
+        auto it = ann_.find(seq_name);
+        if (it == ann_.end()) throw std::out_of_range("The provided sequence name: " + seq_name + ", is not defined in the current table");
+        return seq_.substr(it->second.first, it->second.second - it->second.first);
+    }
+    // sequence_tape.rs:105-116
+    static uint64_t get_max_index(const Annotation& a) {
+        uint64_t m = 0;
+        for (const auto& kv : a) m = kv.second.second > m ? kv.second.second : m;
+        return m;
+    }
+    // personalized_genome.rs:97,107: the records of one haplotype, `>{name}_{1|2}\n{seq}\n`
+    std::string fasta_text(int hap_label) const {
+        std::string out;
+        for (const auto& kv : ann_) out += ">" + kv.first + "_" + std::to_string(hap_label) + "\n" + get_seq(kv.first) + "\n";
+        return out;
+    }
+
+private:
+    std::string seq_;
+    Annotation ann_;
+};
+
 // instruction.rs:6-16, as Instruction::from_mutation builds it with validate_s_state taken as true, plus the two facts
 // the device needs to redo that validation per haplotype (include/v2p_taskgen.h).
 struct Instruction {

@@ -52,6 +52,22 @@ static void test_batch_reindexing() {  // haplotype_instruction.rs:94-158 (golde
     CHECK(threw);  // haplotype_instruction.rs:154
 }
 
+static void test_sequence_tape() {  // sequence_tape.rs:17-31 doc-test, :95-104, :122-170 (bad tape)
+    const std::string code = "SEQ1_SEQ2_SEQ3_SEQ4_SEQ5_SEQ6";
+    v2p::Annotation m{{"1", {0, 4}}, {"2", {5, 9}}, {"3", {10, 14}}};
+    v2p::SequenceTape t(code, m);
+    CHECK(t.get_seq("1") == "SEQ1" && t.get_seq("2") == "SEQ2" && t.get_seq("3") == "SEQ3");
+    v2p::Annotation six{{"1", {0, 4}}, {"2", {5, 9}}, {"3", {10, 14}}, {"4", {15, 19}}, {"5", {20, 24}}, {"6", {25, 29}}};
+    CHECK(v2p::SequenceTape::get_max_index(six) == 29);
+    bool threw = false;
+    try { v2p::SequenceTape bad("SEQ1", v2p::Annotation{{"1", {0, 5}}}); } catch (const std::invalid_argument&) { threw = true; }
+    CHECK(threw);
+    threw = false;
+    try { t.get_seq("9"); } catch (const std::out_of_range&) { threw = true; }
+    CHECK(threw);
+    CHECK(v2p::SequenceTape("MK", v2p::Annotation{{"T", {0, 2}}, {"U", {2, 2}}}).fasta_text(2) == ">T_2\nMK\n>U_2\n\n");  // empty record
+}
+
 static void test_task_rs_vector(v2p::Context& ctx) {  // task.rs:118-144
     v2p::GIR g({v2p::Task(0, 1, 1, 8), v2p::Task(0, 4, 1, 4), v2p::Task(0, 6, 2, 6)}, {}, widen("HGFEFCBA"), widen("ABCFEFGH"),
                widen("xxxxxxxxxx"));
@@ -125,6 +141,7 @@ static void test_pipeline_writes_the_golden_records(v2p::Context& ctx, const std
 int main(int argc, char** argv) {
     test_engine_from_str();
     test_batch_reindexing();
+    test_sequence_tape();
     if (argc > 1 && !std::strcmp(argv[1], "--no-gpu")) {
         std::printf("%s (host-only part)\n", failures ? "FAILED" : "OK");
         return failures ? 1 : 0;
