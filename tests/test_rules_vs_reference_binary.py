@@ -111,3 +111,37 @@ def test_every_record_of_the_reference_binary(rules_binary, seed):
         n_rec += len(want)
         n_empty += sum(1 for _, q in want if q == "")
     assert n_rec > 400 and n_empty > 8
+
+
+def test_debug_cpu_exec_validator_against_the_binary(rules_binary):
+    """gir.rs:203-229 (DEBUG_CPU_EXEC): on random haplotypes the reference binary either runs through or prints its
+    execution table and panics at the first task that does not start where the previous one ended -- the same table and
+    the same verdict as the oracle's validator, which is what V2P_FLAG_VALIDATE is tested against on the GPU."""
+    import numpy as np
+
+    from oracle import cengine
+    from tests.helpers import u8
+
+    refs, pool, haps = random_cohort(201, n_tx=20, n_samples=45)
+    n_gap = n_clean = 0
+    for csqs in haps:
+        if not csqs:
+            continue
+        g = T.haplotype_g_rep(T.haplotype_instructions(T.group_muts_per_transcript(csqs), refs), refs)
+        if len(g.tasks) < 2:
+            continue
+        st, bad = cengine.gir_execute(g.tasks, u8(g.ref), u8(g.alt), np.zeros(g.res_len, np.uint8), True, validate=True)
+        records = [([c], [([0], [])]) for c in csqs]
+        _, stdout, rc = refbin.run_reference(refbin.vcf_text(["S1"], records), refs, "st",
+                                             env={"RUN_SELECTED_TEST": "1", "DEBUG_CPU_EXEC": "1"})
+        table = refbin.parse_cpu_exec_table(stdout)
+        if st == cengine.REF_ERR_NOT_CONTIGUOUS:
+            assert rc != 0 and "gir.rs" in stdout, stdout[-600:]
+            assert table == [tuple(t) for t in g.tasks], (table, g.tasks)  # the binary dumps the whole haplotype table
+            assert g.tasks[bad][3] != g.tasks[bad - 1][3] + g.tasks[bad - 1][2]
+            assert all(g.tasks[i][3] == g.tasks[i - 1][3] + g.tasks[i - 1][2] for i in range(1, bad))
+            n_gap += 1
+        else:
+            assert st == 0 and rc == 0, stdout[-600:]
+            n_clean += 1
+    assert n_gap >= 3 and n_clean >= 10, (n_gap, n_clean)
