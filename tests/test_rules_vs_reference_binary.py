@@ -145,3 +145,54 @@ def test_debug_cpu_exec_validator_against_the_binary(rules_binary):
             assert st == 0 and rc == 0, stdout[-600:]
             n_clean += 1
     assert n_gap >= 3 and n_clean >= 10, (n_gap, n_clean)
+
+
+def test_multiword_masks_decode_like_the_binary(rules_binary):
+    """Records with up to 40 consequences each (FORMAT/BCSQ masks of one to three 15-csq words, MaskDecoder.rs:122-153):
+    the VCF text goes to the reference binary; the same mask words go through oracle/maskdecode.py (the checker of the
+    device decode) and the rules; the records must agree -- so the decode oracle is pinned to the binary beyond the
+    reference's own unit vectors, multi-word cells included."""
+    import numpy as np
+
+    from oracle import maskdecode
+
+    refs, pool, haps = random_cohort(301, n_tx=30, n_samples=40)
+    n_samples = len(haps) // 2
+    rng = random.Random(5)
+    order = pool[:]
+    rng.shuffle(order)
+    groups, i = [], 0
+    while i < len(order):  # records of 1 .. 40 consequences
+        k = rng.choice([1, 2, 7, 15, 16, 31, 40])
+        groups.append(order[i:i + k])
+        i += k
+    site_of = {c: j for j, c in enumerate(pool)}
+    records = []
+    for grp in groups:
+        cells = [([k for k, c in enumerate(grp) if c in haps[2 * s]], [k for k, c in enumerate(grp) if c in haps[2 * s + 1]])
+                 for s in range(n_samples)]
+        records.append((grp, cells))
+    samples = ["S%03d" % s for s in range(n_samples)]
+    vcf = refbin.vcf_text(samples, records)
+    got, stdout, rc = refbin.run_reference(vcf, refs, "st")
+    assert rc == 0, stdout[-2000:]
+    # the mask words exactly as the VCF text carries them
+    W = max((len(g) + 14) // 15 for g in groups)
+    masks = np.zeros((len(groups), n_samples, W), np.uint32)
+    body = [l for l in vcf.split("\n") if l and not l.startswith("#")]
+    for r, line in enumerate(body):
+        for s, cell in enumerate(line.split("\t")[9:]):
+            words = [int(x) for x in cell.split(":")[-1].split(",")]
+            masks[r, s, :len(words)] = words
+    assert (masks[:, :, 1:] != 0).any()  # multi-word cells are present
+    csq_begin = np.cumsum([0] + [len(g) for g in groups]).astype(np.uint64)
+    csq_site = np.array([site_of[c] for g in groups for c in g], np.int32)
+    sb, sites = maskdecode.site_lists(masks, csq_begin, csq_site)
+    for s, smp in enumerate(samples):
+        want = []
+        for k in (0, 1):
+            h = 2 * s + k
+            csqs = [pool[j] for j in sites[int(sb[h]):int(sb[h + 1])]]
+            assert sorted(csqs) == sorted(haps[h])  # the decode gives back what was encoded ...
+            want += rules_records(rules_binary, refs, csqs, k + 1)
+        assert [tuple(r) for r in got.get(smp, [])] == sorted(want), smp  # ... and the binary read the same masks
