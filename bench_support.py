@@ -1,0 +1,320 @@
+"""bench_support.py -- pieces of bench.py that are not the timed loop: the synthetic workload, the clock sampler, the CPU
+legs (oracle port = `cpu_baseline` / `--impl reference`; the reference's prebuilt binary timed beside it) and the
+measurements of the rows either side of the hot path (gzip, the whole-cohort pipeline).
+
+This module is test/bench infrastructure like bench.py itself: it is the one place besides tests/ and smoke() that may
+use oracle/ -- as the checker and as the CPU baseline, never as the thing measured on the GPU arm."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_workload(kind: str, n_samples: int, rank: int, layout: str = "packed", fasta: bool = False):
+    from vcf2prot_b200 import cohort as C
+
+    prot = C.make_proteome(seed=0x5EED0001, giant=(20 if kind == "c4" else 0))
+    if kind == "c2":
+        cat = C.make_catalogue(prot, 280000, seed=0x5EED0002)
+    else:
+        cat = C.make_catalogue(prot, 120000, seed=0x5EED0004, mix=C.MIX_C4, fs_mean=60, fs_max=4000, sl_max=500,
+                               long_ins_mean=50, long_ins_max=5000, lognormal_tails=True)
+    n_hap = 2 * n_samples
+    parts = []
+    step = 256
+    for i, h0 in enumerate(range(0, n_hap, step)):
+        parts.append(C.synth_batch(prot, cat, min(step, n_hap - h0), seed=(0x5EED0002 + 7919 * rank) * 1000 + i,
+                                   layout=layout))
+    if fasta:  # record framing as copy segments: the result tape is the .fasta file image
+        parts = [C.fasta_image(prot, b) for b in parts]
+    return prot, cat, C.concat_batches(parts)
+
+
+def alg_bytes(batch) -> int:
+    """sum(len) read + sum(len) written + '.' gap bytes + 16 B per packed task."""
+    covered = int(batch.tasks[:, 1].astype(np.int64).sum())
+    n_out = batch.n_residues
+    return covered + n_out + 16 * len(batch.tasks)  # n_out = covered + gap bytes
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                clk, mxc, p = float(f[1]), float(f[2]), float(f[3])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.1:
+                sm.append(clk)
+                pw.append(p)
+                for n, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------------ CPU side
+def oracle_check_range(batch, prot, h0: int, h1: int, gpu_bytes: np.ndarray) -> bool:
+    """Oracle (1-byte port) on haplotypes [h0,h1) of the cohort vs the GPU's bytes for the same range."""
+    from oracle import cengine
+
+    t0, t1 = int(batch.task_begin[h0]), int(batch.task_begin[h1])
+    a0, a1 = int(batch.alt_base[h0]), int(batch.alt_base[h1])
+    o0, o1 = int(batch.out_base[h0]), int(batch.out_base[h1])
+    out = np.zeros(o1 - o0, np.uint8)
+    rebase = lambda a, x: (a[h0:h1 + 1] - np.uint64(x)).astype(np.uint64)
+    st, _, _ = cengine.batch_execute(rebase(batch.task_begin, t0), batch.tasks[t0:t1], prot.residues, batch.alt[a0:a1],
+                                     rebase(batch.alt_base, a0), out, rebase(batch.out_base, o0), threads=os.cpu_count() or 1)
+    return st == 0 and bool(np.array_equal(out, gpu_bytes))
+
+
+def cpu_engine_rate(batch, prot, n_haps: int, seconds: float, threads: int, width: int, check_against=None):
+    """Reference-equivalent CPU engine (oracle port) on the first n_haps haplotypes; returns residues/s."""
+    from oracle import cengine
+
+    n_haps = min(n_haps, batch.n_hap)
+    t1 = int(batch.task_begin[n_haps])
+    a1, o1 = int(batch.alt_base[n_haps]), int(batch.out_base[n_haps])
+    dt = np.uint32 if width == 4 else np.uint8
+    ref = prot.residues.astype(dt)
+    alt = batch.alt[:a1].astype(dt)
+    out = np.zeros(o1, dt)
+    args = (batch.task_begin[:n_haps + 1], batch.tasks[:t1], ref, alt, batch.alt_base[:n_haps + 1], out,
+            batch.out_base[:n_haps + 1])
+    st, _, _ = cengine.batch_execute(*args, threads=threads)  # warm-up + page-in
+    assert st == 0
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        st, _, _ = cengine.batch_execute(*args, threads=threads)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or reps >= 1000:
+            break
+    ok = None
+    if check_against is not None:
+        ok = bool(np.array_equal(out.astype(np.uint8), check_against[:o1]))
+    return o1 * reps / el, el, reps, n_haps, o1, ok
+
+
+def reference_binary_rate(prot, cat, batch, n_samples: int):
+    """Whole-tool timing of the reference's own prebuilt binary on the first n_samples of the cohort."""
+    from oracle import refbin
+    from vcf2prot_b200 import cohort as C
+
+    if not refbin.available() or n_samples <= 0:
+        return None
+    n_samples = min(n_samples, batch.n_hap // 2)
+    sel = batch.kept_hap < 2 * n_samples if batch.kept_hap is not None else None
+    return None if sel is None else _ref_binary_run(prot, cat, batch, n_samples, sel, refbin, C)
+
+
+def _ref_binary_run(prot, cat, batch, n_samples, sel, refbin, C):
+    hap, site = batch.kept_hap[sel], batch.kept_site[sel]
+    used, inv = np.unique(site, return_inverse=True)
+    mask = np.zeros((len(used), n_samples), np.uint8)
+    np.bitwise_or.at(mask, (inv, hap // 2), (1 << (hap % 2)).astype(np.uint8))  # both haplotypes may carry a site
+    refs = {prot.name(t): prot.seq(t) for t in range(prot.n_tx)}
+    samples = ["S%05d" % i for i in range(n_samples)]
+    lines = [refbin.VCF_HEADER, "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples) + "\n"]
+    cell = ["0|0:0", "1|0:1", "0|1:2", "1|1:3"]
+    for r, i in enumerate(used):
+        lines.append("1\t%d\t.\tC\tT\t.\t.\tAC=1;BCSQ=%s\tGT:BCSQ\t%s\n" %
+                     (100 + r, C.site_csq(prot, cat, int(i)), "\t".join(cell[m] for m in mask[r])))
+    t0 = time.perf_counter()
+    recs, stdout, rc = refbin.run_reference("".join(lines), refs, "mt", verbose=True, timeout=1200)
+    wall = time.perf_counter() - t0
+    st = refbin.stage_seconds(stdout)
+    n_res = sum(len(s) for v in recs.values() for _, s in v)
+    if rc != 0 or not st:
+        return {"error": "reference binary rc=%d" % rc}
+    return {"samples": n_samples, "residues": n_res, "wall_s": round(wall, 2), "parse_s": round(st["parse"], 2),
+            "exec_stage_s": round(st["exec"], 3), "write_s": round(st["write"], 2),
+            "exec_stage_residues_per_s": n_res / max(st["exec"], 1e-9), "whole_tool_residues_per_s": n_res / st["total"],
+            "engine": "mt", "version": "0.1.2 (bins/Linux/vcf2prot)"}
+
+
+def gzip_measure(args, prot, cat, eng, dev, local_rank, torch):
+    """FASTA image of `--gzip-samples` samples produced on the device, then v2p_gzip_files device -> device; only the
+    compressed bytes cross PCIe.  Beside it: zlib level 9 (what flate2 Compression::best amounts to) on one host core."""
+    import zlib
+
+    from vcf2prot_b200 import cohort as C
+    from vcf2prot_b200.gzipdev import DeviceGzip
+
+    ns = args.gzip_samples
+    parts = [C.fasta_image(prot, C.synth_batch(prot, cat, min(256, 2 * ns - h0), seed=0x5EED0011 * 1000 + i, layout="packed"))
+             for i, h0 in enumerate(range(0, 2 * ns, 256))]
+    img = C.concat_batches(parts)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    d = [up(img.task_begin), up(img.tasks), up(img.alt), up(img.alt_base), up(img.out_base)]
+    d_img = torch.empty(img.n_residues + 64, dtype=torch.uint8, device=dev)
+    eng.execute_batch_device(img.n_hap, d[0], d[1], None, d[2], d[3], d_img, d[4], len(img.tasks), len(img.alt), img.n_residues)
+    torch.cuda.synchronize()
+    gz = DeviceGzip(local_rank)
+    file_begin = np.ascontiguousarray(img.out_base[::2])
+    cap = gz.bound(img.n_residues, ns)
+    d_gz = torch.empty(cap, dtype=torch.uint8, device=dev)
+    gz.compress_device(d_img.data_ptr(), file_begin, d_gz.data_ptr(), cap)  # warm-up (allocations)
+    runs = [gz.compress_device(d_img.data_ptr(), file_begin, d_gz.data_ptr(), cap) for _ in range(5)]
+    ob, res = runs[-1]
+    ms = sorted(r.ms for _, r in runs)
+    h_gz = torch.empty(int(ob[-1]), dtype=torch.uint8).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    h_gz.copy_(d_gz[: int(ob[-1])], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    d2h_ms = e0.elapsed_time(e1)
+    # the judge: zlib inflates the first and the last sample's member back to the image the device produced
+    image = d_img[: img.n_residues].cpu().numpy()
+    ok = True
+    for s_ in (0, ns - 1):
+        dec = zlib.decompressobj(wbits=31)
+        got = dec.decompress(h_gz.numpy()[int(ob[s_]):int(ob[s_ + 1])].tobytes())
+        ok = ok and dec.eof and got == image[int(file_begin[s_]):int(file_begin[s_ + 1])].tobytes()
+    one = image[int(file_begin[0]):int(file_begin[1])].tobytes()
+    t0 = time.perf_counter()
+    z9 = len(zlib.compress(one, 9))
+    t_z9 = time.perf_counter() - t0
+    gz.close()
+    return {"samples": ns, "image_bytes": int(res.in_bytes), "gz_bytes": int(res.out_bytes), "ratio": res.in_bytes / max(1, res.out_bytes),
+            "chunks": int(res.n_chunks), "stored_chunks": int(res.n_stored_chunks), "ms_median": ms[len(ms) // 2], "ms_best": ms[0],
+            "image_gbs": res.in_bytes / (ms[len(ms) // 2] * 1e-3) / 1e9, "d2h_ms_of_gz_bytes": d2h_ms,
+            "d2h_ms_if_uncompressed": d2h_ms * res.in_bytes / max(1, res.out_bytes), "inflates_to_the_image": bool(ok),
+            "cpu_zlib9_one_core": {"mbs": len(one) / t_z9 / 1e6, "ratio": len(one) / z9, "sample_bytes": len(one)},
+            "what": "v2p_gzip_files, device -> device: one gzip member per sample file, 16 KiB dynamic-Huffman chunks"}
+
+
+def oracle_file_text(batch, prot, s: int) -> bytes:
+    """Sample s's .fasta text from the ORACLE's tapes (hap-1 records, then hap-2 records, tape order)."""
+    from oracle import cengine
+    from vcf2prot_b200 import cohort as C
+
+    h0, h1 = 2 * s, 2 * s + 2
+    t0, t1 = int(batch.task_begin[h0]), int(batch.task_begin[h1])
+    a0, a1 = int(batch.alt_base[h0]), int(batch.alt_base[h1])
+    o0, o1 = int(batch.out_base[h0]), int(batch.out_base[h1])
+    tape = np.zeros(o1 - o0, np.uint8)
+    rebase = lambda a, x: (a[h0:h1 + 1] - np.uint64(x)).astype(np.uint64)
+    st, _, _ = cengine.batch_execute(rebase(batch.task_begin, t0), batch.tasks[t0:t1], prot.residues, batch.alt[a0:a1],
+                                     rebase(batch.alt_base, a0), tape, rebase(batch.out_base, o0))
+    assert st == 0
+    txt = []
+    for k in (0, 1):
+        base = int(batch.out_base[h0 + k]) - o0
+        lo, hi = np.searchsorted(batch.ann_hap, [h0 + k, h0 + k + 1])
+        for r in range(lo, hi):
+            seq = tape[base + int(batch.ann_start[r]): base + int(batch.ann_end[r])].tobytes()
+            txt.append(b">" + prot.name(int(batch.ann_tx[r])).encode() + b"_%d\n" % (k + 1) + seq + b"\n")
+    return b"".join(txt)
+
+
+def pipeline_measure(args, prot, cat, batch, eng, local_rank, barrier, shard, dev):
+    """v2p_pipeline_run_lists on the timed cohort: the per-haplotype site lists go up (4 B/site), every sample's .fasta
+    (then .fasta.gz) image lands in the pipeline's pinned ring and is handed to a sink; tasks, tapes and images never
+    exist on the host.  First and last file are compared with the oracle's text."""
+    import zlib
+
+    from vcf2prot_b200.pipeline import DevicePipeline, csr_lists
+
+    ns = batch.n_hap // 2 if args.pipeline_samples < 0 else min(args.pipeline_samples, batch.n_hap // 2)
+    sel = batch.kept_hap < 2 * ns
+    sb, sites = csr_lists(batch.kept_hap[sel], batch.kept_site[sel], 2 * ns)
+    n_res = int((batch.ann_end - batch.ann_start)[batch.ann_hap < 2 * ns].sum())
+    want_first, want_last = oracle_file_text(batch, prot, 0), oracle_file_text(batch, prot, ns - 1)
+    pipe = DevicePipeline(eng, prot, cat, lanes=2, device=local_rank)
+    out = {"samples": ns, "chunk_samples": args.pipeline_chunk, "lanes": 2, "residues": n_res,
+           "api": "v2p_pipeline_run_lists (host site lists in, file images to a sink through the pipeline's pinned ring)"}
+    warm = min(ns, 2 * args.pipeline_chunk)
+    for gz in (False, True):
+        got = {}
+
+        def sink(first, n, data, begins):
+            if first == 0:
+                got["first"] = bytes(data[: int(begins[1])])
+            if first + n == ns:
+                got["last"] = bytes(data[int(begins[n - 1]): int(begins[n])])
+            return 0
+
+        pipe.run_lists(sb[: 2 * warm + 1], sites[: int(sb[2 * warm])], warm, args.pipeline_chunk, gz, sink=lambda *a: 0)  # allocations
+        barrier()
+        _, r = pipe.run_lists(sb, sites, ns, args.pipeline_chunk, gz, sink=sink)
+        un = (lambda b: zlib.decompress(b, wbits=31)) if gz else (lambda b: b)
+        wall = shard.max_over_ranks(r.wall_s, dev)  # all ranks run their own sample range at once (weak scaling)
+        out["fasta_gz" if gz else "fasta"] = {
+            "residues_per_s": shard.sum_over_ranks(n_res, dev) / wall, "wall_s": wall, "h2d_bytes": int(r.h2d_bytes), "d2h_bytes": int(r.out_bytes),
+            "image_bytes": int(r.image_bytes), "records": int(r.n_records), "tasks": int(r.n_tasks), "chunks": int(r.n_chunks),
+            "gen_ms": r.gen_ms, "exec_ms": r.exec_ms, "gzip_ms": r.gzip_ms,
+            "first_and_last_file_equal_oracle_text": bool(un(got["first"]) == want_first and un(got["last"]) == want_last)}
+    # ---- and onto the file system: {tmpdir}/{proband}.fasta[.gz] through the native directory writer (rank 0 only)
+    nw = min(args.written_samples, ns)
+    if nw > 0 and int(os.environ.get("RANK", "0")) == 0:
+        import shutil
+        import tempfile
+
+        from vcf2prot_b200.pipeline import DirWriter
+
+        n_res_w = int((batch.ann_end - batch.ann_start)[batch.ann_hap < 2 * nw].sum())
+        names = ["S%06d" % i for i in range(nw)]
+        out["written"] = {"samples": nw, "residues": n_res_w, "writer_threads": 8,
+                          "what": "v2p_pipeline_run_lists -> v2p_dir_writer_sink: write(2) of the file images, one file per proband"}
+        for gz in (False, True):
+            tmpdir = tempfile.mkdtemp(prefix="v2p_written_")
+            try:
+                w = DirWriter(tmpdir, names, compressed=gz, threads=8)
+                _, r = pipe.run_lists(sb[: 2 * nw + 1], sites[: int(sb[2 * nw])], nw, args.pipeline_chunk, gz, sink=w)
+                one = open(os.path.join(tmpdir, names[0] + (".fasta.gz" if gz else ".fasta")), "rb").read()
+                ok = (zlib.decompress(one, wbits=31) if gz else one) == want_first and w.files_written == nw
+                out["written"]["fasta_gz" if gz else "fasta"] = {
+                    "residues_per_s": n_res_w / r.wall_s, "wall_s": r.wall_s, "bytes": w.bytes_written, "files": w.files_written,
+                    "file_gbs": w.bytes_written / r.wall_s / 1e9, "first_file_equals_oracle_text": bool(ok)}
+                w.close()
+            finally:
+                shutil.rmtree(tmpdir, ignore_errors=True)
+    pipe.close()
+    return out
