@@ -119,3 +119,21 @@ def test_dir_writer_sink_writes_one_file_per_proband(lib, tmp_path):
     assert lib.v2p_dir_writer_sink(w2._h, 0, 4, data.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.POINTER(C.c_uint64))) != 0
     assert "missing_dir" in w2.last_error() and ".fasta.gz" in w2.last_error()
     w2.close()
+
+
+def test_copy_kernel_is_built_on_tma_and_has_no_tensor_core_code(lib):
+    """The sm_100a build keeps what DESIGN.md section 4 says it has: TMA bulk loads and stores with mbarrier completion
+    and cp.async staging in k_copy_tiles, and not one tensor-core instruction anywhere (the path has no flops)."""
+    import shutil
+
+    from vcf2prot_b200 import _lib
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True, check=True).stdout
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    copy = "".join(b for b in sass.split("Function : ")[1:] if b.startswith("_ZN3v2p12k_copy_tilesILi8192ELi2ELi3ELi3"))
+    assert copy, "default copy-kernel instantiation missing"
+    for op in ("UBLKCP.G.S", "UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "LDGSTS.E.128", "FENCE.VIEW.ASYNC"):
+        assert op in copy, "%s not in k_copy_tiles" % op
+    assert not re.search(r"\b(HMMA|IMMA|QMMA|UTCHMMA|UTCQMMA|UTCIMMA)\b", sass)
