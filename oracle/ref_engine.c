@@ -52,6 +52,13 @@ static uint64_t first_gap_soa(uint64_t n, const uint64_t *len, const uint64_t *s
              const uint64_t *spr, const T *ref, uint64_t n_ref, const T *alt, uint64_t n_alt, T *res,    \
              uint64_t n_res, int fill_dot, int validate, uint64_t *bad_index) {                          \
         if (bad_index) *bad_index = 0;                                                                   \
+        /* haplotype_instruction.rs:140-157: update_task panics on a stream code outside {0,1} while the */ \
+        /* Task array is being BUILT -- before the validator and before any copy                        */ \
+        for (uint64_t t = 0; t < n_tasks; ++t)                                                           \
+            if (code[t] > 1) {                                                                           \
+                if (bad_index) *bad_index = t;                                                           \
+                return REF_ERR_BAD_STREAM;                                                               \
+            }                                                                                            \
         if (validate) { /* gir.rs:203-229 runs before anything is copied */                              \
             uint64_t g = first_gap_soa(n_tasks, len, spr);                                               \
             if (g) {                                                                                     \
@@ -63,7 +70,6 @@ static uint64_t first_gap_soa(uint64_t n, const uint64_t *len, const uint64_t *s
             for (uint64_t i = 0; i < n_res; ++i) res[i] = (T)'.';                                        \
         for (uint64_t t = 0; t < n_tasks; ++t) { /* gir.rs:233 */                                        \
             if (bad_index) *bad_index = t;                                                               \
-            if (code[t] > 1) return REF_ERR_BAD_STREAM;                                                  \
             uint64_t end_res = spr[t] + len[t], end_src = sp[t] + len[t]; /* task.rs:40-41 */            \
             if (end_res < spr[t] || end_res > n_res) return REF_ERR_RES_OOB;                             \
             const T *src = code[t] == 0 ? ref : alt;                                                     \
@@ -109,6 +115,12 @@ static int exec_one_hap(batch_job *j, uint64_t h, uint64_t *bad) {
     const uint8_t *ref = (const uint8_t *)j->ref + rb * w;
     const uint8_t *alt = (const uint8_t *)j->alt + j->alt_base[h] * w;
     *bad = 0;
+    /* construction of this haplotype's Task array (haplotype_instruction.rs:140-157) comes first */
+    for (uint64_t t = 0; t < n; ++t)
+        if (tk[t].stream > 1) {
+            *bad = t;
+            return REF_ERR_BAD_STREAM;
+        }
     if (j->validate)
         for (uint64_t i = 1; i < n; ++i)
             if ((uint64_t)tk[i].dst_off != (uint64_t)tk[i - 1].dst_off + tk[i - 1].len) {
@@ -123,7 +135,6 @@ static int exec_one_hap(batch_job *j, uint64_t h, uint64_t *bad) {
     }
     for (uint64_t t = 0; t < n; ++t) {
         *bad = t;
-        if (tk[t].stream > 1) return REF_ERR_BAD_STREAM;
         uint64_t l = tk[t].len, d = tk[t].dst_off, s = tk[t].src_off;
         if (d + l > n_res) return REF_ERR_RES_OOB;
         if (s + l > (tk[t].stream == 0 ? n_ref : n_alt)) return REF_ERR_SRC_OOB;

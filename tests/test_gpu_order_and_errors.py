@@ -1,0 +1,146 @@
+"""GPU suite (-m gpu): what round 1's review found untested on the engine's error and order paths.
+
+  * a rejected task with a garbage destination in FRONT of another haplotype's first task (plan_one's lb[] scatter
+    must stay in range; the launch fails with the task's own status, nothing else is corrupted),
+  * the reference's order of events: haplotype after haplotype; inside one, the stream-code panic of the Task-array
+    construction (haplotype_instruction.rs:154) before the validator (gir.rs:203-229) before slice panics (task.rs:44/48),
+  * per-haplotype serial order (gir.rs:233): ONE unsorted / overlapping haplotype among hundreds takes the span-parallel
+    serial kernel, everybody else stays on the tile kernel -- same bytes as the oracle, and no cliff in time.
+"""
+import time
+
+import numpy as np
+import pytest
+
+from oracle import cengine
+from tests.randtasks import random_batch
+from tests.test_gpu_parity import gpu_batch, oracle_batch
+from vcf2prot_b200 import EngineError
+from vcf2prot_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def test_garbage_destination_in_front_of_the_next_haplotype_is_a_clean_error(gpu_engine):
+    base = random_batch(71, 40, 30_000, gap_prob=0.0, empty_hap_prob=0.0)
+    tb = base["task_begin"]
+    _, _, _, want = oracle_batch(base)
+    for h in (0, 7, 38):  # the LAST task of haplotype h; haplotype h+1 is not empty
+        for dst in (0xFFFFFFF0, 0x80000000, int(base["out_base"][-1])):
+            b = dict(base)
+            b["tasks"] = base["tasks"].copy()
+            k = int(tb[h + 1]) - 1
+            b["tasks"][k, 2] = dst
+            with pytest.raises(EngineError) as ei:
+                gpu_batch(gpu_engine, b)
+            st, bh, bi, _ = oracle_batch(b)
+            assert st == cengine.REF_ERR_RES_OOB and ei.value.status == L.ERR_RES_OOB
+            assert (ei.value.bad_hap, ei.value.bad_task) == (bh, bi) == (h, k - int(tb[h]))
+            # the context is intact: the same engine still produces the oracle's bytes
+            out, _ = gpu_batch(gpu_engine, base)
+            assert np.array_equal(out, want)
+
+
+def test_error_precedence_follows_the_reference_order_of_events(gpu_engine):
+    base = random_batch(72, 12, 6000, gap_prob=0.0, empty_hap_prob=0.0)
+    tb = base["task_begin"]
+
+    def corrupt(*edits):
+        b = dict(base)
+        b["tasks"] = base["tasks"].copy()
+        for h, k, col, val in edits:
+            b["tasks"][int(tb[h]) + k, col] = val
+        return b
+
+    # same haplotype: slice error at task 3, bad stream at task 5 -> the construction panic (task 5) comes first
+    b = corrupt((4, 3, 1, 0x7FFFFFFF), (4, 5, 3, 7))
+    with pytest.raises(EngineError) as ei:
+        gpu_batch(gpu_engine, b)
+    st, bh, bi, _ = oracle_batch(b)
+    assert st == cengine.REF_ERR_BAD_STREAM and (bh, bi) == (4, 5)
+    assert ei.value.status == L.ERR_BAD_STREAM and (ei.value.bad_hap, ei.value.bad_task) == (4, 5)
+    # ... and with the validator on, a gap at task 2 of that haplotype still loses to the stream code
+    k = next(i for i in range(1, 5) if base["tasks"][int(tb[4]) + i, 1] >= 2)
+    b = corrupt((4, k, 1, int(base["tasks"][int(tb[4]) + k, 1]) - 1), (4, 6, 3, 2))
+    with pytest.raises(EngineError) as ei:
+        gpu_batch(gpu_engine, b, validate=True)
+    st, bh, bi, _ = oracle_batch(b, validate=True)
+    assert st == cengine.REF_ERR_BAD_STREAM and (bh, bi) == (4, 6)
+    assert ei.value.status == L.ERR_BAD_STREAM and (ei.value.bad_hap, ei.value.bad_task) == (4, 6)
+    # different haplotypes: the earlier haplotype's slice panic happens before the later one is even built
+    b = corrupt((2, 1, 1, 0x7FFFFFFF), (9, 0, 3, 2))
+    with pytest.raises(EngineError) as ei:
+        gpu_batch(gpu_engine, b)
+    st, bh, bi, _ = oracle_batch(b)
+    assert st == cengine.REF_ERR_RES_OOB and (bh, bi) == (2, 1)
+    assert ei.value.status == L.ERR_RES_OOB and (ei.value.bad_hap, ei.value.bad_task) == (2, 1)
+    # SoA entry (one haplotype): stream code at the end beats the slice error in front of it
+    with pytest.raises(EngineError) as ei:
+        gpu_engine.execute_soa([(0, 0, 9, 0), (0, 0, 1, 0), (2, 0, 0, 0)], "ABCDEFGH", "xyz", 8, fill_dot=True)
+    assert ei.value.status == L.ERR_BAD_STREAM and ei.value.bad_task == 2
+
+
+def _shuffle_haplotype(b, h, rng, overlap=True):
+    tb = b["task_begin"]
+    s, e = int(tb[h]), int(tb[h + 1])
+    t = b["tasks"]
+    t[s:e] = t[s:e][rng.permutation(e - s)]
+    if overlap and e - s > 2:  # a later task rewrites an earlier one's bytes: the later one must win (gir.rs:233)
+        t[e - 1] = t[s]
+        t[e - 1, 0], t[e - 1, 3] = 0, 0
+        t[e - 1, 1] = min(int(t[e - 1, 1]), 1000)
+
+
+@pytest.mark.parametrize("variant", [0, 8])
+@pytest.mark.parametrize("n_hap,mean_res,odd", [(60, 20_000, (17,)), (300, 9_000, (0, 299)), (41, 120_000, (5, 6, 7)),
+                                                (9, 3000, tuple(range(9)))])
+def test_only_the_unsorted_haplotypes_take_the_serial_kernel(gpu_engine, variant, n_hap, mean_res, odd):
+    gpu_engine.set_tuning(variant, 0)
+    try:
+        rng = np.random.default_rng(n_hap)
+        b = random_batch(200 + n_hap, n_hap, mean_res, empty_hap_prob=0.05)
+        b["tasks"] = b["tasks"].copy()
+        for h in odd:
+            _shuffle_haplotype(b, h, rng)
+        st, _, _, want = oracle_batch(b)
+        assert st == 0
+        out, _ = gpu_batch(gpu_engine, b)
+        assert np.array_equal(out, want)
+        gpu_engine.set_reference(b["ref"], "replicas")  # and with the registered tape (TMA path for everybody else)
+        out, _ = gpu_engine.execute_batch(b["task_begin"], b["tasks"], None, b["alt"], b["alt_base"], b["out_base"])
+        assert np.array_equal(out, want)
+    finally:
+        gpu_engine.set_tuning(-1, 0)
+
+
+def test_one_unsorted_haplotype_among_500_costs_no_cliff(gpu_engine):
+    """one odd haplotype used to send the whole batch to one-CTA-per-haplotype serial execution."""
+    import torch
+
+    rng = np.random.default_rng(500)
+    good = random_batch(500, 500, 400_000, gap_prob=0.0, empty_hap_prob=0.0, len_mix=(0.3, 0.2, 0.45, 0.05))
+    bad = dict(good)
+    bad["tasks"] = good["tasks"].copy()
+    _shuffle_haplotype(bad, 250, rng, overlap=False)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    n_out = int(good["out_base"][-1])
+    out = torch.empty(n_out + 16, dtype=torch.uint8, device=dev)
+    times = {}
+    for name, b in (("sorted", good), ("one_unsorted", bad)):
+        d = {k: up(v) for k, v in b.items() if v is not None}
+        args = (500, d["task_begin"], d["tasks"], d["ref"], d["alt"], d["alt_base"], out, d["out_base"], len(b["tasks"]),
+                len(b["alt"]), n_out)
+        for _ in range(3):
+            gpu_engine.execute_batch_device(*args)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            gpu_engine.execute_batch_device(*args)  # synchronous: includes the serial kernel when one is needed
+        torch.cuda.synchronize()
+        times[name] = (time.perf_counter() - t0) / 10
+        st, _, _, want = oracle_batch(b)
+        assert st == 0 and np.array_equal(out[:n_out].cpu().numpy(), want)
+    print("500 haplotypes, %.1f MB: sorted %.3f ms, one unsorted haplotype %.3f ms" %
+          (n_out / 1e6, times["sorted"] * 1e3, times["one_unsorted"] * 1e3))
+    assert times["one_unsorted"] < 1.5 * times["sorted"] + 0.3e-3

@@ -118,3 +118,44 @@ def test_fasta_flag_errors(world):
     hap, site = C.select_sites(cat, 2, np.random.default_rng(1))
     with pytest.raises(EngineError):  # a file image cannot contain pad bytes
         dc.generate(hap, site, 2, aligned=True, fasta=True)
+
+
+def test_site_lists_are_validated_on_the_device(world):
+    """a list entry that is not a catalogue site, or lists that are not strictly ascending inside a haplotype,
+    are V2P_ERR_INVALID_ARG naming the entry -- never an out-of-range read of the catalogue tables."""
+    from vcf2prot_b200 import EngineError
+    from vcf2prot_b200 import _lib as L
+
+    prot, cat, dc = world
+    hap, site = C.select_sites(cat, 8, np.random.default_rng(77))
+    dc.generate(hap, site, 8, False)  # fine as produced
+    for bad_value, where in ((cat.n, 5), (0xFFFFFFF0, len(site) - 1)):
+        s = site.copy()
+        s[where] = bad_value
+        with pytest.raises(EngineError) as ei:
+            dc.generate(hap, s, 8, False)
+        assert ei.value.status == L.ERR_INVALID_ARG and "entry %d " % where in str(ei.value)
+    j = int(np.flatnonzero(hap[1:] == hap[:-1])[3]) + 1  # entries j-1, j belong to one haplotype
+    swapped, dup = site.copy(), site.copy()
+    swapped[j - 1], swapped[j] = site[j], site[j - 1]
+    dup[j] = site[j - 1]
+    for s in (swapped, dup):
+        with pytest.raises(EngineError) as ei:
+            dc.generate(hap, s, 8, False)
+        assert ei.value.status == L.ERR_INVALID_ARG and "entry %d " % j in str(ei.value)
+    dc.generate(hap, site, 8, False)  # the object is still usable
+
+
+def test_catalogue_arguments_are_checked():
+    from vcf2prot_b200 import EngineError
+
+    prot = C.make_proteome(seed=3, n_tx=50, mu=5.0, sigma=0.5, hi=900)
+    cat = C.make_catalogue(prot, 400, seed=4)
+    bad = C.Catalogue(cat.t.copy(), cat.p, cat.cls, cat.rlen, cat.doff, cat.dlen, cat.af, cat.pool)
+    bad.t[7] = prot.n_tx  # not a transcript
+    with pytest.raises(EngineError):
+        DeviceCatalogue(prot, bad, 0)
+    bad = C.Catalogue(cat.t, cat.p, cat.cls, cat.rlen, cat.doff.copy(), cat.dlen, cat.af, cat.pool)
+    bad.doff[-1] = len(cat.pool)  # payload beyond the pool
+    with pytest.raises(EngineError):
+        DeviceCatalogue(prot, bad, 0)

@@ -34,7 +34,7 @@ struct DevBuf {
 };
 
 struct Scratch {  // per-stream planning scratch
-    DevBuf lb, tile_hap, chunk_hap, order, status;
+    DevBuf lb, tile_hap, chunk_hap, order, status, hap_flags, ser_list;
 };
 
 constexpr int kSlots = 3;
@@ -163,6 +163,11 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     const uint64_t n_chunks = (kp.n_tasks + kPlanWarpTasks - 1) / kPlanWarpTasks;
     if ((rc = reserve(e, sc.chunk_hap, std::max<uint64_t>(n_chunks, 1) * sizeof(uint32_t)))) return rc;
     kp.chunk_hap = (uint32_t*)sc.chunk_hap.p;
+    // per-haplotype "needs serial order" flags (+ one counter word behind them) and the compacted list of those
+    if ((rc = reserve(e, sc.hap_flags, (kp.n_hap + 1) * sizeof(uint32_t)))) return rc;
+    if ((rc = reserve(e, sc.ser_list, std::max<uint64_t>(kp.n_hap, 1) * sizeof(uint32_t)))) return rc;
+    kp.hap_flags = (uint32_t*)sc.hap_flags.p;
+    kp.ser_list = (uint32_t*)sc.ser_list.p;
     // tile order: 16-byte header (s_max) + one slot per (tile rank within its haplotype, haplotype)
     if (kp.n_tiles >= 0xFFF00000ull) return fail(e, V2P_ERR_INVALID_ARG, "more than 2^32 tiles in one launch");
     // tape order = identity over n_tiles (n_hap "1"): the cap then only has to hold the identity
@@ -182,6 +187,7 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     if (ev_start) CUDA_TRY(e, cudaEventRecord(ev_start, s));
     CUDA_TRY(e, cudaMemsetAsync(kp.lb, 0xFF, (kp.n_tiles + 1) * sizeof(uint32_t), s));
     CUDA_TRY(e, cudaMemsetAsync(kp.order_hdr, 0, 16, s));
+    CUDA_TRY(e, cudaMemsetAsync(kp.hap_flags, 0, (kp.n_hap + 1) * sizeof(uint32_t), s));
     if (order_cap) CUDA_TRY(e, cudaMemsetAsync(kp.order, 0xFF, order_cap * sizeof(uint32_t), s));
     if (init_status) {
         k_init_status<<<1, 1, 0, s>>>(kp.status);
@@ -197,7 +203,8 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     }
     if (kp.n_tasks) {
         k_plan_tasks<<<(unsigned)((kp.n_tasks + kPlanChunk - 1) / kPlanChunk), 256, 0, s>>>(kp);
-        e->launches++;
+        k_plan_fix<<<(unsigned)((kp.n_hap + 255) / 256), 256, 0, s>>>(kp, kp.hap_flags + kp.n_hap);
+        e->launches += 2;
     }
     if (ev_copy) CUDA_TRY(e, cudaEventRecord(ev_copy, s));
     if (kp.n_tiles) {
@@ -214,8 +221,8 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     CUDA_TRY(e, cudaGetLastError());
     // status rides the stream right behind the kernels, so a later launch cannot overwrite it first; it is stored
     // into mapped pinned memory by a kernel (v2p_mapped.cuh) so it never queues behind a result tape on the copy engine
-    static_assert(sizeof(DevStatus) == 24, "DevStatus is published as three 8-byte words");
-    CUDA_TRY(e, publish_words(reinterpret_cast<unsigned long long*>(h_status), kp.status, 3, s));
+    static_assert(sizeof(DevStatus) == 32, "DevStatus is published as four 8-byte words");
+    CUDA_TRY(e, publish_words(reinterpret_cast<unsigned long long*>(h_status), kp.status, 4, s));
     e->launches++;
     return V2P_OK;
 }
@@ -225,46 +232,50 @@ void decode_status(const DevStatus& st, const uint64_t* task_begin_host, uint64_
     res->status = V2P_OK;
     res->bad_hap = 0;
     res->bad_task = 0;
-    uint64_t bad = 0;
     if (st.bad_args) {
         res->status = V2P_ERR_INVALID_ARG;
         return;
     }
-    // Precedence follows the reference's own order of events: a bad stream code panics while the Task
-    // array is built (haplotype_instruction.rs:154), the contiguity validator runs before execution
-    // (gir.rs:203-229), slice panics happen during execution (task.rs:44/48).
-    const bool has_err = st.err_key != ~0ull, has_gap = st.gap_key != ~0ull;
-    if (has_err && (int)(st.err_key & 0xFF) == V2P_ERR_BAD_STREAM) {
-        res->status = V2P_ERR_BAD_STREAM;
-        bad = st.err_key >> 8;
-    } else if (has_gap) {
-        res->status = V2P_ERR_NOT_CONTIGUOUS;
-        bad = st.gap_key;
-    } else if (has_err) {
-        res->status = (int)(st.err_key & 0xFF);
-        bad = st.err_key >> 8;
-    } else {
-        return;
+    // The reference handles one haplotype after the other (personalized_genome.rs:64-65, parts/exec.rs:34-40), and
+    // inside one haplotype in this order: a bad stream code panics while the Task array is built
+    // (haplotype_instruction.rs:154), then the contiguity validator runs (gir.rs:203-229), then slices panic
+    // during execution (task.rs:44/48).  So: the lowest haplotype with any finding wins; inside it, that precedence.
+    struct Finding {
+        int status;
+        uint64_t task;  // launch-relative global index
+        uint64_t hap;
+    } f[3] = {{V2P_ERR_BAD_STREAM, st.stream_key, 0},
+              {V2P_ERR_NOT_CONTIGUOUS, st.gap_key, 0},
+              {st.err_key != ~0ull ? (int)(st.err_key & 0xFF) : 0, st.err_key != ~0ull ? st.err_key >> 8 : ~0ull, 0}};
+    const bool have_tb = task_begin_host && n_hap;
+    const Finding* best = nullptr;
+    for (Finding& c : f) {
+        if (c.task == ~0ull) continue;
+        if (have_tb) {
+            size_t h = std::upper_bound(task_begin_host, task_begin_host + n_hap + 1, c.task + task_origin) - task_begin_host;
+            h = h ? h - 1 : 0;
+            c.hap = h >= n_hap ? n_hap - 1 : h;
+        }
+        if (!best || c.hap < best->hap) best = &c;  // (ties keep the earlier class)
     }
-    res->bad_task = bad;  // launch-relative global index unless task_begin is known on the host
-    if (task_begin_host && n_hap) {
-        const uint64_t abs_t = bad + task_origin;
-        size_t h = std::upper_bound(task_begin_host, task_begin_host + n_hap + 1, abs_t) - task_begin_host;
-        h = h ? h - 1 : 0;
-        if (h >= n_hap) h = n_hap - 1;
-        res->bad_hap = h;
-        res->bad_task = abs_t - task_begin_host[h];
+    if (!best) return;
+    res->status = best->status;
+    res->bad_task = best->task;  // launch-relative global index unless task_begin is known on the host
+    if (have_tb) {
+        res->bad_hap = best->hap;
+        res->bad_task = best->task + task_origin - task_begin_host[best->hap];
     }
 }
 
 bool needs_serial(const DevStatus& st) {
-    return !st.bad_args && st.err_key == ~0ull && st.gap_key == ~0ull && st.unsorted;
+    return !st.bad_args && st.err_key == ~0ull && st.gap_key == ~0ull && st.stream_key == ~0ull && st.unsorted;
 }
 
-// serial-order fallback, launched only after the plan reported unsorted/overlapping tasks
-int launch_serial(v2p_engine* e, cudaStream_t s, const KParams& kp) {
-    unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(kp.n_hap, 1), (uint64_t)e->sm_count * 8);
-    k_serial<<<grid, kThreads, 0, s>>>(kp);
+// serial-order kernel over the n_ser haplotypes the plan flagged (unsorted / overlapping tasks); everybody else
+// was written by the tile kernel of the same launch group
+int launch_serial(v2p_engine* e, cudaStream_t s, const KParams& kp, uint32_t n_ser) {
+    unsigned grid = (unsigned)e->sm_count * 4;
+    k_serial<<<grid, kSerialThreads, 0, s>>>(kp, n_ser);
     e->launches++;
     CUDA_TRY(e, cudaGetLastError());
     return V2P_OK;
@@ -321,7 +332,7 @@ int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
         return finish(fail(e, V2P_ERR_CUDA, "launch group failed: %s", cudaGetErrorString(cudaGetLastError())));
     const DevStatus& st = *ev->h_status;
     if (needs_serial(st)) {
-        int rc = launch_serial(e, ev->stream, ev->kp);
+        int rc = launch_serial(e, ev->stream, ev->kp, st.unsorted);
         if (rc) return finish(rc);
         if (ev->slot && ev->out_bytes &&
             cudaMemcpyAsync(ev->h_out, ev->kp.out, ev->out_bytes, cudaMemcpyDeviceToHost, ev->stream) != cudaSuccess)
@@ -394,11 +405,11 @@ void v2p_engine_destroy(v2p_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&e->sc.order, &e->sc.chunk_hap, &e->sc.lb,     &e->sc.tile_hap, &e->sc.status, &e->d_soa[0], &e->d_soa[1],  &e->d_soa[2], &e->d_soa[3],
+    DevBuf* bufs[] = {&e->sc.hap_flags, &e->sc.ser_list, &e->sc.order, &e->sc.chunk_hap, &e->sc.lb,     &e->sc.tile_hap, &e->sc.status, &e->d_soa[0], &e->d_soa[1],  &e->d_soa[2], &e->d_soa[3],
                       &e->soa_tasks, &e->soa_ref,     &e->soa_alt,   &e->soa_out,  &e->soa_bases, &e->ref_rep};
     for (DevBuf* b : bufs) release(*b);
     for (Slot& sl : e->slots) {
-        DevBuf* sb[] = {&sl.sc.order, &sl.sc.chunk_hap, &sl.sc.lb,      &sl.sc.tile_hap, &sl.sc.status,  &sl.d_tasks, &sl.d_task_begin, &sl.d_ref,
+        DevBuf* sb[] = {&sl.sc.hap_flags, &sl.sc.ser_list, &sl.sc.order, &sl.sc.chunk_hap, &sl.sc.lb,      &sl.sc.tile_hap, &sl.sc.status,  &sl.d_tasks, &sl.d_task_begin, &sl.d_ref,
                         &sl.d_ref_base, &sl.d_alt,       &sl.d_alt_base, &sl.d_out,   &sl.d_out_base};
         for (DevBuf* b : sb) release(*b);
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -682,7 +693,7 @@ int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, co
     if (rc) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(s));
     if (needs_serial(*e->h_status)) {
-        if ((rc = launch_serial(e, s, kp))) return rc;
+        if ((rc = launch_serial(e, s, kp, e->h_status->unsorted))) return rc;
         CUDA_TRY(e, cudaStreamSynchronize(s));
     }
     v2p_result r;

@@ -30,10 +30,15 @@ constexpr int kThreads = kWarpsPerCta * 32;
 
 // Device-side status block, written by the plan kernels with atomics.
 struct DevStatus {
-    unsigned long long err_key;  // min over ((global task idx << 8) | V2P_ERR_*) of hard errors; ~0 = none
-    unsigned long long gap_key;  // min global task idx violating gir.rs:208 contiguity (VALIDATE); ~0 = none
-    unsigned int unsorted;       // some haplotype's tasks are not sorted / overlap -> serial semantics needed
-    unsigned int bad_args;       // base arrays not monotone / totals inconsistent
+    unsigned long long err_key;     // min over ((global task idx << 8) | V2P_ERR_*) of slice errors; ~0 = none
+    unsigned long long gap_key;     // min global task idx violating gir.rs:208 contiguity (VALIDATE); ~0 = none
+    unsigned long long stream_key;  // min global task idx whose stream code is not 0/1; ~0 = none.  Kept apart from
+                                    // err_key: the reference panics on it while the Task array is BUILT
+                                    // (haplotype_instruction.rs:154), before any validator or copy runs, so it wins
+                                    // over a slice error or a gap at a smaller index
+    unsigned int unsorted;          // number of haplotypes whose tasks are not sorted / overlap (hap_flags[h] = 1):
+                                    // those take the serial-order kernel, everybody else the tile kernel
+    unsigned int bad_args;          // base arrays not monotone / totals inconsistent
 };
 
 struct KParams {
@@ -53,6 +58,9 @@ struct KParams {
     uint32_t* lb;        // n_tiles+1
     uint32_t* tile_hap;  // n_tiles
     uint32_t* chunk_hap;  // haplotype of the first task of every k_plan_tasks warp (kPlanWarpTasks tasks each)
+    uint32_t* hap_flags;  // n_hap: 1 = this haplotype's tasks are unsorted / overlapping (reference order semantics:
+                          // the tile kernel skips its tasks, k_serial applies them in array order afterwards)
+    uint32_t* ser_list;   // the flagged haplotypes, compacted by k_plan_fix (ser_list[0 .. status->unsorted))
     // Tile processing order (see k_copy_tiles): order_hdr[0] = s_max = most tile GROUPS (2^order_gshift consecutive
     // tiles) any haplotype owns (k_plan_haps); order[((g * n_hap + h) << gshift) + i] = tile i of group g of haplotype h,
     // or ~0 (k_plan_tiles).  When that does not fit order_cap (wildly uneven haplotypes) order[] is the identity.
@@ -92,6 +100,7 @@ __device__ __forceinline__ uint64_t hap_of_task(const KParams& p, uint64_t t, ui
 __global__ void k_init_status(DevStatus* s) {
     s->err_key = ~0ull;
     s->gap_key = ~0ull;
+    s->stream_key = ~0ull;
     s->unsorted = 0;
     s->bad_args = 0;
 }
@@ -141,6 +150,7 @@ constexpr int kPlanWarpTasks = 32 * 16;         // consecutive tasks per warp
 constexpr int kPlanChunk = kPlanWarpTasks * 8;  // ... per 256-thread CTA
 
 struct PlanHap {  // bases of one haplotype, launch-relative
+    uint32_t h;         // its index
     uint32_t tb0, tb1;  // its tasks [tb0, tb1)
     uint64_t orel;      // start of its result tape
     uint64_t n_res, n_alt, n_ref;
@@ -148,6 +158,7 @@ struct PlanHap {  // bases of one haplotype, launch-relative
 
 __device__ __forceinline__ PlanHap plan_hap_load(const KParams& p, uint64_t h) {
     PlanHap c;
+    c.h = (uint32_t)h;
     c.tb0 = (uint32_t)(__ldg(p.task_begin + h) - p.task_origin);
     c.tb1 = (uint32_t)min(__ldg(p.task_begin + h + 1) - p.task_origin, p.n_tasks);
     const uint64_t o0 = __ldg(p.out_base + h);
@@ -199,23 +210,26 @@ __device__ __forceinline__ void plan_one(const KParams& p, const PlanHap& m, con
     const bool bad_res = (uint64_t)dst + len > m.n_res;                            // task.rs:44/48 (result slice)
     const bool bad_src = (uint64_t)src + len > (stream == 0 ? m.n_ref : m.n_alt);  // task.rs:44/48 (source slice)
     if (bad_stream | bad_res | bad_src) {
-        const unsigned long long key = (unsigned long long)tr << 8;
-        atomicMin(&p.status->err_key, key | (bad_stream ? V2P_ERR_BAD_STREAM : bad_res ? V2P_ERR_RES_OOB : V2P_ERR_SRC_OOB));
+        if (bad_stream) atomicMin(&p.status->stream_key, (unsigned long long)tr);
+        else atomicMin(&p.status->err_key, ((unsigned long long)tr << 8) | (bad_res ? V2P_ERR_RES_OOB : V2P_ERR_SRC_OOB));
         return;
     }
     if (tr != m.tb0) {  // previous task is in the same haplotype: gir.rs:208 contiguity + sortedness
         const uint64_t pend = (uint64_t)p_dst + p_len;
-        if (dst < pend) {
-            atomicExch(&p.status->unsorted, 1u);
+        if (dst < pend) {  // this haplotype needs the reference's order semantics (later task wins): k_serial
+            if (atomicExch(p.hap_flags + m.h, 1u) == 0u) atomicAdd(&p.status->unsorted, 1u);
             return;
         }
         if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
     }
-    // only tasks that start a new tile (or follow whole tiles of '.') write lb[]; kt <= n_tiles after the checks above,
-    // and kprev == ~0 (task 0) wraps to tile 0
-    if (kt != kprev) p.lb[kprev + 1u] = tr;
-    if (kt - kprev > 1u && kt != kprev)
+    // Only tasks that start a new tile (or follow whole tiles of '.') write lb[].  kt and kprev are clamped to
+    // n_tiles by the caller (the task in FRONT of this one may be a rejected one with a garbage dst -- the launch
+    // then fails with its status, but lb[] must not be written out of range meanwhile); valid sorted input has
+    // kt >= kprev, and kprev == ~0 (task 0) wraps to tile 0.
+    if (kprev == 0xFFFFFFFFu || kt > kprev) {
+        p.lb[kprev + 1u] = tr;
         for (uint32_t k = kprev + 2u; k <= kt; ++k) p.lb[k] = tr;
+    }
 }
 
 #ifndef V2P_PLAN_MINB
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
     if (first > 0) {
         const uint4 pt = __ldg(tk + first - 1);
         const uint64_t porel = first - 1 >= c.tb0 ? c.orel : plan_hap_of(p, first - 1).orel;
-        o_kt = (uint32_t)((porel + pt.z) >> p.tile_shift);
+        o_kt = (uint32_t)min((porel + pt.z) >> p.tile_shift, p.n_tiles);
         o_dst = pt.z, o_len = pt.y;
     }
 
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
             const uint32_t len = raw[u].y, dst = raw[u].z;
             const bool whole = t0 + 32u <= min(c.tb1, end);  // warp-uniform: all 32 tasks exist and belong to c
             if (whole) {
-                const uint32_t kt = (uint32_t)((c.orel + dst) >> p.tile_shift);  // tile in which this task starts
+                const uint32_t kt = (uint32_t)min((c.orel + dst) >> p.tile_shift, p.n_tiles);  // tile in which this task starts
                 const uint32_t kprev = __shfl_sync(0xffffffffu, lane == 31u ? o_kt : kt, rot);
                 const uint32_t p_dst = __shfl_sync(0xffffffffu, lane == 31u ? o_dst : dst, rot);
                 const uint32_t p_len = __shfl_sync(0xffffffffu, lane == 31u ? o_len : len, rot);
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
             } else {  // a haplotype boundary or the end of the range inside these 32 tasks: per-lane bases
                 PlanHap m = c;
                 if (tr >= c.tb1 && tr < end) m = plan_hap_of(p, tr);
-                const uint32_t kt = (uint32_t)((m.orel + dst) >> p.tile_shift);
+                const uint32_t kt = (uint32_t)min((m.orel + dst) >> p.tile_shift, p.n_tiles);
                 const uint32_t kprev = __shfl_sync(0xffffffffu, lane == 31u ? o_kt : kt, rot);
                 const uint32_t p_dst = __shfl_sync(0xffffffffu, lane == 31u ? o_dst : dst, rot);
                 const uint32_t p_len = __shfl_sync(0xffffffffu, lane == 31u ? o_len : len, rot);
@@ -283,6 +297,23 @@ __global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
             }
         }
     }
+}
+
+// One thread per haplotype, after k_plan_tasks: haplotypes flagged as unsorted / overlapping are compacted into
+// ser_list[] (the work list of k_serial) and taken out of the tile kernel's view.  Their tasks wrote lb[] entries that
+// mean nothing (lb[] is "first task at or after this tile" only for sorted input), and the tile kernel walks
+// [lb[k]-1, lb[k+1]) -- so every tile boundary inside the haplotype's tape gets the entry it would have if the
+// haplotype had no tasks at all: the first task BEHIND it.  (Its tasks wrote only entries of tiles in its own tape --
+// plan_one writes (kprev, kt] and both are tiles of validated destinations of this haplotype -- so nothing outside
+// needs repair.)  Two flagged neighbours may both write a shared boundary entry; either value is a valid bound.
+__global__ void k_plan_fix(KParams p, unsigned int* ser_count) {
+    const uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (h >= p.n_hap || !p.hap_flags[h]) return;
+    p.ser_list[atomicAdd(ser_count, 1u)] = (uint32_t)h;
+    const uint64_t o0 = p.out_base[h] - p.out_origin, o1 = p.out_base[h + 1] - p.out_origin;
+    const uint32_t tb1 = (uint32_t)min(p.task_begin[h + 1] - p.task_origin, p.n_tasks);
+    const uint64_t k0 = (o0 + p.tile_bytes - 1) >> p.tile_shift, k1 = min(o1 >> p.tile_shift, p.n_tiles);
+    for (uint64_t k = k0; k <= k1; ++k) p.lb[k] = tb1;
 }
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -315,6 +346,9 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(sdst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -451,7 +485,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     }
     __syncthreads();
 
-    if (p.status->bad_args || p.status->unsorted || p.status->err_key != ~0ull || p.status->gap_key != ~0ull) return;
+    if (p.status->bad_args || p.status->err_key != ~0ull || p.status->gap_key != ~0ull || p.status->stream_key != ~0ull)
+        return;
     if (lane == 0) mbar_init(mbar, 1);
     __syncwarp();
 
@@ -499,6 +534,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         const uint32_t tr = first_task(lo) + lane;
         if (tr < min(hi, n_tasks32)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
         if (base_on) cp_async8(st_bases + lane, base_arr + hp + base_add);
+        if (lane == 5) cp_async4(st_bases + 5, p.hap_flags + hp);  // 1: the haplotype is left to k_serial
         cp_async_commit();
     };
     // k: this warp's tile (tape order) or slot (interleaved order; then t0/t1/t2 are the tiles of slots k, k + n_warps,
@@ -530,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
         const uint64_t hb_t0 = st_bases[0], hb_t1 = st_bases[1], hb_out = st_bases[2], hb_alt = st_bases[3];
         const uint64_t hb_ref = p.ref_base ? st_bases[4] : p.ref_origin;
+        const bool hb_serial = *reinterpret_cast<const uint32_t*>(st_bases + 5) != 0u;
         __syncwarp();
         // advance the pipeline: stage the next tile (its metadata was fetched one slot ago), fetch metadata two ahead
         c_lo = n_lo, c_hi = n_hi, c_hap = n_hap;
@@ -586,16 +623,18 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 const uint4 raw = tb == t_lo ? raw0 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
                 const uint64_t t_abs = tr + p.task_origin;
                 uint64_t o_b = hb_out, a_b = hb_alt, r_b = hb_ref;
+                bool serial = hb_serial;
                 if (t_abs < hb_t0 || t_abs >= hb_t1) {  // another haplotype (tile spans a haplotype boundary)
                     const uint64_t h = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, t_abs) - 1;
                     o_b = __ldg(p.out_base + h);
                     a_b = __ldg(p.alt_base + h);
                     r_b = p.ref_base ? __ldg(p.ref_base + h) : p.ref_origin;
+                    serial = __ldg(p.hap_flags + h) != 0u;
                 }
                 const long long g = (long long)(o_b - p.out_origin + raw.z) - (long long)tile_start;
                 const long long ge = g + raw.y;
                 const int s = (int)max(g, 0ll), e = (int)min(ge, (long long)tile_len);
-                if (e > s) {
+                if (e > s && !serial) {  // (a haplotype in serial order keeps its prefill here; k_serial paints it)
                     const uint8_t* sb = raw.w ? p.alt + (a_b - p.alt_origin) : p.ref + (r_b - p.ref_origin);
                     p0 = (long long)(sb + raw.x) - g;
                     const int vh = s >> 4, vt = (e - 1) >> 4;
@@ -680,8 +719,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     if (n > 3) tv[v + 3] = realign16(c3, c4, sh);
                 }
             }
+            __syncwarp();  // orders this batch's tile stores before the next batch's read-modify-writes
             if (!__any_sync(0xffffffffu, has_lead)) continue;  // nothing for the register path in this batch
-            __syncwarp();
 
             // ---- B: owner of every vector = last task (in this batch) whose covered range started at or before it
             {
@@ -766,27 +805,71 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     if (lane == 0) bulk_wait0();
 }
 
-// ------------------------------------------------------------------------------------------------ serial fallback
-// Reference order semantics for task arrays that are not sorted / non-overlapping by destination:
-// one CTA per haplotype, tasks applied strictly in array order (gir.rs:233), each copy spread over the CTA.
-// Launched by the host only after the plan reported `unsorted` and no error (status is not re-read here:
-// a later asynchronous launch may already have re-initialised the shared status block).
-__global__ void __launch_bounds__(kThreads) k_serial(const KParams p) {
-    for (uint64_t h = blockIdx.x; h < p.n_hap; h += gridDim.x) {
+// ------------------------------------------------------------------------------------------------ serial order
+// Reference order semantics (gir.rs:233: tasks applied strictly in array order, a later task overwrites an earlier
+// one) for the haplotypes the plan flagged as unsorted / overlapping -- and only for those; everybody else was
+// written by the tile kernel.  Output-stationary like the tile kernel, so one odd haplotype is spread over the
+// whole GPU instead of one CTA: a work item is a kSerialSpan-byte span of one flagged haplotype's result tape.  The
+// CTA prefills its span, then walks ALL of the haplotype's tasks in array order (kSerialThreads per step, one
+// coalesced load; the next window is in flight while this one is judged) and applies the ones that overlap the
+// span, clipped to it, one after the other.  Every byte therefore sees its writers in array order, with no
+// inter-CTA ordering needed; the price is that every span re-reads the haplotype's task array (L2-resident, ~20k
+// tasks), which is why this is not the main path.
+// Launched by the host only after the plan reported `unsorted` and no error (status is not re-read here: a later
+// asynchronous launch may already have re-initialised the shared status block; the count is passed by value).
+constexpr int kSerialThreads = 512;
+constexpr uint32_t kSerialSpan = 16384;
+__global__ void __launch_bounds__(kSerialThreads) k_serial(const KParams p, const uint32_t n_ser) {
+    __shared__ uint32_t s_cnt[kSerialThreads / 32];
+    __shared__ const uint8_t* s_src[kSerialThreads];
+    __shared__ uint32_t s_dst[kSerialThreads], s_len[kSerialThreads];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t i = 0; i < n_ser; ++i) {
+        const uint64_t h = p.ser_list[i];
         const uint64_t o0 = p.out_base[h] - p.out_origin, n_res = p.out_base[h + 1] - p.out_base[h];
-        uint8_t* res = p.out + o0;
-        if (!p.keep_out)
-            for (uint64_t i = threadIdx.x; i < n_res; i += blockDim.x)
-                res[i] = (uint8_t)(p.fill_word >> (8u * (uint32_t)((o0 + i) & 3u)));
-        __syncthreads();
-        const uint8_t* ref = p.ref + (p.ref_base ? p.ref_base[h] - p.ref_origin : 0ull);
-        const uint8_t* alt = p.alt + (p.alt_base[h] - p.alt_origin);
+        uint8_t* const res = p.out + o0;
+        const uint8_t* const ref = p.ref + (p.ref_base ? p.ref_base[h] - p.ref_origin : 0ull);
+        const uint8_t* const alt = p.alt + (p.alt_base[h] - p.alt_origin);
         const uint64_t t0 = p.task_begin[h] - p.task_origin, t1 = p.task_begin[h + 1] - p.task_origin;
-        for (uint64_t t = t0; t < t1; ++t) {
-            const v2p_task16 tk = p.tasks[t];
-            const uint8_t* src = (tk.stream ? alt : ref) + tk.src_off;
-            uint8_t* dst = res + tk.dst_off;
-            for (uint32_t i = threadIdx.x; i < tk.len; i += blockDim.x) dst[i] = src[i];
+        const uint64_t n_spans = (n_res + kSerialSpan - 1) / kSerialSpan;
+        const uint4* __restrict__ tk = reinterpret_cast<const uint4*>(p.tasks);
+        for (uint64_t j = blockIdx.x; j < n_spans; j += gridDim.x) {
+            const uint64_t r0 = j * kSerialSpan, r1 = min(r0 + kSerialSpan, n_res);
+            if (!p.keep_out)
+                for (uint64_t x = r0 + tid; x < r1; x += kSerialThreads)
+                    res[x] = (uint8_t)(p.fill_word >> (8u * (uint32_t)((o0 + x) & 3u)));
+            uint4 nxt = t0 + tid < t1 ? __ldg(tk + t0 + tid) : make_uint4(0u, 0u, 0u, 0u);
+            for (uint64_t t = t0; t < t1; t += kSerialThreads) {
+                const uint4 raw = nxt;
+                const uint64_t tn = t + kSerialThreads + tid;
+                nxt = tn < t1 ? __ldg(tk + tn) : make_uint4(0u, 0u, 0u, 0u);
+                // overlap of [dst, dst+len) with [r0, r1)   (lanes past t1 hold len == 0)
+                const uint64_t d0 = max((uint64_t)raw.z, r0), d1 = min((uint64_t)raw.z + raw.y, r1);
+                const bool hit = d1 > d0;
+                if (!__syncthreads_or(hit)) continue;  // (also orders the prefill / the previous window's copies)
+                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_cnt[warp] = __popc(bal);
+                __syncthreads();
+                uint32_t before = 0, total = 0;
+                for (uint32_t w = 0; w < kSerialThreads / 32; ++w) {
+                    const uint32_t c = s_cnt[w];
+                    before += w < warp ? c : 0u;
+                    total += c;
+                }
+                if (hit) {
+                    const uint32_t q = before + __popc(bal & ((1u << lane) - 1u));
+                    s_src[q] = (raw.w ? alt : ref) + raw.x + (d0 - raw.z);
+                    s_dst[q] = (uint32_t)(d0 - r0);
+                    s_len[q] = (uint32_t)(d1 - d0);
+                }
+                __syncthreads();
+                for (uint32_t q = 0; q < total; ++q) {  // array order; a barrier between two writers of a byte
+                    const uint8_t* __restrict__ src = s_src[q];
+                    uint8_t* dst = res + r0 + s_dst[q];
+                    for (uint32_t x = tid; x < s_len[q]; x += kSerialThreads) dst[x] = src[x];
+                    __syncthreads();
+                }
+            }
             __syncthreads();
         }
     }
@@ -818,7 +901,7 @@ __global__ void k_soa_pack(uint64_t n, const uint64_t* __restrict__ code, const 
     v2p_task16 o = {0u, 0u, 0u, 0u};
     if (validate && t > 0 && d != spr[t - 1] + len[t - 1]) atomicMin(&status->gap_key, (unsigned long long)t);
     if (c > 1) {
-        atomicMin(&status->err_key, key | V2P_ERR_BAD_STREAM);
+        atomicMin(&status->stream_key, (unsigned long long)t);
     } else if (d + l < d || d + l > n_res) {
         atomicMin(&status->err_key, key | V2P_ERR_RES_OOB);
     } else if (s + l < s || s + l > (c == 0 ? n_ref : n_alt)) {

@@ -75,6 +75,16 @@ int pfail(v2p_pipeline* p, int code, const char* fmt, ...) {
             return pfail((p), V2P_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__); \
     } while (0)
 
+// inside the chunk loop: record the failure and leave the loop, so that the drain loop still waits for every copy in flight
+#define PCU_BREAK(p, rc, call)                                                                                        \
+    {                                                                                                                 \
+        cudaError_t _st = (call);                                                                                     \
+        if (_st != cudaSuccess) {                                                                                     \
+            (rc) = pfail((p), V2P_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__); \
+            break;                                                                                                    \
+        }                                                                                                             \
+    }
+
 int grow_dev(v2p_pipeline* p, void*& ptr, size_t& cap, size_t bytes) {
     bytes = std::max<size_t>(bytes, 256);
     if (cap >= bytes) return V2P_OK;
@@ -139,7 +149,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
             res->h2d_bytes += sb[nh] * 4 + (nh + 1) * 8;
         } else {
             if ((rc = grow_dev(p, l.d_begin, l.d_begin_cap, (nh + 1) * 8))) break;
-            PCU(p, cudaMemcpy(l.d_begin, sb.data(), (nh + 1) * 8, cudaMemcpyHostToDevice));
+            PCU_BREAK(p, rc, cudaMemcpy(l.d_begin, sb.data(), (nh + 1) * 8, cudaMemcpyHostToDevice));
             v2p_site_lists lists;
             memset(&lists, 0, sizeof lists);
             lists.n_hap = nh, lists.n_sites = sb[nh];
@@ -159,9 +169,9 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
             break;
         }
         // ---- file bounds: sample s owns haplotypes 2s, 2s+1
-        PCU(p, l.pub.reserve(nh + 1));
-        PCU(p, v2p::publish_words(l.pub.p, g.batch.out_base, nh + 1, p->aux));
-        PCU(p, cudaStreamSynchronize(p->aux));
+        PCU_BREAK(p, rc, l.pub.reserve(nh + 1));
+        PCU_BREAK(p, rc, v2p::publish_words(l.pub.p, g.batch.out_base, nh + 1, p->aux));
+        PCU_BREAK(p, rc, cudaStreamSynchronize(p->aux));
         l.fb_rel.resize(ns + 1);
         for (uint64_t s = 0; s <= ns; ++s) l.fb_rel[s] = l.pub.p[2 * s];
         const uint8_t* d_src = g.batch.out;
@@ -193,8 +203,8 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
             if ((rc = grow_host(p, l, bytes))) break;
             h_dst = l.h_buf;
         }
-        if (bytes) PCU(p, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, l.copy));
-        PCU(p, cudaEventRecord(l.landed, l.copy));
+        if (bytes) PCU_BREAK(p, rc, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, l.copy));
+        PCU_BREAK(p, rc, cudaEventRecord(l.landed, l.copy));
         l.pending = true, l.first_sample = s0, l.n = ns, l.h_data = h_dst;
         if (file_begin)
             for (uint64_t s = 1; s <= ns; ++s) file_begin[s0 + s] = total + l.fb_rel[s];
@@ -308,10 +318,14 @@ int v2p_pipeline_run_masks(v2p_pipeline* p, uint64_t n_records, uint64_t n_sampl
         local.decode_ms = lists.decode_ms;
         if (!(mask_flags & V2P_FLAG_DEVICE_PTRS)) local.h2d_bytes += n_records * n_samples * words_per_cell * 4;
         std::vector<uint64_t> sb(2 * n_samples + 1);
-        PCU(p, cudaSetDevice(p->device));
-        PCU(p, cudaMemcpy(sb.data(), lists.site_begin, sb.size() * 8, cudaMemcpyDeviceToHost));
-        ListSource src{sb.data(), nullptr, lists.sites};
-        rc = run(p, n_samples, src, chunk_samples, flags, out, out_capacity, file_begin, sink, user, &local);
+        cudaError_t st = cudaSetDevice(p->device);
+        if (st == cudaSuccess) st = cudaMemcpy(sb.data(), lists.site_begin, sb.size() * 8, cudaMemcpyDeviceToHost);
+        if (st != cudaSuccess) {
+            rc = pfail(p, V2P_ERR_CUDA, "reading the decoded list bounds failed: %s", cudaGetErrorString(st));
+        } else {
+            ListSource src{sb.data(), nullptr, lists.sites};
+            rc = run(p, n_samples, src, chunk_samples, flags, out, out_capacity, file_begin, sink, user, &local);
+        }
     }
     local.wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (res) *res = local;

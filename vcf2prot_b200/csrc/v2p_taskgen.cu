@@ -48,6 +48,8 @@ struct Sel {  // one generation
     const uint32_t* sites;       // catalogue index of selected site j
     const uint64_t* site_begin;  // n_hap+1
     uint32_t* site_hap;          // haplotype of j
+    uint64_t n_cat;              // catalogue sites (every list entry must be below it)
+    unsigned long long* bad;     // min list position j whose entry is not a catalogue site or not ascending; ~0 = none
     uint8_t* flags;              // bit0 keep, bit1 newg, bit2 lastg, bit3 long payload
     uint64_t *cnt, *slen, *acon, *newg, *shortc, *slotl;              // scan inputs  (n_sel+1, last = 0)
     uint64_t *task_x, *l_x, *a_x, *g_x, *sh_x, *sl_x;                  // exclusive scans
@@ -67,6 +69,10 @@ __global__ void k_tg_site_hap(Sel s) {
         if (s.site_begin[mid] <= j) lo = mid + 1; else hi = mid;
     }
     s.site_hap[j] = (uint32_t)(lo - 1);
+    // the lists index the catalogue tables in every later kernel: reject what is not a site, and lists that are not
+    // strictly ascending inside a haplotype (ascending in a (transcript, position)-sorted catalogue = grouped by transcript)
+    const uint32_t si = s.sites[j];
+    if (si >= s.n_cat || (j > s.site_begin[lo - 1] && s.sites[j - 1] >= si)) atomicMin(s.bad, (unsigned long long)j);
 }
 
 // what one kept site emits (transcript_instructions.rs:654-780 per class, :508-651 for the follow-up copy)
@@ -94,6 +100,7 @@ __device__ __forceinline__ SiteTasks site_tasks(const Cat& c, uint32_t si, bool 
 __global__ void k_tg_classify(Sel s, Cat c) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= s.n_sel) return;
+    if (*s.bad != ~0ull) return;  // a bad list entry (k_tg_site_hap): the host reports it at its next hand-off
     const uint32_t h = s.site_hap[j];
     const uint64_t j0 = s.site_begin[h], j1 = s.site_begin[h + 1];
     const uint32_t si = s.sites[j];
@@ -301,6 +308,7 @@ struct InsGen {
     const uint64_t* site_begin;
     const uint32_t* site_hap;
     uint64_t *newg, *g_x;  // per site (+ sentinel)
+    const unsigned long long* bad_site;  // k_tg_site_hap's verdict on the lists (~0 = fine)
     // per group (+ sentinel)
     uint64_t *g_first, *g_size;
     uint32_t *g_hap, *g_tx, *g_nsites;
@@ -315,6 +323,10 @@ __global__ void k_ti_mark(InsGen g, InsCat c) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j > g.n_sel) return;
     if (j == g.n_sel) {
+        g.newg[j] = 0;
+        return;
+    }
+    if (*g.bad_site != ~0ull) {
         g.newg[j] = 0;
         return;
     }
@@ -571,7 +583,7 @@ struct v2p_catalogue {
     Buf name_off, names;  // v2p_catalogue_set_names
     bool has_names = false;
     // per-generation buffers
-    Buf sites, site_begin, site_hap, flags, scan_in[6], scan_out[6], cub_tmp, totals;
+    Buf sites, site_begin, site_hap, flags, scan_in[6], scan_out[6], cub_tmp, totals, sel_err;
     Buf g_first, g_len, g_slot, g_slot_x, g_hap, g_tx, ann_start, ann_end;
     Buf tasks, task_begin, alt_base, out_base, alt_per_hap, short_tot, mut_dst, alt, out;
     // mask decode (v2p_sites_from_masks)
@@ -640,6 +652,10 @@ int v2p_catalogue_create(int cuda_device, uint64_t n_tx, const uint64_t* tx_offs
     if (!out || !tx_offsets || (n_sites && (!site_tx || !site_pos || !site_cls || !site_rlen || !site_doff || !site_dlen)))
         return V2P_ERR_INVALID_ARG;
     *out = nullptr;
+    for (uint64_t i = 0; i < n_sites; ++i)  // the kernels index tx_offsets[] and pool[] with these
+        if (site_tx[i] >= n_tx || site_cls[i] > V2P_CLS_0 || site_doff[i] + site_dlen[i] > n_pool ||
+            (i && (site_tx[i] < site_tx[i - 1] || (site_tx[i] == site_tx[i - 1] && site_pos[i] < site_pos[i - 1]))))
+            return V2P_ERR_INVALID_ARG;
     v2p_catalogue* c = new (std::nothrow) v2p_catalogue();
     if (!c) return V2P_ERR_INVALID_ARG;
     c->device = cuda_device;
@@ -707,7 +723,7 @@ void v2p_catalogue_destroy(v2p_catalogue* c) {
                   &c->gi_x[0], &c->gi_x[1], &c->gi_x[2], &c->gi_x[3], &c->gi_x[4], &c->gi_x[5], &c->gi_x[6],
                   &c->name_off, &c->names,
                   &c->tx_off, &c->tx, &c->pos, &c->rlen, &c->dlen, &c->cls, &c->doff, &c->pool, &c->sites, &c->site_begin,
-                  &c->site_hap, &c->flags, &c->cub_tmp, &c->totals, &c->g_first, &c->g_len, &c->g_slot, &c->g_slot_x, &c->g_hap,
+                  &c->site_hap, &c->flags, &c->cub_tmp, &c->totals, &c->sel_err, &c->g_first, &c->g_len, &c->g_slot, &c->g_slot_x, &c->g_hap,
                   &c->g_tx, &c->ann_start, &c->ann_end, &c->tasks, &c->task_begin, &c->alt_base, &c->out_base, &c->alt_per_hap,
                   &c->short_tot, &c->mut_dst, &c->alt, &c->out, &c->md_masks, &c->md_csq_begin, &c->md_csq_site, &c->md_keys[0],
                   &c->md_keys[1], &c->md_uniq, &c->md_begin, &c->md_sites, &c->md_ctr};
@@ -871,7 +887,7 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
     cudaStream_t st = c->stream;
     int rc;
     if ((rc = need(c, c->site_hap, n_sel * 4 + 16)) || (rc = need(c, c->flags, n_sel + 16)) || (rc = need(c, c->mut_dst, n_sel * 8 + 16)) ||
-        (rc = need(c, c->totals, 64)))
+        (rc = need(c, c->totals, 64)) || (rc = need(c, c->sel_err, 16)))
         return rc;
     for (int i = 0; i < 6; ++i)
         if ((rc = need(c, c->scan_in[i], (n_sel + 1) * 8)) || (rc = need(c, c->scan_out[i], (n_sel + 1) * 8))) return rc;
@@ -886,6 +902,8 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
     s.n_sel = n_sel, s.n_hap = n_hap;
     s.sites = d_sites, s.site_begin = d_site_begin;
     s.site_hap = (uint32_t*)c->site_hap.p, s.flags = (uint8_t*)c->flags.p;
+    s.n_cat = c->n_sites, s.bad = (unsigned long long*)c->sel_err.p;
+    CU(c, cudaMemsetAsync(s.bad, 0xFF, 8, st));
     uint64_t** ins[6] = {&s.cnt, &s.slen, &s.acon, &s.newg, &s.shortc, &s.slotl};
     uint64_t** outs[6] = {&s.task_x, &s.l_x, &s.a_x, &s.g_x, &s.sh_x, &s.sl_x};
     for (int i = 0; i < 6; ++i) *ins[i] = (uint64_t*)c->scan_in[i].p, *outs[i] = (uint64_t*)c->scan_out[i].p;
@@ -904,11 +922,15 @@ int generate_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, const u
     CU(c, c->pub.reserve(64));
     {
         v2p::PubList pl{};
-        pl.src[0] = (const unsigned long long*)(s.task_x + n_sel), pl.src[1] = (const unsigned long long*)(s.g_x + n_sel), pl.n = 2;
+        pl.src[0] = (const unsigned long long*)(s.task_x + n_sel), pl.src[1] = (const unsigned long long*)(s.g_x + n_sel);
+        pl.src[2] = s.bad, pl.n = 3;
         v2p::k_publish_list<<<1, 32, 0, st>>>(c->pub.p, pl);
     }
     CU(c, cudaStreamSynchronize(st));
     const uint64_t n_tasks = c->pub.p[0], n_groups = c->pub.p[1];
+    if (c->pub.p[2] != ~0ull)
+        return cfail(c, V2P_ERR_INVALID_ARG, "site list entry %llu is not a catalogue site (< %llu) in strictly ascending order "
+                     "inside its haplotype", c->pub.p[2], (unsigned long long)c->n_sites);
 
     Grp g{};
     g.n_groups = n_groups;
@@ -990,7 +1012,7 @@ int generate_ins_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, con
     if (fasta && !c->has_names) return cfail(c, V2P_ERR_INVALID_ARG, "V2P_GEN_FASTA needs v2p_catalogue_set_names first");
     int rc;
     if ((rc = need(c, c->site_hap, n_sel * 4 + 16)) || (rc = need(c, c->gi_newg, (n_sel + 1) * 8)) ||
-        (rc = need(c, c->gi_gx, (n_sel + 1) * 8)) || (rc = need(c, c->gi_err, 16)) || (rc = need(c, c->task_begin, (n_hap + 1) * 8)) ||
+        (rc = need(c, c->gi_gx, (n_sel + 1) * 8)) || (rc = need(c, c->gi_err, 16)) || (rc = need(c, c->sel_err, 16)) || (rc = need(c, c->task_begin, (n_hap + 1) * 8)) ||
         (rc = need(c, c->alt_base, (n_hap + 1) * 8)) || (rc = need(c, c->out_base, (n_hap + 1) * 8)))
         return rc;
     CU(c, c->pub.reserve(64));
@@ -1007,20 +1029,26 @@ int generate_ins_on_device(v2p_catalogue* c, uint64_t n_hap, uint64_t n_sel, con
     g.skip_aborts = (flags & V2P_GEN_SKIP_ABORTS) ? 1 : 0;
     CU(c, cudaMemsetAsync(g.err, 0xFF, 8, st));
     CU(c, cudaMemsetAsync(g.err + 1, 0, 8, st));
+    g.bad_site = (const unsigned long long*)c->sel_err.p;
+    CU(c, cudaMemsetAsync(c->sel_err.p, 0xFF, 8, st));
     if (n_sel) {
         Sel sh{};
         sh.n_sel = n_sel, sh.n_hap = n_hap, sh.site_begin = d_site_begin, sh.site_hap = (uint32_t*)c->site_hap.p;
+        sh.sites = d_sites, sh.n_cat = c->n_sites, sh.bad = (unsigned long long*)c->sel_err.p;
         k_tg_site_hap<<<blocks(n_sel), 256, 0, st>>>(sh);
     }
     k_ti_mark<<<blocks(n_sel + 1), 256, 0, st>>>(g, cat);
     if ((rc = xsum(c, g.newg, g.g_x, n_sel + 1))) return rc;
     {
         v2p::PubList pl{};
-        pl.src[0] = (const unsigned long long*)(g.g_x + n_sel), pl.n = 1;
+        pl.src[0] = (const unsigned long long*)(g.g_x + n_sel), pl.src[1] = g.bad_site, pl.n = 2;
         v2p::k_publish_list<<<1, 32, 0, st>>>(c->pub.p, pl);
     }
     CU(c, cudaStreamSynchronize(st));
     const uint64_t G = c->pub.p[0];
+    if (c->pub.p[1] != ~0ull)
+        return cfail(c, V2P_ERR_INVALID_ARG, "site list entry %llu is not a catalogue site (< %llu) in strictly ascending order "
+                     "inside its haplotype", c->pub.p[1], (unsigned long long)c->n_sites);
     g.n_groups = G;
     if ((rc = need(c, c->gi_first, (G + 1) * 8)) || (rc = need(c, c->gi_size, (G + 1) * 8)) || (rc = need(c, c->gi_hap, (G + 1) * 4)) ||
         (rc = need(c, c->gi_tx, (G + 1) * 4)) || (rc = need(c, c->gi_nsites, (G + 1) * 4)) || (rc = need(c, c->gi_status, G + 1)))
