@@ -33,8 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from bench_support import (ClockSampler, alg_bytes, cpu_engine_rate, gzip_measure, make_workload, oracle_check_range,  # noqa: E402
-                           pipeline_measure, reference_binary_rate)
+from bench_support import (ClockSampler, StreamChecker, alg_bytes, c3_measure, cpu_engine_rate, gzip_measure,  # noqa: E402
+                           make_workload, pipeline_measure, reference_binary_rate)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -76,9 +76,31 @@ def parse_args():
     ap.add_argument("--pipeline-chunk", type=int, default=128, help="samples per pipeline chunk")
     ap.add_argument("--written-samples", type=int, default=256,
                     help="samples whose files the pipeline also WRITES, {tmpdir}/{proband}.fasta and .fasta.gz (0 = skip)")
+    ap.add_argument("--c3-samples", type=int, default=50000,
+                    help="samples of the ONE cohort that is sharded over the ranks and streamed (BASELINE configs[2]); 0 = skip")
+    ap.add_argument("--c3-chunk-samples", type=int, default=1024, help="samples per streamed chunk of the c3 section")
+    ap.add_argument("--no-c3-parity", action="store_true", help="skip the whole-cohort oracle check of the c3 section")
+    ap.add_argument("--no-parity", action="store_true", help="skip the whole-cohort oracle check of the timed output")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
                     help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
     return ap.parse_args()
+
+
+def ncu_traffic(args, n_res):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this configuration
+    (profiles/ncu_traffic.json), scaled by residues when the capture is of another cohort size.
+    -> (bytes per launch, note, bytes per residue) or (None, None, None)."""
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath) and not args.fasta_image:
+        mode = "plain" if (args.no_registered_ref or args.ref_mode == "plain") else "replicas"
+        for ent in json.load(open(tpath)).get("entries", []):
+            if (ent["workload"], ent["mode"], ent["layout"]) == (args.workload, mode, args.layout) and ent["dram_bytes_per_launch"]:
+                per_res = ent["dram_bytes_per_launch"] / ent["residues"]
+                if ent["samples"] == args.samples:
+                    return ent["dram_bytes_per_launch"], "ncu --set full capture of this configuration (%s)" % ent["capture"], per_res
+                return (int(per_res * n_res), "scaled by residues from the %d-sample ncu --set full capture (%s)" %
+                        (ent["samples"], ent["capture"]), per_res)
+    return None, None, None
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -216,28 +238,46 @@ def main():
             batch.kept_hap is not None and not args.no_cpu_baseline):
         pipeline_line = pipeline_measure(args, prot, cat, batch, eng, local_rank, barrier, shard, dev)
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    traffic, traffic_note, dram_per_res = ncu_traffic(args, n_res)
+
+    # ---- parity of everything that was timed: the WHOLE result tape of every rank against the oracle (gir.rs:230-234)
+    parity = None
+    if not args.no_parity and not args.no_cpu_baseline:
+        threads = max(1, (os.cpu_count() or 1) // world)
+        ck = StreamChecker(torch, dev, prot.residues, threads)
+        ck.check(d_out[:n_out], batch.task_begin, batch.tasks, batch.alt, batch.alt_base, batch.out_base)
+        bad_all, haps_all = shard.sum_over_ranks(ck.bad_haps, dev), shard.sum_over_ranks(ck.checked_haps, dev)
+        e2e_all = None if e2e_matches_device is None else shard.sum_over_ranks(0 if e2e_matches_device else 1, dev) == 0
+        parity = {"checked_haplotypes": haps_all // world, "haplotypes_per_gpu": n_hap, "residues": shard.sum_over_ranks(ck.checked_bytes, dev),
+                  "mismatching_haplotypes": bad_all, "gpu_equals_oracle": bad_all == 0 and haps_all == total_haps,
+                  "all_ranks": True, "ranks": world, "oracle_threads_per_rank": threads, "seconds": round(ck.seconds, 2),
+                  "first_mismatching_haplotype": ck.first_bad, "e2e_equals_device_path": e2e_all,
+                  "what": "every rank: the whole device-resident result tape of the timed step, D2H in 1 GiB pieces, "
+                          "re-executed haplotype by haplotype by the oracle (ref_batch_check, u8 tapes)"}
+        del ck
+
+    # ---- BASELINE configs[2]: ONE 50k-sample cohort, contiguous ranges over the ranks, streamed (strong scaling)
+    c3_line = None
+    if args.c3_samples > 0 and not args.no_registered_ref and not args.fasta_image and args.layout == "packed":
+        c3_line = c3_measure(args, eng, prot, rank, world, local_rank, dev, shard, barrier, peak, dram_per_res)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- CPU baseline (rank 0, N == 1 only): oracle port on a bounded sample, also the parity checker
+    # ---- CPU baseline (rank 0, N == 1 only): oracle port on a bounded sample of the same cohort
     cpu = None
-    parity = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         nh = min(args.cpu_sample_haps, n_hap)
-        o1 = int(batch.out_base[nh])
-        gpu_sample = d_out[:o1].cpu().numpy()
-        rate32, el, reps, nh, nres, ok = cpu_engine_rate(batch, prot, nh, args.cpu_seconds, threads, 4, gpu_sample)
-        rate8, _, _, _, _, ok8 = cpu_engine_rate(batch, prot, nh, min(3.0, args.cpu_seconds), threads, 1, gpu_sample)
-        # the tail of the cohort sits beyond 4 GiB of result tape: check those offsets against the oracle too
-        nt = min(16, n_hap)
-        t_o0, t_o1 = int(batch.out_base[n_hap - nt]), int(batch.out_base[n_hap])
-        tail_ok = oracle_check_range(batch, prot, n_hap - nt, n_hap, d_out[t_o0:t_o1].cpu().numpy())
-        parity = {"checked_haplotypes": nh + nt, "residues": nres + (t_o1 - t_o0), "gpu_equals_oracle": bool(ok and ok8 and tail_ok),
-                  "head_haplotypes": nh, "tail_haplotypes": nt, "tail_result_tape_offset": t_o0,
-                  "e2e_equals_device_path": e2e_matches_device}
+        rate32, el, reps, nh, nres, _ = cpu_engine_rate(batch, prot, nh, args.cpu_seconds, threads, 4)
+        rate8, _, _, _, _, _ = cpu_engine_rate(batch, prot, nh, min(3.0, args.cpu_seconds), threads, 1)
         cpu = {"value": rate32, "unit": "residues/s", "cores": threads, "kind": "port",
                "sample": "first %d haplotypes (%d residues) of the same cohort, UTF-32 tapes like the reference "
                          "(gir.rs:18-22), %d passes in %.1f s, haplotypes over %d threads (exec.rs:34-40)" %
@@ -251,7 +291,7 @@ def main():
     taskgen = None
     other_line = None
     if world == 1 and not args.no_taskgen and not args.fasta_image and batch.kept_hap is not None:
-        from vcf2prot_b200 import cohort as C
+        from synth import cohort as C
         from vcf2prot_b200.taskgen import DeviceCatalogue
 
         dc = DeviceCatalogue(prot, cat, local_rank)
@@ -349,38 +389,16 @@ def main():
     if world == 1 and args.gzip_samples > 0 and not args.no_registered_ref:
         gzip_line = gzip_measure(args, prot, cat, eng, dev, local_rank, torch)
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
-    else:
-        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     copy_avg_ms = float(np.mean(copy_ms))
     achieved = b_alg / (copy_avg_ms * 1e-3) / 1e9
-    # the kernel must WRITE every residue once: measure this GPU's write-only ceiling (torch fill_, best of 5) beside it
-    wbuf = d_out[: min(n_out, 8 << 30)]
-    wbest = 1e9
-    for _ in range(6):
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        wbuf.fill_(46)
-        w1.record()
-        torch.cuda.synchronize()
-        wbest = min(wbest, w0.elapsed_time(w1))
-    write_peak = wbuf.numel() / (wbest * 1e-3) / 1e9
-    write_rate = n_out / (copy_avg_ms * 1e-3) / 1e9
-    traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.isfile(tpath) and not args.fasta_image:
-        mode = "plain" if (args.no_registered_ref or args.ref_mode == "plain") else "replicas"
-        for ent in json.load(open(tpath)).get("entries", []):
-            if (ent["workload"], ent["mode"], ent["layout"]) == (args.workload, mode, args.layout) and ent["dram_bytes_per_launch"]:
-                if ent["samples"] == args.samples:
-                    traffic, traffic_note = ent["dram_bytes_per_launch"], "ncu --set full capture of this configuration (%s)" % ent["capture"]
-                else:  # same mix, reference mode and layout at another cohort size: DRAM bytes scale with residues
-                    traffic = int(ent["dram_bytes_per_launch"] * (n_res / ent["residues"]))
-                    traffic_note = "scaled by residues from the %d-sample ncu --set full capture (%s)" % (ent["samples"], ent["capture"])
-                break
+    # the kernel must WRITE every residue once: this GPU's write-only ceiling, measured live with the repo's own store-only
+    # kernels (cudaMemsetAsync; TMA bulk stores of 8 KiB tiles -- the copy kernel's own store) over the result buffer
+    from synth import devgen
 
+    torch.cuda.synchronize()
+    ceil = devgen.store_ceiling_gbs(local_rank, d_out.data_ptr(), min(n_out, 16 << 30))
+    write_peak = ceil["tma_bulk_store_8k"]
+    write_rate = n_out / (copy_avg_ms * 1e-3) / 1e9
     value = total_res / (ms_per_step * 1e-3)  # every rank holds its own same-sized sample range (weak scaling)
     line = {
         "metric": "generated residues/sec", "value": value, "unit": "residues/s", "n_gpus": world,
@@ -405,12 +423,19 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_copy_tiles", "peak_source": peak_src,
+                     "dram_gbs": None if traffic is None else traffic / (copy_avg_ms * 1e-3) / 1e9,
+                     "dram_frac": None if traffic is None else traffic / (copy_avg_ms * 1e-3) / 1e9 / peak,
+                     "dram_note": "what DRAM itself moved (ncu dram__bytes_read + dram__bytes_write per launch) / live kernel time / "
+                                  "peak: the source tape is L2-resident, so `frac` (algorithmic bytes, SURVEY 8d) counts ~20 GB of "
+                                  "L2 hits per launch that never reach DRAM",
                      "alg_bytes_per_launch": b_alg, "kernel_ms": copy_avg_ms, "launch_group_ms": float(np.mean(group_ms)),
                      "kernel_share_of_step": copy_avg_ms / ms_per_step,
                      "write_only": {"achieved_gbs": write_rate, "peak_gbs": write_peak, "frac": write_rate / write_peak,
-                                    "note": "result-tape bytes written / kernel time vs torch fill_ on the same GPU: the "
-                                            "hard floor of this path is one DRAM write per residue"}},
-        "cpu_baseline": cpu, "parity": parity, "other_layout": other_line, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
+                                    "ceilings_gbs": ceil,
+                                    "note": "result-tape bytes written / kernel time vs a store-only kernel on the same GPU and buffer "
+                                            "(TMA bulk stores of 8 KiB tiles, the copy kernel's own store instruction and grid); the hard "
+                                            "floor of this path is one DRAM write per residue"}},
+        "cpu_baseline": cpu, "parity": parity, "c3": c3_line, "other_layout": other_line, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
     }
     print(json.dumps(line))
     if world > 1:

@@ -21,7 +21,7 @@ if ROOT not in sys.path:
 
 # ------------------------------------------------------------------------------------------------ workload
 def make_workload(kind: str, n_samples: int, rank: int, layout: str = "packed", fasta: bool = False):
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
 
     prot = C.make_proteome(seed=0x5EED0001, giant=(20 if kind == "c4" else 0))
     if kind == "c2":
@@ -144,7 +144,7 @@ def cpu_engine_rate(batch, prot, n_haps: int, seconds: float, threads: int, widt
 def reference_binary_rate(prot, cat, batch, n_samples: int):
     """Whole-tool timing of the reference's own prebuilt binary on the first n_samples of the cohort."""
     from oracle import refbin
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
 
     if not refbin.available() or n_samples <= 0:
         return None
@@ -183,7 +183,7 @@ def gzip_measure(args, prot, cat, eng, dev, local_rank, torch):
     compressed bytes cross PCIe.  Beside it: zlib level 9 (what flate2 Compression::best amounts to) on one host core."""
     import zlib
 
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
     from vcf2prot_b200.gzipdev import DeviceGzip
 
     ns = args.gzip_samples
@@ -233,7 +233,7 @@ def gzip_measure(args, prot, cat, eng, dev, local_rank, torch):
 def oracle_file_text(batch, prot, s: int) -> bytes:
     """Sample s's .fasta text from the ORACLE's tapes (hap-1 records, then hap-2 records, tape order)."""
     from oracle import cengine
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
 
     h0, h1 = 2 * s, 2 * s + 2
     t0, t1 = int(batch.task_begin[h0]), int(batch.task_begin[h1])
@@ -260,6 +260,7 @@ def pipeline_measure(args, prot, cat, batch, eng, local_rank, barrier, shard, de
     exist on the host.  First and last file are compared with the oracle's text."""
     import zlib
 
+    from synth import cohort as C
     from vcf2prot_b200.pipeline import DevicePipeline, csr_lists
 
     ns = batch.n_hap // 2 if args.pipeline_samples < 0 else min(args.pipeline_samples, batch.n_hap // 2)
@@ -267,7 +268,7 @@ def pipeline_measure(args, prot, cat, batch, eng, local_rank, barrier, shard, de
     sb, sites = csr_lists(batch.kept_hap[sel], batch.kept_site[sel], 2 * ns)
     n_res = int((batch.ann_end - batch.ann_start)[batch.ann_hap < 2 * ns].sum())
     want_first, want_last = oracle_file_text(batch, prot, 0), oracle_file_text(batch, prot, ns - 1)
-    pipe = DevicePipeline(eng, prot, cat, lanes=2, device=local_rank)
+    pipe = DevicePipeline(eng, prot, cat, C.default_names(prot), lanes=2, device=local_rank)
     out = {"samples": ns, "chunk_samples": args.pipeline_chunk, "lanes": 2, "residues": n_res,
            "api": "v2p_pipeline_run_lists (host site lists in, file images to a sink through the pipeline's pinned ring)"}
     warm = min(ns, 2 * args.pipeline_chunk)
@@ -318,3 +319,188 @@ def pipeline_measure(args, prot, cat, batch, eng, local_rank, barrier, shard, de
                 shutil.rmtree(tmpdir, ignore_errors=True)
     pipe.close()
     return out
+
+
+# ------------------------------------------------------------------------------------------------ whole-cohort parity
+class _DevPtr:
+    """A raw device pointer as a __cuda_array_interface__ object (so torch can view library-owned HBM)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def dev_view(torch, ptr: int, nbytes: int, dev):
+    return torch.as_tensor(_DevPtr(ptr, nbytes), device=dev) if nbytes else torch.empty(0, dtype=torch.uint8, device=dev)
+
+
+class StreamChecker:
+    """GPU result tapes against the oracle, whole batches at a time and at copy speed: the tape comes back in
+    ~256-haplotype pieces through two pinned buffers while the previous piece is checked by oracle.batch_check on
+    `threads` host threads (each haplotype is executed into a cache-resident scratch tape and compared)."""
+
+    def __init__(self, torch, dev, ref: np.ndarray, threads: int, piece_bytes: int = 1 << 30):
+        self.torch, self.dev, self.ref, self.threads = torch, dev, np.ascontiguousarray(ref, np.uint8), max(1, threads)
+        self.bufs = [torch.empty(piece_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.stream = torch.cuda.Stream(device=dev)
+        self.checked_haps = self.checked_bytes = self.bad_haps = 0
+        self.first_bad = None
+        self.seconds = 0.0
+
+    def check(self, d_out, task_begin, tasks, alt, alt_base, out_base, hap_offset: int = 0):
+        """d_out: torch uint8 tensor on the device holding the tapes of out_base[0]..out_base[-1]; the other arrays
+        are host numpy arrays of the same batch (v2p_batch layout)."""
+        from oracle import cengine
+
+        torch = self.torch
+        t_start = time.perf_counter()
+        n_hap = len(out_base) - 1
+        ob = out_base.astype(np.int64) - int(out_base[0])
+        cap = self.bufs[0].numel()
+        pieces, h0 = [], 0
+        while h0 < n_hap:  # as many haplotypes as fit one pinned buffer (at least one)
+            h1 = int(np.searchsorted(ob, ob[h0] + cap, side="right")) - 1
+            h1 = min(max(h1, h0 + 1), n_hap)
+            if ob[h1] - ob[h0] > cap:
+                raise ValueError("one haplotype is larger than the pinned piece buffer")
+            pieces.append((h0, h1))
+            h0 = h1
+        result = {}
+
+        def work(i, a, b, host):
+            t0, t1 = int(task_begin[a]), int(task_begin[b])
+            a0, a1 = int(alt_base[a]), int(alt_base[b])
+            result[i] = cengine.batch_check(task_begin[a:b + 1], tasks[t0 - int(task_begin[0]):t1 - int(task_begin[0])], self.ref,
+                                            alt[a0 - int(alt_base[0]):a1 - int(alt_base[0])], alt_base[a:b + 1], host,
+                                            out_base[a:b + 1], threads=self.threads)
+
+        th = None
+        for i, (a, b) in enumerate(pieces):
+            buf = self.bufs[i % 2]
+            n = int(ob[b] - ob[a])
+            with torch.cuda.stream(self.stream):
+                buf[:n].copy_(d_out[int(ob[a]):int(ob[b])], non_blocking=True)
+            self.stream.synchronize()
+            if th is not None:
+                th.join()  # piece i-1 checked (its buffer is the other one; buffer i%2 was checked before this copy began)
+            th = threading.Thread(target=work, args=(i, a, b, buf[:n].numpy()))
+            th.start()
+            # the NEXT copy goes into the other buffer, whose check (piece i-1) has just been joined
+        if th is not None:
+            th.join()
+        for i, (a, b) in enumerate(pieces):
+            nb, fb = result[i]
+            if nb and self.first_bad is None:
+                self.first_bad = hap_offset + a + fb
+            self.bad_haps += nb
+        self.checked_haps += n_hap
+        self.checked_bytes += int(ob[-1])
+        self.seconds += time.perf_counter() - t_start
+        return self.bad_haps == 0
+
+
+# ------------------------------------------------------------------------------------------------ C3: the 50k-sample cohort
+def c3_measure(args, eng, prot, rank, world, local_rank, dev, shard, barrier, peak_gbs, dram_bytes_per_residue):
+    """BASELINE.json configs[2] / north_star: ONE seeded 50,000-sample cohort, contiguous sample ranges over the ranks
+    (parts/exec.rs:34-40: the reference's parallel unit is the proband), every rank streaming its range through HBM
+    in chunks: [synthetic site lists, made on the device] -> v2p_generate_tasks_from_lists -> v2p_execute_batch
+    (DEVICE_PTRS).  At N = 1 all ~320 GB of result tape go through the one GPU.  STRONG scaling: total work is fixed.
+    Timed pass: device time (CUDA events) of every chunk's launch group, summed, max over ranks.  Check pass: every
+    chunk's tapes and Task arrays come back and the oracle re-executes ALL of them (every rank its own range)."""
+    import torch
+
+    from synth import cohort as C
+    from synth import devgen
+    from vcf2prot_b200 import _lib as L
+    from vcf2prot_b200.taskgen import DeviceCatalogue, execute_generated
+
+    n_samples, chunk = args.c3_samples, args.c3_chunk_samples
+    seed = 0x5EED0003
+    cat = C.make_catalogue(prot, 280000, seed=seed)
+    gen = devgen.DeviceCohort(cat, seed, local_rank)
+    dc = DeviceCatalogue(prot, cat, local_rank)
+
+    def generate(s0, ns):
+        begin, sites, n = gen.lists(2 * s0, 2 * ns)
+        lists = L.SiteLists()
+        lists.n_hap, lists.n_sites, lists.site_begin, lists.sites = 2 * ns, n, begin.data_ptr(), sites.data_ptr()
+        return dc.generate_from_lists(lists, aligned=False), n
+
+    # ---- pass 0 (planning, untimed): result-tape bytes of every sample -> contiguous ranges balanced by bytes
+    t0 = time.perf_counter()
+    weights = np.zeros(n_samples, np.int64)
+    for s0 in range(0, n_samples, chunk):
+        ns = min(chunk, n_samples - s0)
+        g, _ = generate(s0, ns)
+        ob = dc.read(g.batch.out_base, 2 * ns + 1, np.uint64).astype(np.int64)
+        weights[s0:s0 + ns] = ob[2::2] - ob[:-2:2]
+    ranges = shard.balanced_ranges(weights.tolist(), world)
+    lo, hi = ranges[rank]
+    per_rank = [int(weights[a:b].sum()) for a, b in ranges]
+    plan_s = time.perf_counter() - t0
+
+    # ---- timed pass
+    chunks = [(s0, min(chunk, hi - s0)) for s0 in range(lo, hi, chunk)]
+    for s0, ns in chunks[:1]:  # warm-up: allocations of the largest buffers
+        g, _ = generate(s0, ns)
+        for _ in range(3):
+            execute_generated(eng, g)
+    launches0 = eng.launch_count()
+    barrier()
+    w0 = time.perf_counter()
+    exec_ms = copy_ms = gen_ms = 0.0
+    n_res = n_tasks = n_sites = 0
+    for s0, ns in chunks:
+        g, n = generate(s0, ns)
+        gm, cm = execute_generated(eng, g)
+        exec_ms, copy_ms, gen_ms = exec_ms + gm, copy_ms + cm, gen_ms + g.gen_ms
+        n_res, n_tasks, n_sites = n_res + int(g.batch.n_out), n_tasks + int(g.batch.n_tasks), n_sites + n
+    torch.cuda.synchronize()
+    wall_s = time.perf_counter() - w0
+    launches = eng.launch_count() - launches0
+    alg = 2 * n_res + 16 * n_tasks  # SURVEY 8d: read + written + 16 B/task (these classes leave no '.' gaps)
+    t_exec = shard.max_over_ranks(exec_ms, dev)
+    t_copy = shard.max_over_ranks(copy_ms, dev)
+    t_gen_exec = shard.max_over_ranks(exec_ms + gen_ms, dev)
+    t_wall = shard.max_over_ranks(wall_s, dev)
+    tot_res, tot_tasks, tot_alg = shard.sum_over_ranks(n_res, dev), shard.sum_over_ranks(n_tasks, dev), shard.sum_over_ranks(alg, dev)
+
+    # ---- check pass: every haplotype of this rank's range against the oracle
+    parity = None
+    if not args.no_c3_parity:
+        threads = max(1, (os.cpu_count() or 1) // world)
+        ck = StreamChecker(torch, dev, prot.residues, threads)
+        for s0, ns in chunks:
+            g, _ = generate(s0, ns)
+            execute_generated(eng, g)
+            b = g.batch
+            nh = 2 * ns
+            ck.check(dev_view(torch, b.out, b.n_out, dev), dc.read(b.task_begin, nh + 1, np.uint64),
+                     dc.read(b.tasks, 4 * b.n_tasks, np.uint32).reshape(-1, 4), dc.read(b.alt, b.n_alt, np.uint8),
+                     dc.read(b.alt_base, nh + 1, np.uint64), dc.read(b.out_base, nh + 1, np.uint64), hap_offset=2 * s0)
+        bad_all = shard.sum_over_ranks(ck.bad_haps, dev)
+        haps_all = shard.sum_over_ranks(ck.checked_haps, dev)
+        bytes_all = shard.sum_over_ranks(ck.checked_bytes, dev)
+        parity = {"checked_haplotypes": haps_all, "haplotypes": 2 * n_samples, "checked_residues": bytes_all,
+                  "mismatching_haplotypes": bad_all, "gpu_equals_oracle": bad_all == 0 and haps_all == 2 * n_samples,
+                  "all_ranks": True, "oracle_threads_per_rank": threads, "seconds": round(shard.max_over_ranks(ck.seconds, dev), 1),
+                  "what": "every chunk's result tape + Task arrays D2H, oracle.batch_check re-executes every haplotype (u8 tapes)"}
+    gen.close()
+    dc.close()
+    kernel_gbs = tot_alg / (t_copy * 1e-3) / 1e9
+    return {"workload": "c3: ONE %d-sample phased cohort (seed 0x5EED0003, %d haplotypes) x 20k-transcript proteome, missense-dominated "
+                        "mix, contiguous sample ranges balanced by result-tape bytes over %d rank(s), streamed in %d-sample chunks"
+                        % (n_samples, 2 * n_samples, world, chunk),
+            "scaling": "strong", "n_gpus": world, "samples": n_samples, "residues": tot_res, "tasks": tot_tasks,
+            "value": tot_res / (t_exec * 1e-3), "unit": "residues/s", "exec_ms_max_rank": t_exec, "copy_kernel_ms_max_rank": t_copy,
+            "value_with_task_generation": tot_res / (t_gen_exec * 1e-3), "gen_plus_exec_ms_max_rank": t_gen_exec,
+            "wall_s_max_rank": t_wall, "haplotypes_per_s": 2 * n_samples / (t_exec * 1e-3),
+            "chunks_this_rank": len(chunks), "chunk_samples": chunk, "sample_range_rank0": [int(ranges[0][0]), int(ranges[0][1])],
+            "range_bytes_max_over_mean": max(per_rank) / (sum(per_rank) / world), "plan_pass_s": round(plan_s, 2),
+            "gpu_launches": int(launches), "sites": shard.sum_over_ranks(n_sites, dev),
+            "roofline": {"bound": "hbm", "alg_bytes": tot_alg, "alg_gbs_kernel": kernel_gbs, "peak_gbs_aggregate": peak_gbs * world,
+                         "frac": kernel_gbs / (peak_gbs * world),
+                         "dram_gbs_kernel": None if dram_bytes_per_residue is None else dram_bytes_per_residue * tot_res / (t_copy * 1e-3) / 1e9,
+                         "dram_frac": None if dram_bytes_per_residue is None else dram_bytes_per_residue * tot_res / (t_copy * 1e-3) / 1e9 / (peak_gbs * world),
+                         "note": "kernel = k_copy_tiles time summed over this rank's chunks, max over ranks; alg = SURVEY 8d bytes; dram = "
+                                 "ncu DRAM bytes per residue of the C2 capture x residues"},
+            "parity": parity}

@@ -31,6 +31,8 @@ def load() -> C.CDLL:
         lib.ref_gir_execute_u8.argtypes = soa
         lib.ref_batch_execute.argtypes = [U64, P, P, P, P, U64, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(U64), C.POINTER(U64)]
+        lib.ref_batch_check.argtypes = [U64, P, P, P, P, U64, P, P, P, P, C.c_int, C.c_int, C.POINTER(U64)]
+        lib.ref_batch_check.restype = U64
         lib.ref_widen_u8_to_u32.argtypes = [P, P, U64]
         lib.ref_widen_u8_to_u32.restype = None
         _lib = lib
@@ -75,3 +77,23 @@ def batch_execute(task_begin: np.ndarray, tasks: np.ndarray, ref: np.ndarray, al
                                _p(alt_base), _p(out), _p(out_base), width, int(fill_dot), int(validate), int(threads),
                                C.byref(bh), C.byref(bi))
     return st, bh.value, bi.value
+
+
+def batch_check(task_begin: np.ndarray, tasks: np.ndarray, ref: np.ndarray, alt: np.ndarray, alt_base: np.ndarray,
+                got: np.ndarray, out_base: np.ndarray, ref_base: Optional[np.ndarray] = None, threads: int = 1) -> Tuple[int, int]:
+    """Whole-batch checker: every haplotype is executed into a thread-private scratch tape and compared with `got`
+    (somebody else's result tape in the same layout; `got[out_base[h] - out_base[0] ...]` when the bases do not start
+    at 0).  The base arrays may be slices of cohort-wide arrays: everything is rebased on entry [0].
+    Returns (number of haplotypes that differ or fail, lowest such haplotype)."""
+    lib = load()
+    width = got.dtype.itemsize
+    assert width in (1, 4) and ref.dtype == got.dtype and alt.dtype == got.dtype
+    rb = lambda a: np.ascontiguousarray(a, np.uint64) - np.uint64(a[0]) if len(a) else np.ascontiguousarray(a, np.uint64)
+    task_begin, alt_base, out_base = rb(task_begin), rb(alt_base), rb(out_base)
+    tasks = np.ascontiguousarray(tasks, np.uint32)
+    if ref_base is not None:
+        ref_base = rb(ref_base)
+    fb = C.c_uint64(0)
+    n_bad = lib.ref_batch_check(len(task_begin) - 1, _p(task_begin), _p(tasks), _p(ref), _p(ref_base), len(ref), _p(alt),
+                                _p(alt_base), _p(got), _p(out_base), width, int(threads), C.byref(fb))
+    return int(n_bad), int(fb.value)

@@ -190,6 +190,71 @@ int ref_batch_execute(uint64_t n_hap, const uint64_t *task_begin, const ref_task
     return j.status;
 }
 
+/* ---- whole-cohort checker: execute every haplotype into a thread-private scratch tape (which stays in the cache)
+ * and compare it with the bytes somebody else produced for it (`got`, laid out like `out`).  Same serial loop per
+ * haplotype as above; haplotypes over `threads` host threads.  Nothing cohort-sized is allocated, so a 320 GB cohort
+ * can be checked chunk by chunk at memcpy speed.  Returns the number of haplotypes that differ (or fail to execute);
+ * *first_bad = the lowest such haplotype. */
+typedef struct {
+    batch_job j;
+    const uint8_t *got;
+    uint64_t n_bad, first_bad;
+} check_job;
+
+static void *check_worker(void *arg) {
+    check_job *c = (check_job *)arg;
+    batch_job *j = &c->j;
+    size_t w = (size_t)j->width, cap = 0;
+    uint8_t *scratch = NULL;
+    batch_job mine = *j; /* private view whose `out` is the scratch, shifted so that out_base[h] lands at scratch[0] */
+    for (;;) {
+        uint64_t h = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (h >= j->n_hap) break;
+        size_t n = (size_t)(j->out_base[h + 1] - j->out_base[h]) * w;
+        if (n > cap) {
+            free(scratch);
+            cap = n + n / 4 + 64;
+            scratch = (uint8_t *)malloc(cap);
+        }
+        mine.out = scratch - j->out_base[h] * w;
+        uint64_t bad;
+        int st = exec_one_hap(&mine, h, &bad);
+        if (st != REF_OK || memcmp(scratch, c->got + j->out_base[h] * w, n) != 0) {
+            pthread_mutex_lock(&j->mu);
+            if (c->n_bad == 0 || h < c->first_bad) c->first_bad = h;
+            c->n_bad++;
+            pthread_mutex_unlock(&j->mu);
+        }
+    }
+    free(scratch);
+    return NULL;
+}
+
+uint64_t ref_batch_check(uint64_t n_hap, const uint64_t *task_begin, const ref_task16 *tasks, const void *ref,
+                         const uint64_t *ref_base, uint64_t n_ref, const void *alt, const uint64_t *alt_base,
+                         const void *got, const uint64_t *out_base, int width, int threads, uint64_t *first_bad) {
+    check_job c;
+    memset(&c, 0, sizeof c);
+    batch_job *j = &c.j;
+    j->n_hap = n_hap, j->task_begin = task_begin, j->tasks = tasks, j->ref = ref, j->ref_base = ref_base;
+    j->n_ref = n_ref, j->alt = alt, j->alt_base = alt_base, j->out = NULL, j->out_base = out_base;
+    j->fill_dot = 1, j->validate = 0, j->width = width, j->status = REF_OK;
+    c.got = (const uint8_t *)got;
+    pthread_mutex_init(&j->mu, NULL);
+    if (threads < 1) threads = 1;
+    if (threads == 1) {
+        check_worker(&c);
+    } else {
+        pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+        for (int i = 0; i < threads; ++i) pthread_create(&th[i], NULL, check_worker, &c);
+        for (int i = 0; i < threads; ++i) pthread_join(th[i], NULL);
+        free(th);
+    }
+    pthread_mutex_destroy(&j->mu);
+    if (first_bad) *first_bad = c.first_bad;
+    return c.n_bad;
+}
+
 /* widen a u8 tape to the reference's UTF-32 residue width (baseline set-up, not timed) */
 void ref_widen_u8_to_u32(const uint8_t *src, uint32_t *dst, uint64_t n) {
     for (uint64_t i = 0; i < n; ++i) dst[i] = src[i];

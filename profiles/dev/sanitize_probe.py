@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 from oracle import cengine
 from tests.randtasks import random_batch
 from vcf2prot_b200 import GpuEngine
-from vcf2prot_b200 import cohort as C
+from synth import cohort as C
 
 eng = GpuEngine(0)
 ok = True
@@ -45,7 +45,7 @@ plain = C.build_batch(prot, cat, hap, site, 8, "global", "packed")
 img = C.fasta_image(prot, plain)
 want = np.zeros(img.n_residues, np.uint8)
 assert cengine.batch_execute(img.task_begin, img.tasks, prot.residues, img.alt, img.alt_base, want, img.out_base)[0] == 0
-pipe = DevicePipeline(eng, prot, cat, lanes=2)
+pipe = DevicePipeline(eng, prot, cat, C.default_names(prot), lanes=2)
 sb, sites = csr_lists(hap, site, 8)
 for gz in (False, True):
     out = np.zeros(len(want) + 4096, np.uint8)

@@ -5,7 +5,7 @@ import pytest
 
 from oracle import cengine, taskgen
 from tests.helpers import hap_gir, tape_to_str
-from vcf2prot_b200 import cohort as C
+from synth import cohort as C
 
 RICH_MIX = (0.55, 0.10, 0.10, 0.08, 0.07, 0.05, 0.05)
 

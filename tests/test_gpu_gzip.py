@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import cengine, gzip_twin as G
-from vcf2prot_b200 import cohort as C
+from synth import cohort as C
 from vcf2prot_b200.engine import EngineError
 from vcf2prot_b200.gzipdev import DeviceGzip
 

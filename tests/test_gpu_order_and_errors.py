@@ -44,6 +44,9 @@ def test_garbage_destination_in_front_of_the_next_haplotype_is_a_clean_error(gpu
 def test_error_precedence_follows_the_reference_order_of_events(gpu_engine):
     base = random_batch(72, 12, 6000, gap_prob=0.0, empty_hap_prob=0.0)
     tb = base["task_begin"]
+    roomy = [h for h in range(12) if int(tb[h + 1]) - int(tb[h]) >= 8]  # haplotypes with at least 8 tasks
+    assert len(roomy) >= 3
+    ha, hb, hc = roomy[0], roomy[1], roomy[-1]  # ha < hb < hc
 
     def corrupt(*edits):
         b = dict(base)
@@ -52,28 +55,25 @@ def test_error_precedence_follows_the_reference_order_of_events(gpu_engine):
             b["tasks"][int(tb[h]) + k, col] = val
         return b
 
+    def both(b, validate=False):
+        with pytest.raises(EngineError) as ei:
+            gpu_batch(gpu_engine, b, validate=validate)
+        st, bh, bi, _ = oracle_batch(b, validate=validate)
+        return (st, bh, bi), (ei.value.status, ei.value.bad_hap, ei.value.bad_task)
+
     # same haplotype: slice error at task 3, bad stream at task 5 -> the construction panic (task 5) comes first
-    b = corrupt((4, 3, 1, 0x7FFFFFFF), (4, 5, 3, 7))
-    with pytest.raises(EngineError) as ei:
-        gpu_batch(gpu_engine, b)
-    st, bh, bi, _ = oracle_batch(b)
-    assert st == cengine.REF_ERR_BAD_STREAM and (bh, bi) == (4, 5)
-    assert ei.value.status == L.ERR_BAD_STREAM and (ei.value.bad_hap, ei.value.bad_task) == (4, 5)
-    # ... and with the validator on, a gap at task 2 of that haplotype still loses to the stream code
-    k = next(i for i in range(1, 5) if base["tasks"][int(tb[4]) + i, 1] >= 2)
-    b = corrupt((4, k, 1, int(base["tasks"][int(tb[4]) + k, 1]) - 1), (4, 6, 3, 2))
-    with pytest.raises(EngineError) as ei:
-        gpu_batch(gpu_engine, b, validate=True)
-    st, bh, bi, _ = oracle_batch(b, validate=True)
-    assert st == cengine.REF_ERR_BAD_STREAM and (bh, bi) == (4, 6)
-    assert ei.value.status == L.ERR_BAD_STREAM and (ei.value.bad_hap, ei.value.bad_task) == (4, 6)
+    ref, gpu = both(corrupt((hb, 3, 1, 0x7FFFFFFF), (hb, 5, 3, 7)))
+    assert ref == (cengine.REF_ERR_BAD_STREAM, hb, 5) and gpu == (L.ERR_BAD_STREAM, hb, 5)
+    # ... and with the validator on, a gap in front of it still loses to the stream code
+    k = next(i for i in range(1, 5) if base["tasks"][int(tb[hb]) + i, 1] >= 2)
+    ref, gpu = both(corrupt((hb, k, 1, int(base["tasks"][int(tb[hb]) + k, 1]) - 1), (hb, 6, 3, 2)), validate=True)
+    assert ref == (cengine.REF_ERR_BAD_STREAM, hb, 6) and gpu == (L.ERR_BAD_STREAM, hb, 6)
     # different haplotypes: the earlier haplotype's slice panic happens before the later one is even built
-    b = corrupt((2, 1, 1, 0x7FFFFFFF), (9, 0, 3, 2))
-    with pytest.raises(EngineError) as ei:
-        gpu_batch(gpu_engine, b)
-    st, bh, bi, _ = oracle_batch(b)
-    assert st == cengine.REF_ERR_RES_OOB and (bh, bi) == (2, 1)
-    assert ei.value.status == L.ERR_RES_OOB and (ei.value.bad_hap, ei.value.bad_task) == (2, 1)
+    ref, gpu = both(corrupt((ha, 1, 1, 0x7FFFFFFF), (hc, 0, 3, 2)))
+    assert ref == (cengine.REF_ERR_RES_OOB, ha, 1) and gpu == (L.ERR_RES_OOB, ha, 1)
+    # ... and the other way round
+    ref, gpu = both(corrupt((ha, 2, 3, 9), (hc, 0, 1, 0x7FFFFFFF)))
+    assert ref == (cengine.REF_ERR_BAD_STREAM, ha, 2) and gpu == (L.ERR_BAD_STREAM, ha, 2)
     # SoA entry (one haplotype): stream code at the end beats the slice error in front of it
     with pytest.raises(EngineError) as ei:
         gpu_engine.execute_soa([(0, 0, 9, 0), (0, 0, 1, 0), (2, 0, 0, 0)], "ABCDEFGH", "xyz", 8, fill_dot=True)

@@ -186,7 +186,7 @@ def test_registered_reference_tma_path_bit_exact(gpu_engine, mode, variant, seed
 
 def test_registered_reference_cohort_and_errors(gpu_engine):
     from vcf2prot_b200 import GpuEngine
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
 
     prot = C.make_proteome(seed=5, n_tx=400, mu=5.5, sigma=0.7, hi=6000)
     cat = C.make_catalogue(prot, 9000, seed=6, mix=(0.7, 0.06, 0.06, 0.08, 0.04, 0.03, 0.03), fs_mean=40, fs_max=900)
@@ -371,7 +371,7 @@ def test_full_size_properties(gpu_engine):
 def test_host_pointer_pipeline_three_chunks_in_flight(gpu_engine):
     """The streaming shape: per-chunk host-pointer calls with V2P_FLAG_ASYNC rotate over the engine's 3 staging slots
     (copy-back of chunk i overlaps upload + kernels of chunk i+1); a 4th un-waited batch is refused, not queued."""
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
 
     prot = C.make_proteome(seed=15, n_tx=300, mu=5.5, sigma=0.7, hi=5000)
     cat = C.make_catalogue(prot, 6000, seed=16, mix=(0.8, 0.05, 0.05, 0.05, 0.02, 0.02, 0.01))
@@ -410,7 +410,7 @@ def test_host_pointer_pipeline_three_chunks_in_flight(gpu_engine):
 def test_fasta_file_image_on_device(gpu_engine):
     """record framing as copy segments -> the D2H buffer is the .fasta file image, byte for byte what
     the oracle produces, and it parses into exactly the records of the plain batch."""
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
 
     prot = C.make_proteome(seed=25, n_tx=200, mu=5.2, sigma=0.6, hi=3000)
     cat = C.make_catalogue(prot, 5000, seed=26, mix=(0.7, 0.06, 0.06, 0.08, 0.04, 0.03, 0.03), fs_mean=30, fs_max=500)

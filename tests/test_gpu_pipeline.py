@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import cengine
-from vcf2prot_b200 import cohort as C
+from synth import cohort as C
 from vcf2prot_b200.engine import EngineError
 from vcf2prot_b200.pipeline import DevicePipeline, csr_lists
 
@@ -56,7 +56,7 @@ def test_files_equal_the_oracle_text(world, gpu_engine, lanes, chunk, gzip):
     want, n_res = oracle_files(prot, cat, hap, site, n_samples)
     assert want[0] == b""
     gpu_engine.set_reference(prot.residues)
-    pipe = DevicePipeline(gpu_engine, prot, cat, lanes=lanes)
+    pipe = DevicePipeline(gpu_engine, prot, cat, C.default_names(prot), lanes=lanes)
     sb, sites = csr_lists(hap, site, 2 * n_samples)
     out = np.zeros(sum(len(w) for w in want) + 64 * n_samples + 1024, np.uint8)
     fb, res = pipe.run_lists(sb, sites, n_samples, chunk, gzip, out=out)
@@ -95,7 +95,7 @@ def test_masks_to_files(world, gpu_engine, gzip):
     masks = C.encode_masks(rec, n_samples, hap, site)
     want, _ = oracle_files(prot, cat, hap, site, n_samples)
     gpu_engine.set_reference(prot.residues)
-    pipe = DevicePipeline(gpu_engine, prot, cat, lanes=2)
+    pipe = DevicePipeline(gpu_engine, prot, cat, C.default_names(prot), lanes=2)
     out = np.zeros(sum(len(w) for w in want) + 64 * n_samples + 1024, np.uint8)
     fb, res = pipe.run_masks(masks, rec.csq_begin, rec.csq_site, chunk_samples=8, gzip=gzip, out=out)
     for s in range(n_samples):
@@ -108,7 +108,7 @@ def test_masks_to_files(world, gpu_engine, gzip):
 def test_pipeline_errors(world, gpu_engine):
     prot, cat = world
     gpu_engine.set_reference(prot.residues)
-    pipe = DevicePipeline(gpu_engine, prot, cat, lanes=2)
+    pipe = DevicePipeline(gpu_engine, prot, cat, C.default_names(prot), lanes=2)
     hap, site = cohort_sites(cat, 4, 3)
     sb, sites = csr_lists(hap, site, 8)
     with pytest.raises(EngineError) as ei:  # destination too small: V2P_ERR_RES_OOB, like v2p_gzip_files
@@ -138,7 +138,7 @@ def test_files_on_disk_through_the_native_writer(world, gpu_engine, tmp_path, gz
     hap, site = cohort_sites(cat, n_samples, 11, drop=(6, 7))
     want, _ = oracle_files(prot, cat, hap, site, n_samples)
     gpu_engine.set_reference(prot.residues)
-    pipe = DevicePipeline(gpu_engine, prot, cat, lanes=2)
+    pipe = DevicePipeline(gpu_engine, prot, cat, C.default_names(prot), lanes=2)
     names = ["NA%05d" % (7 * i) for i in range(n_samples)]
     w = DirWriter(str(tmp_path), names, compressed=gzip, threads=4)
     sb, sites = csr_lists(hap, site, 2 * n_samples)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import cengine
-from vcf2prot_b200 import cohort as C
+from synth import cohort as C
 from vcf2prot_b200.taskgen import DeviceCatalogue, execute_generated
 
 pytestmark = pytest.mark.gpu

@@ -257,7 +257,7 @@ def test_pipeline_over_the_general_catalogue(gpu_engine, gzip):
 def test_general_catalogue_equals_the_class_tables_on_a_synthetic_cohort(gpu_engine, fasta):
     """Two implementations of the same rules -- one thread per site over class tables, one thread per transcript over
     Instruction values -- give the same arrays on a cohort with all seven classes (packed layout, plain and FASTA)."""
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
 
     prot = C.make_proteome(seed=71, n_tx=300, mu=5.3, sigma=0.7, lo=30, hi=3000)
     cat = C.make_catalogue(prot, 8000, seed=72, mix=(0.55, 0.10, 0.10, 0.08, 0.07, 0.05, 0.05), fs_mean=30, fs_max=600, sl_max=120)

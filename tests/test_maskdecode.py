@@ -31,7 +31,7 @@ def test_site_lists_transpose_sort_dedup():
 def test_encode_masks_is_the_inverse_of_the_decode():
     """cohort.encode_masks writes what bcftools csq would put into FORMAT/BCSQ; decoding it gives the carrier lists back,
     with unsupported entries in between and records wider than one 15-entry word."""
-    from vcf2prot_b200 import cohort as C
+    from synth import cohort as C
 
     prot = C.make_proteome(seed=41, n_tx=120, mu=5.0, sigma=0.6, lo=30, hi=1500)
     cat = C.make_catalogue(prot, 1500, seed=42)

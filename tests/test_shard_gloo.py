@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vcf2prot_b200 import cohort as C
+from synth import cohort as C
 from vcf2prot_b200 import shard
 
 

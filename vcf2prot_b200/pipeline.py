@@ -51,21 +51,20 @@ class DirWriter:
 
 class DevicePipeline:
     """`eng` must have the proteome registered.  One DeviceCatalogue per lane (chunk in flight) is created here from
-    (prot, cat) -- or pass `cats`: ready catalogue objects (e.g. DeviceCatalogue.from_instructions, the general
-    catalogue), one per lane, names already set."""
+    (prot, cat) and `names` = (name_off[n_tx+1], pool), the transcript names of the FASTA headers -- or pass `cats`:
+    ready catalogue objects (e.g. DeviceCatalogue.from_instructions, the general catalogue), one per lane, names set."""
 
     def __init__(self, eng: GpuEngine, prot=None, cat=None, names=None, lanes: int = 2, device: int = 0, cats=None):
-        from . import cohort
-
         self._lib = L.load()
         self._eng = eng
         if cats is not None:
             self._cats, lanes = list(cats), len(cats)
         else:
             self._cats = [DeviceCatalogue(prot, cat, device) for _ in range(lanes)]
-            nm = cohort.default_names(prot) if names is None else names
+            if names is None:
+                raise ValueError("DevicePipeline needs the transcript names (name_off, pool) of the FASTA headers")
             for c in self._cats:
-                c.set_names(*nm)
+                c.set_names(*names)
         arr = (C.c_void_p * lanes)(*[c._h for c in self._cats])
         h = C.c_void_p()
         st = self._lib.v2p_pipeline_create(eng._h, arr, lanes, C.byref(h))
