@@ -247,7 +247,7 @@ def main():
 
     # ---- parity of everything that was timed: the WHOLE result tape of every rank against the oracle (gir.rs:230-234)
     parity = None
-    if not args.no_parity and not args.no_cpu_baseline:
+    if not args.no_parity:
         threads = max(1, (os.cpu_count() or 1) // world)
         ck = StreamChecker(torch, dev, prot.residues, threads)
         ck.check(d_out[:n_out], batch.task_begin, batch.tasks, batch.alt, batch.alt_base, batch.out_base)

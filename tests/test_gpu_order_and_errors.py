@@ -65,9 +65,11 @@ def test_error_precedence_follows_the_reference_order_of_events(gpu_engine):
     ref, gpu = both(corrupt((hb, 3, 1, 0x7FFFFFFF), (hb, 5, 3, 7)))
     assert ref == (cengine.REF_ERR_BAD_STREAM, hb, 5) and gpu == (L.ERR_BAD_STREAM, hb, 5)
     # ... and with the validator on, a gap in front of it still loses to the stream code
-    k = next(i for i in range(1, 5) if base["tasks"][int(tb[hb]) + i, 1] >= 2)
-    ref, gpu = both(corrupt((hb, k, 1, int(base["tasks"][int(tb[hb]) + k, 1]) - 1), (hb, 6, 3, 2)), validate=True)
-    assert ref == (cengine.REF_ERR_BAD_STREAM, hb, 6) and gpu == (L.ERR_BAD_STREAM, hb, 6)
+    n_b = int(tb[hb + 1]) - int(tb[hb])
+    k = next(i for i in range(1, n_b - 1) if base["tasks"][int(tb[hb]) + i, 1] >= 2)  # shortening it opens a gap
+    last = n_b - 1
+    ref, gpu = both(corrupt((hb, k, 1, int(base["tasks"][int(tb[hb]) + k, 1]) - 1), (hb, last, 3, 2)), validate=True)
+    assert ref == (cengine.REF_ERR_BAD_STREAM, hb, last) and gpu == (L.ERR_BAD_STREAM, hb, last)
     # different haplotypes: the earlier haplotype's slice panic happens before the later one is even built
     ref, gpu = both(corrupt((ha, 1, 1, 0x7FFFFFFF), (hc, 0, 3, 2)))
     assert ref == (cengine.REF_ERR_RES_OOB, ha, 1) and gpu == (L.ERR_RES_OOB, ha, 1)

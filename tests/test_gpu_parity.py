@@ -10,7 +10,7 @@ import pytest
 
 from oracle import cengine, taskgen
 from tests.helpers import batch_from_girs, cohort_haplotype_csqs, hap_gir, load_golden, tape_to_str, u32, u8
-from tests.randtasks import random_batch
+from tests.randtasks import chain_batch, random_batch
 from vcf2prot_b200 import GIR, Engine, EngineError
 from vcf2prot_b200 import _lib as L
 
@@ -136,6 +136,29 @@ def test_tile_order_never_changes_results(gpu_engine, variant, seed, n_hap, mean
             out, _ = gpu_engine.execute_batch(b["task_begin"], b["tasks"], b["ref"], b["alt"], b["alt_base"], b["out_base"],
                                               aligned_layout=hint)
             assert np.array_equal(out, want), hint
+    finally:
+        gpu_engine.set_tuning(-1, 0)
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 3, 6, 8, 9])
+@pytest.mark.parametrize("seed,n_hap,mean_res,run_mean", [(81, 3, 4000, 40.0), (82, 40, 60_000, 12.0), (83, 25, 200_000, 250.0),
+                                                          (84, 200, 30_000, 60.0), (85, 6, 900_000, 400.0)])
+def test_missense_chains_and_their_near_misses_bit_exact(gpu_engine, variant, seed, n_hap, mean_res, run_mean):
+    """The copy kernel fuses `R A R` (same source - destination offset, 1-residue alteration in the hole) into one run
+    plus a byte patch.  chain_batch is that pattern with every near-miss of it (randtasks.py); all tape modes."""
+    gpu_engine.set_tuning(variant, 0)
+    try:
+        b = chain_batch(seed, n_hap, mean_res, run_mean=run_mean)
+        st, _, _, want = oracle_batch(b)
+        assert st == 0
+        out, _ = gpu_batch(gpu_engine, b)  # caller-supplied tape: register path / in-phase TMA only
+        assert np.array_equal(out, want)
+        for mode in ("replicas", "plain"):
+            gpu_engine.set_reference(b["ref"], mode)
+            for hint in (False, True):
+                out, _ = gpu_engine.execute_batch(b["task_begin"], b["tasks"], None, b["alt"], b["alt_base"], b["out_base"],
+                                                  aligned_layout=hint)
+                assert np.array_equal(out, want), (mode, hint)
     finally:
         gpu_engine.set_tuning(-1, 0)
 

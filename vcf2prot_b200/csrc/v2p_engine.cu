@@ -211,7 +211,7 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
         const int per_sm = e->ctas_per_sm > 0 ? e->ctas_per_sm : cv.ctas_per_sm;
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
-        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + 16 + 576) + 17 * 16;
+        size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + kTileScratch) + 17 * 16;
         void (*fn)(const KParams) = interleave ? cv.fn_il : cv.fn;
         if (smem > 48 * 1024) CUDA_TRY(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<grid, kThreads, smem, s>>>(kp);

@@ -457,6 +457,8 @@ __device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const ui
 }
 
 constexpr int kLaneRunBytes = 512;  // out-of-phase runs up to this many fully covered bytes are copied by one lane
+constexpr int kTileScratch = 16 + 576 + 64;  // per warp, behind tile | lead[]: mbarrier | staged tasks (32 x 16 B) + bases / flag
+                                             // (8 x 8 B) | metadata ring (4 x {tile, lb[k], lb[k+1], tile_hap[k]})
 
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
 // parallelism); MINB: CTAs per SM the register allocation is held to.
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     constexpr int NV = TILE / 16;   // 16-byte vectors per tile
     constexpr int LW = NV / 32;     // lead[] bytes per lane in the scan (4, 8 or 16)
     constexpr int LWW = LW / 4;     // ... as 32-bit words
-    constexpr int STRIDE = TILE + NV + 16 + 576;  // tile | lead[] | mbarrier | staged tasks (32 x 16 B) + bases (5 x 8 B)
+    constexpr int STRIDE = TILE + NV + kTileScratch;
     static_assert(LW == 4 || LW == 8 || LW == 16, "TILE must be 2048, 4096 or 8192");
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -478,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     uint32_t mbar_phase = 0;
     uint4* const st_tasks = reinterpret_cast<uint4*>(tile + TILE + NV + 16);
     uint64_t* const st_bases = reinterpret_cast<uint64_t*>(tile + TILE + NV + 16 + 512);
+    uint32_t* const st_meta = reinterpret_cast<uint32_t*>(tile + TILE + NV + 16 + 576);
     uint4* const lo16 = reinterpret_cast<uint4*>(smem + kWarpsPerCta * STRIDE);  // 17 masks, shared by the CTA
     if (threadIdx.x < 17 * 4) {
         const int x = threadIdx.x >> 2, w = threadIdx.x & 3, nb = min(max(x - 4 * w, 0), 4);
@@ -506,81 +509,85 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         const uint64_t ns = tile_order_slots(p, __ldg(p.order_hdr));
         if (ns) n_slots = ns;  // else order[] is the identity over n_tiles
     }
-    // Software pipeline over this warp's slots: metadata (tile, lb[k], lb[k+1], tile_hap[k]) is fetched two slots ahead,
-    // the first batch of tasks and the owning haplotype's bases one ahead, so that a tile starts with its
-    // dependent loads already landed.
-    auto load_meta = [&](uint64_t kk, uint32_t& lo, uint32_t& hi, uint32_t& hp) {  // kk: tile (~0 / past the end: none)
-        lo = hi = hp = 0;
-        if (kk < p.n_tiles) {
-            lo = __ldg(p.lb + kk);
-            hi = __ldg(p.lb + kk + 1);
-            hp = __ldg(p.tile_hap + kk);
-        }
-    };
-    auto tile_of_slot = [&](uint64_t slot) -> uint32_t {  // interleaved order only; ~0 = no tile
-        return slot < n_slots ? __ldg(p.order + slot) : 0xFFFFFFFFu;
-    };
+    // Software pipeline over this warp's slots, three dependent fetches deep, all of them cp.async into a 4-entry ring
+    // in shared memory (no register is carried from tile to tile, and nobody waits on a load it issued for later):
+    //   iteration i   waits for everything issued at i-1, then issues
+    //     stage(i+1)       first 32 tasks + the owning haplotype's bases / serial flag   <- needs meta(i+1)
+    //     fetch_meta(i+2)  lb[k], lb[k+1], tile_hap[k]                                   <- needs tile(i+2)
+    //     fetch_tile(i+3)  order[slot]  (interleaved order; tape order: slot itself)
+    // A ring entry is {tile (~0: none), lb[k], lb[k+1], tile_hap[k]}.
     const uint32_t n_tasks32 = (uint32_t)p.n_tasks;  // < 2^32 - 1 (checked by the host)
     auto first_task = [&](uint32_t lo) -> uint32_t {
         const uint32_t t = min(lo, n_tasks32);
         return t > 0u ? t - 1u : 0u;  // the task before may extend into the tile
     };
-    // stage(): cp.async the first 32 tasks of a tile and its haplotype's five bases into this warp's staging area
+    auto ring = [&](uint32_t it) -> uint32_t* { return st_meta + ((it & 3u) << 2); };
+    auto fetch_tile = [&](uint32_t it, uint64_t slot) {
+        if (lane == 0) {
+            uint32_t* m = ring(it);
+            if (slot >= n_slots) m[0] = 0xFFFFFFFFu;
+            else if constexpr (kOrder) cp_async4(m, p.order + slot);
+            else m[0] = (uint32_t)slot;
+        }
+    };
+    auto fetch_meta = [&](uint32_t it) {
+        uint32_t* m = ring(it);
+        const uint32_t t = m[0];
+        if (lane < 3) {
+            if (t == 0xFFFFFFFFu) m[1 + lane] = 0u;
+            else cp_async4(m + 1 + lane, lane == 2 ? p.tile_hap + t : p.lb + t + lane);
+        }
+    };
     // lane j < 5 fetches base j of a haplotype: task_begin[h], task_begin[h+1], out_base[h], alt_base[h], ref_base[h]
     const uint64_t* const base_arr = lane < 2 ? p.task_begin : lane == 2 ? p.out_base : lane == 3 ? p.alt_base : p.ref_base;
     const bool base_on = lane < 5 && base_arr != nullptr;
     const uint32_t base_add = lane == 1 ? 1u : 0u;
-    auto stage = [&](uint32_t lo, uint32_t hi, uint32_t hp) {
+    auto stage = [&](uint32_t it) {
+        const uint32_t* m = ring(it);
+        if (m[0] == 0xFFFFFFFFu) return;
+        const uint32_t lo = m[1], hi = m[2], hp = m[3];
         const uint32_t tr = first_task(lo) + lane;
         if (tr < min(hi, n_tasks32)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
         if (base_on) cp_async8(st_bases + lane, base_arr + hp + base_add);
         if (lane == 5) cp_async4(st_bases + 5, p.hap_flags + hp);  // 1: the haplotype is left to k_serial
-        cp_async_commit();
     };
-    // k: this warp's tile (tape order) or slot (interleaved order; then t0/t1/t2 are the tiles of slots k, k + n_warps,
-    // k + 2 n_warps -- the slot -> tile entry is fetched three ahead, its metadata two ahead, its tasks one ahead)
-    uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
-    uint32_t c_lo, c_hi, c_hap, n_lo, n_hi, n_hap;
-    uint32_t t0 = 0xFFFFFFFFu, t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu;
-    if constexpr (kOrder) {
-        t0 = tile_of_slot(k), t1 = tile_of_slot(k + n_warps), t2 = tile_of_slot(k + 2 * n_warps);
-        load_meta(t0, c_lo, c_hi, c_hap);
-        load_meta(t1, n_lo, n_hi, n_hap);
-        if (t0 != 0xFFFFFFFFu) stage(c_lo, c_hi, c_hap);
-    } else {
-        load_meta(k, c_lo, c_hi, c_hap);
-        load_meta(k + n_warps, n_lo, n_hi, n_hap);
-        if (k < p.n_tiles) stage(c_lo, c_hi, c_hap);
-    }
-    for (; k < n_slots; k += n_warps) {
-        const uint32_t tile_no = t0;  // interleaved order: ~0 = an empty slot
-        const uint64_t tile_start = (kOrder ? (uint64_t)(tile_no == 0xFFFFFFFFu ? 0u : tile_no) : k) * (uint64_t)TILE;
-        const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
-        uint8_t* const gout = p.out + tile_start;
-        const uint32_t t_lo = first_task(c_lo);
-        const uint32_t t_hi = min(c_hi, n_tasks32);
+    uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp;  // this warp's slot (a tile, or a slot of the interleaved order)
+    fetch_tile(0, k), fetch_tile(1, k + n_warps), fetch_tile(2, k + 2 * n_warps);
+    cp_async_commit();
+    cp_async_wait0();
+    __syncwarp();
+    fetch_meta(0), fetch_meta(1);
+    cp_async_commit();
+    cp_async_wait0();
+    __syncwarp();
+    stage(0);
+    cp_async_commit();
+    for (uint32_t it = 0; k < n_slots; k += n_warps, ++it) {
         // this tile's tasks and bases were staged while the previous tile was being assembled
         cp_async_wait0();
         __syncwarp();
+        const uint32_t* const mc = ring(it);
+        const uint32_t tile_no = mc[0];  // ~0 = an empty slot of the interleaved order
+        const uint32_t c_lo = mc[1], c_hi = mc[2];
         const uint4 raw0 = st_tasks[lane];
         // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
         const uint64_t hb_t0 = st_bases[0], hb_t1 = st_bases[1], hb_out = st_bases[2], hb_alt = st_bases[3];
         const uint64_t hb_ref = p.ref_base ? st_bases[4] : p.ref_origin;
         const bool hb_serial = *reinterpret_cast<const uint32_t*>(st_bases + 5) != 0u;
         __syncwarp();
-        // advance the pipeline: stage the next tile (its metadata was fetched one slot ago), fetch metadata two ahead
-        c_lo = n_lo, c_hi = n_hi, c_hap = n_hap;
-        if constexpr (kOrder) {
-            t0 = t1;
-            if (t0 != 0xFFFFFFFFu) stage(c_lo, c_hi, c_hap);
-            t1 = t2;
-            load_meta(t1, n_lo, n_hi, n_hap);
-            t2 = tile_of_slot(k + 3 * n_warps);
-            if (tile_no == 0xFFFFFFFFu) continue;  // an empty slot
-        } else {
-            if (k + n_warps < p.n_tiles) stage(c_lo, c_hi, c_hap);
-            load_meta(k + 2 * n_warps, n_lo, n_hi, n_hap);
-        }
+        stage(it + 1);
+        fetch_meta(it + 2);
+        fetch_tile(it + 3, k + 3 * n_warps);
+        cp_async_commit();
+        if (tile_no == 0xFFFFFFFFu) continue;
+        const uint64_t tile_start = (uint64_t)tile_no * (uint64_t)TILE;
+        const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
+        uint8_t* const gout = p.out + tile_start;
+        const uint32_t t_lo = first_task(c_lo);
+        const uint32_t t_hi = min(c_hi, n_tasks32);
+        // the second batch of tasks (tiles of more than 32) is requested now and consumed after the first batch
+        const uint4 raw1 = t_lo + 32u + lane < t_hi ? __ldg(reinterpret_cast<const uint4*>(p.tasks) + t_lo + 32u + lane)
+                                                    : make_uint4(0u, 0u, 0u, 0u);
 
         // the previous tile's bulk store must have finished READING shared memory before we overwrite it
         if (lane == 0) bulk_wait_read0();
@@ -607,6 +614,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         fence_async_smem();  // the prefill must be ordered before TMA loads land in the same bytes
         __syncwarp();
         bool tma_used = false;
+        // 1-residue patches of fused chains (below), first / second batch of the tile: bit 31 of pd = armed, low bits =
+        // tile offset; pv = the byte.  They are applied after the chain's TMA load has landed (phase D).
+        uint32_t pv0 = 0, pd0 = 0, pv1 = 0, pd1 = 0;
 
         for (uint32_t tb = t_lo; tb < t_hi; tb += 32) {
             // ---- A: one lane per task: partial head/tail vectors, and the start of its fully covered vector range
@@ -619,12 +629,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             bool has_lead = false, onT = false, onH = false, onM = false;
             int lane_v0 = 0, lane_v1 = 0;  // fully covered vectors of a short out-of-phase run, copied by this lane
             int pvh = 0, pvt = 0, pa1 = 0, pb2 = 16;
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+            int s = 0, e = 0;       // this task clipped to the tile; e > s: something to do
+            bool main_hap = false;  // the task belongs to the haplotype that owns the tile's first byte
             if (tr < t_hi) {
-                const uint4 raw = tb == t_lo ? raw0 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
+                raw = tb == t_lo ? raw0 : tb == t_lo + 32u ? raw1 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
                 const uint64_t t_abs = tr + p.task_origin;
                 uint64_t o_b = hb_out, a_b = hb_alt, r_b = hb_ref;
                 bool serial = hb_serial;
-                if (t_abs < hb_t0 || t_abs >= hb_t1) {  // another haplotype (tile spans a haplotype boundary)
+                main_hap = t_abs >= hb_t0 && t_abs < hb_t1;
+                if (!main_hap) {  // another haplotype (tile spans a haplotype boundary)
                     const uint64_t h = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, t_abs) - 1;
                     o_b = __ldg(p.out_base + h);
                     a_b = __ldg(p.alt_base + h);
@@ -633,48 +647,83 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 }
                 const long long g = (long long)(o_b - p.out_origin + raw.z) - (long long)tile_start;
                 const long long ge = g + raw.y;
-                const int s = (int)max(g, 0ll), e = (int)min(ge, (long long)tile_len);
+                s = (int)max(g, 0ll), e = (int)min(ge, (long long)tile_len);
                 if (e > s && !serial) {  // (a haplotype in serial order keeps its prefill here; k_serial paints it)
                     const uint8_t* sb = raw.w ? p.alt + (a_b - p.alt_origin) : p.ref + (r_b - p.ref_origin);
                     p0 = (long long)(sb + raw.x) - g;
-                    const int vh = s >> 4, vt = (e - 1) >> 4;
-                    const int v0b = (s + 15) & ~15, v1b = e & ~15;
-                    if (v1b > v0b) {
-                        if ((p0 & 15) == 0) {
-                            // source and destination are in phase: a plain aligned TMA bulk copy straight from the
-                            // source tape (any stream; this is what the aligned producer layout arranges)
-                            tma_src = reinterpret_cast<const uint8_t*>(p0 + v0b);
-                            tma_alt = raw.w != 0u;
-                            tma_dst = (uint32_t)v0b;
-                            tma_bytes = (uint32_t)(v1b - v0b);
-                        } else if (p.tma_mode && raw.w == 0u) {
-                            const long long q = p0 - (long long)p.ref;  // ref offset of tile byte 0
-                            // replica r = (-q) mod 16 holds this run at the same 16-byte phase as the output
-                            const uint32_t r = (uint32_t)(-q) & 15u;
-                            tma_src = p.ref_rep + (uint64_t)r * p.rep_stride + (uint64_t)(q + v0b) + r;
-                            tma_dst = (uint32_t)v0b;
-                            tma_bytes = (uint32_t)(v1b - v0b);
-                        } else if (v1b - v0b <= kLaneRunBytes) {
-                            // a short out-of-phase run (an alteration payload, typically): this lane copies it alone,
-                            // below -- cheaper than waking the whole-tile owner scan for a few vectors
-                            lane_v0 = v0b >> 4, lane_v1 = v1b >> 4;
-                        } else {
-                            lead[v0b >> 4] = (uint8_t)(lane + 1);
-                            v1 = (uint32_t)(v1b >> 4);
-                            has_lead = true;
-                        }
+                } else {
+                    s = e = 0;
+                }
+            }
+            // ---- A': chain fusion.  `R A R` -- two reference runs with the same (source - destination) offset and a
+            // 1-residue alteration exactly filling the hole between them (a missense patch, transcript_instructions.rs
+            // :654-663) -- is one reference run with one byte replaced afterwards.  The reference lanes of such a chain
+            // (lanes i, i+2, i+4, ... of this batch) collapse into its first lane, whose extent grows to the end of the
+            // last one; the patch lanes keep one byte each for phase D.  Fewer, longer bulk copies and no partial-vector
+            // work around the patches.  (First two batches of a tile only: the patch registers are per batch.)
+            if (tb - t_lo < 64u) {
+                const uint32_t full = 0xffffffffu;
+                const bool ok = e > s && main_hap;
+                const uint32_t prev_end = __shfl_up_sync(full, raw.z + raw.y, 1);
+                const uint32_t delta = raw.x - raw.z, delta2 = __shfl_up_sync(full, delta, 2);
+                const uint32_t Bref = __ballot_sync(full, ok && raw.w == 0u);
+                const uint32_t Bpat = __ballot_sync(full, ok && raw.w == 1u && raw.y == 1u);
+                const uint32_t Bc = __ballot_sync(full, lane > 0 && raw.z == prev_end);  // starts where the lane before ends
+                const uint32_t Bb = __ballot_sync(full, raw.x < raw.z);                  // (33rd bit of source - destination)
+                const uint32_t Bd = __ballot_sync(full, lane > 1 && delta == delta2);
+                const uint32_t link = Bref & (Bref << 2) & (Bpat << 1) & Bc & (Bc << 1) & ~(Bb ^ (Bb << 2)) & Bd;
+                if (link) {  // (warp-uniform)
+                    const bool cont = (link >> lane) & 1u;                           // linked to the reference lane two below
+                    const bool patch = lane < 31 && ((link >> (lane + 1)) & 1u);   // the byte between two linked runs
+                    uint32_t tail = lane;
+                    if (lane < 30 && !cont) tail = lane + (uint32_t)__ffs((int)~((link >> (lane + 2)) | 0xAAAAAAAAu)) - 1u;
+                    const int e_tail = __shfl_sync(full, e, tail);
+                    if (patch) {
+                        const uint8_t* sp = reinterpret_cast<const uint8_t*>(p0 + s);
+                        if (tb == t_lo) pv0 = __ldg(sp), pd0 = 0x80000000u | (uint32_t)s;
+                        else pv1 = __ldg(sp), pd1 = 0x80000000u | (uint32_t)s;
                     }
-                    // classify the partial vectors (see Piece): H = [a1,16) of vh, T = [0,b2) of vt, M = [a1,b1) of vh
-                    pvh = vh, pvt = vt;
-                    pa1 = s & 15, pb2 = e - (vt << 4);
-                    if (vt > vh) {
-                        onH = pa1 != 0;
-                        onT = pb2 != 16;
-                    } else if (pa1 != 0 || pb2 != 16) {  // the whole (clipped) task sits inside one vector
-                        if (pa1 == 0) onT = true;
-                        else if (pb2 == 16) onH = true;
-                        else onM = true;
+                    if (cont || patch) s = e = 0;  // nothing else to do for these lanes
+                    else if (e > s) e = e_tail;
+                }
+            }
+            if (e > s) {
+                // Source in phase with the destination: the tape itself, or for an out-of-phase reference run with a
+                // registered tape the replica r = (-q) mod 16 that holds it at the output's 16-byte phase; then the
+                // fully covered vectors are ONE TMA bulk copy and the partial ones single aligned loads.
+                if ((p0 & 15) != 0 && p.tma_mode && raw.w == 0u) {
+                    const long long q = p0 - (long long)p.ref;  // ref offset of tile byte 0
+                    const uint32_t r = (uint32_t)(-q) & 15u;
+                    p0 = (long long)(p.ref_rep + (uint64_t)r * p.rep_stride + r) + q;
+                }
+                const int vh = s >> 4, vt = (e - 1) >> 4;
+                const int v0b = (s + 15) & ~15, v1b = e & ~15;
+                if (v1b > v0b) {
+                    if ((p0 & 15) == 0) {
+                        tma_src = reinterpret_cast<const uint8_t*>(p0 + v0b);
+                        tma_alt = raw.w != 0u;
+                        tma_dst = (uint32_t)v0b;
+                        tma_bytes = (uint32_t)(v1b - v0b);
+                    } else if (v1b - v0b <= kLaneRunBytes) {
+                        // a short out-of-phase run (an alteration payload, typically): this lane copies it alone,
+                        // below -- cheaper than waking the whole-tile owner scan for a few vectors
+                        lane_v0 = v0b >> 4, lane_v1 = v1b >> 4;
+                    } else {
+                        lead[v0b >> 4] = (uint8_t)(lane + 1);
+                        v1 = (uint32_t)(v1b >> 4);
+                        has_lead = true;
                     }
+                }
+                // classify the partial vectors (see Piece): H = [a1,16) of vh, T = [0,b2) of vt, M = [a1,b1) of vh
+                pvh = vh, pvt = vt;
+                pa1 = s & 15, pb2 = e - (vt << 4);
+                if (vt > vh) {
+                    onH = pa1 != 0;
+                    onT = pb2 != 16;
+                } else if (pa1 != 0 || pb2 != 16) {  // the whole (clipped) task sits inside one vector
+                    if (pa1 == 0) onT = true;
+                    else if (pb2 == 16) onH = true;
+                    else onM = true;
                 }
             }
             // TMA bulk loads first (they take the longest), the register-path pieces overlap with them
@@ -790,6 +839,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             mbar_wait(mbar, mbar_phase);
             mbar_phase ^= 1u;
         }
+        if (pd0 >> 31) tile[pd0 & 0xFFFFu] = (uint8_t)pv0;  // the patches of fused chains, over the landed reference bytes
+        if (pd1 >> 31) tile[pd1 & 0xFFFFu] = (uint8_t)pv1;
         fence_async_smem();
         __syncwarp();
         const uint32_t bulk = tile_len & ~15u;
