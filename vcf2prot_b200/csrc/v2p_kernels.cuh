@@ -389,6 +389,12 @@ __device__ __forceinline__ void bulk_load_g2s_nohint(void* sdst, const void* gsr
                  "l"(gsrc), "r"(bytes), "r"(mbar)
                  : "memory");
 }
+// dst = *p if pred (one byte, zero-extended), else dst keeps its value.  A predicated load INTO the caller's register:
+// nothing consumes the loaded value here, so the warp does not wait for it (a C++ `if (c) x = __ldg(p)` that the
+// compiler turns into load-to-temporary + move stalls on the move for the whole memory latency).
+__device__ __forceinline__ void ldg_u8_if(uint32_t& dst, const uint8_t* p, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.u8 %0, [%1];\n\t}" : "+r"(dst) : "l"(p), "r"((uint32_t)pred));
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // bytes [sh, sh+16) of the 32-byte little-endian concatenation A||B  (sh in [0,16))
@@ -493,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     if (lane == 0) mbar_init(mbar, 1);
     __syncwarp();
 
-    const uint64_t n_warps = (uint64_t)gridDim.x * kWarpsPerCta;
+    const uint32_t n_warps = gridDim.x * kWarpsPerCta;
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     const uint4 fillv = make_uint4(p.fill_word, p.fill_word, p.fill_word, p.fill_word);
 
@@ -504,10 +510,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     // large the replica set is -- instead of sweeping all 171 MB of it once per ~9 haplotypes.  Slots without a tile
     // (shorter haplotypes) hold ~0.  Without the flag, slots are tiles in tape order (phase-aligned layouts, whose
     // runs come from the one plain tape, gain nothing from the interleave).
-    uint64_t n_slots = p.n_tiles;
+    uint32_t n_slots = (uint32_t)p.n_tiles;  // (tiles and order slots of one launch stay below 2^32 - 2^20: checked by the host)
     if constexpr (kOrder) {
         const uint64_t ns = tile_order_slots(p, __ldg(p.order_hdr));
-        if (ns) n_slots = ns;  // else order[] is the identity over n_tiles
+        if (ns) n_slots = (uint32_t)ns;  // else order[] is the identity over n_tiles
     }
     // Software pipeline over this warp's slots, three dependent fetches deep, all of them cp.async into a 4-entry ring
     // in shared memory (no register is carried from tile to tile, and nobody waits on a load it issued for later):
@@ -522,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         return t > 0u ? t - 1u : 0u;  // the task before may extend into the tile
     };
     auto ring = [&](uint32_t it) -> uint32_t* { return st_meta + ((it & 3u) << 2); };
-    auto fetch_tile = [&](uint32_t it, uint64_t slot) {
+    auto fetch_tile = [&](uint32_t it, uint32_t slot) {
         if (lane == 0) {
             uint32_t* m = ring(it);
             if (slot >= n_slots) m[0] = 0xFFFFFFFFu;
@@ -538,20 +544,23 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             else cp_async4(m + 1 + lane, lane == 2 ? p.tile_hap + t : p.lb + t + lane);
         }
     };
-    // lane j < 5 fetches base j of a haplotype: task_begin[h], task_begin[h+1], out_base[h], alt_base[h], ref_base[h]
-    const uint64_t* const base_arr = lane < 2 ? p.task_begin : lane == 2 ? p.out_base : lane == 3 ? p.alt_base : p.ref_base;
-    const bool base_on = lane < 5 && base_arr != nullptr;
-    const uint32_t base_add = lane == 1 ? 1u : 0u;
     auto stage = [&](uint32_t it) {
         const uint32_t* m = ring(it);
         if (m[0] == 0xFFFFFFFFu) return;
         const uint32_t lo = m[1], hi = m[2], hp = m[3];
         const uint32_t tr = first_task(lo) + lane;
         if (tr < min(hi, n_tasks32)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
-        if (base_on) cp_async8(st_bases + lane, base_arr + hp + base_add);
+        // lanes 0-5: the owning haplotype's bases task_begin[h], task_begin[h+1], out_base[h], alt_base[h], ref_base[h]
+        // and its serial-order flag (spelled out per lane: a lane-dependent array pointer kept in registers across the
+        // tile loop is what used to spill)
+        if (lane == 0) cp_async8(st_bases + 0, p.task_begin + hp);
+        if (lane == 1) cp_async8(st_bases + 1, p.task_begin + hp + 1);
+        if (lane == 2) cp_async8(st_bases + 2, p.out_base + hp);
+        if (lane == 3) cp_async8(st_bases + 3, p.alt_base + hp);
+        if (lane == 4 && p.ref_base) cp_async8(st_bases + 4, p.ref_base + hp);
         if (lane == 5) cp_async4(st_bases + 5, p.hap_flags + hp);  // 1: the haplotype is left to k_serial
     };
-    uint64_t k = (uint64_t)blockIdx.x * kWarpsPerCta + warp;  // this warp's slot (a tile, or a slot of the interleaved order)
+    uint32_t k = blockIdx.x * kWarpsPerCta + warp;  // this warp's slot (a tile, or a slot of the interleaved order)
     fetch_tile(0, k), fetch_tile(1, k + n_warps), fetch_tile(2, k + 2 * n_warps);
     cp_async_commit();
     cp_async_wait0();
@@ -571,8 +580,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         const uint32_t c_lo = mc[1], c_hi = mc[2];
         const uint4 raw0 = st_tasks[lane];
         // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
-        const uint64_t hb_t0 = st_bases[0], hb_t1 = st_bases[1], hb_out = st_bases[2], hb_alt = st_bases[3];
-        const uint64_t hb_ref = p.ref_base ? st_bases[4] : p.ref_origin;
+        // (launch-relative 32-bit task numbers; the tape bases folded into what a task needs: where the haplotype's
+        // result tape starts relative to this tile, and where its two source tapes start)
+        const uint32_t hb_t0 = (uint32_t)(st_bases[0] - p.task_origin), hb_t1 = (uint32_t)min(st_bases[1] - p.task_origin, p.n_tasks);
+        const uint64_t hb_out = st_bases[2];
+        const uint8_t* const hb_altp = p.alt + (st_bases[3] - p.alt_origin);
+        const uint8_t* const hb_refp = p.ref + ((p.ref_base ? st_bases[4] : p.ref_origin) - p.ref_origin);
         const bool hb_serial = *reinterpret_cast<const uint32_t*>(st_bases + 5) != 0u;
         __syncwarp();
         stage(it + 1);
@@ -583,6 +596,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         const uint64_t tile_start = (uint64_t)tile_no * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
+        const long long hb_rel = (long long)(hb_out - p.out_origin) - (long long)tile_start;  // tape start - tile start
         const uint32_t t_lo = first_task(c_lo);
         const uint32_t t_hi = min(c_hi, n_tasks32);
         // the second batch of tasks (tiles of more than 32) is requested now and consumed after the first batch
@@ -634,23 +648,22 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             bool main_hap = false;  // the task belongs to the haplotype that owns the tile's first byte
             if (tr < t_hi) {
                 raw = tb == t_lo ? raw0 : tb == t_lo + 32u ? raw1 : __ldg(reinterpret_cast<const uint4*>(p.tasks) + tr);
-                const uint64_t t_abs = tr + p.task_origin;
-                uint64_t o_b = hb_out, a_b = hb_alt, r_b = hb_ref;
+                long long rel = hb_rel;
+                const uint8_t *altp = hb_altp, *refp = hb_refp;
                 bool serial = hb_serial;
-                main_hap = t_abs >= hb_t0 && t_abs < hb_t1;
+                main_hap = tr >= hb_t0 && tr < hb_t1;
                 if (!main_hap) {  // another haplotype (tile spans a haplotype boundary)
-                    const uint64_t h = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, t_abs) - 1;
-                    o_b = __ldg(p.out_base + h);
-                    a_b = __ldg(p.alt_base + h);
-                    r_b = p.ref_base ? __ldg(p.ref_base + h) : p.ref_origin;
+                    const uint64_t h = upper_bound_u64(p.task_begin, 0, p.n_hap + 1, tr + p.task_origin) - 1;
+                    rel = (long long)(__ldg(p.out_base + h) - p.out_origin) - (long long)tile_start;
+                    altp = p.alt + (__ldg(p.alt_base + h) - p.alt_origin);
+                    refp = p.ref + ((p.ref_base ? __ldg(p.ref_base + h) : p.ref_origin) - p.ref_origin);
                     serial = __ldg(p.hap_flags + h) != 0u;
                 }
-                const long long g = (long long)(o_b - p.out_origin + raw.z) - (long long)tile_start;
+                const long long g = rel + raw.z;
                 const long long ge = g + raw.y;
                 s = (int)max(g, 0ll), e = (int)min(ge, (long long)tile_len);
                 if (e > s && !serial) {  // (a haplotype in serial order keeps its prefill here; k_serial paints it)
-                    const uint8_t* sb = raw.w ? p.alt + (a_b - p.alt_origin) : p.ref + (r_b - p.ref_origin);
-                    p0 = (long long)(sb + raw.x) - g;
+                    p0 = (long long)((raw.w ? altp : refp) + raw.x) - g;
                 } else {
                     s = e = 0;
                 }
@@ -678,11 +691,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     uint32_t tail = lane;
                     if (lane < 30 && !cont) tail = lane + (uint32_t)__ffs((int)~((link >> (lane + 2)) | 0xAAAAAAAAu)) - 1u;
                     const int e_tail = __shfl_sync(full, e, tail);
-                    if (patch) {
-                        const uint8_t* sp = reinterpret_cast<const uint8_t*>(p0 + s);
-                        if (tb == t_lo) pv0 = __ldg(sp), pd0 = 0x80000000u | (uint32_t)s;
-                        else pv1 = __ldg(sp), pd1 = 0x80000000u | (uint32_t)s;
-                    }
+                    const bool first = tb == t_lo;
+                    const uint8_t* sp = reinterpret_cast<const uint8_t*>(p0 + s);
+                    ldg_u8_if(pv0, sp, patch && first);
+                    ldg_u8_if(pv1, sp, patch && !first);
+                    if (patch && first) pd0 = 0x80000000u | (uint32_t)s;
+                    if (patch && !first) pd1 = 0x80000000u | (uint32_t)s;
                     if (cont || patch) s = e = 0;  // nothing else to do for these lanes
                     else if (e > s) e = e_tail;
                 }
@@ -726,7 +740,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     else onM = true;
                 }
             }
-            // TMA bulk loads first (they take the longest), the register-path pieces overlap with them
+            // The loads of the partial vectors go out first, so that their latency runs under the (serial, one elected
+            // lane at a time) issue of the TMA bulk loads; nothing consumes them before that loop is through.
+            const Piece pcT = piece_load(p0, pvt, 0, pb2, onT), pcH = piece_load(p0, pvh, pa1, 16, onH);
+            uint32_t m_first = 0;  // first byte of a piece strictly inside one vector (a 1-residue task, typically)
+            ldg_u8_if(m_first, reinterpret_cast<const uint8_t*>(p0) + (pvh << 4) + pa1, onM);
             {
                 const uint32_t total = __reduce_add_sync(0xffffffffu, tma_bytes);
                 if (total) {
@@ -742,7 +760,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 }
             }
             {
-                const Piece pcT = piece_load(p0, pvt, 0, pb2, onT), pcH = piece_load(p0, pvh, pa1, 16, onH);
                 if (onT) piece_merge(tile, lo16, pcT, pvt, pb2, false);
                 __syncwarp();
                 if (onH) piece_merge(tile, lo16, pcH, pvh, pa1, true);
@@ -750,7 +767,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 if (onM) {
                     const uint8_t* __restrict__ sp = reinterpret_cast<const uint8_t*>(p0) + (pvh << 4);
                     uint8_t* d = tile + (pvh << 4);
-                    for (int j = pa1; j < pb2; ++j) d[j] = __ldg(sp + j);
+                    d[pa1] = (uint8_t)m_first;
+                    for (int j = pa1 + 1; j < pb2; ++j) d[j] = __ldg(sp + j);
                 }
             }
             if (lane_v1 > lane_v0) {  // four vectors per round: five aligned loads in flight, then realign + store
