@@ -7,7 +7,7 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADERS = [os.path.join(ROOT, "include", h) for h in ("v2p_engine.h", "v2p_taskgen.h", "v2p_gzip.h", "v2p_pipeline.h")]
+HEADERS = [os.path.join(ROOT, "include", h) for h in ("v2p_engine.h", "v2p_taskgen.h", "v2p_gzip.h", "v2p_pipeline.h", "v2p_cohort.h")]
 
 
 @pytest.fixture(scope="module")

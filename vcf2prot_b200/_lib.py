@@ -60,6 +60,24 @@ class PipelineResult(C.Structure):
                 ("wall_s", C.c_double), ("n_skipped", C.c_uint64), ("n_aborted", C.c_uint64)]
 
 
+COHORT_MAX_DEVICES = 16
+COHORT_CONCURRENT_SINK = 0x100
+
+
+class CohortInputs(C.Structure):  # include/v2p_cohort.h: v2p_cohort_inputs
+    _fields_ = [("proteome", C.c_void_p), ("n_proteome", C.c_uint64), ("n_tx", C.c_uint64), ("tx_offsets", C.c_void_p),
+                ("name_off", C.c_void_p), ("names", C.c_void_p), ("general", C.c_int), ("n_sites", C.c_uint64),
+                ("site_tx", C.c_void_p), ("site_pos", C.c_void_p), ("site_cls", C.c_void_p), ("site_rlen", C.c_void_p),
+                ("ins_code", C.c_void_p), ("ins_flags", C.c_void_p), ("ins_pos_ref", C.c_void_p), ("ins_pos_res", C.c_void_p),
+                ("ins_len", C.c_void_p), ("site_doff", C.c_void_p), ("site_dlen", C.c_void_p), ("pool", C.c_void_p),
+                ("n_pool", C.c_uint64)]
+
+
+class CohortResult(C.Structure):  # v2p_cohort_result
+    _fields_ = [("n_devices", C.c_uint32), ("total", PipelineResult), ("per_device", PipelineResult * COHORT_MAX_DEVICES),
+                ("first_sample", C.c_uint64 * (COHORT_MAX_DEVICES + 1))]
+
+
 # int sink(void* user, uint64_t first_sample, uint64_t n_samples, const uint8_t* data, const uint64_t* file_begin)
 FILE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64))
 PIPE_GZIP, PIPE_SKIP_ABORTS = 1, 2
@@ -112,6 +130,12 @@ SYMBOLS = {
     "v2p_dir_writer_files": (C.c_uint64, [_P]),
     "v2p_dir_writer_last_error": (C.c_char_p, [_P]),
     "v2p_dir_writer_destroy": (None, [_P]),
+    # include/v2p_cohort.h
+    "v2p_cohort_create": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(CohortInputs), C.c_uint32, C.POINTER(_P)]),
+    "v2p_cohort_destroy": (None, [_P]),
+    "v2p_cohort_last_error": (C.c_char_p, [_P]),
+    "v2p_cohort_run_lists": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.c_uint32, FILE_SINK, _P, C.POINTER(CohortResult)]),
+    "v2p_cohort_launch_count": (C.c_uint64, [_P]),
     "v2p_pipeline_run_masks": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _P, C.c_uint64, _P, FILE_SINK, _P, C.POINTER(PipelineResult)]),
 }
