@@ -33,8 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from bench_support import (ClockSampler, StreamChecker, alg_bytes, c3_measure, cpu_engine_rate, gzip_measure,  # noqa: E402
-                           make_workload, pipeline_measure, reference_binary_rate)
+from bench_support import (ClockSampler, StreamChecker, alg_bytes, c3_measure, cpu_engine_rate, dropin_measure,  # noqa: E402
+                           gzip_measure, make_workload, pipeline_measure, reference_binary_rate)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -80,6 +80,8 @@ def parse_args():
                     help="samples of the ONE cohort that is sharded over the ranks and streamed (BASELINE configs[2]); 0 = skip")
     ap.add_argument("--c3-chunk-samples", type=int, default=1024, help="samples per streamed chunk of the c3 section")
     ap.add_argument("--no-c3-parity", action="store_true", help="skip the whole-cohort oracle check of the c3 section")
+    ap.add_argument("--dropin-haps", type=int, default=32,
+                    help="haplotypes driven through v2p_gir_execute from concurrent host threads (the literal drop-in); 0 = skip")
     ap.add_argument("--no-parity", action="store_true", help="skip the whole-cohort oracle check of the timed output")
     ap.add_argument("--ref-binary-samples", type=int, default=0,
                     help="also time the reference's prebuilt whole-tool binary on this many samples (slow)")
@@ -384,6 +386,11 @@ def main():
             del d_masks
         dc.close()
 
+    # ---- the literal drop-in (gir.rs:236-239 replacement), called like the reference calls it: many threads, one haplotype each
+    dropin_line = None
+    if world == 1 and args.dropin_haps > 0 and not args.no_cpu_baseline:
+        dropin_line = dropin_measure(args, eng, prot, cat, args.dropin_haps)
+
     # ---- the -c path.  FASTA image in HBM -> one .fasta.gz per sample, compressed on the device
     gzip_line = None
     if world == 1 and args.gzip_samples > 0 and not args.no_registered_ref:
@@ -435,7 +442,7 @@ def main():
                                     "note": "result-tape bytes written / kernel time vs a store-only kernel on the same GPU and buffer "
                                             "(TMA bulk stores of 8 KiB tiles, the copy kernel's own store instruction and grid); the hard "
                                             "floor of this path is one DRAM write per residue"}},
-        "cpu_baseline": cpu, "parity": parity, "c3": c3_line, "other_layout": other_line, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
+        "cpu_baseline": cpu, "parity": parity, "c3": c3_line, "dropin": dropin_line, "other_layout": other_line, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
     }
     print(json.dumps(line))
     if world > 1:

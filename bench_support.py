@@ -504,3 +504,88 @@ def c3_measure(args, eng, prot, rank, world, local_rank, dev, shard, barrier, pe
                          "note": "kernel = k_copy_tiles time summed over this rank's chunks, max over ranks; alg = SURVEY 8d bytes; dram = "
                                  "ncu DRAM bytes per residue of the C2 capture x residues"},
             "parity": parity}
+
+
+# ------------------------------------------------------------------------------------------------ the literal drop-in
+def dropin_measure(args, eng, prot, cat, n_haps: int = 32, seconds: float = 4.0):
+    """Throughput of the call INTEGRATION.md section 3 pastes into gir.rs:236-239 -- v2p_gir_execute, one haplotype per
+    call, the reference's own GIR hand-off (four usize arrays + UTF-32 `char` tapes, per-haplotype ref tape) -- driven
+    the way the reference drives it: many host threads at once (rayon workers, parts/exec.rs:36-39).  Beside it the
+    CPU port on the SAME inputs and thread count.  Both sides are bounded by moving 4-byte residues through host
+    memory; the GPU side also crosses PCIe, so this entry is parity, not speed -- the batch ABI is the fast path."""
+    import ctypes as C_
+    import threading
+
+    from oracle import cengine
+    from synth import cohort as C
+    from vcf2prot_b200 import _lib as L
+
+    threads = max(1, min(16, os.cpu_count() or 1))
+    b = C.synth_batch(prot, cat, n_haps, seed=0x5EED0D01, ref_mode="per_hap")
+    lib = L.load()
+    calls, total_res = [], 0
+    for h in range(n_haps):
+        t0, t1 = int(b.task_begin[h]), int(b.task_begin[h + 1])
+        tk = b.tasks[t0:t1].astype(np.uint64)
+        cols = [np.ascontiguousarray(tk[:, i]) for i in (3, 0, 1, 2)]  # exec_code, start_pos, length, start_pos_res
+        ref = b.ref[int(b.ref_base[h]):int(b.ref_base[h + 1])].astype(np.uint32)
+        alt = b.alt[int(b.alt_base[h]):int(b.alt_base[h + 1])].astype(np.uint32)
+        n_res = int(b.out_base[h + 1] - b.out_base[h])
+        res = np.zeros(n_res, np.uint32)
+        calls.append((cols, ref, alt, res, n_res))
+        total_res += n_res
+    p = lambda a: a.ctypes.data_as(C_.c_void_p)
+
+    def one(c):
+        cols, ref, alt, res, n_res = c
+        bad = C_.c_uint64(0)
+        st = lib.v2p_gir_execute(eng._h, L.ENGINE_GPU, len(cols[0]), p(cols[0]), p(cols[1]), p(cols[2]), p(cols[3]), p(ref), len(ref),
+                                 p(alt), len(alt), p(res), n_res, L.FLAG_FILL_DOT, C_.byref(bad))
+        if st:
+            raise RuntimeError("v2p_gir_execute failed: %d" % st)
+
+    for c in calls[:threads]:
+        one(c)  # warm-up: slot allocations
+    # parity of the warm-up results against the oracle (UTF-32 tapes)
+    ok = True
+    for cols, ref, alt, res, n_res in calls[:min(4, threads)]:
+        out = np.zeros(n_res, np.uint32)
+        lib2 = cengine.load()
+        bad = C_.c_uint64(0)
+        st = lib2.ref_gir_execute_u32(len(cols[0]), p(cols[0]), p(cols[1]), p(cols[2]), p(cols[3]), p(ref), len(ref), p(alt), len(alt),
+                                      p(out), n_res, 1, 0, C_.byref(bad))
+        ok = ok and st == 0 and bool(np.array_equal(out, res))
+    done = [0] * threads
+    stop = time.perf_counter() + seconds
+
+    def worker(w):
+        i = w
+        while time.perf_counter() < stop:
+            one(calls[i % n_haps])
+            done[w] += calls[i % n_haps][4]
+            i += threads
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=worker, args=(w,)) for w in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    el = time.perf_counter() - t0
+    gpu_rate = sum(done) / el
+    # the CPU port on the same inputs: UTF-32 tapes, per-haplotype ref tapes, haplotypes over the same number of threads
+    ref32, alt32 = b.ref.astype(np.uint32), b.alt.astype(np.uint32)
+    out32 = np.zeros(int(b.out_base[-1]), np.uint32)
+    a = (b.task_begin, b.tasks, ref32, alt32, b.alt_base, out32, b.out_base)
+    cengine.batch_execute(*a, ref_base=b.ref_base, threads=threads)
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < min(seconds, 3.0):
+        cengine.batch_execute(*a, ref_base=b.ref_base, threads=threads)
+        reps += 1
+    cpu_rate = total_res * reps / (time.perf_counter() - t0)
+    return {"api": "v2p_gir_execute (gir.rs:283-299 hand-off: 4 x usize arrays + UTF-32 tapes, one haplotype per call)",
+            "host_threads": threads, "haplotypes": n_haps, "mean_residues_per_haplotype": total_res // n_haps,
+            "haplotypes_per_s": gpu_rate / (total_res / n_haps), "residues_per_s": gpu_rate,
+            "cpu_port_same_inputs_residues_per_s": cpu_rate, "ratio_vs_cpu_port": gpu_rate / cpu_rate,
+            "gpu_equals_oracle": bool(ok), "seconds": round(el, 2),
+            "note": "both sides move 4-byte residues through host memory (the CPU engine IS a memcpy of that size); the GPU side "
+                    "narrows / widens them on the host and crosses PCIe as well: this entry exists for parity with the reference's "
+                    "call site, the batched ABI (e2e) is the fast path"}

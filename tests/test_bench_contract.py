@@ -35,7 +35,7 @@ def test_reference_arm_line():
 def test_our_arm_line_on_a_tiny_cohort():
     d = run_bench("--samples", "24", "--steps", "3", "--warmup", "3", "--e2e-steps", "1", "--e2e-chunk-haps", "16", "--cpu-sample-haps", "8",
                   "--cpu-seconds", "0.5", "--maskdecode-samples", "8", "--gzip-samples", "8", "--pipeline-chunk", "5",
-                  "--written-samples", "6", "--c3-samples", "40", "--c3-chunk-samples", "16")
+                  "--written-samples", "6", "--c3-samples", "40", "--c3-chunk-samples", "16", "--dropin-haps", "6")
     assert BASE <= set(d) and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] == "u8" and d["vs_baseline"] is None
     assert d["gpu_launches"] == 7 * d["steps"] and d["warmup"] >= 3  # init, plan x4, copy, status hand-off
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
@@ -49,6 +49,7 @@ def test_our_arm_line_on_a_tiny_cohort():
     p = d["parity"]
     assert p["gpu_equals_oracle"] is True and p["e2e_equals_device_path"] is True
     assert p["checked_haplotypes"] == d["config"]["haplotypes_per_gpu"] == p["haplotypes_per_gpu"] and p["all_ranks"] is True
+    assert d["dropin"]["gpu_equals_oracle"] is True and d["dropin"]["haplotypes_per_s"] > 0 and d["dropin"]["host_threads"] >= 1
     c3 = d["c3"]
     assert c3["scaling"] == "strong" and c3["samples"] == 40 and c3["value"] > 0 and c3["chunks_this_rank"] == 3
     assert c3["parity"]["gpu_equals_oracle"] is True and c3["parity"]["checked_haplotypes"] == 80 == c3["parity"]["haplotypes"]

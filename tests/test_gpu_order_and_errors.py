@@ -146,3 +146,53 @@ def test_one_unsorted_haplotype_among_500_costs_no_cliff(gpu_engine):
     print("500 haplotypes, %.1f MB: sorted %.3f ms, one unsorted haplotype %.3f ms" %
           (n_out / 1e6, times["sorted"] * 1e3, times["one_unsorted"] * 1e3))
     assert times["one_unsorted"] < 1.5 * times["sorted"] + 0.3e-3
+
+
+def test_gir_execute_from_many_threads_at_once(gpu_engine):
+    """parts/exec.rs:36-39: GIR::execute is called from many rayon workers concurrently, one haplotype each.  Every
+    caller owns a slot of the engine for the call (the entry used to hold the engine lock across
+    its copies): 12 threads x 6 calls with different haplotypes, tapes, errors and a non-ASCII tape in between."""
+    import threading
+
+    from synth import cohort as C
+
+    prot = C.make_proteome(seed=91, n_tx=500, mu=5.6, sigma=0.7, hi=7000)
+    cat = C.make_catalogue(prot, 15000, seed=92, mix=(0.7, 0.06, 0.06, 0.08, 0.04, 0.03, 0.03))
+    cat.af[:] = 0.2
+    b = C.synth_batch(prot, cat, 24, 93, ref_mode="per_hap")
+    haps = []
+    for h in range(24):
+        t0, t1 = int(b.task_begin[h]), int(b.task_begin[h + 1])
+        tk = b.tasks[t0:t1]
+        tasks = [(int(r[3]), int(r[0]), int(r[1]), int(r[2])) for r in tk]  # (exe_code, start_pos, length, start_pos_res)
+        ref = b.ref[int(b.ref_base[h]):int(b.ref_base[h + 1])].astype(np.uint32)
+        alt = b.alt[int(b.alt_base[h]):int(b.alt_base[h + 1])].astype(np.uint32)
+        n_res = int(b.out_base[h + 1] - b.out_base[h])
+        want = np.zeros(n_res, np.uint32)
+        assert cengine.gir_execute(tasks, ref, alt, want, True)[0] == 0
+        haps.append((tasks, ref, alt, n_res, want))
+    errors = []
+
+    def worker(w):
+        try:
+            for i in range(6):
+                tasks, ref, alt, n_res, want = haps[(w * 5 + i * 7) % 24]
+                if (w + i) % 5 == 0:  # a rejected call in between leaves the slot reusable
+                    with pytest.raises(EngineError) as ei:
+                        gpu_engine.execute_soa(tasks[:3] + [(2, 0, 0, 0)], ref, alt, n_res, fill_dot=True)
+                    assert ei.value.status == L.ERR_BAD_STREAM and ei.value.bad_task == 3
+                if (w + i) % 7 == 0:  # code points above 0xFF take the UTF-32 path on the same slot
+                    r2 = ref.copy()
+                    r2[::97] = 0x4E2D
+                    w2 = np.zeros(n_res, np.uint32)
+                    assert cengine.gir_execute(tasks, r2, alt, w2, True)[0] == 0
+                    assert np.array_equal(gpu_engine.execute_soa(tasks, r2, alt, n_res, fill_dot=True), w2)
+                got = gpu_engine.execute_soa(tasks, ref, alt, n_res, fill_dot=True)
+                assert np.array_equal(got, want)
+        except BaseException as ex:  # noqa: BLE001 -- reported by the main thread
+            errors.append((w, repr(ex)))
+
+    th = [threading.Thread(target=worker, args=(w,)) for w in range(12)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors

@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +48,18 @@ struct Slot {  // one in-flight host-pointer batch
     bool busy = false;
 };
 
+constexpr int kSoaSlots = 16;  // concurrent v2p_execute_soa / v2p_gir_execute callers (rayon workers, parts/exec.rs:36-39)
+
+struct SoaSlot {  // everything one in-flight single-haplotype call needs: nobody else touches it until the call returns
+    cudaStream_t stream = nullptr;
+    Scratch sc;
+    DevBuf d_soa[4], tasks, ref, alt, out, bases;
+    DevStatus* h_status = nullptr;  // pinned + mapped
+    uint8_t* h_stage = nullptr;     // pinned staging of the 1-byte tapes (ref | alt | res), grown on demand
+    size_t stage_cap = 0;
+    bool busy = false;
+};
+
 }  // namespace
 
 struct v2p_event {
@@ -65,17 +79,17 @@ struct v2p_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     std::mutex mu;
-    std::string err;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     int variant = -1;     // -1 = auto: 8 KiB tiles on the TMA path, 4 KiB tiles on the register path
     int ctas_per_sm = 0;  // 0 = the variant's default
     Scratch sc;           // for e->stream
     Slot slots[kSlots];
     int next_slot = 0;
     std::vector<v2p_event*> event_pool;  // CUDA events + pinned status blocks are recycled (no per-call alloc/free)
-    // staging for the SoA call
-    DevBuf d_soa[4], soa_tasks, soa_ref, soa_alt, soa_out, soa_bases;
-    DevStatus* h_status = nullptr;  // pinned scratch for the SoA call
+    // the single-haplotype entry: per-caller slots, handed out under soa_mu (held only for the hand-out)
+    SoaSlot soa[kSoaSlots];
+    std::mutex soa_mu;
+    std::condition_variable soa_cv;
     // registered reference: replica r (0..15) at ref_rep + r*rep_stride, holding ref[x] at offset x + r
     DevBuf ref_rep;
     uint64_t rep_stride = 0, reg_n_ref = 0;
@@ -88,13 +102,18 @@ struct v2p_engine {
 
 namespace {
 
+// The message of the last failed call is per host THREAD: the engine is called concurrently (one haplotype per rayon
+// worker in the reference, parts/exec.rs:36-39), and a shared string could be overwritten under the reader's eyes.
+thread_local std::string t_err;
+
 int fail(v2p_engine* e, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (e) e->err = buf;
+    (void)e;
+    t_err = buf;
     return code;
 }
 
@@ -385,8 +404,7 @@ int v2p_engine_create(int cuda_device, v2p_engine** out) {
     e->device = cuda_device;
     cudaDeviceProp prop;
     bool ok = cudaSetDevice(cuda_device) == cudaSuccess && cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaHostAlloc((void**)&e->h_status, sizeof(DevStatus), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
+              cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < kSlots; ++i)
         ok = cudaStreamCreateWithFlags(&e->slots[i].stream, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {
@@ -405,9 +423,16 @@ void v2p_engine_destroy(v2p_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&e->sc.hap_flags, &e->sc.ser_list, &e->sc.order, &e->sc.chunk_hap, &e->sc.lb,     &e->sc.tile_hap, &e->sc.status, &e->d_soa[0], &e->d_soa[1],  &e->d_soa[2], &e->d_soa[3],
-                      &e->soa_tasks, &e->soa_ref,     &e->soa_alt,   &e->soa_out,  &e->soa_bases, &e->ref_rep};
+    DevBuf* bufs[] = {&e->sc.hap_flags, &e->sc.ser_list, &e->sc.order, &e->sc.chunk_hap, &e->sc.lb, &e->sc.tile_hap, &e->sc.status, &e->ref_rep};
     for (DevBuf* b : bufs) release(*b);
+    for (SoaSlot& sl : e->soa) {
+        DevBuf* sb[] = {&sl.sc.hap_flags, &sl.sc.ser_list, &sl.sc.order, &sl.sc.chunk_hap, &sl.sc.lb, &sl.sc.tile_hap, &sl.sc.status,
+                        &sl.d_soa[0], &sl.d_soa[1], &sl.d_soa[2], &sl.d_soa[3], &sl.tasks, &sl.ref, &sl.alt, &sl.out, &sl.bases};
+        for (DevBuf* b : sb) release(*b);
+        if (sl.h_status) cudaFreeHost(sl.h_status);
+        if (sl.h_stage) cudaFreeHost(sl.h_stage);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     for (Slot& sl : e->slots) {
         DevBuf* sb[] = {&sl.sc.hap_flags, &sl.sc.ser_list, &sl.sc.order, &sl.sc.chunk_hap, &sl.sc.lb,      &sl.sc.tile_hap, &sl.sc.status,  &sl.d_tasks, &sl.d_task_begin, &sl.d_ref,
                         &sl.d_ref_base, &sl.d_alt,       &sl.d_alt_base, &sl.d_out,   &sl.d_out_base};
@@ -415,12 +440,11 @@ void v2p_engine_destroy(v2p_engine* e) {
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     for (v2p_event* ev : e->event_pool) free_event(ev);
-    if (e->h_status) cudaFreeHost(e->h_status);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
-const char* v2p_last_error(v2p_engine* e) { return e ? e->err.c_str() : "engine is NULL"; }
+const char* v2p_last_error(v2p_engine* e) { return e ? t_err.c_str() : "engine is NULL"; }
 
 int v2p_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return V2P_ERR_INVALID_ARG;
@@ -428,7 +452,7 @@ int v2p_host_alloc(void** ptr, size_t bytes) {
 }
 int v2p_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? V2P_OK : V2P_ERR_CUDA; }
 
-uint64_t v2p_kernel_launch_count(v2p_engine* e) { return e ? e->launches : 0; }
+uint64_t v2p_kernel_launch_count(v2p_engine* e) { return e ? e->launches.load() : 0; }
 
 int v2p_engine_set_tuning(v2p_engine* e, int variant, int ctas_per_sm) {
     if (!e || variant < -1 || variant >= kNumVariants || ctas_per_sm < 0 || ctas_per_sm > 32) return V2P_ERR_INVALID_ARG;
@@ -457,7 +481,7 @@ int v2p_engine_set_stream(v2p_engine* e, void* cuda_stream) {
 int v2p_engine_set_reference(v2p_engine* e, const uint8_t* ref, uint64_t n_ref, uint32_t flags) {
     if (!e || (n_ref && !ref)) return V2P_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);
-    e->err.clear();
+    t_err.clear();
     CUDA_TRY(e, cudaSetDevice(e->device));
     CUDA_TRY(e, cudaDeviceSynchronize());  // nothing in flight may still read the previous tape
     e->has_ref = false;
@@ -490,7 +514,7 @@ int v2p_engine_set_reference(v2p_engine* e, const uint8_t* ref, uint64_t n_ref, 
 int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_result* res, v2p_event** done) {
     if (!e) return V2P_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);
-    e->err.clear();
+    t_err.clear();
     if (!b) return fail(e, V2P_ERR_INVALID_ARG, "batch is NULL");
     if (b->n_hap && (!b->task_begin || !b->alt_base || !b->out_base))
         return fail(e, V2P_ERR_INVALID_ARG, "task_begin/alt_base/out_base must not be NULL");
@@ -618,18 +642,166 @@ int v2p_execute_batch(v2p_engine* e, const v2p_batch* b, uint32_t flags, v2p_res
 
 int v2p_event_wait(v2p_engine* e, v2p_event* ev, v2p_result* res) {
     if (!e || !ev) return V2P_ERR_INVALID_ARG;
+    // block on the caller's own event BEFORE taking the engine lock: other threads keep submitting meanwhile
+    cudaSetDevice(e->device);
+    cudaEventSynchronize(ev->ev_done);
     std::lock_guard<std::mutex> g(e->mu);
     return wait_locked(e, ev, res);
 }
 
 // ---- reference-faithful single-haplotype call ------------------------------------------------------
+// Called concurrently, one haplotype per rayon worker (parts/exec.rs:36-39 -> personalized_genome.rs:64-65 ->
+// gir.rs:236-239).  Every caller gets its own slot (stream, device buffers, pinned staging, status block) for the
+// duration of the call; the engine lock is not taken, so uploads, kernels and copy-backs of different callers overlap.
+// When every residue of the three tapes is a code point below 256 (always, for protein FASTA) the tapes cross PCIe
+// and are processed as 1-byte residues: narrowed into the slot's pinned staging on the way up, widened into the
+// caller's `char` tape on the way back -- a quarter of the bytes of the UTF-32 path, same result.
+namespace {
+
+SoaSlot* soa_acquire(v2p_engine* e) {
+    std::unique_lock<std::mutex> g(e->soa_mu);
+    for (;;) {
+        for (SoaSlot& sl : e->soa)
+            if (!sl.busy) {
+                sl.busy = true;
+                return &sl;
+            }
+        e->soa_cv.wait(g);
+    }
+}
+void soa_release(v2p_engine* e, SoaSlot* sl) {
+    {
+        std::lock_guard<std::mutex> g(e->soa_mu);
+        sl->busy = false;
+    }
+    e->soa_cv.notify_one();
+}
+
+// dst[i] = (uint8_t)src[i]; returns the OR of all units (> 0xFF: some residue does not fit a byte)
+uint32_t narrow_u32(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n) {
+    uint32_t acc = 0;
+    for (size_t i = 0; i < n; ++i) {
+        acc |= src[i];
+        dst[i] = (uint8_t)src[i];
+    }
+    return acc;
+}
+void widen_u8(const uint8_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n) {
+    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+
+int soa_run(v2p_engine* e, SoaSlot* sl, size_t n_tasks, const uint64_t* exec_code, const uint64_t* start_pos,
+            const uint64_t* length, const uint64_t* start_pos_res, const uint32_t* ref_utf32, size_t n_ref,
+            const uint32_t* alt_utf32, size_t n_alt, uint32_t* res_utf32, size_t n_res, uint32_t flags, uint64_t* bad_index) {
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    if (!sl->stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&sl->stream, cudaStreamNonBlocking));
+    if (!sl->h_status)
+        CUDA_TRY(e, cudaHostAlloc((void**)&sl->h_status, sizeof(DevStatus), cudaHostAllocMapped | cudaHostAllocPortable));
+    cudaStream_t s = sl->stream;
+    const bool keep = !(flags & V2P_FLAG_FILL_DOT);
+    int rc;
+    // ---- narrow the tapes into pinned staging (ref | alt | res), unless a residue needs more than a byte
+    const size_t stage_need = n_ref + n_alt + n_res + 64;
+    if (sl->stage_cap < stage_need) {
+        if (sl->h_stage) CUDA_TRY(e, cudaFreeHost(sl->h_stage));
+        sl->h_stage = nullptr, sl->stage_cap = 0;
+        CUDA_TRY(e, cudaHostAlloc((void**)&sl->h_stage, stage_need + stage_need / 4, cudaHostAllocPortable));
+        sl->stage_cap = stage_need + stage_need / 4;
+    }
+    uint8_t* const h_ref = sl->h_stage;
+    uint8_t* const h_alt = h_ref + n_ref;
+    uint8_t* const h_res = h_alt + n_alt;
+    uint32_t wide = narrow_u32(ref_utf32, h_ref, n_ref) | narrow_u32(alt_utf32, h_alt, n_alt);
+    if (keep) wide |= narrow_u32(res_utf32, h_res, n_res);
+    const uint32_t unit = wide > 0xFFu ? 4u : 1u;  // bytes per residue on the device
+    const size_t tb = n_tasks * sizeof(uint64_t);
+    for (int i = 0; i < 4; ++i)
+        if ((rc = reserve(e, sl->d_soa[i], tb))) return rc;
+    if ((rc = reserve(e, sl->tasks, n_tasks * sizeof(v2p_task16))) || (rc = reserve(e, sl->ref, n_ref * unit + 32)) ||
+        (rc = reserve(e, sl->alt, n_alt * unit + 32)) || (rc = reserve(e, sl->out, n_res * unit + 32)) ||
+        (rc = reserve(e, sl->bases, 64)) || (rc = reserve(e, sl->sc.status, sizeof(DevStatus))))
+        return rc;
+    const uint64_t* soa[4] = {exec_code, start_pos, length, start_pos_res};
+    for (int i = 0; i < 4; ++i)
+        if (tb) CUDA_TRY(e, cudaMemcpyAsync(sl->d_soa[i].p, soa[i], tb, cudaMemcpyHostToDevice, s));
+    if (unit == 1) {
+        if (n_ref) CUDA_TRY(e, cudaMemcpyAsync(sl->ref.p, h_ref, n_ref, cudaMemcpyHostToDevice, s));
+        if (n_alt) CUDA_TRY(e, cudaMemcpyAsync(sl->alt.p, h_alt, n_alt, cudaMemcpyHostToDevice, s));
+        if (keep && n_res) CUDA_TRY(e, cudaMemcpyAsync(sl->out.p, h_res, n_res, cudaMemcpyHostToDevice, s));
+    } else {
+        if (n_ref) CUDA_TRY(e, cudaMemcpyAsync(sl->ref.p, ref_utf32, n_ref * 4, cudaMemcpyHostToDevice, s));
+        if (n_alt) CUDA_TRY(e, cudaMemcpyAsync(sl->alt.p, alt_utf32, n_alt * 4, cudaMemcpyHostToDevice, s));
+        if (keep && n_res) CUDA_TRY(e, cudaMemcpyAsync(sl->out.p, res_utf32, n_res * 4, cudaMemcpyHostToDevice, s));
+    }
+    // task_begin | alt_base | out_base, two entries each (staged in the pinned status block's neighbourhood is not
+    // worth it: 48 bytes from the stack, consumed before this frame returns because the call is synchronous)
+    const uint64_t bases[6] = {0, n_tasks, 0, n_alt * unit, 0, n_res * unit};
+    CUDA_TRY(e, cudaMemcpyAsync(sl->bases.p, bases, sizeof bases, cudaMemcpyHostToDevice, s));
+
+    KParams kp;
+    memset(&kp, 0, sizeof kp);
+    const uint64_t* db = (const uint64_t*)sl->bases.p;
+    kp.tasks = (const v2p_task16*)sl->tasks.p;
+    kp.task_begin = db;
+    kp.ref = (const uint8_t*)sl->ref.p;
+    kp.alt = (const uint8_t*)sl->alt.p;
+    kp.alt_base = db + 2;
+    kp.out = (uint8_t*)sl->out.p;
+    kp.out_base = db + 4;
+    kp.n_hap = 1;
+    kp.n_tasks = n_tasks;
+    kp.n_ref = n_ref * unit;
+    kp.n_alt = n_alt * unit;
+    kp.n_out = n_res * unit;
+    kp.fill_word = unit == 1 ? 0x2E2E2E2Eu : 0x0000002Eu;  // '.' per byte, or as one UTF-32 unit
+    kp.keep_out = keep ? 1 : 0;
+    kp.validate = (flags & V2P_FLAG_VALIDATE) ? 1 : 0;
+
+    // pack (and judge every reference panic on the original 64-bit values), then plan + copy
+    kp.status = (DevStatus*)sl->sc.status.p;
+    k_init_status<<<1, 1, 0, s>>>(kp.status);
+    e->launches++;
+    if (n_tasks) {
+        k_soa_pack<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(
+            n_tasks, (const uint64_t*)sl->d_soa[0].p, (const uint64_t*)sl->d_soa[1].p, (const uint64_t*)sl->d_soa[2].p,
+            (const uint64_t*)sl->d_soa[3].p, n_ref, n_alt, n_res, unit, kp.validate, (v2p_task16*)sl->tasks.p, kp.status);
+        e->launches++;
+    }
+    rc = launch_group(e, s, sl->sc, kp, nullptr, nullptr, sl->h_status, /*init_status=*/false, nullptr, false);
+    if (rc) return rc;
+    CUDA_TRY(e, cudaStreamSynchronize(s));
+    if (needs_serial(*sl->h_status)) {
+        if ((rc = launch_serial(e, s, kp, sl->h_status->unsorted))) return rc;
+        CUDA_TRY(e, cudaStreamSynchronize(s));
+    }
+    v2p_result r;
+    memset(&r, 0, sizeof r);
+    decode_status(*sl->h_status, nullptr, 0, 0, &r);
+    if (r.status != V2P_OK) {
+        if (bad_index) *bad_index = r.bad_task;
+        return fail(e, r.status, "task %llu rejected with status %d", (unsigned long long)r.bad_task, r.status);
+    }
+    if (n_res) {
+        if (unit == 1) {
+            CUDA_TRY(e, cudaMemcpyAsync(h_res, sl->out.p, n_res, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(e, cudaStreamSynchronize(s));
+            widen_u8(h_res, res_utf32, n_res);
+        } else {
+            CUDA_TRY(e, cudaMemcpyAsync(res_utf32, sl->out.p, n_res * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(e, cudaStreamSynchronize(s));
+        }
+    }
+    return V2P_OK;
+}
+
+}  // namespace
+
 int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, const uint64_t* start_pos,
                     const uint64_t* length, const uint64_t* start_pos_res, const uint32_t* ref_utf32, size_t n_ref,
                     const uint32_t* alt_utf32, size_t n_alt, uint32_t* res_utf32, size_t n_res, uint32_t flags,
                     uint64_t* bad_index) {
     if (!e) return V2P_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> g(e->mu);
-    e->err.clear();
+    t_err.clear();
     if (bad_index) *bad_index = 0;
     if (n_tasks && (!exec_code || !start_pos || !length || !start_pos_res))
         return fail(e, V2P_ERR_INVALID_ARG, "NULL task array");
@@ -638,76 +810,12 @@ int v2p_execute_soa(v2p_engine* e, size_t n_tasks, const uint64_t* exec_code, co
     const uint64_t lim = 0xFFFFFFFFull / 4;
     if (n_ref > lim || n_alt > lim || n_res > lim)
         return fail(e, V2P_ERR_INVALID_ARG, "tape longer than 2^30 residues: use v2p_execute_batch");
-    CUDA_TRY(e, cudaSetDevice(e->device));
-    cudaStream_t s = e->stream;
-    int rc;
-    const size_t tb = n_tasks * sizeof(uint64_t);
-    for (int i = 0; i < 4; ++i)
-        if ((rc = reserve(e, e->d_soa[i], tb))) return rc;
-    if ((rc = reserve(e, e->soa_tasks, n_tasks * sizeof(v2p_task16))) || (rc = reserve(e, e->soa_ref, n_ref * 4 + 32)) ||
-        (rc = reserve(e, e->soa_alt, n_alt * 4 + 32)) || (rc = reserve(e, e->soa_out, n_res * 4 + 32)) ||
-        (rc = reserve(e, e->soa_bases, 64)) || (rc = reserve(e, e->sc.status, sizeof(DevStatus))))
-        return rc;
-    const uint64_t* soa[4] = {exec_code, start_pos, length, start_pos_res};
-    for (int i = 0; i < 4; ++i)
-        if (tb) CUDA_TRY(e, cudaMemcpyAsync(e->d_soa[i].p, soa[i], tb, cudaMemcpyHostToDevice, s));
-    if (n_ref) CUDA_TRY(e, cudaMemcpyAsync(e->soa_ref.p, ref_utf32, n_ref * 4, cudaMemcpyHostToDevice, s));
-    if (n_alt) CUDA_TRY(e, cudaMemcpyAsync(e->soa_alt.p, alt_utf32, n_alt * 4, cudaMemcpyHostToDevice, s));
-    const bool keep = !(flags & V2P_FLAG_FILL_DOT);
-    if (keep && n_res) CUDA_TRY(e, cudaMemcpyAsync(e->soa_out.p, res_utf32, n_res * 4, cudaMemcpyHostToDevice, s));
-    // task_begin | alt_base | out_base, two entries each
-    const uint64_t bases[6] = {0, n_tasks, 0, n_alt * 4, 0, n_res * 4};
-    CUDA_TRY(e, cudaMemcpyAsync(e->soa_bases.p, bases, sizeof bases, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(e, cudaStreamSynchronize(s));  // `bases` lives on this stack frame
-
-    KParams kp;
-    memset(&kp, 0, sizeof kp);
-    const uint64_t* db = (const uint64_t*)e->soa_bases.p;
-    kp.tasks = (const v2p_task16*)e->soa_tasks.p;
-    kp.task_begin = db;
-    kp.ref = (const uint8_t*)e->soa_ref.p;
-    kp.alt = (const uint8_t*)e->soa_alt.p;
-    kp.alt_base = db + 2;
-    kp.out = (uint8_t*)e->soa_out.p;
-    kp.out_base = db + 4;
-    kp.n_hap = 1;
-    kp.n_tasks = n_tasks;
-    kp.n_ref = n_ref * 4;
-    kp.n_alt = n_alt * 4;
-    kp.n_out = n_res * 4;
-    kp.fill_word = 0x0000002Eu;  // '.' as one UTF-32 unit
-    kp.keep_out = keep ? 1 : 0;
-    kp.validate = (flags & V2P_FLAG_VALIDATE) ? 1 : 0;
-
-    // pack (and judge every reference panic on the original 64-bit values), then plan + copy
-    kp.status = (DevStatus*)e->sc.status.p;
-    k_init_status<<<1, 1, 0, s>>>(kp.status);
-    e->launches++;
-    if (n_tasks) {
-        k_soa_pack<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(
-            n_tasks, (const uint64_t*)e->d_soa[0].p, (const uint64_t*)e->d_soa[1].p, (const uint64_t*)e->d_soa[2].p,
-            (const uint64_t*)e->d_soa[3].p, n_ref, n_alt, n_res, 4u, kp.validate, (v2p_task16*)e->soa_tasks.p, kp.status);
-        e->launches++;
-    }
-    rc = launch_group(e, s, e->sc, kp, nullptr, nullptr, e->h_status, /*init_status=*/false, nullptr, false);
-    if (rc) return rc;
-    CUDA_TRY(e, cudaStreamSynchronize(s));
-    if (needs_serial(*e->h_status)) {
-        if ((rc = launch_serial(e, s, kp, e->h_status->unsorted))) return rc;
-        CUDA_TRY(e, cudaStreamSynchronize(s));
-    }
-    v2p_result r;
-    memset(&r, 0, sizeof r);
-    decode_status(*e->h_status, nullptr, 0, 0, &r);
-    if (r.status != V2P_OK) {
-        if (bad_index) *bad_index = r.bad_task;
-        return fail(e, r.status, "task %llu rejected with status %d", (unsigned long long)r.bad_task, r.status);
-    }
-    if (n_res) {
-        CUDA_TRY(e, cudaMemcpyAsync(res_utf32, e->soa_out.p, n_res * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(e, cudaStreamSynchronize(s));
-    }
-    return V2P_OK;
+    SoaSlot* sl = soa_acquire(e);
+    const int rc = soa_run(e, sl, n_tasks, exec_code, start_pos, length, start_pos_res, ref_utf32, n_ref, alt_utf32, n_alt,
+                           res_utf32, n_res, flags, bad_index);
+    if (rc != V2P_OK && sl->stream) cudaStreamSynchronize(sl->stream);  // nothing of a failed call may still be in flight
+    soa_release(e, sl);
+    return rc;
 }
 
 int v2p_gir_execute(v2p_engine* e, int engine_kind, size_t n_tasks, const uint64_t* exec_code, const uint64_t* start_pos,
