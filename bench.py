@@ -79,6 +79,9 @@ def parse_args():
     ap.add_argument("--c3-samples", type=int, default=50000,
                     help="samples of the ONE cohort that is sharded over the ranks and streamed (BASELINE configs[2]); 0 = skip")
     ap.add_argument("--c3-chunk-samples", type=int, default=1024, help="samples per streamed chunk of the c3 section")
+    ap.add_argument("--only-c3", action="store_true",
+                    help="print only the c3 section (one cohort of --c3-samples samples, sharded over the ranks and streamed): the "
+                         "point of the C5 scaling sweep, profiles/dev/c5_sweep.sh")
     ap.add_argument("--no-c3-parity", action="store_true", help="skip the whole-cohort oracle check of the c3 section")
     ap.add_argument("--dropin-haps", type=int, default=32,
                     help="haplotypes driven through v2p_gir_execute from concurrent host threads (the literal drop-in); 0 = skip")
@@ -130,6 +133,28 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.only_c3:  # the C5 sweep point: nothing but the sharded, streamed cohort
+        from synth import cohort as C
+
+        prot = C.make_proteome(seed=0x5EED0001)
+        eng = GpuEngine(local_rank)
+        eng.set_reference(torch.from_numpy(prot.residues).to(dev), args.ref_mode)
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.isfile(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else FALLBACK_HBM_GBS
+        _, _, dram_per_res = ncu_traffic(args, 1)
+        line = c3_measure(args, eng, prot, rank, world, local_rank, dev, shard, barrier, peak, dram_per_res)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     t_gen = time.perf_counter()
     prot, cat, batch = make_workload(args.workload, args.samples, rank, args.layout, args.fasta_image)
     t_gen = time.perf_counter() - t_gen
@@ -153,12 +178,6 @@ def main():
     side = torch.cuda.Stream(device=dev)
     eng.set_stream(side.cuda_stream)
     dargs = (n_hap, d_task_begin, d_tasks, d_ref_arg, d_alt, d_alt_base, d_out, d_out_base, n_tasks, len(batch.alt), n_out)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     dkw = {"aligned_layout": args.layout == "aligned"}  # the producer's hint (V2P_FLAG_ALIGNED_LAYOUT)
     for _ in range(max(args.warmup, 3)):
@@ -191,6 +210,18 @@ def main():
     total_haps = shard.sum_over_ranks(n_hap, dev)
     total_alg = shard.sum_over_ranks(b_alg, dev)
     ms_per_step = max_ms / args.steps
+
+    # ---- load balance of the copy grid: wall time of every warp of the persistent grid, one extra launch
+    eng.profile_warps(True)
+    eng.execute_batch_device(*dargs, **dkw)
+    wns = eng.read_warp_ns().astype(np.float64)
+    eng.profile_warps(False)
+    skew = None
+    if wns.size:
+        skew = {"warps": int(wns.size), "warp_ms_max": float(wns.max() / 1e6), "warp_ms_mean": float(wns.mean() / 1e6),
+                "warp_ms_min": float(wns.min() / 1e6), "max_over_mean": float(wns.max() / wns.mean()),
+                "what": "wall time (%globaltimer) of every warp of k_copy_tiles' persistent grid in one launch: a long segment "
+                        "that pinned one worker would show up as max >> mean"}
 
     # ---- end to end through the C ABI with HOST buffers: per step, every chunk's tasks/alt go H2D from pinned
     #      memory and every result tape comes back D2H into a pinned staging buffer (the FASTA writer's input)
@@ -442,7 +473,7 @@ def main():
                                     "note": "result-tape bytes written / kernel time vs a store-only kernel on the same GPU and buffer "
                                             "(TMA bulk stores of 8 KiB tiles, the copy kernel's own store instruction and grid); the hard "
                                             "floor of this path is one DRAM write per residue"}},
-        "cpu_baseline": cpu, "parity": parity, "c3": c3_line, "dropin": dropin_line, "other_layout": other_line, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
+        "load_balance": skew, "cpu_baseline": cpu, "parity": parity, "c3": c3_line, "dropin": dropin_line, "other_layout": other_line, "taskgen": taskgen, "gzip": gzip_line, "pipeline": pipeline_line, "gen_seconds": round(t_gen, 1),
     }
     print(json.dumps(line))
     if world > 1:

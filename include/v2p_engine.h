@@ -162,6 +162,13 @@ int v2p_event_wait(v2p_engine* e, v2p_event* ev, v2p_result* res); /* also relea
 
 /* Launch-level introspection for bench.py: kernels launched by this context since creation. */
 uint64_t v2p_kernel_launch_count(v2p_engine* e);
+/* Load-balance evidence (skew stress): with profiling on, every warp of the copy kernel's persistent
+ * grid records its wall time (ns, %globaltimer) for device-pointer batches on the engine stream;
+ * v2p_engine_read_warp_ns returns the last launch's values (n_warps entries; call with ns_out == NULL to size it).
+ * max / mean of them is what a skewed Task array would push up if a long segment pinned one worker. */
+int v2p_engine_profile_warps(v2p_engine* e, int on);
+int v2p_engine_read_warp_ns(v2p_engine* e, uint64_t* ns_out, uint64_t cap, uint64_t* n_warps);
+
 /* Kernel tunables for profiling sweeps: copy-kernel variant (-1 = automatic choice, the default) and CTAs per SM
  * (0 = the variant's own). */
 int v2p_engine_set_tuning(v2p_engine* e, int variant, int ctas_per_sm);

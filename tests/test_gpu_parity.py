@@ -497,3 +497,48 @@ def test_pinned_host_allocator_roundtrip(gpu_engine):
     st, _, _, want = oracle_batch(b)
     assert st == 0 and np.array_equal(got, want)
     assert lib.v2p_host_free(p) == 0
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 5, 8, 9])
+def test_skew_stress_c4_mix_with_giant_transcripts(gpu_engine, variant):
+    """SURVEY 8d C4 / BASELINE configs[3]: 35 % frameshift (log-normal tails up to 4,000), 20 % long inframe insertions
+    (up to 5,000), 10 % stop_lost tails, 35 % missense, on a proteome with 35,000-residue transcripts -- the segments of
+    transcript_instructions.rs:666-679 (frameshift tails) and :696-710 (stop_lost).  240 haplotypes, every tape mode,
+    whole tapes against the oracle; and no warp of the persistent grid is pinned by a long segment."""
+    from synth import cohort as C
+
+    prot = C.make_proteome(seed=0x5EED0001, n_tx=1500, giant=12)
+    cat = C.make_catalogue(prot, 9000, seed=0x5EED0004, mix=C.MIX_C4, fs_mean=150, fs_max=4000, sl_max=500, long_ins_mean=120,
+                           long_ins_max=5000, lognormal_tails=True)  # (tails longer than C4's own, so that 9,000 sites reach the caps)
+    cat.af[:] = np.random.default_rng(4).choice([0.02, 0.1, 0.3], size=cat.n).astype(np.float32)
+    cat.af[cat.dlen > 400] = 0.4  # the long payloads are carried often
+    b = C.synth_batch(prot, cat, 240, seed=0x5EED0004)
+    lens, is_alt = b.tasks[:, 1], b.tasks[:, 3] == 1
+    assert lens.max() > 5000 and lens[is_alt].max() > 1500  # giant reference runs and long alteration payloads
+    want = np.zeros(b.n_residues, np.uint8)
+    assert cengine.batch_execute(b.task_begin, b.tasks, prot.residues, b.alt, b.alt_base, want, b.out_base, threads=4)[0] == 0
+    gpu_engine.set_tuning(variant, 0)
+    try:
+        out, _ = gpu_engine.execute_batch(b.task_begin, b.tasks, prot.residues, b.alt, b.alt_base, b.out_base, validate=True)
+        assert np.array_equal(out, want)
+        for mode in ("replicas", "plain"):
+            gpu_engine.set_reference(prot.residues, mode)
+            out, _ = gpu_engine.execute_batch(b.task_begin, b.tasks, None, b.alt, b.alt_base, b.out_base)
+            assert np.array_equal(out, want), mode
+        if variant == -1:  # load balance of the persistent grid on this input
+            import torch
+
+            dev = torch.device("cuda:0")
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+            d_out = torch.empty(b.n_residues + 16, dtype=torch.uint8, device=dev)
+            args = (b.n_hap, up(b.task_begin), up(b.tasks), None, up(b.alt), up(b.alt_base), d_out, up(b.out_base), len(b.tasks),
+                    len(b.alt), b.n_residues)
+            gpu_engine.profile_warps(True)
+            for _ in range(3):
+                gpu_engine.execute_batch_device(*args)
+            ns = gpu_engine.read_warp_ns().astype(np.float64)
+            gpu_engine.profile_warps(False)
+            assert np.array_equal(d_out[: b.n_residues].cpu().numpy(), want)
+            assert ns.size > 0 and ns.max() / ns.mean() < 1.6, (ns.max(), ns.mean())
+    finally:
+        gpu_engine.set_tuning(-1, 0)

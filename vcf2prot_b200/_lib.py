@@ -100,6 +100,8 @@ SYMBOLS = {
     "v2p_kernel_launch_count": (C.c_uint64, [_P]),
     "v2p_engine_set_tuning": (C.c_int, [_P, C.c_int, C.c_int]),
     "v2p_engine_set_stream": (C.c_int, [_P, _P]),
+    "v2p_engine_profile_warps": (C.c_int, [_P, C.c_int]),
+    "v2p_engine_read_warp_ns": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "v2p_engine_set_reference": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32]),
     # include/v2p_taskgen.h
     "v2p_catalogue_create": (C.c_int, [C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_uint64,

@@ -98,6 +98,10 @@ struct v2p_engine {
     int order_gshift = 2;  // interleave groups of 2^2 consecutive tiles (measured best: profiles/r1);
                            // env V2P_TILE_ORDER=tape: tiles in tape order; =gN: groups of 2^N tiles (A/B knobs)
     bool tape_order = false;
+    // profiling: per-warp wall time of the copy grid of the last launch group on e->stream (v2p_engine_profile_warps)
+    bool profile_warps = false;
+    DevBuf warp_ns;
+    uint32_t warp_ns_n = 0;
 };
 
 namespace {
@@ -231,6 +235,12 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
         uint64_t want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->sm_count * per_sm);
         size_t smem = (size_t)kWarpsPerCta * (cv.tile + cv.tile / 16 + kTileScratch) + 17 * 16;
+        kp.warp_ns = nullptr;
+        if (e->profile_warps && s == e->stream) {
+            if ((rc = reserve(e, e->warp_ns, (size_t)grid * kWarpsPerCta * sizeof(unsigned long long)))) return rc;
+            kp.warp_ns = (unsigned long long*)e->warp_ns.p;
+            e->warp_ns_n = grid * kWarpsPerCta;
+        }
         void (*fn)(const KParams) = interleave ? cv.fn_il : cv.fn;
         if (smem > 48 * 1024) CUDA_TRY(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<grid, kThreads, smem, s>>>(kp);
@@ -423,7 +433,7 @@ void v2p_engine_destroy(v2p_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&e->sc.hap_flags, &e->sc.ser_list, &e->sc.order, &e->sc.chunk_hap, &e->sc.lb, &e->sc.tile_hap, &e->sc.status, &e->ref_rep};
+    DevBuf* bufs[] = {&e->warp_ns, &e->sc.hap_flags, &e->sc.ser_list, &e->sc.order, &e->sc.chunk_hap, &e->sc.lb, &e->sc.tile_hap, &e->sc.status, &e->ref_rep};
     for (DevBuf* b : bufs) release(*b);
     for (SoaSlot& sl : e->soa) {
         DevBuf* sb[] = {&sl.sc.hap_flags, &sl.sc.ser_list, &sl.sc.order, &sl.sc.chunk_hap, &sl.sc.lb, &sl.sc.tile_hap, &sl.sc.status,
@@ -459,6 +469,24 @@ int v2p_engine_set_tuning(v2p_engine* e, int variant, int ctas_per_sm) {
     std::lock_guard<std::mutex> g(e->mu);
     e->variant = variant;
     e->ctas_per_sm = ctas_per_sm;
+    return V2P_OK;
+}
+
+int v2p_engine_profile_warps(v2p_engine* e, int on) {
+    if (!e) return V2P_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->profile_warps = on != 0;
+    return V2P_OK;
+}
+
+int v2p_engine_read_warp_ns(v2p_engine* e, uint64_t* ns_out, uint64_t cap, uint64_t* n_warps) {
+    if (!e || !n_warps) return V2P_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    *n_warps = e->warp_ns_n;
+    if (!ns_out || cap < e->warp_ns_n || !e->warp_ns_n) return e->warp_ns_n && ns_out ? V2P_ERR_INVALID_ARG : V2P_OK;
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaMemcpy(ns_out, e->warp_ns.p, (size_t)e->warp_ns_n * 8, cudaMemcpyDeviceToHost));
     return V2P_OK;
 }
 

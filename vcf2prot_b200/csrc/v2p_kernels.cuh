@@ -75,6 +75,7 @@ struct KParams {
     int keep_out;        // 1: uncovered bytes keep the caller's content (soa call without FILL_DOT)
     int validate;        // V2P_FLAG_VALIDATE
     DevStatus* status;
+    unsigned long long* warp_ns;  // profiling (v2p_engine_profile_warps): wall time of every warp of the copy grid, or nullptr
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -497,6 +498,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     if (p.status->bad_args || p.status->err_key != ~0ull || p.status->gap_key != ~0ull || p.status->stream_key != ~0ull)
         return;
     if (lane == 0) mbar_init(mbar, 1);
+    if (p.warp_ns && lane == 0) {  // load-balance evidence: when did this warp start (kept in shared memory)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        st_bases[6] = t;
+    }
     __syncwarp();
 
     const uint32_t n_warps = gridDim.x * kWarpsPerCta;
@@ -872,6 +878,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         if (bulk + lane < tile_len) gout[bulk + lane] = tile[bulk + lane];  // < 16 trailing bytes of the whole output
     }
     if (lane == 0) bulk_wait0();
+    if (p.warp_ns && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.warp_ns[blockIdx.x * kWarpsPerCta + warp] = t - st_bases[6];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ serial order

@@ -118,6 +118,22 @@ class GpuEngine:
         if st:
             raise EngineError(st, "set_tuning")
 
+    def profile_warps(self, on: bool = True):
+        st = self._lib.v2p_engine_profile_warps(self._h, int(on))
+        if st:
+            raise EngineError(st, "profile_warps")
+
+    def read_warp_ns(self) -> np.ndarray:
+        """Wall time (ns) of every warp of the copy grid in the last device-pointer launch group (profile_warps on)."""
+        n = C.c_uint64(0)
+        self._lib.v2p_engine_read_warp_ns(self._h, None, 0, C.byref(n))
+        out = np.zeros(n.value, np.uint64)
+        if n.value:
+            st = self._lib.v2p_engine_read_warp_ns(self._h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
+            if st:
+                raise EngineError(st, self.last_error())
+        return out
+
     def set_stream(self, cuda_stream: Optional[int]):
         st = self._lib.v2p_engine_set_stream(self._h, C.c_void_p(cuda_stream or 0))
         if st:
