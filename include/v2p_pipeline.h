@@ -35,6 +35,9 @@ typedef struct v2p_pipeline v2p_pipeline;
 #define V2P_PIPE_MAX_LANES 4
 #define V2P_PIPE_GZIP 0x1u /* deliver one gzip member per sample instead of the plain FASTA text */
 #define V2P_PIPE_SKIP_ABORTS 0x2u /* general catalogue lanes: V2P_GEN_SKIP_ABORTS (count, do not fail; v2p_taskgen.h) */
+#define V2P_PIPE_ALL_RECORDS 0x4u /* the reference's `-a` flag (write_all, personalized_genome.rs:120-210): after a haplotype's
+                                   * altered records, every OTHER transcript of the proteome unchanged, `>{name}_{1|2}\n{ref}\n`;
+                                   * needs v2p_pipeline_enable_all_records                                                      */
 
 /* `e`: engine with the proteome registered (v2p_engine_set_reference).  `lanes`: 1..4 catalogue objects created from
  * the SAME arrays, names set (v2p_catalogue_set_names); each lane owns the device buffers of one chunk in flight.
@@ -42,6 +45,13 @@ typedef struct v2p_pipeline v2p_pipeline;
 int v2p_pipeline_create(v2p_engine* e, v2p_catalogue* const* lanes, uint32_t n_lanes, v2p_pipeline** out);
 void v2p_pipeline_destroy(v2p_pipeline* p);
 const char* v2p_pipeline_last_error(v2p_pipeline* p);
+
+/* Prepares V2P_PIPE_ALL_RECORDS: registers an extended reference tape on the pipeline's engine -- the proteome followed
+ * by `>{name}_1\n>{name}_2\n` for every transcript -- so that an unaltered transcript's record is three reference-stream
+ * copy segments (header, residues, newline) for the same hot path.  Replaces the engine's registered reference (tasks
+ * index the proteome part exactly as before).  Host pointers, copied. */
+int v2p_pipeline_enable_all_records(v2p_pipeline* p, const uint8_t* proteome, uint64_t n_proteome, uint64_t n_tx,
+                                    const uint64_t* tx_offsets, const uint64_t* name_off, const uint8_t* names);
 
 /* Called once per chunk, in sample order, when the chunk's bytes have landed in (pinned) host memory:
  * file of sample first_sample+i = data[file_begin[i] .. file_begin[i+1]).  `data` is only valid during the call.

@@ -127,8 +127,8 @@ def stage_seconds(stdout: str) -> Optional[Dict[str, float]]:
 
 
 def run_reference(vcf: str, ref_seqs: Dict[str, str], engine: str = "st", env: Optional[Dict[str, str]] = None,
-                  verbose: bool = False, keep_dir: Optional[str] = None, timeout: float = 600.0):
-    """Run the reference binary; returns (records_by_sample, stdout, returncode)."""
+                  verbose: bool = False, keep_dir: Optional[str] = None, timeout: float = 600.0, write_all: bool = False):
+    """Run the reference binary; returns (records_by_sample, stdout, returncode).  write_all: its `-a` flag."""
     if not available():
         raise RuntimeError("reference binary missing: run `make -C oracle ref` in the authoring container")
     d = keep_dir or tempfile.mkdtemp(prefix="v2p_ref_")
@@ -146,6 +146,8 @@ def run_reference(vcf: str, ref_seqs: Dict[str, str], engine: str = "st", env: O
                "-o", os.path.join(d, "out")]
         if verbose:
             cmd.append("-v")
+        if write_all:
+            cmd.append("-a")
         p = subprocess.run(cmd, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
         stdout = p.stdout.decode("utf-8", "replace")
         recs = {}

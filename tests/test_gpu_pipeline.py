@@ -150,3 +150,58 @@ def test_files_on_disk_through_the_native_writer(world, gpu_engine, tmp_path, gz
     assert want[3] == b"" and (tmp_path / ("NA00021" + (".fasta.gz" if gzip else ".fasta"))).exists()
     w.close()
     pipe.close()
+
+
+def oracle_files_all(prot, cat, hap, site, n_samples):
+    """`-a` file text from the ORACLE's tapes: per haplotype the altered records (tape order), then every other
+    transcript of the proteome unchanged, proteome order (the record set of personalized_genome.rs:120-210, pinned on
+    the reference binary by tests/test_rules_vs_reference_binary.py::test_write_all_record_set_of_the_reference_binary)."""
+    b = C.build_batch(prot, cat, hap, site, 2 * n_samples, "global", "packed")
+    tape = np.zeros(b.n_residues, np.uint8)
+    assert cengine.batch_execute(b.task_begin, b.tasks, prot.residues, b.alt, b.alt_base, tape, b.out_base)[0] == 0
+    files = []
+    for s in range(n_samples):
+        txt = []
+        for k in (0, 1):
+            recs = C.fasta_records(prot, b, tape, 2 * s + k, k + 1)
+            altered = {n[:-2] for n, _ in recs}
+            txt += [">%s\n%s\n" % r for r in recs]
+            txt += [">%s_%d\n%s\n" % (prot.name(t), k + 1, prot.seq(t)) for t in range(prot.n_tx) if prot.name(t) not in altered]
+        files.append("".join(txt).encode("ascii"))
+    return files
+
+
+@pytest.mark.parametrize("lanes,chunk,gzip", [(1, 3, False), (2, 2, False), (2, 5, True)])
+def test_all_records_flag_writes_the_unaltered_reference_too(world, lanes, chunk, gzip):
+    from vcf2prot_b200 import GpuEngine
+
+    prot, cat = world
+    n_samples = 7
+    hap, site = cohort_sites(cat, n_samples, 500 + lanes, drop=(2, 3))  # sample 1 carries nothing: its file is the proteome twice
+    want = oracle_files_all(prot, cat, hap, site, n_samples)
+    assert want[1].count(b">") == 2 * prot.n_tx and all(w.count(b">") == 2 * prot.n_tx for w in want)
+    sb, sites = csr_lists(hap, site, 2 * n_samples)
+    with GpuEngine(0) as eng:  # (its registered reference is replaced by the extended tape)
+        eng.set_reference(prot.residues)
+        pipe = DevicePipeline(eng, prot, cat, C.default_names(prot), lanes=lanes)
+        with pytest.raises(EngineError):  # not prepared yet
+            pipe.run_lists(sb, sites, n_samples, chunk, gzip, sink=lambda *a: 0, all_records=True)
+        pipe.enable_all_records(prot.residues, prot.offsets, C.default_names(prot))
+        got = {}
+
+        def sink(first, n, data, begins):
+            for i in range(n):
+                got[first + i] = bytes(data[int(begins[i]):int(begins[i + 1])])
+            return 0
+
+        _, res = pipe.run_lists(sb, sites, n_samples, chunk, gzip, sink=sink, all_records=True)
+        un = (lambda b: zlib.decompress(b, wbits=31)) if gzip else (lambda b: b)
+        for s in range(n_samples):
+            assert un(got[s]) == want[s], s
+        assert int(res.n_records) == 2 * n_samples * prot.n_tx
+        # the same pipeline still writes the altered-only files (tasks index the proteome part of the extended tape)
+        want_altered, _ = oracle_files(prot, cat, hap, site, n_samples)
+        got.clear()
+        pipe.run_lists(sb, sites, n_samples, chunk, False, sink=sink)
+        assert [got[s] for s in range(n_samples)] == want_altered
+        pipe.close()

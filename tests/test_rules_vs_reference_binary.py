@@ -196,3 +196,28 @@ def test_multiword_masks_decode_like_the_binary(rules_binary):
             assert sorted(csqs) == sorted(haps[h])  # the decode gives back what was encoded ...
             want += rules_records(rules_binary, refs, csqs, k + 1)
         assert [tuple(r) for r in got.get(smp, [])] == sorted(want), smp  # ... and the binary read the same masks
+
+
+def test_write_all_record_set_of_the_reference_binary():
+    """`-a` (write_all, personalized_genome.rs:120-210), pinned on the reference binary itself: per haplotype the altered
+    records (the annotation map's keys -- start_lost's empty record included) and then every OTHER transcript of the
+    proteome unchanged with the same `_1` / `_2` suffix.  This is the record set V2P_PIPE_ALL_RECORDS builds on the
+    device (tests/test_gpu_pipeline.py holds it to the same expectation)."""
+    from oracle import refbin, taskgen
+    from tests.helpers import cohort_haplotype_csqs, load_golden
+
+    if not refbin.available():
+        pytest.skip("reference binary not present (oracle/_ref/vcf2prot)")
+    for name in ("cohort_a.json", "cohort_b.json"):
+        co = load_golden(name)
+        recs, _, rc = refbin.run_reference(refbin.vcf_text(co["samples"], co["records"]), co["refs"], "st", write_all=True)
+        assert rc == 0
+        per_hap = cohort_haplotype_csqs(co)
+        for smp in co["samples"]:
+            want = []
+            for hap in (1, 2):
+                altered = taskgen.haplotype_records(per_hap.get((smp, hap), []), co["refs"], hap)
+                keys = {h[: -2] for h, _ in altered}
+                want += altered + [("%s_%d" % (k, hap), v) for k, v in co["refs"].items() if k not in keys]
+            assert sorted(recs[smp]) == sorted(want), (name, smp)
+            assert len(recs[smp]) == 2 * len(co["refs"])

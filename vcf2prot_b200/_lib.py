@@ -80,7 +80,7 @@ class CohortResult(C.Structure):  # v2p_cohort_result
 
 # int sink(void* user, uint64_t first_sample, uint64_t n_samples, const uint8_t* data, const uint64_t* file_begin)
 FILE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64))
-PIPE_GZIP, PIPE_SKIP_ABORTS = 1, 2
+PIPE_GZIP, PIPE_SKIP_ABORTS, PIPE_ALL_RECORDS = 1, 2, 4
 
 SYMBOLS = {
     "v2p_abi_version": (C.c_int, []),
@@ -123,6 +123,7 @@ SYMBOLS = {
     # include/v2p_pipeline.h
     "v2p_pipeline_create": (C.c_int, [_P, C.POINTER(_P), C.c_uint32, C.POINTER(_P)]),
     "v2p_pipeline_destroy": (None, [_P]),
+    "v2p_pipeline_enable_all_records": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "v2p_pipeline_last_error": (C.c_char_p, [_P]),
     "v2p_pipeline_run_lists": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint64, _P, FILE_SINK, _P,
                                          C.POINTER(PipelineResult)]),

@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include "v2p_allrecords.cuh"
 #include "v2p_mapped.cuh"
 #include "v2p_pipeline.h"
 
@@ -39,6 +40,9 @@ struct Lane {
     v2p::MappedBuf pub;        // out_base of the chunk, published by a kernel (v2p_mapped.cuh)
     uint8_t* h_buf = nullptr;  // pinned staging (sink mode)
     size_t h_cap = 0;
+    // `-a` expansion of the chunk (V2P_PIPE_ALL_RECORDS, v2p_allrecords.cuh): scratch, the merged Task array, its tape
+    void* ar[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ar_cap[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     // the chunk in flight
     bool pending = false;
     uint64_t first_sample = 0, n = 0;
@@ -55,6 +59,11 @@ struct v2p_pipeline {
     cudaStream_t aux = nullptr;  // small kernels of the pipeline itself (never behind a copy-back)
     Lane lanes[V2P_PIPE_MAX_LANES];
     std::string err;
+    // `-a`: tables of the extended reference tape (v2p_pipeline_enable_all_records)
+    bool all_on = false;
+    v2p_ar::Tables tab{};
+    void* d_tab[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t n_proteome = 0;
 };
 
 namespace {
@@ -115,6 +124,58 @@ int retire(v2p_pipeline* p, Lane& l, v2p_file_sink sink, void* user) {
     return V2P_OK;
 }
 
+// `-a`: the generated chunk's Task array with three reference-stream segments per unaltered transcript appended to
+// every haplotype (v2p_allrecords.cuh).  -> *xb, a device-pointer batch whose arrays live in the lane; *n_extra_records.
+int expand_all_records(v2p_pipeline* p, Lane& l, const v2p_generated& g, v2p_batch* xb, uint64_t* n_extra_records) {
+    using namespace v2p_ar;
+    const uint64_t nh = g.batch.n_hap, nr = g.n_rows, nt = g.batch.n_tasks;
+    cudaStream_t st = p->aux;
+    int rc;
+    auto buf = [&](int i, size_t bytes) -> int { return grow_dev(p, l.ar[i], l.ar_cap[i], bytes); };
+    if ((rc = buf(0, (nh + 1) * 8)) || (rc = buf(1, (nr + 1) * 8)) || (rc = buf(2, (nr + 1) * 8)) || (rc = buf(3, (nh + 1) * 8)) ||
+        (rc = buf(4, (nh + 1) * 8)) || (rc = buf(5, (nh + 1) * 8)) || (rc = buf(6, (nh + 1) * 8)) || (rc = buf(7, (nh + 1) * 8)) ||
+        (rc = buf(8, (nh + 1) * 8)))
+        return rc;
+    Chunk c{};
+    c.n_hap = nh, c.n_rows = nr, c.n_tasks = nt;
+    c.ann_hap = g.ann_hap, c.ann_tx = g.ann_tx, c.task_begin = g.batch.task_begin, c.out_base = g.batch.out_base, c.tasks = g.batch.tasks;
+    c.row_begin = (uint64_t*)l.ar[0], c.row_bytes = (uint64_t*)l.ar[1], c.row_x = (uint64_t*)l.ar[2];
+    c.ut = (uint64_t*)l.ar[3], c.ut_x = (uint64_t*)l.ar[4], c.ub = (uint64_t*)l.ar[5], c.ub_x = (uint64_t*)l.ar[6];
+    c.new_tb = (uint64_t*)l.ar[7], c.new_ob = (uint64_t*)l.ar[8];
+    auto blocks = [](uint64_t n) { return (unsigned)((n + 255) / 256); };
+    auto xsum = [&](const uint64_t* in, uint64_t* out, uint64_t n) -> int {
+        size_t tmp = 0;
+        PCU(p, cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int64_t)n, st));
+        int r = buf(9, tmp);
+        if (r) return r;
+        PCU(p, cub::DeviceScan::ExclusiveSum(l.ar[9], tmp, in, out, (int64_t)n, st));
+        return V2P_OK;
+    };
+    k_ar_rows<<<blocks(std::max(nh, nr) + 1), 256, 0, st>>>(c, p->tab);
+    if ((rc = xsum(c.row_bytes, c.row_x, nr + 1))) return rc;
+    k_ar_hap<<<blocks(nh + 1), 256, 0, st>>>(c, p->tab);
+    if ((rc = xsum(c.ut, c.ut_x, nh + 1)) || (rc = xsum(c.ub, c.ub_x, nh + 1))) return rc;
+    k_ar_bases<<<blocks(nh + 1), 256, 0, st>>>(c);
+    PCU(p, l.pub.reserve(64));
+    v2p::PubList pl{};
+    pl.src[0] = (const unsigned long long*)(c.ut_x + nh), pl.src[1] = (const unsigned long long*)(c.ub_x + nh), pl.n = 2;
+    v2p::k_publish_list<<<1, 32, 0, st>>>(l.pub.p, pl);
+    PCU(p, cudaStreamSynchronize(st));
+    const uint64_t extra_tasks = l.pub.p[0], extra_bytes = l.pub.p[1];
+    const uint64_t n_tasks = nt + extra_tasks, n_out = g.batch.n_out + extra_bytes;
+    if ((rc = buf(10, (n_tasks + 1) * sizeof(v2p_task16))) || (rc = buf(11, n_out + 64))) return rc;
+    c.new_tasks = (v2p_task16*)l.ar[10];
+    if (nt) k_ar_move<<<blocks(nt), 256, 0, st>>>(c);
+    if (nh && p->tab.n_tx) k_ar_emit<<<blocks(nh * p->tab.n_tx), 256, 0, st>>>(c, p->tab, p->n_proteome);
+    PCU(p, cudaGetLastError());
+    PCU(p, cudaStreamSynchronize(st));
+    *xb = g.batch;
+    xb->task_begin = c.new_tb, xb->tasks = c.new_tasks, xb->out = (uint8_t*)l.ar[11], xb->out_base = c.new_ob;
+    xb->n_tasks = n_tasks, xb->n_out = n_out;
+    *n_extra_records = extra_tasks / 3;
+    return V2P_OK;
+}
+
 // What differs between the two entry points: how chunk [h0,h1) gets its Task batch.
 struct ListSource {
     const uint64_t* site_begin;  // host, n_hap+1 (absolute indices into `sites`)
@@ -127,7 +188,9 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
     if (!out && !sink) return pfail(p, V2P_ERR_INVALID_ARG, "neither an output buffer nor a sink was given");
     if (out && !file_begin) return pfail(p, V2P_ERR_INVALID_ARG, "file_begin is NULL");
     if (!chunk_samples) chunk_samples = 128;
-    const bool gzip = (flags & V2P_PIPE_GZIP) != 0;
+    const bool gzip = (flags & V2P_PIPE_GZIP) != 0, all_records = (flags & V2P_PIPE_ALL_RECORDS) != 0;
+    if (all_records && !p->all_on)
+        return pfail(p, V2P_ERR_INVALID_ARG, "V2P_PIPE_ALL_RECORDS needs v2p_pipeline_enable_all_records first");
     const uint32_t gen_flags = V2P_GEN_FASTA | ((flags & V2P_PIPE_SKIP_ABORTS) ? V2P_GEN_SKIP_ABORTS : 0u);
     PCU(p, cudaSetDevice(p->device));
     for (uint32_t i = 0; i < p->n_lanes; ++i) p->lanes[i].pending = false;
@@ -161,27 +224,31 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
             pfail(p, rc, "task generation failed at sample %llu: %s", (unsigned long long)s0, v2p_catalogue_last_error(l.cat));
             break;
         }
+        // ---- `-a`: the unaltered transcripts' records behind every haplotype's altered ones (write_all)
+        v2p_batch xb = g.batch;
+        uint64_t extra_records = 0;
+        if (all_records && (rc = expand_all_records(p, l, g, &xb, &extra_records))) break;
         // ---- the hot path: every haplotype's result tape == its FASTA text
         v2p_result er;
-        if ((rc = v2p_execute_batch(p->eng, &g.batch, V2P_FLAG_DEVICE_PTRS, &er, nullptr))) {
+        if ((rc = v2p_execute_batch(p->eng, &xb, V2P_FLAG_DEVICE_PTRS, &er, nullptr))) {
             pfail(p, rc, "execution failed at sample %llu (haplotype %llu task %llu): %s", (unsigned long long)s0,
                   (unsigned long long)er.bad_hap, (unsigned long long)er.bad_task, v2p_last_error(p->eng));
             break;
         }
         // ---- file bounds: sample s owns haplotypes 2s, 2s+1
         PCU_BREAK(p, rc, l.pub.reserve(nh + 1));
-        PCU_BREAK(p, rc, v2p::publish_words(l.pub.p, g.batch.out_base, nh + 1, p->aux));
+        PCU_BREAK(p, rc, v2p::publish_words(l.pub.p, xb.out_base, nh + 1, p->aux));
         PCU_BREAK(p, rc, cudaStreamSynchronize(p->aux));
         l.fb_rel.resize(ns + 1);
         for (uint64_t s = 0; s <= ns; ++s) l.fb_rel[s] = l.pub.p[2 * s];
-        const uint8_t* d_src = g.batch.out;
-        uint64_t bytes = g.batch.n_out;
+        const uint8_t* d_src = xb.out;
+        uint64_t bytes = xb.n_out;
         if (gzip) {
-            const uint64_t cap = v2p_gzip_bound(g.batch.n_out, ns);
+            const uint64_t cap = v2p_gzip_bound(xb.n_out, ns);
             if ((rc = grow_dev(p, l.d_gz, l.d_gz_cap, cap))) break;
             std::vector<uint64_t> fb_abs(l.fb_rel);
             v2p_gzip_result zr;
-            if ((rc = v2p_gzip_files(l.gz, g.batch.out, fb_abs.data(), ns, (uint8_t*)l.d_gz, cap, l.fb_rel.data(),
+            if ((rc = v2p_gzip_files(l.gz, xb.out, fb_abs.data(), ns, (uint8_t*)l.d_gz, cap, l.fb_rel.data(),
                                      V2P_FLAG_DEVICE_PTRS, &zr))) {
                 pfail(p, rc, "gzip failed at sample %llu: %s", (unsigned long long)s0, v2p_gzip_last_error(l.gz));
                 break;
@@ -209,8 +276,8 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
         if (file_begin)
             for (uint64_t s = 1; s <= ns; ++s) file_begin[s0 + s] = total + l.fb_rel[s];
         total += bytes;
-        res->n_sites += g.n_sites, res->n_tasks += g.batch.n_tasks, res->n_records += g.n_rows;
-        res->image_bytes += g.batch.n_out, res->out_bytes += bytes;
+        res->n_sites += g.n_sites, res->n_tasks += xb.n_tasks, res->n_records += g.n_rows + extra_records;
+        res->image_bytes += xb.n_out, res->out_bytes += bytes;
         res->gen_ms += g.gen_ms, res->exec_ms += er.kernel_ms;
         res->n_skipped += g.n_skipped, res->n_aborted += g.n_aborted;
         res->n_chunks++;
@@ -268,11 +335,59 @@ void v2p_pipeline_destroy(v2p_pipeline* p) {
         if (l.gz) v2p_gzip_destroy(l.gz);
         if (l.d_gz) cudaFree(l.d_gz);
         if (l.d_begin) cudaFree(l.d_begin);
+        for (void* a : l.ar)
+            if (a) cudaFree(a);
         if (l.h_buf) cudaFreeHost(l.h_buf);
         l.pub.release();
     }
+    for (void* t : p->d_tab)
+        if (t) cudaFree(t);
     if (p->aux) cudaStreamDestroy(p->aux);
     delete p;
+}
+
+int v2p_pipeline_enable_all_records(v2p_pipeline* p, const uint8_t* proteome, uint64_t n_proteome, uint64_t n_tx,
+                                    const uint64_t* tx_offsets, const uint64_t* name_off, const uint8_t* names) {
+    if (!p) return V2P_ERR_INVALID_ARG;
+    p->err.clear();
+    if (!tx_offsets || !name_off || (n_proteome && !proteome) || (n_tx && name_off[n_tx] && !names))
+        return pfail(p, V2P_ERR_INVALID_ARG, "NULL argument");
+    if (tx_offsets[n_tx] > n_proteome) return pfail(p, V2P_ERR_INVALID_ARG, "tx_offsets run past the proteome tape");
+    // extended tape: proteome | for every transcript ">{name}_1\n" ">{name}_2\n"
+    std::vector<uint8_t> ext(proteome, proteome + n_proteome);
+    std::vector<uint64_t> hdr(n_tx), rec_x(n_tx + 1, 0);
+    std::vector<uint32_t> nlen(n_tx);
+    for (uint64_t t = 0; t < n_tx; ++t) {
+        if (name_off[t + 1] < name_off[t] || tx_offsets[t + 1] < tx_offsets[t]) return pfail(p, V2P_ERR_INVALID_ARG, "offsets not monotone");
+        const uint64_t nl = name_off[t + 1] - name_off[t];
+        nlen[t] = (uint32_t)nl;
+        hdr[t] = ext.size();
+        for (int k = 1; k <= 2; ++k) {
+            ext.push_back('>');
+            ext.insert(ext.end(), names + name_off[t], names + name_off[t + 1]);
+            ext.push_back('_');
+            ext.push_back((uint8_t)('0' + k));
+            ext.push_back('\n');
+        }
+        rec_x[t + 1] = rec_x[t] + nl + 5 + (tx_offsets[t + 1] - tx_offsets[t]);
+    }
+    if (ext.size() >> 32) return pfail(p, V2P_ERR_INVALID_ARG, "extended reference tape exceeds 4 GiB");
+    int rc = v2p_engine_set_reference(p->eng, ext.data(), ext.size(), 0);
+    if (rc) return pfail(p, rc, "registering the extended reference tape failed: %s", v2p_last_error(p->eng));
+    PCU(p, cudaSetDevice(p->device));
+    const void* src[4] = {tx_offsets, hdr.data(), nlen.data(), rec_x.data()};
+    const size_t bytes[4] = {(n_tx + 1) * 8, n_tx * 8, n_tx * 4, (n_tx + 1) * 8};
+    for (int i = 0; i < 4; ++i) {
+        if (p->d_tab[i]) PCU(p, cudaFree(p->d_tab[i]));
+        p->d_tab[i] = nullptr;
+        PCU(p, cudaMalloc(&p->d_tab[i], bytes[i] + 16));
+        PCU(p, cudaMemcpy(p->d_tab[i], src[i], bytes[i], cudaMemcpyHostToDevice));
+    }
+    p->tab = v2p_ar::Tables{n_tx, (const uint64_t*)p->d_tab[0], (const uint64_t*)p->d_tab[1], (const uint32_t*)p->d_tab[2],
+                            (const uint64_t*)p->d_tab[3]};
+    p->n_proteome = n_proteome;
+    p->all_on = true;
+    return V2P_OK;
 }
 
 const char* v2p_pipeline_last_error(v2p_pipeline* p) { return p ? p->err.c_str() : "pipeline is NULL"; }

@@ -85,6 +85,15 @@ class DevicePipeline:
         except Exception:
             pass
 
+    def enable_all_records(self, proteome: np.ndarray, tx_offsets: np.ndarray, names) -> None:
+        """Prepare all_records=True runs (the reference's `-a`): registers the extended reference tape on the engine."""
+        pr, off = np.ascontiguousarray(proteome, np.uint8), np.ascontiguousarray(tx_offsets, np.uint64)
+        no, pl = np.ascontiguousarray(names[0], np.uint64), np.ascontiguousarray(names[1], np.uint8)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        st = self._lib.v2p_pipeline_enable_all_records(self._h, p(pr), len(pr), len(off) - 1, p(off), p(no), p(pl))
+        if st:
+            raise EngineError(st, self._err())
+
     def _err(self) -> str:
         return (self._lib.v2p_pipeline_last_error(self._h) or b"").decode()
 
@@ -117,7 +126,7 @@ class DevicePipeline:
 
     def run_lists(self, site_begin: np.ndarray, sites: np.ndarray, n_samples: int, chunk_samples: int = 128, gzip: bool = False,
                   out: Optional[np.ndarray] = None, sink: Optional[Callable] = None,
-                  skip_aborts: bool = False) -> Tuple[Optional[np.ndarray], L.PipelineResult]:
+                  skip_aborts: bool = False, all_records: bool = False) -> Tuple[Optional[np.ndarray], L.PipelineResult]:
         """site_begin[2*n_samples+1], sites: the cohort's CSR site lists.  Either `out` (uint8 host array; returns the
         file_begin offsets into it) or `sink(first_sample, n, data, file_begin)` called per chunk in sample order."""
         sb, st_ = np.ascontiguousarray(site_begin, np.uint64), np.ascontiguousarray(sites, np.uint32)
@@ -125,7 +134,8 @@ class DevicePipeline:
         cb, user, keep = self._sink(sink)
         res = L.PipelineResult()
         st = self._lib.v2p_pipeline_run_lists(self._h, n_samples, sb.ctypes.data_as(C.c_void_p), st_.ctypes.data_as(C.c_void_p),
-                                              chunk_samples, (L.PIPE_GZIP if gzip else 0) | (L.PIPE_SKIP_ABORTS if skip_aborts else 0),
+                                              chunk_samples, (L.PIPE_GZIP if gzip else 0) | (L.PIPE_SKIP_ABORTS if skip_aborts else 0) |
+                                              (L.PIPE_ALL_RECORDS if all_records else 0),
                                               op, cap, fbp, cb, user, C.byref(res))
         del keep
         if st:
