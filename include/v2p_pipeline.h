@@ -69,6 +69,8 @@ typedef struct {
     double wall_s;                        /* host wall clock of the whole call                                 */
     uint64_t n_skipped, n_aborted;        /* general catalogue: transcripts skipped ("must be the last mutation") and
                                              left out where the reference would abort (V2P_PIPE_SKIP_ABORTS)    */
+    double gen_wall_s, exec_wall_s, gzip_wall_s, wait_wall_s, sink_wall_s; /* host wall clock of the calling thread inside
+                                             task generation, execution, gzip, waiting for a copy-back to land, the sink */
 } v2p_pipeline_result;
 
 /* Destination: either `out` (host memory, pinned for full PCIe rate; files are concatenated, file s =

@@ -57,7 +57,8 @@ class PipelineResult(C.Structure):
     _fields_ = [("n_samples", C.c_uint64), ("n_chunks", C.c_uint64), ("n_sites", C.c_uint64), ("n_tasks", C.c_uint64),
                 ("n_records", C.c_uint64), ("image_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("decode_ms", C.c_float), ("gen_ms", C.c_float), ("exec_ms", C.c_float), ("gzip_ms", C.c_float),
-                ("wall_s", C.c_double), ("n_skipped", C.c_uint64), ("n_aborted", C.c_uint64)]
+                ("wall_s", C.c_double), ("n_skipped", C.c_uint64), ("n_aborted", C.c_uint64), ("gen_wall_s", C.c_double),
+                ("exec_wall_s", C.c_double), ("gzip_wall_s", C.c_double), ("wait_wall_s", C.c_double), ("sink_wall_s", C.c_double)]
 
 
 COHORT_MAX_DEVICES = 16

@@ -105,6 +105,8 @@ void add(v2p_pipeline_result& t, const v2p_pipeline_result& r) {
     t.n_records += r.n_records, t.image_bytes += r.image_bytes, t.out_bytes += r.out_bytes, t.h2d_bytes += r.h2d_bytes;
     t.decode_ms += r.decode_ms, t.gen_ms += r.gen_ms, t.exec_ms += r.exec_ms, t.gzip_ms += r.gzip_ms;
     t.n_skipped += r.n_skipped, t.n_aborted += r.n_aborted;
+    t.gen_wall_s += r.gen_wall_s, t.exec_wall_s += r.exec_wall_s, t.gzip_wall_s += r.gzip_wall_s;
+    t.wait_wall_s += r.wait_wall_s, t.sink_wall_s += r.sink_wall_s;
 }
 
 }  // namespace

@@ -114,12 +114,19 @@ int grow_host(v2p_pipeline* p, Lane& l, size_t bytes) {
     return V2P_OK;
 }
 
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // the chunk's bytes have landed: hand them to the sink (chunks retire in sample order, lanes rotate)
-int retire(v2p_pipeline* p, Lane& l, v2p_file_sink sink, void* user) {
+int retire(v2p_pipeline* p, Lane& l, v2p_file_sink sink, void* user, v2p_pipeline_result* res) {
     if (!l.pending) return V2P_OK;
     l.pending = false;
+    const double t0 = now_s();
     PCU(p, cudaEventSynchronize(l.landed));
-    if (sink && sink(user, l.first_sample, l.n, l.h_data, l.fb_rel.data()) != 0)
+    const double t1 = now_s();
+    res->wait_wall_s += t1 - t0;
+    const int stop = sink ? sink(user, l.first_sample, l.n, l.h_data, l.fb_rel.data()) : 0;
+    res->sink_wall_s += now_s() - t1;
+    if (stop != 0)
         return pfail(p, V2P_ERR_INVALID_ARG, "the file sink stopped the run at sample %llu", (unsigned long long)l.first_sample);
     return V2P_OK;
 }
@@ -202,11 +209,12 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
     for (uint64_t s0 = 0; s0 < n_samples && rc == V2P_OK; s0 += chunk_samples, ++ci) {
         const uint64_t ns = std::min<uint64_t>(chunk_samples, n_samples - s0), h0 = 2 * s0, nh = 2 * ns;
         Lane& l = p->lanes[ci % p->n_lanes];
-        if ((rc = retire(p, l, sink, user))) break;
+        if ((rc = retire(p, l, sink, user, res))) break;
         // ---- Task batch of the chunk, generated on the device with the record framing in it
         sb.resize(nh + 1);
         for (uint64_t h = 0; h <= nh; ++h) sb[h] = src.site_begin[h0 + h] - src.site_begin[h0];
         v2p_generated g;
+        const double t_gen0 = now_s();
         if (src.h_sites) {
             rc = v2p_generate_tasks(l.cat, nh, sb.data(), src.h_sites + src.site_begin[h0], gen_flags, &g);
             res->h2d_bytes += sb[nh] * 4 + (nh + 1) * 8;
@@ -228,6 +236,8 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
         v2p_batch xb = g.batch;
         uint64_t extra_records = 0;
         if (all_records && (rc = expand_all_records(p, l, g, &xb, &extra_records))) break;
+        const double t_exec0 = now_s();
+        res->gen_wall_s += t_exec0 - t_gen0;
         // ---- the hot path: every haplotype's result tape == its FASTA text
         v2p_result er;
         if ((rc = v2p_execute_batch(p->eng, &xb, V2P_FLAG_DEVICE_PTRS, &er, nullptr))) {
@@ -235,6 +245,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
                   (unsigned long long)er.bad_hap, (unsigned long long)er.bad_task, v2p_last_error(p->eng));
             break;
         }
+        res->exec_wall_s += now_s() - t_exec0;
         // ---- file bounds: sample s owns haplotypes 2s, 2s+1
         PCU_BREAK(p, rc, l.pub.reserve(nh + 1));
         PCU_BREAK(p, rc, v2p::publish_words(l.pub.p, xb.out_base, nh + 1, p->aux));
@@ -254,6 +265,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
                 break;
             }
             res->gzip_ms += zr.ms;
+            res->gzip_wall_s += zr.ms * 1e-3;
             d_src = (const uint8_t*)l.d_gz;
             bytes = l.fb_rel[ns];
         }
@@ -285,7 +297,7 @@ int run(v2p_pipeline* p, uint64_t n_samples, const ListSource& src, uint32_t chu
     // drain in order: the oldest chunk sits in the lane the next chunk would have taken
     for (uint32_t k = 0; k < p->n_lanes; ++k) {
         Lane& l = p->lanes[(ci + k) % p->n_lanes];
-        if (rc == V2P_OK) rc = retire(p, l, sink, user);
+        if (rc == V2P_OK) rc = retire(p, l, sink, user, res);
         else if (l.pending) cudaEventSynchronize(l.landed), l.pending = false;
     }
     return rc;
