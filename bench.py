@@ -457,7 +457,14 @@ def main():
         "e2e": {"value": total_res * args.e2e_steps / e2e_s, "unit": "residues/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": n_out, "steps": args.e2e_steps, "chunk_haplotypes": args.e2e_chunk_haps,
                 "chunks_in_flight": depth,
-                "api": "v2p_execute_batch (host pointers, pinned, ASYNC), one call per chunk"},
+                "api": "v2p_execute_batch (host pointers, pinned, ASYNC), one call per chunk",
+                "what": "raw result tapes: 1 byte per residue must cross PCIe, and one GPU's link delivers 53-56 GB/s to the host "
+                        "whatever moves the bytes (profiles/r2/pcie_probe_2gpu.jsonl: copy engine, several streams, write-combined or "
+                        "registered huge pages, SM zero-copy stores)",
+                "fasta": None if not pipeline_line else {k: pipeline_line["fasta"][k] for k in ("residues_per_s", "h2d_bytes", "d2h_bytes")},
+                "fasta_gz": None if not pipeline_line else {k: pipeline_line["fasta_gz"][k] for k in ("residues_per_s", "h2d_bytes", "d2h_bytes")},
+                "fasta_note": "the same cohort as .fasta / .fasta.gz FILE IMAGES through v2p_pipeline_run_lists (site lists up, file bytes "
+                              "down; the reference's -c flag): compressing on the device is the one lever on a PCIe-bound result"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_copy_tiles", "peak_source": peak_src,
