@@ -445,10 +445,10 @@ __device__ __forceinline__ Piece piece_load(const long long p0, const int vx, co
     return pc;
 }
 // lo16[x] = 16-byte mask whose first x bytes are 0xFF (x = 0..16), staged in shared memory
-__device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const uint4* __restrict__ lo16, const Piece& pc,
+__device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const uint4* __restrict__ lo16, const uint4 r,
                                             const int vx, const int nlow, const bool keep_low) {
-    // keep_low: the piece is [nlow,16) (H) -> old bytes below nlow are kept; else the piece is [0,nlow) (T)
-    const uint4 r = realign16(pc.A, pc.B, pc.sh);
+    // r: the piece's source vector, realigned; keep_low: the piece is [nlow,16) (H) -> old bytes below nlow are kept;
+    // else the piece is [0,nlow) (T)
     const uint4 m = lo16[nlow];
     uint4* dst = reinterpret_cast<uint4*>(tile) + vx;
     const uint4 o = *dst;
@@ -516,11 +516,20 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     // large the replica set is -- instead of sweeping all 171 MB of it once per ~9 haplotypes.  Slots without a tile
     // (shorter haplotypes) hold ~0.  Without the flag, slots are tiles in tape order (phase-aligned layouts, whose
     // runs come from the one plain tape, gain nothing from the interleave).
-    uint32_t n_slots = (uint32_t)p.n_tiles;  // (tiles and order slots of one launch stay below 2^32 - 2^20: checked by the host)
-    if constexpr (kOrder) {
-        const uint64_t ns = tile_order_slots(p, __ldg(p.order_hdr));
-        if (ns) n_slots = (uint32_t)ns;  // else order[] is the identity over n_tiles
+    // (tiles and order slots of one launch stay below 2^32 - 2^20: checked by the host).  The slot count lives in this
+    // warp's shared-memory scratch, not in a register: the tile loop is out of registers, and a spilled loop bound is
+    // reloaded from LOCAL memory behind the queue of cp.async requests (8 % of all stall samples before this).
+    {
+        uint32_t ns32 = (uint32_t)p.n_tiles;
+        if constexpr (kOrder) {
+            const uint64_t ns = tile_order_slots(p, __ldg(p.order_hdr));
+            if (ns) ns32 = (uint32_t)ns;  // else order[] is the identity over n_tiles
+        }
+        if (lane == 0) *reinterpret_cast<uint32_t*>(st_bases + 7) = ns32;
+        __syncwarp();
     }
+    const volatile uint32_t* const n_slots_p = reinterpret_cast<const volatile uint32_t*>(st_bases + 7);
+#define n_slots (*n_slots_p)
     // Software pipeline over this warp's slots, three dependent fetches deep, all of them cp.async into a 4-entry ring
     // in shared memory (no register is carried from tile to tile, and nobody waits on a load it issued for later):
     //   iteration i   waits for everything issued at i-1, then issues
@@ -766,9 +775,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                 }
             }
             {
-                if (onT) piece_merge(tile, lo16, pcT, pvt, pb2, false);
+                // (with a registered tape every reference piece comes from the in-phase replica: shift 0, nothing to realign)
+                const bool shifted = __any_sync(0xffffffffu, (onT && pcT.sh != 0u) || (onH && pcH.sh != 0u));
+                if (onT) piece_merge(tile, lo16, shifted ? realign16(pcT.A, pcT.B, pcT.sh) : pcT.A, pvt, pb2, false);
                 __syncwarp();
-                if (onH) piece_merge(tile, lo16, pcH, pvh, pa1, true);
+                if (onH) piece_merge(tile, lo16, shifted ? realign16(pcH.A, pcH.B, pcH.sh) : pcH.A, pvh, pa1, true);
                 __syncwarp();
                 if (onM) {
                     const uint8_t* __restrict__ sp = reinterpret_cast<const uint8_t*>(p0) + (pvh << 4);
@@ -883,6 +894,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         p.warp_ns[blockIdx.x * kWarpsPerCta + warp] = t - st_bases[6];
     }
+#undef n_slots
 }
 
 // ------------------------------------------------------------------------------------------------ serial order
