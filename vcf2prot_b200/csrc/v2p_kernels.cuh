@@ -463,6 +463,86 @@ __device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const ui
     *dst = n;
 }
 
+// ---- the register path of the copy kernel, out of line.  With a registered reference tape (TMA mode) these run for
+// out-of-phase alteration payloads only; kept out of the tile loop's body they do not count against its register
+// budget (80 registers at 3 CTAs/SM, and every spilled value there costs a local-memory round trip per tile).
+
+// A short out-of-phase run copied by its own lane: four vectors per round, five aligned loads in flight, then realign + store.
+__device__ __noinline__ void lane_run_copy(uint8_t* __restrict__ tile, const long long p0, const int lane_v0, const int lane_v1) {
+    const unsigned long long sa = (unsigned long long)(p0 + (long long)lane_v0 * 16);
+    const uint32_t sh = (uint32_t)sa & 15u;  // != 0: in-phase runs went to the TMA unit
+    const uint4* ap = reinterpret_cast<const uint4*>(sa - sh);
+    uint4* const tv = reinterpret_cast<uint4*>(tile);
+    for (int v = lane_v0; v < lane_v1; v += 4, ap += 4) {
+        const int n = lane_v1 - v;
+        const uint4 c0 = __ldg(ap), c1 = __ldg(ap + 1);
+        const uint4 c2 = n > 1 ? __ldg(ap + 2) : c1, c3 = n > 2 ? __ldg(ap + 3) : c1, c4 = n > 3 ? __ldg(ap + 4) : c1;
+        tv[v] = realign16(c0, c1, sh);
+        if (n > 1) tv[v + 1] = realign16(c1, c2, sh);
+        if (n > 2) tv[v + 2] = realign16(c2, c3, sh);
+        if (n > 3) tv[v + 3] = realign16(c3, c4, sh);
+    }
+}
+
+// B: owner of every vector = last task (of this batch) whose covered range started at or before it (warp max-scan over
+// lead[]); C: one lane per fully covered 16-byte vector, loads of G vectors issued before any is used.  Whole warp.
+template <int TILE, int G>
+__device__ __noinline__ void owner_scan_copy(uint8_t* __restrict__ tile, uint8_t* __restrict__ lead, const long long p0,
+                                             const uint32_t v1, const int lane) {
+    constexpr int NV = TILE / 16, LWW = NV / 32 / 4;
+    {
+        uint32_t wv[LWW];
+        uint32_t top = 0;
+#pragma unroll
+        for (int w = 0; w < LWW; ++w) {  // inclusive max-scan over this lane's LW owner bytes
+            wv[w] = bytescan_max(reinterpret_cast<uint32_t*>(lead)[lane * LWW + w]);
+            wv[w] = __vmaxu4(wv[w], top * 0x01010101u);
+            top = wv[w] >> 24;
+        }
+        uint32_t incl = top;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl = max(incl, o);
+        }
+        uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0;
+        const uint32_t bc = excl * 0x01010101u;
+#pragma unroll
+        for (int w = 0; w < LWW; ++w) reinterpret_cast<uint32_t*>(lead)[lane * LWW + w] = __vmaxu4(wv[w], bc);
+    }
+    __syncwarp();
+    const uint32_t p0lo = (uint32_t)(unsigned long long)p0, p0hi = (uint32_t)((unsigned long long)p0 >> 32);
+#pragma unroll
+    for (int r0 = 0; r0 < NV / 32; r0 += G) {
+        uint4 A[G], B[G];
+        uint32_t shv[G];
+        bool on[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int v = lane + 32 * (r0 + i);
+            const uint32_t owner = lead[v];
+            const int srcl = (int)((owner - 1u) & 31u);
+            const uint32_t qlo = __shfl_sync(0xffffffffu, p0lo, srcl);
+            const uint32_t qhi = __shfl_sync(0xffffffffu, p0hi, srcl);
+            const uint32_t qv1 = __shfl_sync(0xffffffffu, v1, srcl);
+            on[i] = owner != 0u && (uint32_t)v < qv1;
+            const unsigned long long sa = (((unsigned long long)qhi << 32) | qlo) + (unsigned long long)(v * 16);
+            shv[i] = (uint32_t)sa & 15u;
+            const uint4* ap = reinterpret_cast<const uint4*>(sa - shv[i]);
+            A[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (on[i]) A[i] = __ldg(ap);
+            B[i] = A[i];
+            if (on[i] && shv[i]) B[i] = __ldg(ap + 1);
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int v = lane + 32 * (r0 + i);
+            if (on[i]) reinterpret_cast<uint4*>(tile)[v] = realign16(A[i], B[i], shv[i]);
+        }
+    }
+}
+
 constexpr int kLaneRunBytes = 512;  // out-of-phase runs up to this many fully covered bytes are copied by one lane
 constexpr int kTileScratch = 16 + 576 + 64;  // per warp, behind tile | lead[]: mbarrier | staged tasks (32 x 16 B) + bases / flag
                                              // (8 x 8 B) | metadata ring (4 x {tile, lb[k], lb[k+1], tile_hap[k]})
@@ -788,78 +868,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     for (int j = pa1 + 1; j < pb2; ++j) d[j] = __ldg(sp + j);
                 }
             }
-            if (lane_v1 > lane_v0) {  // four vectors per round: five aligned loads in flight, then realign + store
-                const unsigned long long sa = (unsigned long long)(p0 + (long long)lane_v0 * 16);
-                const uint32_t sh = (uint32_t)sa & 15u;  // != 0: in-phase runs went to the TMA unit
-                const uint4* ap = reinterpret_cast<const uint4*>(sa - sh);
-                uint4* const tv = reinterpret_cast<uint4*>(tile);
-                for (int v = lane_v0; v < lane_v1; v += 4, ap += 4) {
-                    const int n = lane_v1 - v;
-                    const uint4 c0 = __ldg(ap), c1 = __ldg(ap + 1);
-                    const uint4 c2 = n > 1 ? __ldg(ap + 2) : c1, c3 = n > 2 ? __ldg(ap + 3) : c1, c4 = n > 3 ? __ldg(ap + 4) : c1;
-                    tv[v] = realign16(c0, c1, sh);
-                    if (n > 1) tv[v + 1] = realign16(c1, c2, sh);
-                    if (n > 2) tv[v + 2] = realign16(c2, c3, sh);
-                    if (n > 3) tv[v + 3] = realign16(c3, c4, sh);
-                }
-            }
+            if (lane_v1 > lane_v0) lane_run_copy(tile, p0, lane_v0, lane_v1);
             __syncwarp();  // orders this batch's tile stores before the next batch's read-modify-writes
             if (!__any_sync(0xffffffffu, has_lead)) continue;  // nothing for the register path in this batch
 
-            // ---- B: owner of every vector = last task (in this batch) whose covered range started at or before it
-            {
-                uint32_t wv[LWW];
-                uint32_t top = 0;
-#pragma unroll
-                for (int w = 0; w < LWW; ++w) {  // inclusive max-scan over this lane's LW owner bytes
-                    wv[w] = bytescan_max(reinterpret_cast<uint32_t*>(lead)[lane * LWW + w]);
-                    wv[w] = __vmaxu4(wv[w], top * 0x01010101u);
-                    top = wv[w] >> 24;
-                }
-                uint32_t incl = top;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl = max(incl, o);
-                }
-                uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0) excl = 0;
-                const uint32_t bc = excl * 0x01010101u;
-#pragma unroll
-                for (int w = 0; w < LWW; ++w) reinterpret_cast<uint32_t*>(lead)[lane * LWW + w] = __vmaxu4(wv[w], bc);
-            }
-            __syncwarp();
-
-            // ---- C: one lane per fully covered 16-byte vector; loads of G vectors are issued before any is used
-            const uint32_t p0lo = (uint32_t)(unsigned long long)p0, p0hi = (uint32_t)((unsigned long long)p0 >> 32);
-#pragma unroll
-            for (int r0 = 0; r0 < NV / 32; r0 += G) {
-                uint4 A[G], B[G];
-                uint32_t shv[G];
-                bool on[G];
-#pragma unroll
-                for (int i = 0; i < G; ++i) {
-                    const int v = lane + 32 * (r0 + i);
-                    const uint32_t owner = lead[v];
-                    const int srcl = (int)((owner - 1u) & 31u);
-                    const uint32_t qlo = __shfl_sync(0xffffffffu, p0lo, srcl);
-                    const uint32_t qhi = __shfl_sync(0xffffffffu, p0hi, srcl);
-                    const uint32_t qv1 = __shfl_sync(0xffffffffu, v1, srcl);
-                    on[i] = owner != 0u && (uint32_t)v < qv1;
-                    const unsigned long long sa = (((unsigned long long)qhi << 32) | qlo) + (unsigned long long)(v * 16);
-                    shv[i] = (uint32_t)sa & 15u;
-                    const uint4* ap = reinterpret_cast<const uint4*>(sa - shv[i]);
-                    A[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (on[i]) A[i] = __ldg(ap);
-                    B[i] = A[i];
-                    if (on[i] && shv[i]) B[i] = __ldg(ap + 1);
-                }
-#pragma unroll
-                for (int i = 0; i < G; ++i) {
-                    const int v = lane + 32 * (r0 + i);
-                    if (on[i]) reinterpret_cast<uint4*>(tile)[v] = realign16(A[i], B[i], shv[i]);
-                }
-            }
+            // ---- B, C: owner scan over lead[], then one lane per fully covered vector (register path, out of line)
+            owner_scan_copy<TILE, G>(tile, lead, p0, v1, lane);
             __syncwarp();
             if (tb + 32u < t_hi) {  // another batch follows: reset lead[]
 #pragma unroll
