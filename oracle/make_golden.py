@@ -229,6 +229,30 @@ def make_cohort(seed, n_tx, n_samples, n_sites, engine="st"):
             "records": [[r[0], [[c[0], c[1]] for c in r[1]]] for r in records], "fasta": recs}
 
 
+def canonical_fasta_digest(records):
+    """sha256 of a sample's record-sorted FASTA text (record order in the reference is HashMap-random)."""
+    import hashlib
+
+    return hashlib.sha256("".join(">%s\n%s\n" % (h, s) for h, s in sorted(tuple(r) for r in records)).encode()).hexdigest()
+
+
+def make_cohort_compact(seed, n_tx, n_samples, n_sites, engine="mt"):
+    """The C1 substitute at the size SURVEY 8d planned (64 samples x 1,200 records): too large to commit as text, so the
+    fixture keeps the inputs compactly (one character per genotype cell: bit 0 = haplotype 1 carries the record's csq,
+    bit 1 = haplotype 2) and, of the reference binary's output, a sha256 of every sample's record-sorted FASTA plus the
+    full records of the first and last sample."""
+    refs, samples, records = synth_cohort(seed, n_tx, n_samples, n_sites)
+    recs, stdout, rc = refbin.run_reference(refbin.vcf_text(samples, records), refs, engine, timeout=1800)
+    assert rc == 0, stdout[-2000:]
+    print("cohort seed=%d: %d samples, %d records in the VCF, %d FASTA records, rc=%d" %
+          (seed, n_samples, len(records), sum(len(v) for v in recs.values()), rc))
+    cells = ["".join(str((1 if c[0] else 0) | (2 if c[1] else 0)) for c in r[1]) for r in records]
+    return {"seed": seed, "refs": refs, "samples": samples, "csqs": [r[0][0] for r in records], "cells_compact": cells,
+            "fasta_sha256": {s: canonical_fasta_digest(recs.get(s, [])) for s in samples},
+            "fasta_records": {s: len(recs.get(s, [])) for s in samples},
+            "fasta": {s: recs.get(s, []) for s in (samples[0], samples[-1])}}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "unit_tests.json"), "w") as f:
@@ -239,6 +263,8 @@ def main():
         json.dump(make_cohort(0x5EED0A, 40, 12, 160), f)
     with open(os.path.join(OUT, "cohort_b.json"), "w") as f:
         json.dump(make_cohort(0x5EED0B, 120, 24, 500, engine="mt"), f)
+    with open(os.path.join(OUT, "cohort_c.json"), "w") as f:
+        json.dump(make_cohort_compact(0x5EED0C, 300, 64, 1800), f)  # ~1,200 records survive the spacing rule
 
 
 if __name__ == "__main__":

@@ -14,7 +14,27 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def load_golden(name: str):
     with open(os.path.join(GOLDEN, name)) as f:
-        return json.load(f)
+        d = json.load(f)
+    if isinstance(d, dict) and "cells_compact" in d:  # compact cohort fixture (oracle/make_golden.py::make_cohort_compact)
+        d["records"] = [[[c], [[[0] if int(x) & 1 else [], [0] if int(x) & 2 else []] for x in cells]]
+                        for c, cells in zip(d["csqs"], d["cells_compact"])]
+    return d
+
+
+def fasta_digest(records) -> str:
+    """sha256 of a sample's record-sorted FASTA text -- how the large golden cohort pins the reference binary's output."""
+    import hashlib
+
+    return hashlib.sha256("".join(">%s\n%s\n" % (h, s) for h, s in sorted(tuple(r) for r in records)).encode()).hexdigest()
+
+
+def assert_sample_matches_reference(cohort, smp: str, records) -> None:
+    """`records` = [(header, sequence)] of one sample, any order, against what the reference binary wrote for it."""
+    if smp in cohort.get("fasta", {}):
+        assert sorted([list(r) for r in records]) == sorted([list(r) for r in cohort["fasta"][smp]]), smp
+    if "fasta_sha256" in cohort:
+        assert len(records) == cohort["fasta_records"][smp], smp
+        assert fasta_digest(records) == cohort["fasta_sha256"][smp], smp
 
 
 def cohort_haplotype_csqs(cohort) -> Dict[Tuple[str, int], List[str]]:
