@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "v2p_engine.h"
+#include "v2p_cohort.h"
 #include "v2p_pipeline.h"
 
 namespace v2p {
@@ -335,9 +336,20 @@ public:
     Pipeline(const Pipeline&) = delete;
     Pipeline& operator=(const Pipeline&) = delete;
 
+    // The reference's `-a` flag (write_all, personalized_genome.rs:120-210): call once, then pass write_all = true.
+    void enable_write_all(const std::string& proteome, const std::vector<uint64_t>& tx_offsets, const std::vector<std::string>& tx_names) {
+        std::vector<uint64_t> name_off(1, 0);
+        std::string names;
+        for (const std::string& n : tx_names) names += n, name_off.push_back(names.size());
+        const int st = v2p_pipeline_enable_all_records(p_, reinterpret_cast<const uint8_t*>(proteome.data()), proteome.size(),
+                                                       tx_offsets.size() - 1, tx_offsets.data(), name_off.data(),
+                                                       reinterpret_cast<const uint8_t*>(names.data()));
+        if (st != V2P_OK) throw EngineError(st, v2p_pipeline_last_error(p_));
+    }
+
     // per_haplotype[2 * proband + (hap - 1)] = ascending catalogue indices of the mutations that haplotype carries
     v2p_pipeline_result write(const std::vector<std::vector<uint32_t>>& per_haplotype, DirWriter& writer, bool write_compressed,
-                              uint32_t chunk_probands = 128) {
+                              uint32_t chunk_probands = 128, bool write_all = false) {
         std::vector<uint64_t> begin(1, 0);
         std::vector<uint32_t> sites;
         for (const auto& l : per_haplotype) {
@@ -346,14 +358,67 @@ public:
         }
         v2p_pipeline_result r{};
         const int st = v2p_pipeline_run_lists(p_, per_haplotype.size() / 2, begin.data(), sites.data(), chunk_probands,
-                                              write_compressed ? V2P_PIPE_GZIP : 0u, nullptr, 0, nullptr, v2p_dir_writer_sink,
-                                              writer.get(), &r);
+                                              (write_compressed ? V2P_PIPE_GZIP : 0u) | (write_all ? V2P_PIPE_ALL_RECORDS : 0u), nullptr,
+                                              0, nullptr, v2p_dir_writer_sink, writer.get(), &r);
         if (st != V2P_OK) throw EngineError(st, v2p_pipeline_last_error(p_));
         return r;
     }
 
 private:
     v2p_pipeline* p_ = nullptr;
+};
+
+// parts/exec.rs:34-40 + parts/io.rs:45-57 over EVERY GPU named, from this one process: a worker (host thread, engine
+// with the proteome registered, catalogue lanes, pinned ring, pipeline) per device, contiguous proband ranges, the
+// directory writer as the common sink.  RAII over v2p_cohort_create / v2p_cohort_destroy (include/v2p_cohort.h).
+class Cohort {
+public:
+    Cohort(const std::vector<int>& cuda_devices, const std::string& proteome, const std::vector<uint64_t>& tx_offsets,
+           const std::vector<std::string>& tx_names, const std::vector<Instruction>& ins, unsigned lanes_per_device = 2) {
+        std::vector<uint32_t> tx, pr, ps, ln, dl;
+        std::vector<uint8_t> code, flags;
+        std::vector<uint64_t> doff, name_off(1, 0);
+        std::string pool, names;
+        for (const Instruction& i : ins) {
+            tx.push_back(i.transcript), code.push_back((uint8_t)i.code);
+            flags.push_back((i.star ? V2P_INS_STAR : 0u) | (i.invalidates ? V2P_INS_INVALIDATES : 0u));
+            pr.push_back(i.pos_ref), ps.push_back(i.pos_res), ln.push_back(i.len);
+            doff.push_back(pool.size()), dl.push_back((uint32_t)i.data.size());
+            pool += i.data;
+        }
+        for (const std::string& n : tx_names) names += n, name_off.push_back(names.size());
+        v2p_cohort_inputs in{};
+        in.proteome = reinterpret_cast<const uint8_t*>(proteome.data()), in.n_proteome = proteome.size();
+        in.n_tx = tx_offsets.size() - 1, in.tx_offsets = tx_offsets.data();
+        in.name_off = name_off.data(), in.names = reinterpret_cast<const uint8_t*>(names.data());
+        in.general = 1, in.n_sites = ins.size(), in.site_tx = tx.data();
+        in.ins_code = code.data(), in.ins_flags = flags.data(), in.ins_pos_ref = pr.data(), in.ins_pos_res = ps.data(), in.ins_len = ln.data();
+        in.site_doff = doff.data(), in.site_dlen = dl.data(), in.pool = reinterpret_cast<const uint8_t*>(pool.data()), in.n_pool = pool.size();
+        const int st = v2p_cohort_create(cuda_devices.data(), (uint32_t)cuda_devices.size(), &in, lanes_per_device, &c_);
+        if (st != V2P_OK) throw EngineError(st, "v2p_cohort_create failed (a device is missing? there is no CPU fallback)");
+    }
+    ~Cohort() { v2p_cohort_destroy(c_); }
+    Cohort(const Cohort&) = delete;
+    Cohort& operator=(const Cohort&) = delete;
+
+    v2p_cohort_result write(const std::vector<std::vector<uint32_t>>& per_haplotype, DirWriter& writer, bool write_compressed,
+                            uint32_t chunk_probands = 128) {
+        std::vector<uint64_t> begin(1, 0);
+        std::vector<uint32_t> sites;
+        for (const auto& l : per_haplotype) {
+            sites.insert(sites.end(), l.begin(), l.end());
+            begin.push_back(sites.size());
+        }
+        v2p_cohort_result r{};
+        const int st = v2p_cohort_run_lists(c_, per_haplotype.size() / 2, begin.data(), sites.data(), chunk_probands,
+                                            (write_compressed ? V2P_PIPE_GZIP : 0u) | V2P_COHORT_CONCURRENT_SINK, v2p_dir_writer_sink,
+                                            writer.get(), &r);
+        if (st != V2P_OK) throw EngineError(st, v2p_cohort_last_error(c_));
+        return r;
+    }
+
+private:
+    v2p_cohort* c_ = nullptr;
 };
 
 }  // namespace v2p

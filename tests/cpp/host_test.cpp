@@ -136,6 +136,24 @@ static void test_pipeline_writes_the_golden_records(v2p::Context& ctx, const std
     CHECK(slurp(dir + "/HG1.fasta") == ">T_1\nMEDLHENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVTESTFRAMESHIFT\n");
     CHECK(slurp(dir + "/HG2.fasta") == ">T_1\nMEDLGTESTENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVLSTLRSLNNFISQRVEGGSGLEELERG.\n");
     CHECK(slurp(dir + "/HG3.fasta").empty());
+    // `-a` (write_all, personalized_genome.rs:120-210): a haplotype without an altered form of T gets the reference record
+    pipe.enable_write_all(T, {0, T.size()}, {"T"});
+    v2p::DirWriter wa(dir, {"HG1", "HG2", "HG3"}, false, 2);
+    const v2p_pipeline_result ra = pipe.write({{1}, {2}, {0}, {3}, {}, {}}, wa, false, 2, /*write_all=*/true);
+    CHECK(ra.n_records == 6 && wa.files_written() == 3);
+    CHECK(slurp(dir + "/HG1.fasta") == ">T_1\nMEDLHENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVTESTFRAMESHIFT\n");
+    CHECK(slurp(dir + "/HG3.fasta") == ">T_1\n" + T + "\n>T_2\n" + T + "\n");
+    // parts/exec.rs:34-40 from one process over several workers (the same GPU twice here): same files
+    {
+        v2p::Cohort cohort({0, 0}, T, {0, T.size()}, {"T"}, ins, 1);
+        v2p::DirWriter wc(dir, {"HG1", "HG2", "HG3"}, false, 2);
+        const v2p_cohort_result rc = cohort.write({{1}, {2}, {0}, {3}, {}, {}}, wc, false, 1);
+        CHECK(rc.n_devices == 2 && rc.total.n_samples == 3 && rc.total.n_records == 4 && wc.files_written() == 3);
+        CHECK(rc.first_sample[0] == 0 && rc.first_sample[2] == 3);
+        CHECK(slurp(dir + "/HG1.fasta") == ">T_1\nMEDLHENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVTESTFRAMESHIFT\n");
+        CHECK(slurp(dir + "/HG2.fasta") == ">T_1\nMEDLGTESTENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVLSTLRSLNNFISQRVEGGSGLEELERG.\n");
+        CHECK(slurp(dir + "/HG3.fasta").empty());
+    }
 }
 
 int main(int argc, char** argv) {
