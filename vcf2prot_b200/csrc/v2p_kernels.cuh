@@ -26,6 +26,7 @@
 namespace v2p {
 
 constexpr int kWarpsPerCta = 8;
+constexpr uint32_t kTileHasGap = 0x80000000u;
 constexpr int kThreads = kWarpsPerCta * 32;
 
 // Device-side status block, written by the plan kernels with atomics.
@@ -56,7 +57,8 @@ struct KParams {
     uint64_t n_hap, n_tasks, n_ref, n_alt, n_out;  // totals of THIS launch (relative sizes)
     uint64_t task_origin, ref_origin, alt_origin, out_origin;
     uint32_t* lb;        // n_tiles+1
-    uint32_t* tile_hap;  // n_tiles
+    uint32_t* tile_hap;  // n_tiles: haplotype owning the tile's first byte; bit 31 (kTileHasGap) = some byte of the tile is
+                         // covered by no task of the tile kernel (a '.' gap, or a haplotype left to k_serial): prefill it
     uint32_t* chunk_hap;  // haplotype of the first task of every k_plan_tasks warp (kPlanWarpTasks tasks each)
     uint32_t* hap_flags;  // n_hap: 1 = this haplotype's tasks are unsorted / overlapping (reference order semantics:
                           // the tile kernel skips its tasks, k_serial applies them in array order afterwards)
@@ -215,14 +217,25 @@ __device__ __forceinline__ void plan_one(const KParams& p, const PlanHap& m, con
         else atomicMin(&p.status->err_key, ((unsigned long long)tr << 8) | (bad_res ? V2P_ERR_RES_OOB : V2P_ERR_SRC_OOB));
         return;
     }
+    // bytes no task covers read '.' (haplotype_instruction.rs:78): the tiles that hold any are marked, and only those
+    // are prefilled by the copy kernel (everywhere else every byte of the tile is written by some task)
+    auto mark_gap = [&](uint64_t a, uint64_t b) {  // launch-relative byte range [a, b)
+        for (uint64_t k = a >> p.tile_shift; k <= ((b - 1) >> p.tile_shift) && k < p.n_tiles; ++k) atomicOr(p.tile_hap + k, kTileHasGap);
+    };
     if (tr != m.tb0) {  // previous task is in the same haplotype: gir.rs:208 contiguity + sortedness
         const uint64_t pend = (uint64_t)p_dst + p_len;
         if (dst < pend) {  // this haplotype needs the reference's order semantics (later task wins): k_serial
             if (atomicExch(p.hap_flags + m.h, 1u) == 0u) atomicAdd(&p.status->unsorted, 1u);
             return;
         }
-        if (p.validate && dst != pend) atomicMin(&p.status->gap_key, (unsigned long long)tr);
+        if (dst != pend) {
+            if (p.validate) atomicMin(&p.status->gap_key, (unsigned long long)tr);
+            mark_gap(m.orel + pend, m.orel + dst);
+        }
+    } else if (dst != 0u) {
+        mark_gap(m.orel, m.orel + dst);  // in front of the haplotype's first task
     }
+    if (tr + 1u == m.tb1 && (uint64_t)dst + len < m.n_res) mark_gap(m.orel + dst + len, m.orel + m.n_res);  // behind its last
     // Only tasks that start a new tile (or follow whole tiles of '.') write lb[].  kt and kprev are clamped to
     // n_tiles by the caller (the task in FRONT of this one may be a rejected one with a garbage dst -- the launch
     // then fails with its status, but lb[] must not be written out of range meanwhile); valid sorted input has
@@ -309,9 +322,15 @@ __global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
 // needs repair.)  Two flagged neighbours may both write a shared boundary entry; either value is a valid bound.
 __global__ void k_plan_fix(KParams p, unsigned int* ser_count) {
     const uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (h >= p.n_hap || !p.hap_flags[h]) return;
-    p.ser_list[atomicAdd(ser_count, 1u)] = (uint32_t)h;
+    if (h >= p.n_hap) return;
     const uint64_t o0 = p.out_base[h] - p.out_origin, o1 = p.out_base[h + 1] - p.out_origin;
+    const bool flagged = p.hap_flags[h] != 0u;
+    // a haplotype without tasks is all '.', one in serial order is left to the prefill by the tile kernel: every tile
+    // that holds a byte of it needs the prefill
+    if (o1 > o0 && (flagged || p.task_begin[h + 1] == p.task_begin[h]))
+        for (uint64_t k = o0 >> p.tile_shift; k <= ((o1 - 1) >> p.tile_shift) && k < p.n_tiles; ++k) atomicOr(p.tile_hap + k, kTileHasGap);
+    if (!flagged) return;
+    p.ser_list[atomicAdd(ser_count, 1u)] = (uint32_t)h;
     const uint32_t tb1 = (uint32_t)min(p.task_begin[h + 1] - p.task_origin, p.n_tasks);
     const uint64_t k0 = (o0 + p.tile_bytes - 1) >> p.tile_shift, k1 = min(o1 >> p.tile_shift, p.n_tiles);
     for (uint64_t k = k0; k <= k1; ++k) p.lb[k] = tb1;
@@ -642,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     auto stage = [&](uint32_t it) {
         const uint32_t* m = ring(it);
         if (m[0] == 0xFFFFFFFFu) return;
-        const uint32_t lo = m[1], hi = m[2], hp = m[3];
+        const uint32_t lo = m[1], hi = m[2], hp = m[3] & ~kTileHasGap;
         const uint32_t tr = first_task(lo) + lane;
         if (tr < min(hi, n_tasks32)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
         // lanes 0-5: the owning haplotype's bases task_begin[h], task_begin[h+1], out_base[h], alt_base[h], ref_base[h]
@@ -673,6 +692,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         const uint32_t* const mc = ring(it);
         const uint32_t tile_no = mc[0];  // ~0 = an empty slot of the interleaved order
         const uint32_t c_lo = mc[1], c_hi = mc[2];
+        const bool has_gap = (mc[3] & kTileHasGap) != 0u;  // some byte of the tile is written by nobody: prefill it
         const uint4 raw0 = st_tasks[lane];
         // warp-uniform bases of the haplotype that owns the tile's first byte (the common case for every task here)
         // (launch-relative 32-bit task numbers; the tape bases folded into what a task needs: where the haplotype's
@@ -702,10 +722,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
 
-        // prefill: '.' (haplotype_instruction.rs:78) or the caller's current content
+        // prefill: '.' (haplotype_instruction.rs:78) -- only where the plan found a byte that no task covers (round 2: a
+        // third of the tile's shared-memory traffic for nothing otherwise) -- or the caller's current content
         if (!p.keep_out) {
+            if (has_gap) {
 #pragma unroll
-            for (int i = 0; i < NV / 32; ++i) reinterpret_cast<uint4*>(tile)[lane + 32 * i] = fillv;
+                for (int i = 0; i < NV / 32; ++i) reinterpret_cast<uint4*>(tile)[lane + 32 * i] = fillv;
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < NV / 32; ++i) {
