@@ -156,6 +156,7 @@ struct PlanHap {  // bases of one haplotype, launch-relative
     uint32_t h;         // its index
     uint32_t tb0, tb1;  // its tasks [tb0, tb1)
     uint64_t orel;      // start of its result tape
+    uint32_t otile, orem;  // ... as tile number and offset inside that tile (32-bit tile arithmetic for the hot loop)
     uint64_t n_res, n_alt, n_ref;
 };
 
@@ -166,6 +167,7 @@ __device__ __forceinline__ PlanHap plan_hap_load(const KParams& p, uint64_t h) {
     c.tb1 = (uint32_t)min(__ldg(p.task_begin + h + 1) - p.task_origin, p.n_tasks);
     const uint64_t o0 = __ldg(p.out_base + h);
     c.orel = o0 - p.out_origin;
+    c.otile = (uint32_t)(c.orel >> p.tile_shift), c.orem = (uint32_t)c.orel & (p.tile_bytes - 1u);
     c.n_res = __ldg(p.out_base + h + 1) - o0;
     c.n_alt = __ldg(p.alt_base + h + 1) - __ldg(p.alt_base + h);
     c.n_ref = p.ref_base ? __ldg(p.ref_base + h + 1) - __ldg(p.ref_base + h) : p.n_ref;
@@ -201,6 +203,13 @@ __global__ void k_plan_tiles(KParams p) {
         if (h >= p.n_hap) h = p.n_hap - 1;
         p.chunk_hap[k] = (uint32_t)h;
     }
+}
+
+// tile in which haplotype-relative offset dst of haplotype m starts, clamped to n_tiles (a rejected task's garbage
+// offset must not index lb[] out of range), in 32-bit arithmetic that cannot overflow
+__device__ __forceinline__ uint32_t plan_tile_of(const KParams& p, const PlanHap& m, const uint32_t dst) {
+    const uint32_t k = m.otile + (dst >> p.tile_shift) + (((dst & (p.tile_bytes - 1u)) + m.orem) >> p.tile_shift);
+    return min(k, (uint32_t)p.n_tiles);
 }
 
 // One task of the plan (lane-private): m = bases of its haplotype; (kprev, p_dst, p_len) = the task in front of it.
@@ -271,8 +280,7 @@ __global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
     uint32_t o_kt = 0xFFFFFFFFu, o_dst = 0u, o_len = 0u;  // first == 0: lb[0 .. tile of task 0] = 0
     if (first > 0) {
         const uint4 pt = __ldg(tk + first - 1);
-        const uint64_t porel = first - 1 >= c.tb0 ? c.orel : plan_hap_of(p, first - 1).orel;
-        o_kt = (uint32_t)min((porel + pt.z) >> p.tile_shift, p.n_tiles);
+        o_kt = first - 1 >= c.tb0 ? plan_tile_of(p, c, pt.z) : plan_tile_of(p, plan_hap_of(p, first - 1), pt.z);
         o_dst = pt.z, o_len = pt.y;
     }
 
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
             const uint32_t len = raw[u].y, dst = raw[u].z;
             const bool whole = t0 + 32u <= min(c.tb1, end);  // warp-uniform: all 32 tasks exist and belong to c
             if (whole) {
-                const uint32_t kt = (uint32_t)min((c.orel + dst) >> p.tile_shift, p.n_tiles);  // tile in which this task starts
+                const uint32_t kt = plan_tile_of(p, c, dst);  // tile in which this task starts
                 const uint32_t kprev = __shfl_sync(0xffffffffu, lane == 31u ? o_kt : kt, rot);
                 const uint32_t p_dst = __shfl_sync(0xffffffffu, lane == 31u ? o_dst : dst, rot);
                 const uint32_t p_len = __shfl_sync(0xffffffffu, lane == 31u ? o_len : len, rot);
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(256, V2P_PLAN_MINB) k_plan_tasks(KParams p) {
             } else {  // a haplotype boundary or the end of the range inside these 32 tasks: per-lane bases
                 PlanHap m = c;
                 if (tr >= c.tb1 && tr < end) m = plan_hap_of(p, tr);
-                const uint32_t kt = (uint32_t)min((m.orel + dst) >> p.tile_shift, p.n_tiles);
+                const uint32_t kt = plan_tile_of(p, m, dst);
                 const uint32_t kprev = __shfl_sync(0xffffffffu, lane == 31u ? o_kt : kt, rot);
                 const uint32_t p_dst = __shfl_sync(0xffffffffu, lane == 31u ? o_dst : dst, rot);
                 const uint32_t p_len = __shfl_sync(0xffffffffu, lane == 31u ? o_len : len, rot);
@@ -486,20 +494,54 @@ __device__ __forceinline__ void piece_merge(uint8_t* __restrict__ tile, const ui
 // out-of-phase alteration payloads only; kept out of the tile loop's body they do not count against its register
 // budget (80 registers at 3 CTAs/SM, and every spilled value there costs a local-memory round trip per tile).
 
-// A short out-of-phase run copied by its own lane: four vectors per round, five aligned loads in flight, then realign + store.
-__device__ __noinline__ void lane_run_copy(uint8_t* __restrict__ tile, const long long p0, const int lane_v0, const int lane_v1) {
-    const unsigned long long sa = (unsigned long long)(p0 + (long long)lane_v0 * 16);
-    const uint32_t sh = (uint32_t)sa & 15u;  // != 0: in-phase runs went to the TMA unit
-    const uint4* ap = reinterpret_cast<const uint4*>(sa - sh);
+// The short out-of-phase runs of a batch (alteration payloads of up to kLaneRunBytes, typically), copied by the WHOLE
+// warp: lane i brings its run's vectors [v0, v1) (none: v0 == v1); a warp scan numbers all vectors of all runs, and
+// every round 32 of them are fetched by 32 lanes -- each finds the run its vector belongs to by a 5-step binary search
+// over the scanned counts (shuffles), then two aligned loads, funnel-shift realign, one 16-byte store.  (Round 1 had
+// every lane copy its own run: a 400-byte frameshift tail kept one lane busy for seven dependent load rounds while 31
+// waited -- on the skew stress that serial tail cost more than everything else in the tile.)
+__device__ __noinline__ void coop_run_copy(uint8_t* __restrict__ tile, const long long p0, const int v0, const int v1, const int lane) {
+    const uint32_t full = 0xffffffffu;
+    const uint32_t cnt = (uint32_t)(v1 - v0);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(full, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(full, incl, 31), excl = incl - cnt;
+    const uint32_t p0lo = (uint32_t)(unsigned long long)p0, p0hi = (uint32_t)((unsigned long long)p0 >> 32);
     uint4* const tv = reinterpret_cast<uint4*>(tile);
-    for (int v = lane_v0; v < lane_v1; v += 4, ap += 4) {
-        const int n = lane_v1 - v;
-        const uint4 c0 = __ldg(ap), c1 = __ldg(ap + 1);
-        const uint4 c2 = n > 1 ? __ldg(ap + 2) : c1, c3 = n > 2 ? __ldg(ap + 3) : c1, c4 = n > 3 ? __ldg(ap + 4) : c1;
-        tv[v] = realign16(c0, c1, sh);
-        if (n > 1) tv[v + 1] = realign16(c1, c2, sh);
-        if (n > 2) tv[v + 2] = realign16(c2, c3, sh);
-        if (n > 3) tv[v + 3] = realign16(c3, c4, sh);
+    for (uint32_t j0 = 0; j0 < total; j0 += 64) {  // two vectors per lane and round: four loads in flight
+        uint4 A[2], B[2];
+        uint32_t shv[2];
+        int vv[2];
+        bool on[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t j = j0 + 32u * u + (uint32_t)lane;
+            uint32_t o = 0;  // smallest lane whose inclusive count exceeds j = the run vector j belongs to
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const uint32_t probe = __shfl_sync(full, incl, (int)(o + step - 1));
+                if (probe <= j) o += step;
+            }
+            o = min(o, 31u);
+            const uint32_t oex = __shfl_sync(full, excl, (int)o), ov0 = __shfl_sync(full, (uint32_t)v0, (int)o);
+            const uint32_t qlo = __shfl_sync(full, p0lo, (int)o), qhi = __shfl_sync(full, p0hi, (int)o);
+            on[u] = j < total;
+            vv[u] = (int)(ov0 + (j - oex));
+            const unsigned long long sa = (((unsigned long long)qhi << 32) | qlo) + (unsigned long long)((long long)vv[u] * 16);
+            shv[u] = (uint32_t)sa & 15u;
+            const uint4* ap = reinterpret_cast<const uint4*>(sa - shv[u]);
+            A[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (on[u]) A[u] = __ldg(ap);
+            B[u] = A[u];
+            if (on[u] && shv[u]) B[u] = __ldg(ap + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (on[u]) tv[vv[u]] = realign16(A[u], B[u], shv[u]);
     }
 }
 
@@ -562,7 +604,7 @@ __device__ __noinline__ void owner_scan_copy(uint8_t* __restrict__ tile, uint8_t
     }
 }
 
-constexpr int kLaneRunBytes = 512;  // out-of-phase runs up to this many fully covered bytes are copied by one lane
+constexpr int kLaneRunBytes = 512;  // out-of-phase runs up to this many fully covered bytes go to coop_run_copy (longer: owner scan)
 constexpr int kTileScratch = 16 + 576 + 64;  // per warp, behind tile | lead[]: mbarrier | staged tasks (32 x 16 B) + bases / flag
                                              // (8 x 8 B) | metadata ring (4 x {tile, lb[k], lb[k+1], tile_hap[k]})
 
@@ -837,8 +879,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                         tma_dst = (uint32_t)v0b;
                         tma_bytes = (uint32_t)(v1b - v0b);
                     } else if (v1b - v0b <= kLaneRunBytes) {
-                        // a short out-of-phase run (an alteration payload, typically): this lane copies it alone,
-                        // below -- cheaper than waking the whole-tile owner scan for a few vectors
+                        // a short out-of-phase run (an alteration payload, typically): all such runs of the batch are
+                        // copied by the warp together, below -- cheaper than the whole-tile owner scan for a few vectors
                         lane_v0 = v0b >> 4, lane_v1 = v1b >> 4;
                     } else {
                         lead[v0b >> 4] = (uint8_t)(lane + 1);
@@ -891,7 +933,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
                     for (int j = pa1 + 1; j < pb2; ++j) d[j] = __ldg(sp + j);
                 }
             }
-            if (lane_v1 > lane_v0) lane_run_copy(tile, p0, lane_v0, lane_v1);
+            if (__any_sync(0xffffffffu, lane_v1 > lane_v0)) coop_run_copy(tile, p0, lane_v0, lane_v1, lane);  // (warp-uniform)
             __syncwarp();  // orders this batch's tile stores before the next batch's read-modify-writes
             if (!__any_sync(0xffffffffu, has_lead)) continue;  // nothing for the register path in this batch
 
