@@ -66,4 +66,53 @@ for h in range(10):
     tasks, alt, ann, res_len, _ = w.oracle_hap(h)
     ok &= tape[int(ob[h]):int(ob[h + 1])].tobytes().decode() == T.execute_tasks(tasks, w.tape.tobytes().decode(), alt, res_len)
 dc.close()
+# ---- round 2: fused missense chains and their near-misses, a haplotype in serial order among sorted ones, the skew mix
+#      (warp-cooperative copy of out-of-phase payloads), error paths with garbage destinations, `-a`, the cohort runner
+from tests.randtasks import chain_batch
+from vcf2prot_b200 import EngineError
+
+eng.set_tuning(-1, 0)
+for seed, n_hap, mean, run in ((81, 4, 30000, 30.0), (82, 5, 60000, 300.0)):
+    b = chain_batch(seed, n_hap, mean, run_mean=run)
+    t = b["tasks"].copy()
+    s0, s1 = int(b["task_begin"][1]), int(b["task_begin"][2])
+    t[s0:s1] = t[s0:s1][np.random.default_rng(seed).permutation(s1 - s0)]  # haplotype 1 needs serial order
+    b["tasks"] = t
+    want = np.zeros(int(b["out_base"][-1]), np.uint8)
+    assert cengine.batch_execute(b["task_begin"], b["tasks"], b["ref"], b["alt"], b["alt_base"], want, b["out_base"])[0] == 0
+    for mode in ("replicas", "plain", None):
+        if mode:
+            eng.set_reference(b["ref"], mode)
+        out, _ = eng.execute_batch(b["task_begin"], b["tasks"], None if mode else b["ref"], b["alt"], b["alt_base"], b["out_base"])
+        ok &= bool(np.array_equal(out, want))
+    bad = b["tasks"].copy()
+    bad[int(b["task_begin"][3]) - 1, 2] = 0xFFFFFFF0  # garbage destination in front of the next haplotype
+    try:
+        eng.execute_batch(b["task_begin"], bad, b["ref"], b["alt"], b["alt_base"], b["out_base"])
+        ok = False
+    except EngineError:
+        pass
+prot4 = C.make_proteome(seed=0x5EED0001, n_tx=300, giant=3)
+cat4 = C.make_catalogue(prot4, 2500, seed=0x5EED0004, mix=C.MIX_C4, fs_mean=150, fs_max=4000, sl_max=500, long_ins_mean=120,
+                        long_ins_max=5000, lognormal_tails=True)
+cat4.af[:] = 0.15
+b4 = C.synth_batch(prot4, cat4, 12, seed=4)
+want = np.zeros(b4.n_residues, np.uint8)
+assert cengine.batch_execute(b4.task_begin, b4.tasks, prot4.residues, b4.alt, b4.alt_base, want, b4.out_base)[0] == 0
+eng.set_reference(prot4.residues)
+out, _ = eng.execute_batch(b4.task_begin, b4.tasks, None, b4.alt, b4.alt_base, b4.out_base)
+ok &= bool(np.array_equal(out, want))
+from vcf2prot_b200.cohort_run import CohortRunner
+
+eng.set_reference(prot.residues)
+pipe = DevicePipeline(eng, prot, cat, C.default_names(prot), lanes=2)
+pipe.enable_all_records(prot.residues, prot.offsets, C.default_names(prot))
+n_all = []
+pipe.run_lists(sb, sites, 4, 3, False, sink=lambda f, n, data, begins: n_all.append(bytes(data[: int(begins[n])]).count(b">")) or 0, all_records=True)
+ok &= sum(n_all) == 4 * 2 * prot.n_tx
+pipe.close()
+r = CohortRunner([0, 0], prot.residues, prot.offsets, C.default_names(prot), cat.t, cat.p, cat.cls, cat.rlen, cat.doff, cat.dlen, cat.pool, lanes=1)
+res = r.run_lists(sb, sites, 4, 1, False, sink=lambda *a: 0)
+ok &= int(res.total.n_samples) == 4
+r.close()
 print("SANITIZE_PROBE", "OK" if ok else "MISMATCH")
