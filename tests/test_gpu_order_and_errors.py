@@ -196,3 +196,41 @@ def test_gir_execute_from_many_threads_at_once(gpu_engine):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errors, errors
+
+
+def test_dot_fill_never_depends_on_what_the_tile_buffers_held_before(gpu_engine):
+    """The copy kernel prefills a tile only where the plan found a byte that no task covers.  Dirty every tile buffer of
+    the GPU with letters first, then run batches whose '.' bytes come from every source of a gap: haplotypes without any
+    task (with and without neighbours that have tasks, and a batch with no task at all), gaps between tasks, in front of
+    the first and behind the last task of a haplotype, a haplotype left to the serial kernel."""
+    z64 = lambda *a: np.asarray(a, dtype=np.uint64)
+    dirty = random_batch(901, 64, 400_000, gap_prob=0.0, empty_hap_prob=0.0)
+    ref = dirty["ref"]
+
+    def run(b):
+        gpu_batch(gpu_engine, dirty)  # every warp's tile buffer now holds letters
+        out, _ = gpu_batch(gpu_engine, b)
+        st, _, _, want = oracle_batch(b)
+        assert st == 0 and np.array_equal(out, want)
+        return want
+
+    # no task at all: three haplotypes of 20,000 / 0 / 70,001 residues
+    w = run(dict(task_begin=z64(0, 0, 0, 0), tasks=np.zeros((0, 4), np.uint32), ref=ref, alt=np.zeros(0, np.uint8),
+                 alt_base=z64(0, 0, 0, 0), out_base=z64(0, 20_000, 20_000, 90_001), ref_base=None))
+    assert (w == ord(".")).all()
+    # a haplotype without tasks between two that have some; gaps in front of / between / behind the tasks of the others
+    tasks = np.asarray([(5, 3000, 100, 0), (9000, 12_000, 3200, 0), (17, 40, 30_000, 0),   # haplotype 0 (40,000 residues)
+                        (100, 9000, 0, 0), (20_000, 1, 9000, 0), (7, 5000, 30_000, 0)],   # haplotype 2 (36,000 residues)
+                       np.uint32)
+    w = run(dict(task_begin=z64(0, 3, 3, 6), tasks=tasks, ref=ref, alt=np.zeros(0, np.uint8), alt_base=z64(0, 0, 0, 0),
+                 out_base=z64(0, 40_000, 65_000, 101_000), ref_base=None))
+    assert (w[40_000:65_000] == ord(".")).all() and (w[:100] == ord(".")).all() and w[100] != ord(".") and (w[-1000:] == ord(".")).all()
+    # the same with haplotype 0's tasks out of order (serial kernel) -- its gaps and its neighbours' stay '.'
+    t2 = tasks.copy()
+    t2[[0, 2]] = t2[[2, 0]]
+    run(dict(task_begin=z64(0, 3, 3, 6), tasks=t2, ref=ref, alt=np.zeros(0, np.uint8), alt_base=z64(0, 0, 0, 0),
+             out_base=z64(0, 40_000, 65_000, 101_000), ref_base=None))
+    # SoA entry with FILL_DOT and no task
+    gpu_batch(gpu_engine, dirty)
+    res = gpu_engine.execute_soa([], "ABCDEFGH", "xyz", 50_000, fill_dot=True)
+    assert (res == ord(".")).all()

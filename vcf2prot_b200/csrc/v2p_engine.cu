@@ -226,8 +226,11 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     }
     if (kp.n_tasks) {
         k_plan_tasks<<<(unsigned)((kp.n_tasks + kPlanChunk - 1) / kPlanChunk), 256, 0, s>>>(kp);
+        e->launches++;
+    }
+    if (kp.n_hap) {  // (also without any task: a haplotype that has none is all '.', and k_plan_fix is who marks its tiles)
         k_plan_fix<<<(unsigned)((kp.n_hap + 255) / 256), 256, 0, s>>>(kp, kp.hap_flags + kp.n_hap);
-        e->launches += 2;
+        e->launches++;
     }
     if (ev_copy) CUDA_TRY(e, cudaEventRecord(ev_copy, s));
     if (kp.n_tiles) {

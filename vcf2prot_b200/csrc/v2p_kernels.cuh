@@ -605,8 +605,12 @@ __device__ __noinline__ void owner_scan_copy(uint8_t* __restrict__ tile, uint8_t
 }
 
 constexpr int kLaneRunBytes = 512;  // out-of-phase runs up to this many fully covered bytes go to coop_run_copy (longer: owner scan)
-constexpr int kTileScratch = 16 + 576 + 64;  // per warp, behind tile | lead[]: mbarrier | staged tasks (32 x 16 B) + bases / flag
-                                             // (8 x 8 B) | metadata ring (4 x {tile, lb[k], lb[k+1], tile_hap[k]})
+constexpr int kTileScratch = 16 + 576 + 64 + 16;  // per warp, behind tile | lead[]: mbarrier | staged tasks (32 x 16 B) + bases /
+                                                  // flag (8 x 8 B) | metadata ring (4 x {tile, lb[k], lb[k+1], tile_hap[k]}) |
+                                                  // slot scheduler state (4 x u32)
+constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu, kSlotEnd = 0xFFFFFFFEu;  // ring sentinels: no tile in this slot / no slot left
+constexpr uint32_t kDynBlock = 4;      // slots claimed per atomic in the dynamic tail
+constexpr uint32_t kStaticNum = 3, kStaticDen = 4;  // share of the slots handed out statically (round-robin)
 
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
 // parallelism); MINB: CTAs per SM the register allocation is held to.
@@ -684,25 +688,52 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         return t > 0u ? t - 1u : 0u;  // the task before may extend into the tile
     };
     auto ring = [&](uint32_t it) -> uint32_t* { return st_meta + ((it & 3u) << 2); };
-    auto fetch_tile = [&](uint32_t it, uint32_t slot) {
+    // Which slot comes next for this warp.  The first 3/4 of the slots go round-robin over the warps (slot = warp + i *
+    // n_warps: at any moment the whole grid works on one band of the slot order, which is what keeps the proteome band
+    // in L2); the rest is claimed kDynBlock slots at a time from a global counter.  Without the dynamic tail the grid
+    // finished ragged -- the warp schedulers favour the older CTAs of an SM, whose warps were done 8 % before the
+    // youngest CTA's, which then ran the tail at a third of the occupancy (profiles/dev/warp_time_probe.py).
+    // State (lane 0 only, in the warp's scratch): {next static slot, next claimed slot, claimed slots left, n_static}.
+    volatile uint32_t* const sched = reinterpret_cast<volatile uint32_t*>(tile + TILE + NV + 16 + 576 + 64);
+    if (lane == 0) {
+        const uint32_t ns = n_slots;
+        sched[0] = blockIdx.x * kWarpsPerCta + warp;
+        sched[1] = 0u, sched[2] = 0u;
+        sched[3] = (uint32_t)((uint64_t)ns * kStaticNum / kStaticDen / n_warps) * n_warps;
+    }
+    auto fetch_tile = [&](uint32_t it) {
         if (lane == 0) {
             uint32_t* m = ring(it);
-            if (slot >= n_slots) m[0] = 0xFFFFFFFFu;
+            uint32_t slot = sched[0];
+            const uint32_t n_static = sched[3];
+            if (slot < n_static) {
+                sched[0] = slot + n_warps;
+            } else {
+                uint32_t left = sched[2];
+                slot = sched[1];
+                if (left == 0u) {  // (the counter only grows past n_slots by kDynBlock per warp: no wrap)
+                    slot = n_static + atomicAdd(p.order_hdr + 1, kDynBlock);
+                    left = kDynBlock;
+                    if (slot >= n_slots) left = 0xFFFFFFFFu;  // nothing left anywhere: stop asking
+                }
+                sched[1] = slot + 1u, sched[2] = left - 1u;
+            }
+            if (slot >= n_slots) m[0] = kSlotEnd;
             else if constexpr (kOrder) cp_async4(m, p.order + slot);
-            else m[0] = (uint32_t)slot;
+            else m[0] = slot;
         }
     };
     auto fetch_meta = [&](uint32_t it) {
         uint32_t* m = ring(it);
         const uint32_t t = m[0];
         if (lane < 3) {
-            if (t == 0xFFFFFFFFu) m[1 + lane] = 0u;
+            if (t >= kSlotEnd) m[1 + lane] = 0u;
             else cp_async4(m + 1 + lane, lane == 2 ? p.tile_hap + t : p.lb + t + lane);
         }
     };
     auto stage = [&](uint32_t it) {
         const uint32_t* m = ring(it);
-        if (m[0] == 0xFFFFFFFFu) return;
+        if (m[0] >= kSlotEnd) return;
         const uint32_t lo = m[1], hi = m[2], hp = m[3] & ~kTileHasGap;
         const uint32_t tr = first_task(lo) + lane;
         if (tr < min(hi, n_tasks32)) cp_async16(st_tasks + lane, reinterpret_cast<const uint4*>(p.tasks) + tr);
@@ -716,8 +747,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         if (lane == 4 && p.ref_base) cp_async8(st_bases + 4, p.ref_base + hp);
         if (lane == 5) cp_async4(st_bases + 5, p.hap_flags + hp);  // 1: the haplotype is left to k_serial
     };
-    uint32_t k = blockIdx.x * kWarpsPerCta + warp;  // this warp's slot (a tile, or a slot of the interleaved order)
-    fetch_tile(0, k), fetch_tile(1, k + n_warps), fetch_tile(2, k + 2 * n_warps);
+    __syncwarp();
+    fetch_tile(0), fetch_tile(1), fetch_tile(2);
     cp_async_commit();
     cp_async_wait0();
     __syncwarp();
@@ -727,12 +758,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
     __syncwarp();
     stage(0);
     cp_async_commit();
-    for (uint32_t it = 0; k < n_slots; k += n_warps, ++it) {
+    for (uint32_t it = 0;; ++it) {
         // this tile's tasks and bases were staged while the previous tile was being assembled
         cp_async_wait0();
         __syncwarp();
         const uint32_t* const mc = ring(it);
-        const uint32_t tile_no = mc[0];  // ~0 = an empty slot of the interleaved order
+        const uint32_t tile_no = mc[0];  // kSlotEmpty = an empty slot of the interleaved order
+        if (tile_no == kSlotEnd) break;  // (nothing is in flight: the ring entries behind an end marker are end markers)
         const uint32_t c_lo = mc[1], c_hi = mc[2];
         const bool has_gap = (mc[3] & kTileHasGap) != 0u;  // some byte of the tile is written by nobody: prefill it
         const uint4 raw0 = st_tasks[lane];
@@ -747,9 +779,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
         __syncwarp();
         stage(it + 1);
         fetch_meta(it + 2);
-        fetch_tile(it + 3, k + 3 * n_warps);
+        fetch_tile(it + 3);
         cp_async_commit();
-        if (tile_no == 0xFFFFFFFFu) continue;
+        if (tile_no == kSlotEmpty) continue;
         const uint64_t tile_start = (uint64_t)tile_no * (uint64_t)TILE;
         const uint32_t tile_len = (uint32_t)min((uint64_t)TILE, p.n_out - tile_start);
         uint8_t* const gout = p.out + tile_start;
