@@ -609,7 +609,7 @@ constexpr int kTileScratch = 16 + 576 + 64 + 16;  // per warp, behind tile | lea
                                                   // flag (8 x 8 B) | metadata ring (4 x {tile, lb[k], lb[k+1], tile_hap[k]}) |
                                                   // slot scheduler state (4 x u32)
 constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu, kSlotEnd = 0xFFFFFFFEu;  // ring sentinels: no tile in this slot / no slot left
-constexpr uint32_t kDynBlock = 4;      // slots claimed per atomic in the dynamic tail
+constexpr uint32_t kDynBlock = 8;      // slots claimed per atomic in the dynamic tail
 constexpr uint32_t kStaticNum = 3, kStaticDen = 4;  // share of the slots handed out statically (round-robin)
 
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
