@@ -540,6 +540,8 @@ def test_skew_stress_c4_mix_with_giant_transcripts(gpu_engine, variant):
             ns = gpu_engine.read_warp_ns().astype(np.float64)
             gpu_engine.profile_warps(False)
             assert np.array_equal(d_out[: b.n_residues].cpu().numpy(), want)
+            # (a 100 MB batch is only 3-6 tiles per warp: the bound is one tile's granularity, the full-size figure is
+            # bench.py's load_balance key: 1.005)
             assert ns.size > 0 and ns.max() / ns.mean() < 1.6, (ns.max(), ns.mean())
     finally:
         gpu_engine.set_tuning(-1, 0)

@@ -609,7 +609,7 @@ constexpr int kTileScratch = 16 + 576 + 64 + 16;  // per warp, behind tile | lea
                                                   // flag (8 x 8 B) | metadata ring (4 x {tile, lb[k], lb[k+1], tile_hap[k]}) |
                                                   // slot scheduler state (4 x u32)
 constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu, kSlotEnd = 0xFFFFFFFEu;  // ring sentinels: no tile in this slot / no slot left
-constexpr uint32_t kDynBlock = 8;      // slots claimed per atomic in the dynamic tail
+constexpr uint32_t kDynBlock = 8;      // most slots claimed per atomic in the dynamic tail
 constexpr uint32_t kStaticNum = 3, kStaticDen = 4;  // share of the slots handed out statically (round-robin)
 
 // TILE: output bytes per warp-tile; G: vectors per lane whose loads are issued back to back (memory-level
@@ -711,10 +711,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_copy_tiles(const KParams p) 
             } else {
                 uint32_t left = sched[2];
                 slot = sched[1];
-                if (left == 0u) {  // (the counter only grows past n_slots by kDynBlock per warp: no wrap)
-                    slot = n_static + atomicAdd(p.order_hdr + 1, kDynBlock);
-                    left = kDynBlock;
-                    if (slot >= n_slots) left = 0xFFFFFFFFu;  // nothing left anywhere: stop asking
+                if (left == 0u) {  // (the counter only grows past n_slots by one block per warp: no wrap)
+                    // block size: kDynBlock when every warp can expect several blocks, down to single slots for a small
+                    // launch (a 100 MB batch is three tiles per warp: an 8-slot claim would triple one warp's share)
+                    const uint32_t ns = n_slots;
+                    const uint32_t blk = max(1u, min(kDynBlock, (ns - n_static) / (4u * n_warps)));
+                    slot = n_static + atomicAdd(p.order_hdr + 1, blk);
+                    left = blk;
+                    if (slot >= ns) left = 0xFFFFFFFFu;  // nothing left anywhere: stop asking
                 }
                 sched[1] = slot + 1u, sched[2] = left - 1u;
             }
