@@ -179,6 +179,7 @@ int launch_group(v2p_engine* e, cudaStream_t s, Scratch& sc, KParams& kp, cudaEv
     kp.tile_shift = T == 8192 ? 13u : T == 4096 ? 12u : 11u;
     kp.n_tiles = (kp.n_out + T - 1) / T;
     if (kp.n_tasks >= 0xFFFFFFFEull) return fail(e, V2P_ERR_INVALID_ARG, "more than 2^32-2 tasks in one launch");
+    if (kp.n_hap >= 0x80000000ull) return fail(e, V2P_ERR_INVALID_ARG, "more than 2^31 haplotypes in one launch");  // bit 31 of tile_hap[] is a flag
     int rc;
     if ((rc = reserve(e, sc.lb, (kp.n_tiles + 1) * sizeof(uint32_t)))) return rc;
     if ((rc = reserve(e, sc.tile_hap, std::max<uint64_t>(kp.n_tiles, 1) * sizeof(uint32_t)))) return rc;
