@@ -78,3 +78,62 @@ def test_world2_sharding_matches_single_rank():
     assert sum(r[3] for r in two) == one[0][3] and sum(r[4] for r in two) == one[0][4]
     # the all-reduces every rank sees: total units and the slowest rank's time
     assert all(r[5] == one[0][3] for r in two) and all(r[6] == 3.0 for r in two)
+
+
+def _c3_worker(rank, world, port, n_samples, q):
+    """The host logic of bench.py's c3 section on CPU: ONE counter-based cohort (synth/devgen), every rank plans the same
+    contiguous ranges from per-sample result-tape bytes, builds and 'executes' (oracle) only its own range, and the
+    parity counters are summed over ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import cengine
+        from synth import devgen
+
+        prot = C.make_proteome(seed=3, n_tx=80, mu=5.0, sigma=0.6, hi=2500)
+        cat = C.make_catalogue(prot, 2500, seed=4, mix=(0.7, 0.06, 0.06, 0.08, 0.04, 0.03, 0.03))
+        cat.af[:] = np.random.default_rng(1).choice([0.02, 0.1, 0.3], size=cat.n).astype(np.float32)
+        seed = 0x5EED0003
+        # planning pass (every rank, whole cohort): result-tape bytes per sample -> ranges balanced by bytes
+        hap, site = devgen.site_lists_numpy(cat, seed, 0, 2 * n_samples)
+        whole = C.build_batch(prot, cat, hap, site, 2 * n_samples)
+        ob = whole.out_base.astype(np.int64)
+        weights = (ob[2::2] - ob[:-2:2]).tolist()
+        ranges = shard.balanced_ranges(weights, world)
+        lo, hi = ranges[rank]
+        # this rank's range, generated on its own from the haplotype indices alone
+        h2, s2 = devgen.site_lists_numpy(cat, seed, 2 * lo, 2 * (hi - lo))
+        mine = C.build_batch(prot, cat, h2, s2, 2 * (hi - lo))
+        out = np.zeros(mine.n_residues, np.uint8)
+        assert cengine.batch_execute(mine.task_begin, mine.tasks, prot.residues, mine.alt, mine.alt_base, out, mine.out_base)[0] == 0
+        bad, _ = cengine.batch_check(mine.task_begin, mine.tasks, prot.residues, mine.alt, mine.alt_base, out, mine.out_base, threads=2)
+        digest = int(out.astype(np.int64).sum()) + 31 * int(mine.n_residues)
+        q.put((rank, lo, hi, int(mine.n_residues), digest, shard.sum_over_ranks(int(mine.n_residues)),
+               shard.sum_over_ranks(bad), shard.sum_over_ranks(2 * (hi - lo)), int(whole.n_residues), max(weights)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_one_cohort_sharded_by_bytes_like_the_c3_section():
+    n_samples = 21
+    ctx = mp.get_context("spawn")
+    results = {}
+    for world in (1, 2):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_c3_worker, args=(r, world, port, n_samples, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = [q.get(timeout=180) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        results[world] = sorted(got)
+    one, two = results[1][0], results[2]
+    assert (two[0][1], two[1][2]) == (0, n_samples) and two[0][2] == two[1][1]  # contiguous, covering, no overlap
+    # the union of the ranks' ranges is the single-rank cohort: residues and content digests add up
+    assert sum(r[3] for r in two) == one[3] == one[8] and sum(r[4] for r in two) == one[4]
+    # what every rank sees after the all-reduces: all residues, no mismatching haplotype, every haplotype checked
+    assert all(r[5] == one[3] and r[6] == 0 and r[7] == 2 * n_samples for r in two)
+    # balanced by bytes: no rank is more than one sample's worth above its share
+    assert max(r[3] for r in two) <= one[3] / 2 + one[9]
