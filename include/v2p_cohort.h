@@ -78,8 +78,13 @@ typedef struct {
 #define V2P_COHORT_CONCURRENT_SINK 0x100u /* the sink is thread-safe: workers call it concurrently (v2p_dir_writer_sink
                                            * is); without the flag calls are serialised by a lock                        */
 
+/* Prepares V2P_PIPE_ALL_RECORDS (the reference's `-a`, personalized_genome.rs:120-210) on every worker:
+ * v2p_pipeline_enable_all_records with the proteome, transcript offsets and names of `in` (the same arrays create got;
+ * the catalogue fields are not read).  The workers do it in parallel. */
+int v2p_cohort_enable_all_records(v2p_cohort* c, const v2p_cohort_inputs* in);
+
 /* site_begin[2*n_samples+1] / sites: the whole cohort's CSR lists (host pointers), haplotype h = 2*sample + (hap-1).
- * flags: V2P_PIPE_GZIP, V2P_PIPE_SKIP_ABORTS (include/v2p_pipeline.h), V2P_COHORT_CONCURRENT_SINK.
+ * flags: V2P_PIPE_GZIP, V2P_PIPE_SKIP_ABORTS, V2P_PIPE_ALL_RECORDS (include/v2p_pipeline.h), V2P_COHORT_CONCURRENT_SINK.
  * The sink is called per chunk with cohort-wide sample numbers; inside one worker's range chunks arrive in sample
  * order, chunks of different workers interleave (the reference writes its files from a parallel pool too).
  * The first failing worker's status is returned (its message in v2p_cohort_last_error); the others finish their

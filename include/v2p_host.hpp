@@ -401,8 +401,21 @@ public:
     Cohort(const Cohort&) = delete;
     Cohort& operator=(const Cohort&) = delete;
 
+    // The reference's `-a` flag on every device (v2p_cohort_enable_all_records): call once, then pass write_all = true.
+    void enable_write_all(const std::string& proteome, const std::vector<uint64_t>& tx_offsets, const std::vector<std::string>& tx_names) {
+        std::vector<uint64_t> name_off(1, 0);
+        std::string names;
+        for (const std::string& n : tx_names) names += n, name_off.push_back(names.size());
+        v2p_cohort_inputs in{};
+        in.proteome = reinterpret_cast<const uint8_t*>(proteome.data()), in.n_proteome = proteome.size();
+        in.n_tx = tx_offsets.size() - 1, in.tx_offsets = tx_offsets.data();
+        in.name_off = name_off.data(), in.names = reinterpret_cast<const uint8_t*>(names.data());
+        const int st = v2p_cohort_enable_all_records(c_, &in);
+        if (st != V2P_OK) throw EngineError(st, v2p_cohort_last_error(c_));
+    }
+
     v2p_cohort_result write(const std::vector<std::vector<uint32_t>>& per_haplotype, DirWriter& writer, bool write_compressed,
-                            uint32_t chunk_probands = 128) {
+                            uint32_t chunk_probands = 128, bool write_all = false) {
         std::vector<uint64_t> begin(1, 0);
         std::vector<uint32_t> sites;
         for (const auto& l : per_haplotype) {
@@ -411,7 +424,8 @@ public:
         }
         v2p_cohort_result r{};
         const int st = v2p_cohort_run_lists(c_, per_haplotype.size() / 2, begin.data(), sites.data(), chunk_probands,
-                                            (write_compressed ? V2P_PIPE_GZIP : 0u) | V2P_COHORT_CONCURRENT_SINK, v2p_dir_writer_sink,
+                                            (write_compressed ? V2P_PIPE_GZIP : 0u) | (write_all ? V2P_PIPE_ALL_RECORDS : 0u) | V2P_COHORT_CONCURRENT_SINK,
+                                            v2p_dir_writer_sink,
                                             writer.get(), &r);
         if (st != V2P_OK) throw EngineError(st, v2p_cohort_last_error(c_));
         return r;

@@ -153,6 +153,13 @@ static void test_pipeline_writes_the_golden_records(v2p::Context& ctx, const std
         CHECK(slurp(dir + "/HG1.fasta") == ">T_1\nMEDLHENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVTESTFRAMESHIFT\n");
         CHECK(slurp(dir + "/HG2.fasta") == ">T_1\nMEDLGTESTENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVLSTLRSLNNFISQRVEGGSGLEELERG.\n");
         CHECK(slurp(dir + "/HG3.fasta").empty());
+        // ... and `-a` over the workers
+        cohort.enable_write_all(T, {0, T.size()}, {"T"});
+        v2p::DirWriter wd(dir, {"HG1", "HG2", "HG3"}, false, 2);
+        const v2p_cohort_result rd = cohort.write({{1}, {2}, {0}, {3}, {}, {}}, wd, false, 1, /*write_all=*/true);
+        CHECK(rd.total.n_records == 6 && wd.files_written() == 3);
+        CHECK(slurp(dir + "/HG2.fasta") == ">T_1\nMEDLGTESTENTMVLSTLRSLNNFISQRVEGGSGLEELERGG\n>T_2\nMEDLGENTMVLSTLRSLNNFISQRVEGGSGLEELERG.\n");
+        CHECK(slurp(dir + "/HG3.fasta") == ">T_1\n" + T + "\n>T_2\n" + T + "\n");
     }
 }
 

@@ -107,3 +107,43 @@ def test_directory_writer_from_two_workers_and_error_reporting(world):
         assert int(ok.total.n_samples) == n_samples and r.launch_count() > 0
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("n_workers,gzip", [(2, False), (3, True)])
+def test_all_records_flag_on_every_worker(world, n_workers, gzip):
+    """`-a` (personalized_genome.rs:120-210) through the cohort runner: every file holds 2 x n_tx records, oracle text."""
+    from tests.test_gpu_pipeline import oracle_files_all
+    from vcf2prot_b200 import EngineError
+
+    prot, cat = world
+    n_samples = 9
+    hap, site = cohort_sites(cat, n_samples, 640 + n_workers, drop=(4, 5))  # sample 2 carries nothing
+    want = oracle_files_all(prot, cat, hap, site, n_samples)
+    sb, sites = csr_lists(hap, site, 2 * n_samples)
+    got = {}
+
+    def sink(first, n, data, begins):
+        for i in range(n):
+            assert first + i not in got
+            got[first + i] = bytes(data[int(begins[i]):int(begins[i + 1])])
+        return 0
+
+    r = runner(prot, cat, devices(n_workers))
+    try:
+        with pytest.raises(EngineError) as ei:  # not prepared yet: the worker's message comes back
+            r.run_lists(sb, sites, n_samples, 2, gzip, sink=lambda *a: 0, all_records=True)
+        assert "enable_all_records" in str(ei.value)
+        r.enable_all_records()
+        res = r.run_lists(sb, sites, n_samples, 2, gzip, sink=sink, all_records=True)
+        un = (lambda b: zlib.decompress(b, wbits=31)) if gzip else (lambda b: b)
+        assert sorted(got) == list(range(n_samples))
+        for s in range(n_samples):
+            assert un(got[s]) == want[s], s
+        assert int(res.total.n_records) == 2 * n_samples * prot.n_tx
+        # the altered-only files still come out of the same runner
+        want_altered, _ = oracle_files(prot, cat, hap, site, n_samples)
+        got.clear()
+        r.run_lists(sb, sites, n_samples, 4, False, sink=sink)
+        assert [got[s] for s in range(n_samples)] == want_altered
+    finally:
+        r.close()

@@ -28,6 +28,7 @@ class CohortRunner:
         inp.name_off, inp.names, inp.general, inp.n_sites = p(k["noff"]), p(k["npool"]), 0, len(k["tx"])
         inp.site_tx, inp.site_pos, inp.site_cls, inp.site_rlen = p(k["tx"]), p(k["pos"]), p(k["cls"]), p(k["rlen"])
         inp.site_doff, inp.site_dlen, inp.pool, inp.n_pool = p(k["doff"]), p(k["dlen"]), p(k["pool"]), len(k["pool"])
+        self._inputs = inp
         devs = (C.c_int * len(devices))(*devices)
         h = C.c_void_p()
         st = self._lib.v2p_cohort_create(devs, len(devices), C.byref(inp), lanes, C.byref(h))
@@ -50,13 +51,19 @@ class CohortRunner:
     def launch_count(self) -> int:
         return int(self._lib.v2p_cohort_launch_count(self._h))
 
+    def enable_all_records(self) -> None:
+        """The reference's `-a` (write_all) on every device; afterwards run_lists(..., all_records=True)."""
+        st = self._lib.v2p_cohort_enable_all_records(self._h, C.byref(self._inputs))
+        if st:
+            raise EngineError(st, (self._lib.v2p_cohort_last_error(self._h) or b"").decode())
+
     def run_lists(self, site_begin: np.ndarray, sites: np.ndarray, n_samples: int, chunk_samples: int = 128, gzip: bool = False,
-                  sink: Optional[Callable] = None, concurrent_sink: bool = False) -> L.CohortResult:
+                  sink: Optional[Callable] = None, concurrent_sink: bool = False, all_records: bool = False) -> L.CohortResult:
         """sink(first_sample, n, data, file_begin) per chunk (cohort-wide sample numbers), or a DirWriter."""
         sb, st_ = np.ascontiguousarray(site_begin, np.uint64), np.ascontiguousarray(sites, np.uint32)
         cb, user, keep = DevicePipeline._sink(sink)
         res = L.CohortResult()
-        flags = (L.PIPE_GZIP if gzip else 0) | (L.COHORT_CONCURRENT_SINK if concurrent_sink else 0)
+        flags = (L.PIPE_GZIP if gzip else 0) | (L.COHORT_CONCURRENT_SINK if concurrent_sink else 0) | (L.PIPE_ALL_RECORDS if all_records else 0)
         st = self._lib.v2p_cohort_run_lists(self._h, n_samples, sb.ctypes.data_as(C.c_void_p), st_.ctypes.data_as(C.c_void_p),
                                             chunk_samples, flags, cb, user, C.byref(res))
         del keep

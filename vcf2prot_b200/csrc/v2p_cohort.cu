@@ -163,6 +163,28 @@ void v2p_cohort_destroy(v2p_cohort* c) {
 
 const char* v2p_cohort_last_error(v2p_cohort* c) { return c ? c->err.c_str() : "cohort is NULL"; }
 
+int v2p_cohort_enable_all_records(v2p_cohort* c, const v2p_cohort_inputs* in) {
+    if (!c) return V2P_ERR_INVALID_ARG;
+    {
+        std::lock_guard<std::mutex> g(c->err_mu);
+        c->err.clear();
+    }
+    if (!in || !in->tx_offsets || !in->name_off || (in->n_proteome && !in->proteome))
+        return cofail(c, V2P_ERR_INVALID_ARG, "enable_all_records: proteome / tx_offsets / name_off missing");
+    std::vector<int> rcs(c->n_dev, V2P_OK);
+    std::vector<std::thread> th;
+    for (uint32_t g = 0; g < c->n_dev; ++g)
+        th.emplace_back([c, g, in, &rcs] {
+            rcs[g] = v2p_pipeline_enable_all_records(c->w[g].pipe, in->proteome, in->n_proteome, in->n_tx, in->tx_offsets,
+                                                     in->name_off, in->names);
+        });
+    for (auto& t : th) t.join();
+    for (uint32_t g = 0; g < c->n_dev; ++g)
+        if (rcs[g] != V2P_OK)
+            return cofail(c, rcs[g], "device %d: %s", c->w[g].device, v2p_pipeline_last_error(c->w[g].pipe));
+    return V2P_OK;
+}
+
 uint64_t v2p_cohort_launch_count(v2p_cohort* c) {
     uint64_t n = 0;
     if (c)
@@ -201,7 +223,8 @@ int v2p_cohort_run_lists(v2p_cohort* c, uint64_t n_samples, const uint64_t* site
             for (uint64_t h = 0; h <= 2 * ns; ++h) sb[h] = site_begin[2 * s0 + h] - base;
             SinkShim shim{sink, user, s0, (flags & V2P_COHORT_CONCURRENT_SINK) ? nullptr : &serial, &stop};
             const int rc = v2p_pipeline_run_lists(c->w[g].pipe, ns, sb.data(), sites ? sites + base : nullptr, chunk_samples,
-                                                  flags & (V2P_PIPE_GZIP | V2P_PIPE_SKIP_ABORTS), nullptr, 0, nullptr, shim_sink,
+                                                  flags & (V2P_PIPE_GZIP | V2P_PIPE_SKIP_ABORTS | V2P_PIPE_ALL_RECORDS),
+                                                  nullptr, 0, nullptr, shim_sink,
                                                   &shim, &local.per_device[g]);
             if (rc != V2P_OK && !stop.exchange(1)) {
                 rcs[g] = rc;
