@@ -147,3 +147,42 @@ def test_all_records_flag_on_every_worker(world, n_workers, gzip):
         assert [got[s] for s in range(n_samples)] == want_altered
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("n_workers,gzip", [(2, False), (3, True)])
+def test_masks_to_files_over_the_workers(world, n_workers, gzip):
+    """FORMAT/BCSQ matrix in, files out (MaskDecoder.rs:95-153 + parts/exec.rs:34-40): decoded once, run by every worker."""
+    from vcf2prot_b200 import EngineError
+
+    prot, cat = world
+    n_samples = 29
+    rec = C.make_records(cat, 5, 3, 0.2, 4)
+    hap, site = cohort_sites(cat, n_samples, 77 + n_workers)
+    masks = C.encode_masks(rec, n_samples, hap, site)
+    want, _ = oracle_files(prot, cat, hap, site, n_samples)
+    got = {}
+
+    def sink(first, n, data, begins):
+        for i in range(n):
+            assert first + i not in got
+            got[first + i] = bytes(data[int(begins[i]):int(begins[i + 1])])
+        return 0
+
+    r = runner(prot, cat, devices(n_workers))
+    try:
+        res = r.run_masks(masks, rec.csq_begin, rec.csq_site, chunk_samples=4, gzip=gzip, sink=sink)
+        un = (lambda b: zlib.decompress(b, wbits=31)) if gzip else (lambda b: b)
+        assert sorted(got) == list(range(n_samples))
+        for s in range(n_samples):
+            assert un(got[s]) == want[s], s
+        assert int(res.total.n_samples) == n_samples and res.total.decode_ms > 0 and int(res.total.n_sites) == len(site)
+        assert int(res.total.h2d_bytes) >= masks.nbytes
+        # a mask bit beyond the record's consequences: the decoder's error comes back through the runner
+        bad = masks.copy()
+        r0 = int(np.argmin(np.diff(rec.csq_begin)))
+        bad[r0, 0, -1] |= np.uint32(1 << 29)
+        with pytest.raises(EngineError) as ei:
+            r.run_masks(bad, rec.csq_begin, rec.csq_site, chunk_samples=4, sink=lambda *a: 0)
+        assert "mask decode" in str(ei.value)
+    finally:
+        r.close()

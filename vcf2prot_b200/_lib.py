@@ -141,6 +141,8 @@ SYMBOLS = {
     "v2p_cohort_run_lists": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.c_uint32, FILE_SINK, _P, C.POINTER(CohortResult)]),
     "v2p_cohort_launch_count": (C.c_uint64, [_P]),
     "v2p_cohort_enable_all_records": (C.c_int, [_P, C.POINTER(CohortInputs)]),
+    "v2p_cohort_run_masks": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint32, C.c_uint32, FILE_SINK, _P,
+                                       C.POINTER(CohortResult)]),
     "v2p_pipeline_run_masks": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _P, C.c_uint64, _P, FILE_SINK, _P, C.POINTER(PipelineResult)]),
 }

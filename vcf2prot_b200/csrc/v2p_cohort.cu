@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "v2p_cohort.h"
+#include "v2p_taskgen.h"
 
 namespace {
 
@@ -240,6 +241,35 @@ int v2p_cohort_run_lists(v2p_cohort* c, uint64_t n_samples, const uint64_t* site
     for (uint32_t g = 0; g < c->n_dev; ++g)
         if (rcs[g] != V2P_OK) return rcs[g];
     return V2P_OK;
+}
+
+int v2p_cohort_run_masks(v2p_cohort* c, uint64_t n_records, uint64_t n_samples, uint32_t words_per_cell, const uint32_t* masks,
+                         const uint64_t* csq_begin, const int32_t* csq_site, uint32_t chunk_samples, uint32_t flags,
+                         v2p_file_sink sink, void* user, v2p_cohort_result* res) {
+    if (!c) return V2P_ERR_INVALID_ARG;
+    {
+        std::lock_guard<std::mutex> g(c->err_mu);
+        c->err.clear();
+    }
+    Worker& w0 = c->w[0];
+    if (cudaSetDevice(w0.device) != cudaSuccess) return cofail(c, V2P_ERR_CUDA, "cudaSetDevice(%d) failed", w0.device);
+    v2p_site_lists lists;
+    memset(&lists, 0, sizeof lists);
+    int rc = v2p_sites_from_masks(w0.lanes[0], n_records, n_samples, words_per_cell, masks, csq_begin, csq_site, 0, &lists);
+    if (rc != V2P_OK) return cofail(c, rc, "mask decode on device %d: %s", w0.device, v2p_catalogue_last_error(w0.lanes[0]));
+    std::vector<uint64_t> sb(2 * n_samples + 1, 0);
+    std::vector<uint32_t> sites(lists.n_sites);
+    rc = v2p_device_read(sb.data(), lists.site_begin, sb.size() * sizeof(uint64_t));
+    if (rc == V2P_OK && lists.n_sites) rc = v2p_device_read(sites.data(), lists.sites, sites.size() * sizeof(uint32_t));
+    if (rc != V2P_OK) return cofail(c, rc, "reading the decoded lists back from device %d failed", w0.device);
+    v2p_cohort_result local;
+    memset(&local, 0, sizeof local);
+    rc = v2p_cohort_run_lists(c, n_samples, sb.data(), sites.data(), chunk_samples, flags, sink, user, &local);
+    local.total.decode_ms += lists.decode_ms, local.per_device[0].decode_ms += lists.decode_ms;
+    const uint64_t up = n_records * n_samples * (uint64_t)words_per_cell * sizeof(uint32_t);
+    local.total.h2d_bytes += up, local.per_device[0].h2d_bytes += up;
+    if (res) *res = local;
+    return rc;
 }
 
 }  // extern "C"
