@@ -353,6 +353,19 @@ def test_device_pointer_entry_and_async(gpu_engine):
     with pytest.raises(EngineError) as ei:
         gpu_engine.execute_batch_device(*bad)
     assert ei.value.status == L.ERR_INVALID_ARG
+    # findings are localised (haplotype, task within it) without a host copy of task_begin: every class
+    tb = b["task_begin"]
+    for h, code, field, value in ((7, L.ERR_BAD_STREAM, 3, 9), (11, L.ERR_SRC_OOB, 0, 0xFFFFFF00), (13, L.ERR_RES_OOB, 1, 0x7FFFFFFF)):
+        k = int(tb[h]) + (int(tb[h + 1]) - int(tb[h])) // 2
+        tk = b["tasks"].copy()
+        tk[k, field] = value
+        bad = list(args)
+        bad[2] = t(tk)
+        with pytest.raises(EngineError) as ei:
+            gpu_engine.execute_batch_device(*bad)
+        want_err = cengine.batch_execute(b["task_begin"], tk, b["ref"], b["alt"], b["alt_base"], np.zeros(n_out, np.uint8), b["out_base"])
+        assert (ei.value.status, ei.value.bad_hap, ei.value.bad_task) == (code, h, k - int(tb[h])), (h, code)
+        assert want_err[1] == h and want_err[2] == k - int(tb[h])
     # caller-owned stream (torch's current stream)
     side = torch.cuda.Stream()
     gpu_engine.set_stream(side.cuda_stream)

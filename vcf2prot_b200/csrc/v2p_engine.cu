@@ -375,7 +375,7 @@ int wait_locked(v2p_engine* e, v2p_event* ev, v2p_result* res) {
     }
     std::vector<uint64_t> tb_copy;
     const uint64_t* tb = ev->h_task_begin;
-    if (!tb && ev->kp.n_hap && (st.err_key != ~0ull || st.gap_key != ~0ull)) {  // error path only: fetch task_begin
+    if (!tb && ev->kp.n_hap && (st.err_key != ~0ull || st.gap_key != ~0ull || st.stream_key != ~0ull)) {  // error path only: fetch task_begin
         tb_copy.resize(ev->kp.n_hap + 1);
         if (cudaMemcpy(tb_copy.data(), ev->kp.task_begin, tb_copy.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost) ==
             cudaSuccess)

@@ -411,6 +411,7 @@ int v2p_pipeline_run_lists(v2p_pipeline* p, uint64_t n_samples, const uint64_t* 
     p->err.clear();
     v2p_pipeline_result local;
     memset(&local, 0, sizeof local);
+    if (res) *res = local;  // (also on the argument errors below)
     if (!site_begin || site_begin[0] != 0) return pfail(p, V2P_ERR_INVALID_ARG, "site_begin is NULL or does not start at 0");
     for (uint64_t h = 0; h < 2 * n_samples; ++h)
         if (site_begin[h + 1] < site_begin[h]) return pfail(p, V2P_ERR_INVALID_ARG, "site_begin not monotone at haplotype %llu", (unsigned long long)h);
@@ -492,7 +493,10 @@ int v2p_dir_writer_create(const char* out_dir, const char* const* proband_names,
 int v2p_dir_writer_sink(void* writer, uint64_t first_sample, uint64_t n_samples, const uint8_t* data, const uint64_t* file_begin) {
     v2p_dir_writer* w = static_cast<v2p_dir_writer*>(writer);
     if (!w || !file_begin || first_sample + n_samples > w->names.size()) {
-        if (w) w->err = "chunk beyond the proband list";
+        if (w) {
+            std::lock_guard<std::mutex> g(w->mu);
+            w->err = "chunk beyond the proband list";
+        }
         return 1;
     }
     std::atomic<int> failed{0};
