@@ -65,7 +65,14 @@ def main():
     d_out = torch.empty(n_out + 64, dtype=torch.uint8, device=dev)
     d_alt, d_alt_base, d_out_base = to_dev(b.alt), to_dev(b.alt_base), to_dev(b.out_base)
     res = {}
-    for name, tb, tk in (("as_is", b.task_begin, b.tasks), ("prefused", f_begin, f_tasks)):
+    # floor: every haplotype's tape as ONE reference run (a plain copy through the same kernel: one bulk load per tile;
+    # the plan pass is slow here for an unrelated reason -- 5,008 tasks are ten warps, each lane filling ~500 lb[] entries)
+    n_res_h = np.diff(b.out_base).astype(np.int64)
+    one = np.zeros((b.n_hap, 4), np.uint32)
+    one[:, 0] = np.arange(b.n_hap) % 16  # every source phase, one band of the proteome (the cohort's own access pattern)
+    one[:, 1] = n_res_h
+    one_begin = np.arange(b.n_hap + 1, dtype=np.uint64)
+    for name, tb, tk in (("as_is", b.task_begin, b.tasks), ("prefused", f_begin, f_tasks), ("one_run_per_haplotype", one_begin, one)):
         d_tb, d_tk = to_dev(tb), to_dev(tk)
         args = (b.n_hap, d_tb, d_tk, None, d_alt, d_alt_base, d_out, d_out_base, len(tk), len(b.alt), n_out)
         for _ in range(5):
